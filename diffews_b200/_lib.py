@@ -1,0 +1,72 @@
+"""ctypes binding of the C ABI declared in include/diffews_b200.h.
+
+The product path has no fallback: if the shared library is missing or does not export a symbol, importing this
+module raises; if the device is not sm_100, every compute call returns DFW_ERR_ARCH and `check()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdiffews_b200.so")
+
+DFW_OK, DFW_ERR_INVALID, DFW_ERR_CUDA, DFW_ERR_ARCH = 0, -1, -2, -3
+EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU = 1, 2, 4, 8
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes): mirrors include/diffews_b200.h one to one (tests/test_abi.py checks the header).
+SIGNATURES = {
+    "dfw_version": (_i, []),
+    "dfw_device_ok": (_i, []),
+    "dfw_launch_count": (_ll, []),
+    "dfw_conv2d_igemm": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "dfw_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
+                                  _i, _f, _vp]),
+    "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp]),
+    "dfw_groupnorm_workspace_bytes": (_ll, [_i, _i, _i, _i]),
+    "dfw_groupnorm_silu": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "dfw_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "dfw_softmax_rows": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "dfw_upsample2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "dfw_conv3x3_small_cin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dfw_pointwise_small": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _f, _f, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
+    "dfw_nhwc_f32_to_nchw_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp]),
+    "dfw_seg_post": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
+    "dfw_rthres_workspace_bytes": (_ll, [_i]),
+    "dfw_rthres_iou_hist": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "dfw_iou_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+}
+
+
+class DfwError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise ImportError(f"libdiffews_b200.so does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+_ERR = {DFW_ERR_INVALID: "invalid argument", DFW_ERR_CUDA: "CUDA error", DFW_ERR_ARCH: "device is not sm_100 (B200)"}
+
+
+def check(rc: int, what: str) -> None:
+    if rc != DFW_OK:
+        raise DfwError(f"{what} failed: {_ERR.get(rc, rc)} (see stderr)")

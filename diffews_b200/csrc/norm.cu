@@ -1,0 +1,336 @@
+// K4 / K7 — GroupNorm(+SiLU), LayerNorm and the row softmax of the VAE attention: bandwidth-bound kernels,
+// 128-bit vectorised loads/stores, fp32 statistics, warp-shuffle / fixed-order reductions (deterministic).
+// ref: nn.GroupNorm + SiLU inside diffusers ResnetBlock2D / Transformer2DModel.norm / conv_norm_out
+//      (diffews/models/unet_2d_condition.py:1246-1248), BasicTransformerBlock.norm1/2/3 (upstream).
+#include <atomic>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dfw {
+extern std::atomic<long long> g_launches;
+namespace {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// load 8 consecutive channels as fp32
+template <bool F32>
+__device__ __forceinline__ void load8(const void* base, long long elem_off, float (&v)[8]) {
+    if constexpr (F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+    }
+}
+__device__ __forceinline__ void store8_bf16(void* base, long long elem_off, const float (&v)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm stage 1: per (image, row-chunk) partial sums per group.  blockDim = V * RPI (V = C/8).
+// partial layout: [N, nchunks, groups, 2]
+// ---------------------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
+                                int rows_per_chunk, int RPI) {
+    extern __shared__ float sm[];  // [RPI][C][2]
+    const int V = C / 8;
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int vc = threadIdx.x % V, r = threadIdx.x / V;
+    const int row0 = chunk * rows_per_chunk;
+    const int row1 = min(HW, row0 + rows_per_chunk);
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+    const long long img_off = static_cast<long long>(n) * HW * C;
+    for (int row = row0 + r; row < row1; row += RPI) {
+        float v[8];
+        load8<F32>(x, img_off + static_cast<long long>(row) * C + vc * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+    }
+    float* my = sm + (static_cast<size_t>(r) * C + vc * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[2 * j] = s[j]; my[2 * j + 1] = ss[j]; }
+    __syncthreads();
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float gs = 0.f, gss = 0.f;
+        for (int rr = 0; rr < RPI; ++rr) {
+            const float* base = sm + (static_cast<size_t>(rr) * C + g * cpg) * 2;
+            for (int c = 0; c < cpg; ++c) { gs += base[2 * c]; gss += base[2 * c + 1]; }
+        }
+        float* out = partial + ((static_cast<size_t>(n) * nchunks + chunk) * groups + g) * 2;
+        out[0] = gs; out[1] = gss;
+    }
+}
+
+// stage 2: fold partials (fixed order, double), emit per-(image, channel) scale / shift.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale_shift, int HW, int C,
+                                   int groups, int nchunks, float eps) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.x;
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, ss = 0.0;
+        for (int c = 0; c < nchunks; ++c) {
+            const float* p = partial + ((static_cast<size_t>(n) * nchunks + c) * groups + g) * 2;
+            s += p[0]; ss += p[1];
+        }
+        const double cnt = static_cast<double>(HW) * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = s_rstd[g] * gamma[c];
+        scale_shift[(static_cast<size_t>(n) * C + c) * 2] = sc;
+        scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 1] = beta[c] - s_mean[g] * sc;
+    }
+}
+
+// stage 3: y = [silu](x * scale + shift)
+template <bool F32>
+__global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restrict__ scale_shift,
+                                void* __restrict__ y, long long total_vecs, int HW, int C, int apply_silu) {
+    const int V = C / 8;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vecs; i += stride) {
+        const int vc = static_cast<int>(i % V);
+        const long long rowg = i / V;
+        const int n = static_cast<int>(rowg / HW);
+        float v[8];
+        load8<F32>(x, i * 8, v);
+        const float4* sp = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + vc * 8) * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 q = __ldg(sp + j);  // (scale, shift, scale, shift)
+            float a = fmaf(v[2 * j], q.x, q.y);
+            float b = fmaf(v[2 * j + 1], q.z, q.w);
+            if (apply_silu) { a = silu_f(a); b = silu_f(b); }
+            v[2 * j] = a; v[2 * j + 1] = b;
+        }
+        store8_bf16(y, i * 8, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 2048), exact two-pass statistics.
+// ---------------------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, void* __restrict__ y, int M, int C, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const int V = C / 8;
+    const long long row_off = static_cast<long long>(warp) * C;
+    float v[8][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int vc = lane + 32 * k;
+        if (vc < V) {
+            load8<F32>(x, row_off + vc * 8, v[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[k][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int vc = lane + 32 * k;
+        if (vc < V) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; ss = fmaf(d, d, ss); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / C + eps);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int vc = lane + 32 * k;
+        if (vc < V) {
+            const float4* gp = reinterpret_cast<const float4*>(gamma + vc * 8);
+            const float4* bp = reinterpret_cast<const float4*>(beta + vc * 8);
+            float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+            float o[8];
+            o[0] = (v[k][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[k][1] - mean) * rstd * g0.y + b0.y;
+            o[2] = (v[k][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[k][3] - mean) * rstd * g0.w + b0.w;
+            o[4] = (v[k][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[k][5] - mean) * rstd * g1.y + b1.y;
+            o[6] = (v[k][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[k][7] - mean) * rstd * g1.w + b1.w;
+            store8_bf16(y, row_off + vc * 8, o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row softmax (fp32 logits -> bf16 probabilities), one CTA per row.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int L, float scale) {
+    __shared__ float red[32];
+    const float* row = s + static_cast<long long>(blockIdx.x) * L;
+    __nv_bfloat16* out = p + static_cast<long long>(blockIdx.x) * L;
+    const int nvec = L / 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < nwarps; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    const float c = scale * 1.4426950408889634f;
+    const float mc = m * c;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+        sum += exp2f(fmaf(v.x, c, -mc)) + exp2f(fmaf(v.y, c, -mc)) + exp2f(fmaf(v.z, c, -mc)) +
+               exp2f(fmaf(v.w, c, -mc));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < nwarps; ++w) sum += red[w];
+    const float inv = 1.0f / sum;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+        uint2 o;
+        o.x = pack_bf16x2(exp2f(fmaf(v.x, c, -mc)) * inv, exp2f(fmaf(v.y, c, -mc)) * inv);
+        o.y = pack_bf16x2(exp2f(fmaf(v.z, c, -mc)) * inv, exp2f(fmaf(v.w, c, -mc)) * inv);
+        *reinterpret_cast<uint2*>(out + 4 * i) = o;
+    }
+}
+
+struct GnPlan {
+    int V, RPI, threads, nchunks, rows_per_chunk;
+    size_t smem;
+};
+GnPlan gn_plan(int N, int HW, int C) {
+    GnPlan pl;
+    pl.V = C / 8;
+    pl.RPI = pl.V >= 256 ? 1 : 256 / pl.V;
+    if (pl.RPI > HW) pl.RPI = HW;
+    pl.threads = pl.V * pl.RPI;
+    int want = (4 * 148 + N - 1) / N;                 // ~4 CTAs per SM over the whole batch
+    int max_chunks = (HW + pl.RPI * 8 - 1) / (pl.RPI * 8);  // at least 8 rows per thread
+    if (max_chunks < 1) max_chunks = 1;
+    pl.nchunks = want < max_chunks ? want : max_chunks;
+    if (pl.nchunks < 1) pl.nchunks = 1;
+    pl.rows_per_chunk = (HW + pl.nchunks - 1) / pl.nchunks;
+    pl.nchunks = (HW + pl.rows_per_chunk - 1) / pl.rows_per_chunk;
+    pl.smem = static_cast<size_t>(pl.RPI) * C * 2 * sizeof(float);
+    return pl;
+}
+
+}  // namespace
+}  // namespace dfw
+
+extern "C" {
+
+long long dfw_groupnorm_workspace_bytes(int N, int HW, int C, int groups) {
+    if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % 8 != 0) return -1;
+    dfw::GnPlan pl = dfw::gn_plan(N, HW, C);
+    long long partial = static_cast<long long>(N) * pl.nchunks * groups * 2;
+    long long ss = static_cast<long long>(N) * C * 2;
+    return (partial + ss) * static_cast<long long>(sizeof(float)) + 256;
+}
+
+int dfw_groupnorm_silu(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int N, int HW,
+                       int C, int groups, float eps, int apply_silu, void* workspace, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(x && gamma && beta && y && workspace);
+    DFW_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0);
+    DFW_REQUIRE(C / 8 <= 1024);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    GnPlan pl = gn_plan(N, HW, C);
+    float* partial = reinterpret_cast<float*>(workspace);
+    size_t partial_elems = static_cast<size_t>(N) * pl.nchunks * groups * 2;
+    partial_elems = (partial_elems + 63) / 64 * 64;
+    float* scale_shift = partial + partial_elems;
+    dim3 grid(pl.nchunks, N);
+    if (pl.smem > 48 * 1024) {
+        static bool set0 = false, set1 = false;
+        if (x_f32 && !set1) {
+            DFW_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            set1 = true;
+        }
+        if (!x_f32 && !set0) {
+            DFW_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            set0 = true;
+        }
+    }
+    if (x_f32)
+        gn_stats_kernel<true><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI);
+    else
+        gn_stats_kernel<false><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI);
+    gn_finalize_kernel<<<N, 256, 0, stream>>>(partial, gamma, beta, scale_shift, HW, C, groups, pl.nchunks, eps);
+    const long long total_vecs = static_cast<long long>(N) * HW * (C / 8);
+    long long blocks = (total_vecs + 255) / 256;
+    const long long cap = static_cast<long long>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (x_f32)
+        gn_apply_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(x, scale_shift, y, total_vecs, HW, C, apply_silu);
+    else
+        gn_apply_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(x, scale_shift, y, total_vecs, HW, C, apply_silu);
+    g_launches.fetch_add(3);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_layernorm(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int M, int C, float eps,
+                  void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(x && gamma && beta && y && M > 0 && C > 0 && C % 8 == 0 && C <= 2048);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int warps_per_block = 8;
+    const int blocks = (M + warps_per_block - 1) / warps_per_block;
+    if (x_f32)
+        layernorm_kernel<true><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+    else
+        layernorm_kernel<false><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_softmax_rows(const float* s, void* p, int M, int L, float scale, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(s && p && M > 0 && L > 0 && L % 4 == 0);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    softmax_rows_kernel<<<M, 256, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(p), L, scale);
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""Torch-tensor front end of the C ABI (device memory + current stream come from torch; the math does not).
+
+Every function validates layout/dtype, passes raw pointers to libdiffews_b200.so and raises on a non-zero status.
+Activations are channels-last: a conv input is a contiguous bf16 tensor of shape [N, H, W, C].
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GEGLU, EPI_OUT_F32, EPI_RES_F32, EPI_SILU, check, lib
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.DfwError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def launch_count() -> int:
+    return int(lib.dfw_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_scale=1.0, out_f32=False,
+           silu=False, geglu=False, bias_per_sample=False):
+    """x bf16 [N,H,W,Cin]; w bf16 [Cout, ks*ks*Cin]; bias fp32 [Cout] or [N,Cout]; returns [N,H/s,W/s,Cout_eff]."""
+    _req(x, bf16, "x"); _req(w, bf16, "w")
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.numel() == Cout * ksize * ksize * Cin, (w.shape, Cin, ksize)
+    flags = 0
+    if out_f32: flags |= EPI_OUT_F32
+    if silu: flags |= EPI_SILU
+    if geglu: flags |= EPI_GEGLU
+    cout_eff = Cout // 2 if geglu else Cout
+    Ho, Wo = H // stride, W // stride
+    y = torch.empty((N, Ho, Wo, cout_eff), device=x.device, dtype=torch.float32 if out_f32 else bf16)
+    bss = 0
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+        if bias_per_sample:
+            assert bias.shape == (N, Cout)
+            bss = Cout
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+        if residual.dtype == torch.float32: flags |= EPI_RES_F32
+        else: assert residual.dtype == bf16
+    check(lib.dfw_conv2d_igemm(x.data_ptr(), w.data_ptr(), _ptr(bias), bss, _ptr(residual), y.data_ptr(), N, H, W,
+                               Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale), _stream()),
+          "dfw_conv2d_igemm")
+    return y
+
+
+def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu=False, geglu=False):
+    """x bf16 [..., K]; w bf16 [Nout, K]; returns [..., Nout_eff]."""
+    _req(x, bf16, "x"); _req(w, bf16, "w")
+    K = x.shape[-1]
+    M = x.numel() // K
+    Nout = w.shape[0]
+    assert w.shape[1] == K
+    flags = 0
+    if out_f32: flags |= EPI_OUT_F32
+    if silu: flags |= EPI_SILU
+    if geglu: flags |= EPI_GEGLU
+    nout_eff = Nout // 2 if geglu else Nout
+    y = torch.empty(x.shape[:-1] + (nout_eff,), device=x.device, dtype=torch.float32 if out_f32 else bf16)
+    if bias is not None: _req(bias, torch.float32, "bias")
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+        if residual.dtype == torch.float32: flags |= EPI_RES_F32
+        else: assert residual.dtype == bf16
+    check(lib.dfw_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, K, Nout, flags,
+                         float(out_scale), _stream()), "dfw_linear")
+    return y
+
+
+def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
+    """q [B,Lq,C]; k_self/v_self [B,Ls,C]; k_bank/v_bank [B,Lb,C] or None.  Tensors may be column slices of a wider
+    (e.g. fused QKV) buffer: only the last dim must be unit-stride."""
+    B, Lq, C = q.shape
+    assert C == heads * 64
+    for t in (q, k_self, v_self):
+        assert t.dtype == bf16 and t.is_cuda and t.stride(2) == 1
+    Ls = k_self.shape[1]
+    assert k_self.stride() == v_self.stride()
+    o = torch.empty((B, Lq, C), device=q.device, dtype=bf16)
+    if k_bank is not None:
+        Lb = k_bank.shape[1]
+        assert k_bank.shape[0] == B and k_bank.stride() == v_bank.stride() and k_bank.stride(2) == 1
+        kb, vb, kbs, krs = k_bank.data_ptr(), v_bank.data_ptr(), k_bank.stride(0), k_bank.stride(1)
+    else:
+        Lb, kb, vb, kbs, krs = 0, 0, 0, 0, 0
+    check(lib.dfw_attn_kvfused_fwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
+                                   k_self.stride(0), k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0),
+                                   o.stride(1), B, heads, Lq, Ls, Lb, float(scale), _stream()),
+          "dfw_attn_kvfused_fwd")
+    return o
+
+
+def cross_attn(q, k, v, heads, scale):
+    """q [B,L,C] bf16; k,v [Bk,Lctx,C] with Bk in {1,B}."""
+    _req(q, bf16, "q"); _req(k, bf16, "k"); _req(v, bf16, "v")
+    B, L, C = q.shape
+    Lctx = k.shape[1]
+    kvs = 0 if k.shape[0] == 1 else Lctx * C
+    o = torch.empty_like(q)
+    check(lib.dfw_cross_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), kvs, o.data_ptr(), B, L, heads, Lctx,
+                                 float(scale), _stream()), "dfw_cross_attn_fwd")
+    return o
+
+
+_gn_ws = {}
+
+
+def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False):
+    """x bf16|fp32 [N, ..., C] channels-last; returns bf16 of the same shape."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, torch.float32)
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    need = int(lib.dfw_groupnorm_workspace_bytes(N, HW, C, groups))
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), device=x.device, dtype=torch.uint8)
+        _gn_ws[key] = ws
+    y = torch.empty(x.shape, device=x.device, dtype=bf16)
+    check(lib.dfw_groupnorm_silu(x.data_ptr(), int(x.dtype == torch.float32), gamma.data_ptr(), beta.data_ptr(),
+                                 y.data_ptr(), N, HW, C, groups, float(eps), int(silu), ws.data_ptr(), _stream()),
+          "dfw_groupnorm_silu")
+    return y
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, torch.float32)
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty(x.shape, device=x.device, dtype=bf16)
+    check(lib.dfw_layernorm(x.data_ptr(), int(x.dtype == torch.float32), gamma.data_ptr(), beta.data_ptr(),
+                            y.data_ptr(), M, C, float(eps), _stream()), "dfw_layernorm")
+    return y
+
+
+def softmax_rows(s, scale):
+    _req(s, torch.float32, "s")
+    L = s.shape[-1]
+    M = s.numel() // L
+    p = torch.empty(s.shape, device=s.device, dtype=bf16)
+    check(lib.dfw_softmax_rows(s.data_ptr(), p.data_ptr(), M, L, float(scale), _stream()), "dfw_softmax_rows")
+    return p
+
+
+def upsample2x(x):
+    _req(x, bf16, "x")
+    N, H, W, Cc = x.shape
+    y = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=bf16)
+    check(lib.dfw_upsample2x_nhwc(x.data_ptr(), y.data_ptr(), N, H, W, Cc, _stream()), "dfw_upsample2x_nhwc")
+    return y
+
+
+def concat_channels(a, b):
+    _req(a, bf16, "a"); _req(b, bf16, "b")
+    assert a.shape[:-1] == b.shape[:-1]
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    rows = a.numel() // Ca
+    y = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=bf16)
+    check(lib.dfw_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), rows, Ca, Cb, _stream()),
+          "dfw_concat_channels")
+    return y
+
+
+def conv3x3_small_cin(x_nchw, w, bias):
+    """x fp32 NCHW [N,Cin<=8,H,W]; w fp32 [Cout,3,3,Cin]; returns bf16 NHWC [N,H,W,Cout]."""
+    _req(x_nchw, torch.float32, "x"); _req(w, torch.float32, "w")
+    N, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=bf16)
+    check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), N, H, W, Cin, Cout,
+                                    _stream()), "dfw_conv3x3_small_cin")
+    return y
+
+
+def pointwise_small(x, x_strides, w_host, b_host, y, y_strides, N, HW, in_scale=1.0, out_scale=1.0):
+    """w_host [Cout,Cin] / b_host [Cout]: fp32 CPU tensors (kernel parameters). x, y fp32 CUDA tensors."""
+    assert w_host.device.type == "cpu" and w_host.dtype == torch.float32 and w_host.is_contiguous()
+    Cout, Cin = w_host.shape
+    bptr = 0
+    if b_host is not None:
+        assert b_host.device.type == "cpu" and b_host.dtype == torch.float32
+        bptr = b_host.data_ptr()
+    check(lib.dfw_pointwise_small(x.data_ptr(), *x_strides, w_host.data_ptr(), bptr, float(in_scale),
+                                  float(out_scale), y.data_ptr(), *y_strides, N, HW, Cin, Cout, _stream()),
+          "dfw_pointwise_small")
+    return y
+
+
+def nhwc_f32_to_nchw(x, C, H, W, scale=1.0, shift=0.0, lo=-3.0e38, hi=3.0e38):
+    """x fp32 [N, H*W, row_stride>=C] -> fp32 [N, C, H, W]."""
+    _req(x, torch.float32, "x")
+    N = x.shape[0]
+    row_stride = x.shape[-1]
+    y = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
+    check(lib.dfw_nhwc_f32_to_nchw_f32(x.data_ptr(), row_stride, y.data_ptr(), N, C, H * W, float(scale),
+                                       float(shift), float(lo), float(hi), _stream()), "dfw_nhwc_f32_to_nchw_f32")
+    return y
+
+
+def seg_post(dec, H, W, want_f32=True, want_u8=True):
+    """dec fp32 [N, H*W, row_stride>=3] -> (seg_f32 [N,3,H,W] in [0,255], seg_u8 [N,3,H,W])."""
+    _req(dec, torch.float32, "dec")
+    N = dec.shape[0]
+    rs = dec.shape[-1]
+    f = torch.empty((N, 3, H, W), device=dec.device, dtype=torch.float32) if want_f32 else None
+    u = torch.empty((N, 3, H, W), device=dec.device, dtype=torch.uint8) if want_u8 else None
+    check(lib.dfw_seg_post(dec.data_ptr(), rs, _ptr(f), _ptr(u), N, H * W, _stream()), "dfw_seg_post")
+    return f, u
+
+
+def rthres_iou_hist(pred_u8, gt_u8, ignore_u8=None, r_threshold=0.25, want_mask=True):
+    """pred_u8 [B,3,H,W] uint8; gt_u8 [B,H,W] uint8 {0,1}; returns (area_inter [B,2] i64, area_union [B,2] i64, mask)."""
+    _req(pred_u8, torch.uint8, "pred"); _req(gt_u8, torch.uint8, "gt")
+    B, _, H, W = pred_u8.shape
+    dev = pred_u8.device
+    inter = torch.empty((B, 2), device=dev, dtype=torch.int64)
+    union = torch.empty((B, 2), device=dev, dtype=torch.int64)
+    mask = torch.empty((B, H, W), device=dev, dtype=torch.uint8) if want_mask else None
+    ws = torch.empty(int(lib.dfw_rthres_workspace_bytes(B)), device=dev, dtype=torch.uint8)
+    if ignore_u8 is not None: _req(ignore_u8, torch.uint8, "ignore")
+    check(lib.dfw_rthres_iou_hist(pred_u8.data_ptr(), gt_u8.data_ptr(), _ptr(ignore_u8), float(r_threshold),
+                                  inter.data_ptr(), union.data_ptr(), _ptr(mask), B, H, W, ws.data_ptr(), _stream()),
+          "dfw_rthres_iou_hist")
+    return inter, union, mask
+
+
+def iou_accumulate(inter, union, class_id, inter_buf, union_buf):
+    _req(inter, torch.int64, "inter"); _req(union, torch.int64, "union"); _req(class_id, torch.int64, "class_id")
+    B = inter.shape[0]
+    nclass = inter_buf.shape[1]
+    check(lib.dfw_iou_accumulate(inter.data_ptr(), union.data_ptr(), class_id.data_ptr(), inter_buf.data_ptr(),
+                                 union_buf.data_ptr(), B, nclass, _stream()), "dfw_iou_accumulate")

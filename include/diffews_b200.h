@@ -1,0 +1,166 @@
+/*
+ * diffews_b200 — C ABI of the B200 (sm_100a) hot path of DiffewS.
+ *
+ * Every entry point is `extern "C"`, takes raw DEVICE pointers + sizes + a cudaStream_t (as void*), returns an int
+ * status (0 = DFW_OK, negative = error), never throws, never allocates device memory, keeps no hidden global state
+ * and is stream-ordered.  There is NO CPU / other-arch fallback: on a non-sm_100 device every compute entry point
+ * returns DFW_ERR_ARCH.
+ *
+ * The reference (ga1i13o/DiffewS) has no native code; each entry point below replaces a *library call site* of the
+ * reference's PyTorch path.  "ref:" comments cite /root/reference file:line; "(upstream)" marks diffusers-0.25
+ * modules that the reference imports (requirements.txt:2) and whose source is not vendored in the reference.
+ *
+ * Activation layout everywhere: channels-last (NHWC) — a [N,H,W,C] image tensor is the same memory as the
+ * [N, H*W, C] token tensor the transformer blocks use.  bf16 storage, fp32 accumulation / statistics.
+ */
+#ifndef DIFFEWS_B200_H_
+#define DIFFEWS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFW_OK 0
+#define DFW_ERR_INVALID (-1) /* bad argument (shape / alignment / unsupported combination) */
+#define DFW_ERR_CUDA (-2)    /* a CUDA runtime/driver call failed (message on stderr)        */
+#define DFW_ERR_ARCH (-3)    /* device is not sm_100 (B200) — no fallback by design           */
+
+/* epilogue flags for dfw_conv2d_igemm / dfw_linear */
+#define DFW_EPI_OUT_F32 1   /* y is fp32 (default bf16)                                               */
+#define DFW_EPI_RES_F32 2   /* residual is fp32 (default bf16)                                        */
+#define DFW_EPI_GEGLU 4     /* weight rows are [128 value | 128 gate] interleaved per 256-row block;  */
+                            /* y[:, j] = (v+bv) * gelu_erf(g+bg), y has Cout/2 channels               */
+#define DFW_EPI_SILU 8      /* y = silu(acc + bias) (time-embedding MLP)                              */
+
+/* ABI version: bump on any signature change. */
+int dfw_version(void);
+/* DFW_OK when the current CUDA device is a B200-class (sm_100) GPU. */
+int dfw_device_ok(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches claim). */
+long long dfw_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K3/K6  tcgen05 implicit-GEMM convolution and Linear (TMA-fed, TMEM accumulators, persistent CTAs).
+ * ref: every nn.Conv2d / nn.Linear reached from diffews/models/unet_2d_condition.py:1118-1121,1161,1191,1226,1249
+ *      (ResnetBlock2D / Downsample2D / Upsample2D / Transformer2DModel / BasicTransformerBlock, upstream) and from
+ *      diffews/marigold_pipeline_rgb_latent_noise.py:852-853,901-902 (AutoencoderKL encoder/decoder, upstream).
+ *
+ *   x        bf16 [N, Hin, Win, Cin]                Cin % 64 == 0
+ *   w        bf16 [Cout, ksize, ksize, Cin]         (= torch weight.permute(0,2,3,1)), K index = (kh*ks+kw)*Cin + c
+ *   bias     fp32 [Cout] or, if bias_sample_stride != 0, [N, bias_sample_stride] (per-image bias: conv bias +
+ *            time-embedding projection, ResnetBlock2D temb add (upstream)); may be NULL
+ *   residual bf16/fp32 [N, Hout, Wout, Cout_eff] or NULL;   y = (acc + bias) * out_scale + residual
+ *   y        bf16/fp32 [N, Hout, Wout, Cout_eff]            Cout_eff = Cout (Cout/2 with DFW_EPI_GEGLU)
+ *   ksize 1|3; stride 1|2; pad_mode 0: symmetric (ksize-1)/2 ; 1: VAE-encoder downsample F.pad(0,1,0,1) + pad 0.
+ * ------------------------------------------------------------------------------------------------------------ */
+int dfw_conv2d_igemm(const void* x, const void* w, const float* bias, int bias_sample_stride, const void* residual,
+                     void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode,
+                     int flags, float out_scale, void* stream);
+
+/* y[M, Nout_eff] = epi(x[M,K] @ w[Nout,K]^T + bias).  K % 64 == 0.  ref: nn.Linear in Attention.to_q/k/v/to_out,
+ * Transformer2DModel.proj_in/out, FeedForward (GEGLU + Linear), TimestepEmbedding (upstream). */
+int dfw_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,
+               int Nout, int flags, float out_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1  KV-fused flash attention forward, head_dim 64, tcgen05 + TMEM + TMA.
+ * ref: diffews/models/attention_processor.py:251-271 (MyXFormersAttnProcessor: key = cat([key_self, bank_folded]),
+ *      xformers.ops.memory_efficient_attention(q,k,v,scale)); :351-365 (SDPA variant).
+ *  The concatenation is never materialised: keys/values stream from two sources (self, then bank).
+ *   q       bf16, element (b, l, h, d) at q[b*q_batch_stride + l*q_row_stride + h*64 + d],   l < Lq
+ *   k_self / v_self  same addressing with kv_self_* strides, l < Ls
+ *   k_bank / v_bank  same addressing with kv_bank_* strides, l < Lb (Lb = k_shots * S, shot-major; may be 0/NULL)
+ *   o       bf16 [B, Lq, heads*64] (row stride o_row_stride)
+ *  softmax(q k^T * scale) v over the Ls + Lb keys, fp32 softmax, fp32 accumulation.
+ * ------------------------------------------------------------------------------------------------------------ */
+int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+                         const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
+                         const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
+                         int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
+                         int heads, int Lq, int Ls, int Lb, float scale, void* stream);
+
+/* K2  cross-attention to a short prompt embedding (Lctx <= 128 keys, head_dim 64), CUDA cores.
+ * ref: BasicTransformerBlock.attn2 (upstream) reached from unet_2d_condition.py:1161; Lctx = 2 at eval
+ *      (marigold_pipeline_rgb_latent_noise.py:591-601).
+ *   q bf16 [B, L, heads*64]; k,v bf16 [B, Lctx, heads*64] (kv_batch_stride elements, 0 = shared); o like q. */
+int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv_batch_stride, void* o, int B,
+                       int L, int heads, int Lctx, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K4  GroupNorm(32 groups) (+SiLU), NHWC, fp32 statistics, deterministic two-stage reduction.
+ * ref: nn.GroupNorm(+SiLU) in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out
+ *      (diffews/models/unet_2d_condition.py:1246-1248; upstream blocks).
+ *   x bf16 (or fp32 if x_f32) [N, HW, C]; gamma/beta fp32 [C]; y bf16 [N, HW, C].  C % 8 == 0, C % groups == 0.
+ *   workspace: fp32, dfw_groupnorm_workspace_bytes(N, HW, C) bytes.
+ * ------------------------------------------------------------------------------------------------------------ */
+long long dfw_groupnorm_workspace_bytes(int N, int HW, int C, int groups);
+int dfw_groupnorm_silu(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int N, int HW,
+                       int C, int groups, float eps, int apply_silu, void* workspace, void* stream);
+
+/* K7  LayerNorm over the last dim. x bf16/fp32 [M, C] -> y bf16 [M, C].  C % 8 == 0, C <= 2048.
+ * ref: BasicTransformerBlock.norm1/2/3 (upstream). */
+int dfw_layernorm(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int M, int C, float eps,
+                  void* stream);
+
+/* Row softmax for the VAE mid-block attention (single head, d=512): s fp32 [M, L] -> p bf16 [M, L],
+ * p = softmax(s * scale).  ref: AutoencoderKL mid_block Attention (upstream), pipeline:852,901. */
+int dfw_softmax_rows(const float* s, void* p, int M, int L, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layout / small-channel helpers (CUDA cores, bandwidth-bound).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* nearest 2x upsample NHWC bf16 [N,H,W,C] -> [N,2H,2W,C].  ref: Upsample2D F.interpolate(scale 2, nearest) (upstream) */
+int dfw_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* channel concat: y[N,HW,Ca+Cb] = cat(a[N,HW,Ca], b[N,HW,Cb]).  ref: torch.cat([hidden, skip], dim=1) in up blocks */
+int dfw_concat_channels(const void* a, const void* b, void* y, long long rows, int Ca, int Cb, void* stream);
+/* 3x3 / stride 1 / pad 1 convolution with a tiny input channel count (Cin <= 8), CUDA cores:
+ *   x  fp32 NCHW [N,Cin,H,W] (the reference's image / latent layout);  w fp32 [Cout,3,3,Cin]; bias fp32 [Cout]
+ *   y  bf16 NHWC [N,H,W,Cout], Cout % 64 == 0, Cout <= 512.
+ * ref: UNet conv_in / conv_in_ref (unet_2d_condition.py:301-306,1118-1121), VAE encoder conv_in (3->128),
+ *      VAE decoder conv_in (4->512) (upstream). */
+int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cin,
+                          int Cout, void* stream);
+/* 1x1 conv on <= 8 channels, fp32 math, arbitrary element strides (so it also converts NHWC <-> NCHW):
+ *   y[n,p,co] = (sum_ci w[co,ci] * (x[n,p,ci] * in_scale) + b[co]) * out_scale
+ *   x element (n,p,ci) at x[n*x_ns + p*x_ps + ci*x_cs]; y likewise.  w [Cout,Cin] and b [Cout] are HOST pointers
+ *   (<= 72 floats, passed to the kernel by value).
+ * ref: vae.quant_conv / post_quant_conv and the latent scale factors (pipeline:852-861, 898-901) and the
+ *      DDIM step collapse z0 = -eps (marigold/util/scheduler_customized.py:107-180). */
+int dfw_pointwise_small(const float* x, long long x_ns, long long x_ps, long long x_cs, const float* w_host,
+                        const float* b_host, float in_scale, float out_scale, float* y, long long y_ns,
+                        long long y_ps, long long y_cs, int N, int HW, int Cin, int Cout, void* stream);
+/* fp32 NHWC rows [N*HW, x_row_stride] (first C used) -> fp32 NCHW [N,C,HW]: y = clamp(x*scale + shift, lo, hi). */
+int dfw_nhwc_f32_to_nchw_f32(const float* x, int x_row_stride, float* y, int N, int C, int HW, float scale,
+                             float shift, float lo, float hi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Segmentation tail.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* seg post-processing: dec fp32 NHWC rows [N*HW, row_stride] (3 used) ->
+ *   seg_f32 NCHW [N,3,H,W] = (clip(x,-1,1)*0.5+0.5)*255         (single_infer return value, pipeline:787-795)
+ *   seg_u8  NCHW [N,3,H,W] = uint8 truncation of clip(seg,0,255) (pipeline:534)            (either may be NULL) */
+int dfw_seg_post(const float* dec, int row_stride, float* seg_f32, uint8_t* seg_u8, int N, int HW, void* stream);
+
+/* K8  reverse-threshold binarisation + intersection/union histogram, one launch, integer counts.
+ * ref: evaluation_util/main_oss.py:128-134 (to_tensor, max()*r, mean(dim=1) > thr — CPU fp32 semantics reproduced
+ *      bit-exactly: ((R/255 + G/255) + B/255) / 3  >  fp32(max/255) * r), evaluation_util/common/evaluation.py:12-39
+ *      (histc bins=2 on pred[pred==gt], pred, gt; ignore_index 255), logger.py:35-37 (accumulation, here int64).
+ *   pred_u8 [B,3,H,W] uint8; gt [B,H,W] uint8 in {0,1}; ignore [B,H,W] uint8 {0,1} or NULL;
+ *   r_threshold (0.25); the max is taken PER EPISODE (the reference only runs bsz=1, where they coincide).
+ *   out: area_inter int64 [B,2], area_union int64 [B,2] (bin 0 background, bin 1 foreground);
+ *        mask_out uint8 [B,H,W] (0/1, 255 where ignored) or NULL.
+ *   workspace: dfw_rthres_workspace_bytes(B) bytes (zeroed by the call). */
+long long dfw_rthres_workspace_bytes(int B);
+int dfw_rthres_iou_hist(const uint8_t* pred_u8, const uint8_t* gt, const uint8_t* ignore, float r_threshold,
+                        long long* area_inter, long long* area_union, uint8_t* mask_out, int B, int H, int W,
+                        void* workspace, void* stream);
+/* AverageMeter.update: buf[2, nclass] (int64) += counts[b, :] at column class_id[b].  ref: logger.py:35-37 */
+int dfw_iou_accumulate(const long long* area_inter, const long long* area_union, const long long* class_id,
+                       long long* inter_buf, long long* union_buf, int B, int nclass, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFEWS_B200_H_ */
