@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — episodes/sec of the DiffewS hot path (1-shot 512^2, single-step UNet) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's CPU path = the oracle port, host cores)
+
+A "step" is one pass of the full hot path over one batch of B synthetic episodes per GPU (BASELINE config 2: B = 16,
+1-shot, 512x512): 3 VAE encodes, support + query UNet pass with the KV bank, z0 = -v, VAE decode, uint8, rthres,
+intersection/union, class-indexed accumulation.  Prints ONE JSON line (rank 0).
+
+  value      episodes/s, whole job, inputs resident in HBM (device leg)
+  e2e        episodes/s through the public API with inputs in pinned HOST memory (H2D of the batch and D2H of the
+             per-episode counts inside the timed region)
+  roofline   the dominant kernel family (tcgen05 implicit-GEMM conv/linear): algorithmic FLOPs of the launches in the
+             timed region / their CUDA-event time, against MEASURED_PEAKS.json's sustained bf16 TFLOP/s
+  cpu_baseline  the oracle (kind "port": the reference cannot be imported) on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "episodes/sec (1-shot, 512^2, 1-step UNet)"
+UNIT = "episodes/s"
+FLOPS_PER_EPISODE_1SHOT_512 = 7.58e12
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]            # samples under load: the upper half
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_episode_time(size: int, nshot: int, threads: int, unet_o=None, vae_o=None):
+    """One full episode through the CPU oracle (bsz=1, like the reference's eval loop). Returns seconds."""
+    import torch
+    from diffews_b200.synthetic import make_batch, prompt_embedding
+    from oracle.pipeline import evaluate_episode
+    from oracle.sd21 import build_models
+    torch.set_num_threads(threads)
+    if unet_o is None:
+        unet_o, vae_o = build_models(0)
+    emb = prompt_embedding()
+    warm = make_batch(10_000, 1, 64, nshot)
+    evaluate_episode(unet_o, vae_o, emb, warm)          # warm-up at 64^2 (oneDNN primitive caches, thread pool)
+    batch = make_batch(0, 1, size, nshot)
+    t0 = time.perf_counter()
+    evaluate_episode(unet_o, vae_o, emb, batch)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path = the oracle port (the reference needs
+    diffusers/xformers/accelerate, none installable here), all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from diffews_b200.synthetic import make_batch, prompt_embedding
+    from oracle.pipeline import evaluate_episode
+    from oracle.sd21 import build_models
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    unet_o, vae_o = build_models(0)
+    emb = prompt_embedding()
+    budget_s = 240.0
+    t_start = time.perf_counter()
+    evaluate_episode(unet_o, vae_o, emb, make_batch(10_000, 1, 64, args.nshot))
+    times = []
+    done_warm = 0
+    for i in range(args.warmup + args.steps):
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+        batch = make_batch(i, 1, args.size, args.nshot)
+        t0 = time.perf_counter()
+        evaluate_episode(unet_o, vae_o, emb, batch)
+        dt = time.perf_counter() - t0
+        if done_warm < min(args.warmup, 1):      # CPU steps are ~tens of seconds each: at most one untimed warm-up
+            done_warm += 1
+            continue
+        times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    value = 1000.0 / ms
+    sample = (f"{len(times)} timed episode(s) of the same workload at bsz=1 (the only batch size the reference's eval "
+              f"loop supports), fp32 oracle port, {cores} threads; capped at {budget_s:.0f}s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": done_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.nshot}-shot {args.size}x{args.size} episodes, single-step SD-2.1 UNet + VAE "
+                               "+ rthres/IoU, random-init weights", "episodes_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="episodes per GPU per step (BASELINE config 2: 16)")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--nshot", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernel-timer", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from diffews_b200 import ops
+    from diffews_b200.runner import EpisodeRunner, build_engine_from_modules
+    from diffews_b200.synthetic import make_batch, prompt_embedding
+    from oracle.sd21 import build_models          # weight source: deterministic random init (no checkpoints offline)
+
+    unet_o, vae_o = build_models(0)
+    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding(), device=dev)
+    runner = EpisodeRunner(pipe, "coco", img_size=args.size)
+    B = args.batch
+
+    # a small pool of distinct episode batches (rank-disjoint), pinned on the host
+    pool = 2
+    host_batches = []
+    for i in range(pool):
+        hb = make_batch((rank * pool + i) * B, B, args.size, args.nshot)
+        host_batches.append({k: v.pin_memory() for k, v in hb.items()})
+    dev_batches = [{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in host_batches]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device leg: inputs resident in HBM ------------------------------------------------------------
+    for i in range(args.warmup):
+        runner.step(dev_batches[i % pool])
+    barrier()
+    timer = None if args.no_kernel_timer else ops.KernelTimer()
+    ops.set_timer(timer)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        runner.step(dev_batches[i % pool])
+    if world > 1:
+        runner.meter.all_reduce()
+    ev1.record()
+    barrier()
+    launches = ops.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ops.set_timer(None)
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1000.0)
+
+    # ---------------- e2e leg: public API, host buffers, H2D + D2H inside the timed region ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+        d2h = 2 * B * 2 * 8
+        host_out = torch.empty((2, B, 2), dtype=torch.int64).pin_memory()
+
+        def e2e_step(i):
+            hb = host_batches[i % pool]
+            db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+            inter, union = runner.step(db)
+            host_out[0].copy_(inter, non_blocking=True)
+            host_out[1].copy_(union, non_blocking=True)
+            torch.cuda.current_stream().synchronize()         # the caller reads the counts every step
+            return int(host_out[0, 0, 1])
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        ee1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        e_ms = max(ee0.elapsed_time(ee1), wall_ms)               # host-synchronous loop: wall clock is the honest one
+        te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * args.steps / (float(te.item()) / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    # ---------------- roofline of the dominant kernel family ----------------------------------------------------------
+    peak_tf, peak_gbs, peak_kind = _peaks()
+    roofline = None
+    kernels = None
+    if timer is not None:
+        summ = timer.summary()
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / (v["ms"] * 1e9), 1)
+                       if v["ms"] > 0 else None, "share_of_step": round(v["ms"] / ms_total, 3)} for k, v in summ.items()}
+        ig = summ.get("igemm")
+        if ig and ig["ms"] > 0:
+            achieved = ig["flops"] / (ig["ms"] * 1e9)
+            roofline = {"bound": "tensor", "kernel": "igemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear)",
+                        "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": f"{peak_kind} sustained bf16",
+                        "launches": ig["launches"], "share_of_step": round(ig["ms"] / ms_total, 3)}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        del pipe
+        secs = cpu_oracle_episode_time(args.size, args.nshot, cores, unet_o, vae_o)
+        cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 episode ({args.nshot}-shot {args.size}x{args.size}, bsz=1, fp32 oracle port of the reference "
+                         f"path) after a 64x64 warm-up: {secs:.1f}s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.nshot}-shot {args.size}x{args.size} episodes, batch {B} per GPU, single-step "
+                                   "SD-2.1 UNet (KV-bank attention) + VAE encode x3 / decode + rthres/IoU, random-init "
+                                   "weights (BASELINE config 2)",
+                       "episodes_per_step_per_gpu": B, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs + activations per step (>2 GB) exceed the 126 MB L2; 2 alternating batches",
+                       "precision": "bf16 tensor-core operands, fp32 accumulate / residual stream / statistics"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels,
+            "frac_of_tensor_roofline_whole_path": round(value / world * FLOPS_PER_EPISODE_1SHOT_512 / (peak_tf * 1e12), 4)
+            if (args.size == 512 and args.nshot == 1) else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

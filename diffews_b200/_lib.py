@@ -30,14 +30,15 @@ SIGNATURES = {
     "dfw_groupnorm_silu": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "dfw_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "dfw_softmax_rows": (_i, [_vp, _vp, _i, _i, _f, _vp]),
-    "dfw_upsample2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
-    "dfw_conv3x3_small_cin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dfw_upsample2x_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "dfw_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "dfw_conv3x3_small_cin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dfw_pointwise_small": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _f, _f, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
     "dfw_nhwc_f32_to_nchw_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp]),
     "dfw_seg_post": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "dfw_rthres_workspace_bytes": (_ll, [_i]),
-    "dfw_rthres_iou_hist": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "dfw_rthres_iou_hist": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dfw_iou_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
 }
 

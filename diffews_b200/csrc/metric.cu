@@ -53,7 +53,7 @@ __device__ __forceinline__ bool rthres_pixel(unsigned int r, unsigned int g, uns
 }
 
 __global__ void __launch_bounds__(256)
-rthres_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
+rthres_hist_kernel(const uint8_t* __restrict__ pred, int pred_is_mask, const uint8_t* __restrict__ gt,
                    const uint8_t* __restrict__ ignore, float r_threshold, EpisodeWs* __restrict__ ws,
                    long long* __restrict__ area_inter, long long* __restrict__ area_union,
                    uint8_t* __restrict__ mask_out, int HW) {
@@ -63,15 +63,16 @@ rthres_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__
     if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const float thr = __fmul_rn(__fdiv_rn(static_cast<float>(ws[b].max_u8), 255.0f), r_threshold);
-    const uint8_t* pr = pred + static_cast<long long>(b) * 3 * HW;
-    const uint8_t* pg = pr + HW;
-    const uint8_t* pb = pg + HW;
+    // pred_is_mask: pred is an already-binarised [B,H,W] {0,1} mask (Evaluator.classify_prediction drop-in)
+    const uint8_t* pr = pred + static_cast<long long>(b) * (pred_is_mask ? 1 : 3) * HW;
+    const uint8_t* pg = pred_is_mask ? pr : pr + HW;
+    const uint8_t* pb = pred_is_mask ? pr : pg + HW;
     const uint8_t* gtb = gt + static_cast<long long>(b) * HW;
     const uint8_t* igb = ignore ? ignore + static_cast<long long>(b) * HW : nullptr;
     uint8_t* mo = mask_out ? mask_out + static_cast<long long>(b) * HW : nullptr;
     unsigned int c[6] = {0, 0, 0, 0, 0, 0};
     auto tally = [&](unsigned int r, unsigned int g, unsigned int bl, unsigned int gv, unsigned int ig) -> uint8_t {
-        unsigned int pv = rthres_pixel(r, g, bl, thr) ? 1u : 0u;
+        unsigned int pv = pred_is_mask ? (r ? 1u : 0u) : (rthres_pixel(r, g, bl, thr) ? 1u : 0u);
         if (ig) { gv = 255u; pv = 255u; }          // gt += ignore*255 ; pred[gt==255] = 255
         if (pv == gv && pv < 2u) c[pv]++;          // histc(pred[pred==gt]) drops the 255 bin
         if (pv < 2u) c[2 + pv]++;
@@ -146,9 +147,9 @@ extern "C" {
 
 long long dfw_rthres_workspace_bytes(int B) { return B > 0 ? static_cast<long long>(B) * 64 : -1; }
 
-int dfw_rthres_iou_hist(const uint8_t* pred_u8, const uint8_t* gt, const uint8_t* ignore, float r_threshold,
-                        long long* area_inter, long long* area_union, uint8_t* mask_out, int B, int H, int W,
-                        void* workspace, void* stream_) {
+int dfw_rthres_iou_hist(const uint8_t* pred_u8, int pred_is_mask, const uint8_t* gt, const uint8_t* ignore,
+                        float r_threshold, long long* area_inter, long long* area_union, uint8_t* mask_out, int B,
+                        int H, int W, void* workspace, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
@@ -165,10 +166,10 @@ int dfw_rthres_iou_hist(const uint8_t* pred_u8, const uint8_t* gt, const uint8_t
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid(bx, B);
-    rthres_max_kernel<<<grid, 256, 0, stream>>>(pred_u8, ws, 3LL * HW);
-    rthres_hist_kernel<<<grid, 256, 0, stream>>>(pred_u8, gt, ignore, r_threshold, ws, area_inter, area_union,
-                                                  mask_out, HW);
-    g_launches.fetch_add(2);
+    if (!pred_is_mask) rthres_max_kernel<<<grid, 256, 0, stream>>>(pred_u8, ws, 3LL * HW);
+    rthres_hist_kernel<<<grid, 256, 0, stream>>>(pred_u8, pred_is_mask, gt, ignore, r_threshold, ws, area_inter,
+                                                  area_union, mask_out, HW);
+    g_launches.fetch_add(pred_is_mask ? 1 : 2);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }

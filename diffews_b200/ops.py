@@ -35,6 +35,50 @@ def launch_count() -> int:
     return int(lib.dfw_launch_count())
 
 
+class KernelTimer:
+    """CUDA-event timing of individual tensor-core launches (bench.py's roofline leg).  When installed with
+    `set_timer`, conv2d / linear / attn_kvfused bracket their launch with two events on the launching stream."""
+
+    def __init__(self):
+        self.records = []   # (kind, flops, ev0, ev1)
+
+    def add(self, kind, flops, ev0, ev1):
+        self.records.append((kind, flops, ev0, ev1))
+
+    def summary(self):
+        out = {}
+        for kind, flops, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            d = out.setdefault(kind, {"launches": 0, "flops": 0.0, "ms": 0.0})
+            d["launches"] += 1; d["flops"] += flops; d["ms"] += ms
+        return out
+
+
+_timer = None
+
+
+def set_timer(t):
+    global _timer
+    _timer = t
+
+
+class _Timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if _timer is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _timer is not None:
+            self.e1.record()
+            _timer.add(self.kind, self.flops, self.e0, self.e1)
+        return False
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_scale=1.0, out_f32=False,
            silu=False, geglu=False, bias_per_sample=False):
@@ -60,14 +104,15 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
         assert residual.shape == y.shape and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
         else: assert residual.dtype == bf16
-    check(lib.dfw_conv2d_igemm(x.data_ptr(), w.data_ptr(), _ptr(bias), bss, _ptr(residual), y.data_ptr(), N, H, W,
-                               Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale), _stream()),
-          "dfw_conv2d_igemm")
+    with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin):
+        check(lib.dfw_conv2d_igemm(x.data_ptr(), w.data_ptr(), _ptr(bias), bss, _ptr(residual), y.data_ptr(), N, H, W,
+                                   Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale), _stream()),
+              "dfw_conv2d_igemm")
     return y
 
 
-def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu=False, geglu=False):
-    """x bf16 [..., K]; w bf16 [Nout, K]; returns [..., Nout_eff]."""
+def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu=False, geglu=False, out=None):
+    """x bf16 [..., K]; w bf16 [Nout, K]; returns [..., Nout_eff] (written into `out` if given)."""
     _req(x, bf16, "x"); _req(w, bf16, "w")
     K = x.shape[-1]
     M = x.numel() // K
@@ -78,14 +123,20 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
     if silu: flags |= EPI_SILU
     if geglu: flags |= EPI_GEGLU
     nout_eff = Nout // 2 if geglu else Nout
-    y = torch.empty(x.shape[:-1] + (nout_eff,), device=x.device, dtype=torch.float32 if out_f32 else bf16)
+    odt = torch.float32 if out_f32 else bf16
+    if out is None:
+        y = torch.empty(x.shape[:-1] + (nout_eff,), device=x.device, dtype=odt)
+    else:
+        y = out
+        assert y.is_contiguous() and y.dtype == odt and y.numel() == M * nout_eff and y.is_cuda
     if bias is not None: _req(bias, torch.float32, "bias")
     if residual is not None:
-        assert residual.shape == y.shape and residual.is_contiguous()
+        assert residual.numel() == y.numel() and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
         else: assert residual.dtype == bf16
-    check(lib.dfw_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, K, Nout, flags,
-                         float(out_scale), _stream()), "dfw_linear")
+    with _Timed("igemm", 2.0 * M * K * Nout):
+        check(lib.dfw_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, K, Nout, flags,
+                             float(out_scale), _stream()), "dfw_linear")
     return y
 
 
@@ -105,10 +156,11 @@ def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
         kb, vb, kbs, krs = k_bank.data_ptr(), v_bank.data_ptr(), k_bank.stride(0), k_bank.stride(1)
     else:
         Lb, kb, vb, kbs, krs = 0, 0, 0, 0, 0
-    check(lib.dfw_attn_kvfused_fwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
-                                   k_self.stride(0), k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0),
-                                   o.stride(1), B, heads, Lq, Ls, Lb, float(scale), _stream()),
-          "dfw_attn_kvfused_fwd")
+    with _Timed("attn", 4.0 * B * heads * Lq * (Ls + Lb) * 64):
+        check(lib.dfw_attn_kvfused_fwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
+                                       k_self.stride(0), k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0),
+                                       o.stride(1), B, heads, Lq, Ls, Lb, float(scale), _stream()),
+              "dfw_attn_kvfused_fwd")
     return o
 
 
@@ -165,32 +217,44 @@ def softmax_rows(s, scale):
 
 
 def upsample2x(x):
-    _req(x, bf16, "x")
+    """x bf16|fp32 [N,H,W,C] -> bf16 [N,2H,2W,C]."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, torch.float32)
     N, H, W, Cc = x.shape
     y = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=bf16)
-    check(lib.dfw_upsample2x_nhwc(x.data_ptr(), y.data_ptr(), N, H, W, Cc, _stream()), "dfw_upsample2x_nhwc")
+    check(lib.dfw_upsample2x_nhwc(x.data_ptr(), int(x.dtype == torch.float32), y.data_ptr(), N, H, W, Cc,
+                                  _stream()), "dfw_upsample2x_nhwc")
     return y
 
 
 def concat_channels(a, b):
-    _req(a, bf16, "a"); _req(b, bf16, "b")
-    assert a.shape[:-1] == b.shape[:-1]
+    assert a.is_cuda and a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype
+    assert a.dtype in (bf16, torch.float32) and a.shape[:-1] == b.shape[:-1]
     Ca, Cb = a.shape[-1], b.shape[-1]
     rows = a.numel() // Ca
-    y = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=bf16)
-    check(lib.dfw_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), rows, Ca, Cb, _stream()),
-          "dfw_concat_channels")
+    y = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=a.dtype)
+    check(lib.dfw_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), rows, Ca, Cb, a.element_size(),
+                                  _stream()), "dfw_concat_channels")
     return y
 
 
-def conv3x3_small_cin(x_nchw, w, bias):
-    """x fp32 NCHW [N,Cin<=8,H,W]; w fp32 [Cout,3,3,Cin]; returns bf16 NHWC [N,H,W,Cout]."""
+def cast_bf16(x):
+    """fp32 -> bf16 (no-op for bf16 input)."""
+    if x.dtype == bf16:
+        return x
+    _req(x, torch.float32, "x")
+    y = torch.empty(x.shape, device=x.device, dtype=bf16)
+    check(lib.dfw_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "dfw_cast_f32_to_bf16")
+    return y
+
+
+def conv3x3_small_cin(x_nchw, w, bias, out_f32=False):
+    """x fp32 NCHW [N,Cin<=8,H,W]; w fp32 [Cout,3,3,Cin]; returns bf16 (or fp32) NHWC [N,H,W,Cout]."""
     _req(x_nchw, torch.float32, "x"); _req(w, torch.float32, "w")
     N, Cin, H, W = x_nchw.shape
     Cout = w.shape[0]
-    y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=bf16)
-    check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), N, H, W, Cin, Cout,
-                                    _stream()), "dfw_conv3x3_small_cin")
+    y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=torch.float32 if out_f32 else bf16)
+    check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), int(out_f32), N, H, W,
+                                    Cin, Cout, _stream()), "dfw_conv3x3_small_cin")
     return y
 
 
@@ -231,16 +295,19 @@ def seg_post(dec, H, W, want_f32=True, want_u8=True):
 
 
 def rthres_iou_hist(pred_u8, gt_u8, ignore_u8=None, r_threshold=0.25, want_mask=True):
-    """pred_u8 [B,3,H,W] uint8; gt_u8 [B,H,W] uint8 {0,1}; returns (area_inter [B,2] i64, area_union [B,2] i64, mask)."""
+    """pred_u8 [B,3,H,W] uint8 (or a binarised [B,H,W] {0,1} mask); gt_u8 [B,H,W] uint8 {0,1};
+    returns (area_inter [B,2] i64, area_union [B,2] i64, mask)."""
     _req(pred_u8, torch.uint8, "pred"); _req(gt_u8, torch.uint8, "gt")
-    B, _, H, W = pred_u8.shape
+    is_mask = pred_u8.ndim == 3
+    B, H, W = pred_u8.shape[0], pred_u8.shape[-2], pred_u8.shape[-1]
+    assert gt_u8.shape == (B, H, W)
     dev = pred_u8.device
     inter = torch.empty((B, 2), device=dev, dtype=torch.int64)
     union = torch.empty((B, 2), device=dev, dtype=torch.int64)
     mask = torch.empty((B, H, W), device=dev, dtype=torch.uint8) if want_mask else None
     ws = torch.empty(int(lib.dfw_rthres_workspace_bytes(B)), device=dev, dtype=torch.uint8)
     if ignore_u8 is not None: _req(ignore_u8, torch.uint8, "ignore")
-    check(lib.dfw_rthres_iou_hist(pred_u8.data_ptr(), gt_u8.data_ptr(), _ptr(ignore_u8), float(r_threshold),
+    check(lib.dfw_rthres_iou_hist(pred_u8.data_ptr(), int(is_mask), gt_u8.data_ptr(), _ptr(ignore_u8), float(r_threshold),
                                   inter.data_ptr(), union.data_ptr(), _ptr(mask), B, H, W, ws.data_ptr(), _stream()),
           "dfw_rthres_iou_hist")
     return inter, union, mask

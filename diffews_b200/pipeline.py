@@ -1,0 +1,183 @@
+"""MarigoldPipelineRGBLatentNoise — drop-in for diffews/marigold_pipeline_rgb_latent_noise.py (reference).
+
+Same constructor keywords, `__call__` keywords, `single_infer` / `encode_rgb` / `decode_seg` methods, class-level
+latent scale factors and the externally set `test_timestep` attribute (evaluation_util/main_oss.py:373) as the
+reference; inputs and outputs keep the reference's NCHW fp32 tensor layouts.  What runs underneath is the B200 engine
+(`diffews_b200.unet`, `diffews_b200.vae`).  Differences, all extensions or reference-defect tolerances:
+
+  * `rgb_paths` is accepted and ignored: the reference opens those files only to compute CLIP *image* features that
+    are unused in text-embedding mode (pipeline:311-325, :590-601), and with empty `rgb_paths` it raises NameError
+    (`transforms` is never imported, :321).
+  * `output_type="pt"` returns the uint8 segmentation as a CUDA tensor [B,3,H,W] (batched evaluation, which the
+    reference cannot do: its eval loop only works for bsz=1).  Default "pil" matches the reference.
+  * only `mode='seg'` (any non-'depth' mode is treated as seg by the reference, :280, :532) and
+    `denoising_steps == 1` ("nosample") are on the hot path; others raise NotImplementedError.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .scheduler import DDIMSchedulerCustomized
+
+
+@dataclass
+class MarigoldSegOutput:
+    seg_colored: object                 # PIL.Image | list[PIL.Image] | torch.Tensor (output_type="pt")
+    uncertainty: Optional[object] = None
+    seg_u8: Optional[torch.Tensor] = None   # always: uint8 CUDA tensor [B,3,H,W]
+
+
+class MarigoldPipelineRGBLatentNoise:
+    rgb_latent_scale_factor = 0.18215       # pipeline:120-124
+    depth_latent_scale_factor = 0.18215
+    seg_latent_scale_factor = 0.18215
+    sr_latent_scale_factor = 0.18215
+    normal_latent_scale_factor = 0.18215
+
+    def __init__(self, unet, vae, scheduler=None, tokenizer=None, text_embeds: Optional[torch.Tensor] = None,
+                 text_encoder=None, image_encoder=None, image_projector=None, controlnet=None, customized_head=None):
+        if image_encoder is not None or image_projector is not None:
+            raise NotImplementedError("vision-embedding conditioning is not on the DiffewS hot path")
+        if controlnet is not None or customized_head is not None:
+            raise NotImplementedError("controlnet / customized_head are not on the DiffewS hot path "
+                                      "(reference: customized_head=None, main_oss.py:362)")
+        if text_embeds is None and text_encoder is None:
+            raise ValueError("need text_embeds (the empty-prompt embedding) or a text_encoder")   # pipeline:158-159
+        self.unet, self.vae = unet, vae
+        self.scheduler = scheduler if scheduler is not None else DDIMSchedulerCustomized()
+        self.tokenizer, self.text_encoder = tokenizer, text_encoder
+        self.empty_text_embed = text_embeds
+        self.text_embed_flag, self.vision_embed_flag = True, False
+        self.test_timestep = 1
+        self.device = unet.device
+        self.dtype = torch.float32
+        self._embed_cache = {}
+
+    def to(self, *a, **k):
+        return self
+
+    def enable_xformers_memory_efficient_attention(self, attention_op=None):   # main_oss.py:374-379
+        self.unet.enable_xformers_memory_efficient_attention(attention_op)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def encode_clip_feature(self, clip_rgb_in=None):                            # pipeline:585-601
+        if self.empty_text_embed is not None:
+            return self.empty_text_embed
+        prompt = ""
+        ids = self.tokenizer(prompt, padding="do_not_pad", max_length=self.tokenizer.model_max_length,
+                             truncation=True, return_tensors="pt").input_ids.to(self.text_encoder.device)
+        self.empty_text_embed = self.text_encoder(ids)[0].to(self.dtype)
+        return self.empty_text_embed
+
+    def _batch_embed(self, n: int) -> torch.Tensor:
+        hit = self._embed_cache.get(n)
+        if hit is None:
+            e = self.encode_clip_feature().to(self.device, torch.float32)
+            hit = e.repeat((n, 1, 1)).contiguous()                              # pipeline:690-692
+            self._embed_cache[n] = hit
+        return hit
+
+    def encode_rgb(self, rgb_in: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pipeline:839-862: mean(quant_conv(encoder(x))) * rgb_latent_scale_factor -> [N,4,H/8,W/8] fp32."""
+        lat = self.vae.encode_mean(rgb_in, scale=self.rgb_latent_scale_factor)
+        if out is not None:
+            out.copy_(lat)
+            return out
+        return lat
+
+    def decode_seg(self, seg_latent: torch.Tensor) -> torch.Tensor:
+        """pipeline:887-905: decoder(post_quant_conv(z / scale)).clip(-1, 1) -> [N,3,H,W] fp32."""
+        N, _, hh, ww = seg_latent.shape
+        rows = self.vae.decode_rows(seg_latent, in_scale=1.0 / self.seg_latent_scale_factor)
+        return ops.nhwc_f32_to_nchw(rows, 3, hh * 8, ww * 8, lo=-1.0, hi=1.0)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def single_infer(self, rgb_in_ref: torch.Tensor, rgb_in_tag: torch.Tensor, gt_in_ref: torch.Tensor,
+                     clip_rgb_in=None, num_inference_steps: int = 1, show_pbar: bool = False, mode: str = "seg",
+                     seed=None, _want_u8: bool = False):
+        """pipeline:616-836.  rgb_in_ref / gt_in_ref [B*k,3,H,W], rgb_in_tag [B,3,H,W] in [-1,1] ->
+        seg [B,3,H,W] float in [0,255]."""
+        if mode == "depth":
+            raise NotImplementedError("mode='depth' is not on the DiffewS hot path")
+        if num_inference_steps != 1:
+            raise NotImplementedError("multi-step sampling is not on the 'nosample' hot path (SURVEY §8f rank 4)")
+        device = self.device
+        self.scheduler.set_timesteps(num_inference_steps, device="cpu")          # :644
+        t = int(self.scheduler.timesteps[0])
+        B, Bk = rgb_in_tag.shape[0], rgb_in_ref.shape[0]
+        # :649-651, :674  — three VAE encodes; the support image / mask latents land in the two channel halves
+        rgb_latent_ref = self.encode_rgb(rgb_in_ref.to(device))
+        rgb_latent_tag = self.encode_rgb(rgb_in_tag.to(device))
+        gt_latent_ref = self.encode_rgb(gt_in_ref.to(device))
+        latents_rgb_cond_ref = torch.cat([rgb_latent_ref, gt_latent_ref], dim=1)
+        depth_latent = rgb_latent_tag
+        batch_embed = self._batch_embed(B)                                       # :680-692
+        batch_embed_ref = self._batch_embed(Bk)
+        self.unet.clear_attn_bank()                                              # :715
+        self.unet(latents_rgb_cond_ref, t * self.test_timestep, encoder_hidden_states=batch_embed_ref,
+                  is_target=False)                                               # :719-720 support pass (fills banks)
+        noise_pred = self.unet(depth_latent, t * self.test_timestep, encoder_hidden_states=batch_embed).sample
+        self.unet.clear_attn_bank()                                              # :725
+        # :764-769 scheduler.step(...).pred_original_sample ; :787-795 decode, clip, *0.5+0.5, *255
+        if self.scheduler.is_pure_negation(t):
+            rows = self.vae.decode_rows(noise_pred, in_scale=-1.0 / self.seg_latent_scale_factor)   # z0 = -v, fused
+        else:
+            z0 = self.scheduler.step(noise_pred, t, depth_latent).pred_original_sample
+            rows = self.vae.decode_rows(z0, in_scale=1.0 / self.seg_latent_scale_factor)
+        H, W = rgb_in_tag.shape[-2:]
+        seg_f32, seg_u8 = ops.seg_post(rows, H, W, want_f32=True, want_u8=_want_u8)
+        self._last_noise_pred = noise_pred
+        return (seg_f32, seg_u8) if _want_u8 else seg_f32
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, input_images, denoising_steps: int = 10, ensemble_size: int = 10, processing_res: int = 768,
+                 match_input_res: bool = True, batch_size: int = 0, color_map: str = "Spectral",
+                 show_progress_bar: bool = True, ensemble_kwargs=None, mode: str = "depth", rgb_paths=(),
+                 seed=None, output_type: str = "pil") -> MarigoldSegOutput:
+        if mode == "depth":
+            raise NotImplementedError("mode='depth' is not on the DiffewS hot path")
+        assert processing_res >= 0 and denoising_steps >= 1 and ensemble_size >= 1       # :294-297
+        if len(input_images) != 3:
+            raise ValueError("input_images = [support_imgs, query_img, support_masks]  (main_oss.py:106-110)")
+        ins = []
+        for im in input_images:
+            if not torch.is_tensor(im):
+                im = self._pil_to_tensor(im, processing_res)
+            im = im.to(self.device, torch.float32)
+            assert float(im.min()) >= -1.0 and float(im.max()) <= 1.0                    # :309
+            ins.append(im)
+        ref, tag, gt = ins
+        input_size = tuple(tag.shape[-2:])
+        if ensemble_size > 1:   # :376-383  stack x ensemble, fold into the batch
+            ref, tag, gt = (x.repeat((ensemble_size, 1, 1, 1)) for x in (ref, tag, gt))
+        seg_f32, seg_u8 = self.single_infer(ref, tag, gt, None, denoising_steps, False, mode, seed, _want_u8=True)
+        if ensemble_size > 1:   # :444-468 mean over the ensemble, then the uint8 truncation of :534
+            bs = seg_f32.shape[0] // ensemble_size
+            seg_f32 = seg_f32.view(ensemble_size, bs, *seg_f32.shape[1:]).mean(dim=0)
+            seg_u8 = seg_f32.clip(0, 255).to(torch.uint8)
+        if match_input_res and tuple(seg_u8.shape[-2:]) != input_size:                   # :473-474 (nearest)
+            seg_f32 = torch.nn.functional.interpolate(seg_f32, input_size, mode="nearest")
+            seg_u8 = seg_f32.clip(0, 255).to(torch.uint8)
+        if output_type == "pt":
+            return MarigoldSegOutput(seg_colored=seg_u8, uncertainty=None, seg_u8=seg_u8)
+        from PIL import Image                                                            # :534-545
+        arr = seg_u8.cpu().numpy()
+        imgs = [Image.fromarray(np.ascontiguousarray(a.transpose(1, 2, 0))) for a in arr]
+        return MarigoldSegOutput(seg_colored=imgs[0] if len(imgs) == 1 else imgs, uncertainty=None, seg_u8=seg_u8)
+
+    @staticmethod
+    def _pil_to_tensor(img, processing_res):
+        """pipeline:326-349 for PIL inputs (resize_max_res, RGB, /255*2-1)."""
+        if processing_res > 0:
+            w, h = img.size
+            s = min(processing_res / w, processing_res / h)
+            img = img.resize((int(w * s), int(h * s)))
+        a = np.asarray(img.convert("RGB")).transpose(2, 0, 1)
+        return torch.from_numpy(a / 255.0 * 2.0 - 1.0).float()[None]

@@ -1,0 +1,59 @@
+"""Batched, data-parallel evaluation loop — the B200 counterpart of `test_diffusion` (evaluation_util/main_oss.py:84-171).
+
+One process per GPU; episodes are independent, so rank r takes episodes r, r+world, r+2*world, ... (no data-path
+collective); the only exchange is one NCCL all-reduce of the int64 [2, nclass] intersection/union buffers at the end
+(AverageMeter.all_reduce), after which every rank computes the same mIoU / FB-IoU.
+"""
+from __future__ import annotations
+
+import torch
+
+from .evaluation import AverageMeter, Evaluator
+
+
+def shard_episodes(n_total: int, rank: int, world: int) -> range:
+    """Episode indices owned by `rank` (round-robin, like a DistributedSampler without padding)."""
+    return range(rank, n_total, world)
+
+
+def build_engine_from_modules(unet_module, vae_module, text_embeds, device="cuda", unet_precision=None,
+                              vae_precision=None):
+    from .pipeline import MarigoldPipelineRGBLatentNoise
+    from .unet import MyUNet2DConditionModel
+    from .vae import AutoencoderKL
+    kw_u = {"precision": unet_precision} if unet_precision is not None else {}
+    kw_v = {"precision": vae_precision} if vae_precision is not None else {}
+    unet = MyUNet2DConditionModel.from_module(unet_module, device=device, **kw_u)
+    vae = AutoencoderKL.from_module(vae_module, device=device, **kw_v)
+    return MarigoldPipelineRGBLatentNoise(unet, vae, text_embeds=text_embeds)
+
+
+class EpisodeRunner:
+    def __init__(self, pipe, benchmark: str = "coco", class_ids=None, r_threshold: float = 0.25, img_size: int = 512):
+        self.pipe = pipe
+        self.r_threshold = r_threshold
+        self.img_size = img_size
+        nclass = {"coco": 80, "lvis": 1203, "pascal": 20, "fss": 1000}[benchmark]
+        self.meter = AverageMeter(benchmark=benchmark, class_ids=class_ids if class_ids is not None else range(nclass),
+                                  device=pipe.device)
+
+    @torch.no_grad()
+    def step(self, batch: dict):
+        """`batch` is a collated episode batch ON THE DEVICE (main_oss.py:94 `utils.to_cuda(batch)`).
+        Returns per-episode int64 (area_inter [B,2], area_union [B,2]) and updates the meter."""
+        query_img, query_mask = batch["query_img"], batch["query_mask"]
+        support_imgs, support_masks = batch["support_imgs"], batch["support_masks"]
+        # main_oss.py:99-104: masks [b,k,h,w] -> [b,k,3,h,w] in [-1,1]; shots folded into the batch dim
+        support_masks = support_masks.unsqueeze(2).repeat(1, 1, 3, 1, 1) * 2 - 1
+        support_imgs = support_imgs.reshape(-1, *support_imgs.shape[-3:])
+        support_masks = support_masks.reshape(-1, *support_masks.shape[-3:])
+        out = self.pipe([support_imgs, query_img, support_masks], denoising_steps=1, ensemble_size=1,
+                        processing_res=self.img_size, batch_size=query_img.shape[0], show_progress_bar=False,
+                        mode="seg", rgb_paths=batch.get("rgb_path", []), seed=0, output_type="pt")
+        inter, union = Evaluator.rthres_classify(out.seg_u8, batch, self.r_threshold)
+        self.meter.update_counts(inter, union, batch["class_id"])
+        return inter, union
+
+    def finish(self):
+        self.meter.all_reduce()
+        return self.meter.compute_iou()

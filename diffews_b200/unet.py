@@ -1,0 +1,286 @@
+"""MyUNet2DConditionModel — drop-in for diffews/models/unet_2d_condition.py (reference) on the B200 kernels.
+
+Same call protocol as the reference (`clear_attn_bank()` -> `forward(support, t, ehs, is_target=False)` ->
+`forward(query, t, ehs)` -> `clear_attn_bank()`, unet_2d_condition.py:656-664, :879-895, :1118-1121) and the same
+diffusers state-dict key names, so checkpoints load unchanged.  Inputs / outputs keep the reference layout
+(NCHW fp32 latents); inside everything is channels-last ([N,H,W,C] == [N,HW,C] tokens), so there are no permutes
+between the convolutional and the transformer halves of a block.
+
+Layer schedule = diffusers-0.25 UNet2DConditionModel with the SD-2.1 config: 22 ResnetBlock2D,
+16 Transformer2DModel (one BasicTransformerBlock each), 3 Downsample2D, 3 Upsample2D.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import ops
+from .attention_processor import MyAttention
+from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, _dev
+
+bf16 = torch.bfloat16
+
+
+@dataclass
+class UNet2DConditionOutput:
+    sample: torch.Tensor
+
+
+class CrossAttention:
+    """attn2: attention to the prompt embedding (K/V computed once per encoder_hidden_states and cached)."""
+
+    def __init__(self, sd, prefix, device, heads):
+        self.heads = heads
+        self.scale = 64 ** -0.5
+        self.to_q = Linear(sd, prefix + ".to_q", device)
+        self.to_k = Linear(sd, prefix + ".to_k", device)
+        self.to_v = Linear(sd, prefix + ".to_v", device)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device)
+
+    def kv(self, ehs_bf16):
+        return self.to_k(ehs_bf16), self.to_v(ehs_bf16)
+
+    def __call__(self, x, kv, residual, out_f32):
+        q = self.to_q(x)
+        o = ops.cross_attn(q, kv[0], kv[1], self.heads, self.scale)
+        return self.to_out(o, residual=residual, out_f32=out_f32)
+
+
+class TransformerBlock:
+    def __init__(self, sd, prefix, device, heads, prec: Precision):
+        self.prec = prec
+        self.norm1 = LayerNorm(sd, prefix + ".norm1", device)
+        self.attn1 = MyAttention(sd, prefix + ".attn1", device, heads)
+        self.norm2 = LayerNorm(sd, prefix + ".norm2", device)
+        self.attn2 = CrossAttention(sd, prefix + ".attn2", device, heads)
+        self.norm3 = LayerNorm(sd, prefix + ".norm3", device)
+        self.ff1 = Linear(sd, prefix + ".ff.net.0.proj", device, geglu=True)
+        self.ff2 = Linear(sd, prefix + ".ff.net.2", device)
+
+    def __call__(self, x, kv):
+        f32 = self.prec.stream_f32
+        x = self.attn1(self.norm1(x), residual=x, out_f32=f32)
+        x = self.attn2(self.norm2(x), kv, residual=x, out_f32=f32)
+        g = self.ff1(self.norm3(x))
+        return self.ff2(g, residual=x, out_f32=False)      # feeds proj_out (an MMA operand) -> bf16
+
+
+class Transformer2D:
+    def __init__(self, sd, prefix, device, heads, prec: Precision):
+        self.prec = prec
+        self.norm = GroupNorm(sd, prefix + ".norm", device, eps=1e-6)
+        self.proj_in = Linear(sd, prefix + ".proj_in", device)
+        self.block = TransformerBlock(sd, prefix + ".transformer_blocks.0", device, heads, prec)
+        self.proj_out = Linear(sd, prefix + ".proj_out", device)
+
+    def __call__(self, h, kv):
+        N, H, W, C = h.shape
+        x = self.proj_in(self.norm(h, silu=False).view(N, H * W, C), out_f32=self.prec.stream_f32)
+        x = self.block(x, kv)
+        return self.proj_out(x, residual=h.view(N, H * W, C), out_f32=self.prec.stream_f32).view(N, H, W, C)
+
+
+class MyUNet2DConditionModel:
+    """B200 engine behind the reference's UNet interface."""
+
+    def __init__(self, state_dict, device="cuda", block_out_channels=(320, 640, 1280, 1280), heads=(5, 10, 20, 20),
+                 cross_attention_dim=1024, precision: Optional[Precision] = None):
+        sd = state_dict
+        self.device = torch.device(device)
+        self.prec = precision or Precision()
+        prec, dev = self.prec, self.device
+        c = tuple(block_out_channels)
+        self.config = SimpleNamespace(in_channels=4, in_channels_ref=8, out_channels=4, block_out_channels=c,
+                                      attention_head_dim=tuple(heads), cross_attention_dim=cross_attention_dim,
+                                      layers_per_block=2, norm_num_groups=32, norm_eps=1e-5, sample_size=96)
+        self.dtype = torch.float32
+        # small-Cin input convs run on the direct kernel with fp32 weights [Cout,3,3,Cin]
+        self.conv_in_w = _dev(sd["conv_in.weight"].permute(0, 2, 3, 1), dev, torch.float32)
+        self.conv_in_b = _dev(sd["conv_in.bias"], dev, torch.float32)
+        self.conv_in_ref_w = _dev(sd["conv_in_ref.weight"].permute(0, 2, 3, 1), dev, torch.float32)
+        self.conv_in_ref_b = _dev(sd["conv_in_ref.bias"], dev, torch.float32)
+        # time embedding: evaluated on the host in fp32 once per distinct timestep and folded into conv1 biases
+        self._te = {k: sd[f"time_embedding.{k}"].detach().float().cpu()
+                    for k in ("linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias")}
+        self._temb_cache = {}
+        self._kv_cache = {}
+
+        self.resnets = []          # all resnets in execution order (for the temb bias table)
+        self.transformers = []     # all Transformer2D in execution order (for the cross-attn K/V table)
+
+        def res(prefix):
+            r = Resnet(sd, prefix, dev, 1e-5, prec, has_temb=True)
+            self.resnets.append(r)
+            return r
+
+        def tfm(prefix, h):
+            t = Transformer2D(sd, prefix, dev, h, prec)
+            self.transformers.append(t)
+            return t
+
+        self.down = []
+        for i in range(4):
+            blk = SimpleNamespace(resnets=[], attns=[], down=None)
+            for j in range(2):
+                blk.resnets.append(res(f"down_blocks.{i}.resnets.{j}"))
+                if i < 3:
+                    blk.attns.append(tfm(f"down_blocks.{i}.attentions.{j}", heads[i]))
+            if i < 3:
+                blk.down = Conv(sd, f"down_blocks.{i}.downsamplers.0.conv", dev, stride=2, pad_mode=0)
+            self.down.append(blk)
+        self.mid = SimpleNamespace(res0=res("mid_block.resnets.0"), attn=tfm("mid_block.attentions.0", heads[3]),
+                                   res1=None)
+        self.mid.res1 = res("mid_block.resnets.1")
+        rh = list(reversed(heads))
+        self.up = []
+        for i in range(4):
+            blk = SimpleNamespace(resnets=[], attns=[], up=None)
+            for j in range(3):
+                blk.resnets.append(res(f"up_blocks.{i}.resnets.{j}"))
+                if i > 0:
+                    blk.attns.append(tfm(f"up_blocks.{i}.attentions.{j}", rh[i]))
+            if i < 3:
+                blk.up = Conv(sd, f"up_blocks.{i}.upsamplers.0.conv", dev)
+            self.up.append(blk)
+        self.conv_norm_out = GroupNorm(sd, "conv_norm_out", dev, eps=1e-5)
+        self.conv_out = Conv(sd, "conv_out", dev)
+
+    # ---- reference API ---------------------------------------------------------------------------------------------
+    @classmethod
+    def from_module(cls, module: torch.nn.Module, device="cuda", **kw):
+        """Build from any nn.Module that uses diffusers' UNet2DConditionModel key names (+ conv_in_ref)."""
+        cfg = {}
+        if hasattr(module, "block_out_channels"):
+            cfg = dict(block_out_channels=module.block_out_channels, heads=module.heads)
+        cfg.update(kw)
+        return cls(module.state_dict(), device=device, **cfg)
+
+    def bank_attentions(self):
+        return [t.block.attn1 for t in self.transformers]
+
+    def apply_unet_refonly_block(self):      # unet_2d_condition.py:645-654 — done at construction here
+        for a in self.bank_attentions():
+            a.set_bank()
+            a.set_myprocessor()
+
+    def clear_attn_bank(self):               # unet_2d_condition.py:656-664
+        for a in self.bank_attentions():
+            a.clear_bank()
+
+    def enable_xformers_memory_efficient_attention(self, attention_op=None):
+        for a in self.bank_attentions():
+            a.set_use_memory_efficient_attention_xformers(True, attention_op)
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    # ---- constant folding ------------------------------------------------------------------------------------------
+    def _temb_biases(self, t_value: float):
+        """conv1.bias + time_emb_proj(silu(time_embedding(t)))  per resnet, fp32 (unet_2d_condition.py:1008-1015 and
+        ResnetBlock2D temb add, upstream).  t is a scalar at inference (pipeline:720-722), so this is a constant."""
+        hit = self._temb_cache.get(t_value)
+        if hit is not None:
+            return hit
+        dim = self.config.block_out_channels[0]
+        half = dim // 2
+        exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half
+        ang = torch.tensor([t_value], dtype=torch.float32)[:, None] * torch.exp(exponent)[None, :]
+        emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)      # flip_sin_to_cos=True
+        te = self._te
+        emb = torch.nn.functional.silu(emb @ te["linear_1.weight"].t() + te["linear_1.bias"])
+        emb = emb @ te["linear_2.weight"].t() + te["linear_2.bias"]
+        act = torch.nn.functional.silu(emb)
+        out = [(_dev((act @ r.temb_w.t() + r.temb_b + r.conv1_bias_host)[0], self.device, torch.float32))
+               for r in self.resnets]
+        self._temb_cache[t_value] = out
+        return out
+
+    def _cross_kv(self, ehs: torch.Tensor):
+        key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), ehs.dtype)
+        hit = self._kv_cache.get(key)
+        if hit is not None and hit[0] is ehs:
+            return hit[1]
+        e = ehs.to(device=self.device, dtype=torch.float32)
+        if e.shape[0] > 1 and bool((e == e[:1]).all()):
+            e = e[:1]                         # identical prompt for every sample (pipeline:690-692): share K/V
+        e = ops.cast_bf16(e.contiguous())
+        kvs = [t.block.attn2.kv(e) for t in self.transformers]
+        if len(self._kv_cache) > 8:
+            self._kv_cache.clear()
+        self._kv_cache[key] = (ehs, kvs)
+        return kvs
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, is_target: bool = True, class_labels=None,
+                timestep_cond=None, attention_mask=None, cross_attention_kwargs=None, added_cond_kwargs=None,
+                down_block_additional_residuals=None, mid_block_additional_residual=None,
+                down_intrablock_additional_residuals=None, encoder_attention_mask=None, return_dict: bool = True):
+        for name, v in (("class_labels", class_labels), ("timestep_cond", timestep_cond),
+                        ("attention_mask", attention_mask), ("cross_attention_kwargs", cross_attention_kwargs),
+                        ("added_cond_kwargs", added_cond_kwargs),
+                        ("down_block_additional_residuals", down_block_additional_residuals),
+                        ("mid_block_additional_residual", mid_block_additional_residual),
+                        ("down_intrablock_additional_residuals", down_intrablock_additional_residuals),
+                        ("encoder_attention_mask", encoder_attention_mask)):
+            if v is not None:
+                raise NotImplementedError(f"{name} is not part of the DiffewS hot path")
+        if torch.is_tensor(timestep):
+            tv = timestep.detach().float().reshape(-1)
+            if tv.numel() > 1 and not bool((tv == tv[0]).all()):
+                raise NotImplementedError("per-sample timesteps are not part of the DiffewS hot path")
+            t_value = float(tv[0])
+        else:
+            t_value = float(timestep)
+        if not sample.is_cuda:
+            raise RuntimeError("MyUNet2DConditionModel (B200 engine) needs CUDA tensors: there is no CPU fallback")
+        f32 = self.prec.stream_f32
+        x = sample.to(torch.float32).contiguous()
+        N, Cin, H, W = x.shape
+        if H % 8 or W % 8:
+            raise ValueError("latent height/width must be multiples of 8 (three stride-2 stages)")
+        biases = iter(self._temb_biases(t_value))
+        kvs = iter(self._cross_kv(encoder_hidden_states))
+
+        if is_target:                                                            # unet_2d_condition.py:1118-1121
+            assert Cin == self.config.in_channels
+            h = ops.conv3x3_small_cin(x, self.conv_in_w, self.conv_in_b, out_f32=f32)
+        else:
+            assert Cin == self.config.in_channels_ref
+            h = ops.conv3x3_small_cin(x, self.conv_in_ref_w, self.conv_in_ref_b, out_f32=f32)
+
+        skips = [h]
+        for blk in self.down:                                                    # :1154-1175
+            for j, r in enumerate(blk.resnets):
+                h = r(h, next(biases))
+                if blk.attns:
+                    h = blk.attns[j](h, next(kvs))
+                skips.append(h)
+            if blk.down is not None:
+                h = blk.down(ops.cast_bf16(h), out_f32=f32)
+                skips.append(h)
+        h = self.mid.res0(h, next(biases))                                       # :1189-1200
+        h = self.mid.attn(h, next(kvs))
+        h = self.mid.res1(h, next(biases))
+        for blk in self.up:                                                      # :1214-1243
+            for j, r in enumerate(blk.resnets):
+                h = r(ops.concat_channels(h, skips.pop()), next(biases))
+                if blk.attns:
+                    h = blk.attns[j](h, next(kvs))
+            if blk.up is not None:
+                h = blk.up(ops.upsample2x(h), out_f32=f32)
+        h = self.conv_norm_out(h, silu=True)                                     # :1246-1249
+        y = self.conv_out(h, out_f32=True)                                       # [N,H,W,4] fp32
+        out = ops.nhwc_f32_to_nchw(y.view(N, H * W, 4), 4, H, W)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)
+
+    __call__ = forward

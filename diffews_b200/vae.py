@@ -1,0 +1,168 @@
+"""AutoencoderKL (SD-2.1 VAE) encoder / decoder on the B200 kernels.
+
+Reference call sites: diffews/marigold_pipeline_rgb_latent_noise.py:839-862 (encode_rgb: vae.encoder -> quant_conv ->
+mean * 0.18215) and :887-905 (decode_seg: z / 0.18215 -> post_quant_conv -> vae.decoder -> clip(-1,1)).
+Layer schedule = diffusers-0.25 Encoder / Decoder / UNetMidBlock2D; state-dict keys unchanged.
+
+The mid-block attention is single-head with d = 512 over (H/8 * W/8) tokens; it is only 2 x 34 GFLOP per image, so it
+runs as three tcgen05 GEMMs (Q K^T, fp32 logits; row softmax; P V with V^T produced directly by a transposed
+projection GEMM) instead of a dedicated d=512 flash kernel.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import ops
+from .layers import Conv, GroupNorm, Linear, Precision, Resnet, _dev
+
+bf16 = torch.bfloat16
+
+
+class VaeAttention:
+    """diffusers Attention(heads=1, dim_head=512, bias=True, residual_connection=True, GroupNorm(32, eps 1e-6))."""
+
+    def __init__(self, sd, prefix, device, prec: Precision):
+        self.prec = prec
+        self.norm = GroupNorm(sd, prefix + ".group_norm", device, eps=1e-6)
+        self.to_q = Linear(sd, prefix + ".to_q", device)
+        self.to_k = Linear(sd, prefix + ".to_k", device)
+        # V^T = W_v X^T is produced directly ([C, L] per image, the K-major B operand of P V); its bias is added
+        # after the P V product instead (softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T).
+        self.wv = _dev(sd[prefix + ".to_v.weight"], device, bf16)
+        self.bv = _dev(sd[prefix + ".to_v.bias"], device, torch.float32)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device)
+        self.C = self.wv.shape[0]
+        self.scale = self.C ** -0.5
+
+    def __call__(self, h):
+        N, H, W, C = h.shape
+        L = H * W
+        xn = self.norm(h, silu=False).view(N, L, C)
+        q = self.to_q(xn)
+        k = self.to_k(xn)
+        o = torch.empty((N, L, C), device=h.device, dtype=bf16)
+        for n in range(N):
+            vt = ops.linear(self.wv, xn[n])                               # [C, L] = W_v @ X_n^T
+            s = ops.linear(q[n], k[n], out_f32=True)                      # [L, L] fp32 logits
+            p = ops.softmax_rows(s, self.scale)                           # bf16
+            ops.linear(p, vt, self.bv, out=o[n])                          # P V + b_v
+        y = self.to_out(o, residual=h.view(N, L, C), out_f32=self.prec.stream_f32)
+        return y.view(N, H, W, C)
+
+
+class _Mid:
+    def __init__(self, sd, prefix, device, prec):
+        self.res0 = Resnet(sd, prefix + ".resnets.0", device, 1e-6, prec, has_temb=False)
+        self.attn = VaeAttention(sd, prefix + ".attentions.0", device, prec)
+        self.res1 = Resnet(sd, prefix + ".resnets.1", device, 1e-6, prec, has_temb=False)
+
+    def __call__(self, h):
+        return self.res1(self.attn(self.res0(h)))
+
+
+class AutoencoderKL:
+    def __init__(self, state_dict, device="cuda", block_out_channels=(128, 256, 512, 512),
+                 precision: Optional[Precision] = None):
+        sd = state_dict
+        self.device = dev = torch.device(device)
+        self.prec = prec = precision or Precision(stream_f32=True, mid_f32=False)
+        self.dtype = torch.float32
+        c = tuple(block_out_channels)
+        self.config = SimpleNamespace(block_out_channels=c, latent_channels=4, scaling_factor=0.18215)
+        # ---- encoder
+        self.enc_conv_in_w = _dev(sd["encoder.conv_in.weight"].permute(0, 2, 3, 1), dev, torch.float32)
+        self.enc_conv_in_b = _dev(sd["encoder.conv_in.bias"], dev, torch.float32)
+        self.enc_down = []
+        for i in range(4):
+            blk = SimpleNamespace(
+                resnets=[Resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(2)],
+                down=Conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", dev, stride=2, pad_mode=1) if i < 3 else None)
+            self.enc_down.append(blk)
+        self.enc_mid = _Mid(sd, "encoder.mid_block", dev, prec)
+        self.enc_norm_out = GroupNorm(sd, "encoder.conv_norm_out", dev, eps=1e-6)
+        self.enc_conv_out = Conv(sd, "encoder.conv_out", dev)
+        # quant_conv (1x1, 8->8): only the 4 `mean` channels are consumed (pipeline:858-860); host-side constants
+        self.quant_w = sd["quant_conv.weight"].detach().float().cpu()[:4, :, 0, 0].contiguous()
+        self.quant_b = sd["quant_conv.bias"].detach().float().cpu()[:4].contiguous()
+        # ---- decoder
+        self.post_quant_w = sd["post_quant_conv.weight"].detach().float().cpu()[:, :, 0, 0].contiguous()
+        self.post_quant_b = sd["post_quant_conv.bias"].detach().float().cpu().contiguous()
+        self.dec_conv_in_w = _dev(sd["decoder.conv_in.weight"].permute(0, 2, 3, 1), dev, torch.float32)
+        self.dec_conv_in_b = _dev(sd["decoder.conv_in.bias"], dev, torch.float32)
+        self.dec_mid = _Mid(sd, "decoder.mid_block", dev, prec)
+        self.dec_up = []
+        for i in range(4):
+            blk = SimpleNamespace(
+                resnets=[Resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(3)],
+                up=Conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev) if i < 3 else None)
+            self.dec_up.append(blk)
+        self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6)
+        self.dec_conv_out = Conv(sd, "decoder.conv_out", dev)
+
+    @classmethod
+    def from_module(cls, module: torch.nn.Module, device="cuda", **kw):
+        cfg = {}
+        if hasattr(module, "encoder"):
+            cfg["block_out_channels"] = tuple(b.resnets[0].conv1.out_channels for b in module.encoder.down_blocks)
+        cfg.update(kw)
+        return cls(module.state_dict(), device=device, **cfg)
+
+    def to(self, *a, **k):
+        return self
+
+    # ---- encoder: [N,3,H,W] fp32 in [-1,1] -> latent mean * scale  [N,4,H/8,W/8] fp32 (NCHW, reference layout) -----
+    @torch.no_grad()
+    def encode_mean(self, x_nchw: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        if not x_nchw.is_cuda:
+            raise RuntimeError("AutoencoderKL (B200 engine) needs CUDA tensors: there is no CPU fallback")
+        x = x_nchw.to(torch.float32).contiguous()
+        N, _, H, W = x.shape
+        if H % 8 or W % 8:
+            raise ValueError("image height/width must be multiples of 8")
+        f32 = self.prec.stream_f32
+        h = ops.conv3x3_small_cin(x, self.enc_conv_in_w, self.enc_conv_in_b, out_f32=f32)
+        for blk in self.enc_down:
+            for r in blk.resnets:
+                h = r(h)
+            if blk.down is not None:
+                h = blk.down(ops.cast_bf16(h), out_f32=f32)
+        h = self.enc_mid(h)
+        h = self.enc_norm_out(h, silu=True)
+        m = self.enc_conv_out(h, out_f32=True)                                   # [N,h,w,8] fp32 moments
+        hh, ww = H // 8, W // 8
+        lat = torch.empty((N, 4, hh, ww), device=x.device, dtype=torch.float32)
+        ops.pointwise_small(m, (hh * ww * 8, 8, 1), self.quant_w, self.quant_b, lat, (4 * hh * ww, 1, hh * ww),
+                            N, hh * ww, in_scale=1.0, out_scale=scale)
+        return lat
+
+    # ---- decoder: z [N,4,h,w] fp32 (already divided by the scale factor via in_scale) -> fp32 [N, H*W, 3] rows -----
+    @torch.no_grad()
+    def decode_rows(self, z_nchw: torch.Tensor, in_scale: float = 1.0) -> torch.Tensor:
+        if not z_nchw.is_cuda:
+            raise RuntimeError("AutoencoderKL (B200 engine) needs CUDA tensors: there is no CPU fallback")
+        z = z_nchw.to(torch.float32).contiguous()
+        N, Cz, hh, ww = z.shape
+        f32 = self.prec.stream_f32
+        zq = torch.empty_like(z)
+        ops.pointwise_small(z, (Cz * hh * ww, 1, hh * ww), self.post_quant_w, self.post_quant_b, zq,
+                            (Cz * hh * ww, 1, hh * ww), N, hh * ww, in_scale=in_scale, out_scale=1.0)
+        h = ops.conv3x3_small_cin(zq, self.dec_conv_in_w, self.dec_conv_in_b, out_f32=f32)
+        h = self.dec_mid(h)
+        for blk in self.dec_up:
+            for r in blk.resnets:
+                h = r(h)
+            if blk.up is not None:
+                h = blk.up(ops.upsample2x(h), out_f32=f32)
+        h = self.dec_norm_out(h, silu=True)
+        y = self.dec_conv_out(h, out_f32=True)                                   # [N,H,W,3] fp32
+        return y.view(N, y.shape[1] * y.shape[2], 3)
+
+    @torch.no_grad()
+    def decode(self, z_nchw: torch.Tensor) -> torch.Tensor:
+        """diffusers-style `vae.decoder(post_quant_conv(z))`: returns NCHW fp32 [N,3,H,W]."""
+        N, _, hh, ww = z_nchw.shape
+        rows = self.decode_rows(z_nchw)
+        return ops.nhwc_f32_to_nchw(rows, 3, hh * 8, ww * 8)

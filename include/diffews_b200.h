@@ -111,17 +111,22 @@ int dfw_softmax_rows(const float* s, void* p, int M, int L, float scale, void* s
 /* ------------------------------------------------------------------------------------------------------------
  * Layout / small-channel helpers (CUDA cores, bandwidth-bound).
  * ------------------------------------------------------------------------------------------------------------ */
-/* nearest 2x upsample NHWC bf16 [N,H,W,C] -> [N,2H,2W,C].  ref: Upsample2D F.interpolate(scale 2, nearest) (upstream) */
-int dfw_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);
-/* channel concat: y[N,HW,Ca+Cb] = cat(a[N,HW,Ca], b[N,HW,Cb]).  ref: torch.cat([hidden, skip], dim=1) in up blocks */
-int dfw_concat_channels(const void* a, const void* b, void* y, long long rows, int Ca, int Cb, void* stream);
+/* nearest 2x upsample NHWC [N,H,W,C] (bf16, or fp32 if x_f32) -> bf16 [N,2H,2W,C].  C % 8 == 0.
+ * ref: Upsample2D F.interpolate(scale 2, nearest) (upstream) */
+int dfw_upsample2x_nhwc(const void* x, int x_f32, void* y, int N, int H, int W, int C, void* stream);
+/* channel concat: y[rows,Ca+Cb] = cat(a[rows,Ca], b[rows,Cb]), elem_bytes 2 (bf16) or 4 (fp32).
+ * ref: torch.cat([hidden_states, res_hidden_states], dim=1) in the UNet up blocks (upstream, unet:1226) */
+int dfw_concat_channels(const void* a, const void* b, void* y, long long rows, int Ca, int Cb, int elem_bytes,
+                        void* stream);
+/* fp32 -> bf16 cast (n % 8 == 0): the fp32 residual stream becomes an MMA operand (shortcut / downsample convs). */
+int dfw_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 /* 3x3 / stride 1 / pad 1 convolution with a tiny input channel count (Cin <= 8), CUDA cores:
  *   x  fp32 NCHW [N,Cin,H,W] (the reference's image / latent layout);  w fp32 [Cout,3,3,Cin]; bias fp32 [Cout]
- *   y  bf16 NHWC [N,H,W,Cout], Cout % 64 == 0, Cout <= 512.
+ *   y  bf16 (or fp32 if y_f32) NHWC [N,H,W,Cout], Cout % 64 == 0, Cout <= 512.
  * ref: UNet conv_in / conv_in_ref (unet_2d_condition.py:301-306,1118-1121), VAE encoder conv_in (3->128),
  *      VAE decoder conv_in (4->512) (upstream). */
-int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cin,
-                          int Cout, void* stream);
+int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int y_f32, int N, int H, int W,
+                          int Cin, int Cout, void* stream);
 /* 1x1 conv on <= 8 channels, fp32 math, arbitrary element strides (so it also converts NHWC <-> NCHW):
  *   y[n,p,co] = (sum_ci w[co,ci] * (x[n,p,ci] * in_scale) + b[co]) * out_scale
  *   x element (n,p,ci) at x[n*x_ns + p*x_ps + ci*x_cs]; y likewise.  w [Cout,Cin] and b [Cout] are HOST pointers
@@ -147,15 +152,17 @@ int dfw_seg_post(const float* dec, int row_stride, float* seg_f32, uint8_t* seg_
  * ref: evaluation_util/main_oss.py:128-134 (to_tensor, max()*r, mean(dim=1) > thr — CPU fp32 semantics reproduced
  *      bit-exactly: ((R/255 + G/255) + B/255) / 3  >  fp32(max/255) * r), evaluation_util/common/evaluation.py:12-39
  *      (histc bins=2 on pred[pred==gt], pred, gt; ignore_index 255), logger.py:35-37 (accumulation, here int64).
- *   pred_u8 [B,3,H,W] uint8; gt [B,H,W] uint8 in {0,1}; ignore [B,H,W] uint8 {0,1} or NULL;
+ *   pred_u8 [B,3,H,W] uint8 (or, if pred_is_mask, an already binarised [B,H,W] {0,1} mask: the thresholding is
+ *   skipped and the call is exactly Evaluator.classify_prediction); gt [B,H,W] uint8 in {0,1};
+ *   ignore [B,H,W] uint8 {0,1} or NULL;
  *   r_threshold (0.25); the max is taken PER EPISODE (the reference only runs bsz=1, where they coincide).
  *   out: area_inter int64 [B,2], area_union int64 [B,2] (bin 0 background, bin 1 foreground);
  *        mask_out uint8 [B,H,W] (0/1, 255 where ignored) or NULL.
  *   workspace: dfw_rthres_workspace_bytes(B) bytes (zeroed by the call). */
 long long dfw_rthres_workspace_bytes(int B);
-int dfw_rthres_iou_hist(const uint8_t* pred_u8, const uint8_t* gt, const uint8_t* ignore, float r_threshold,
-                        long long* area_inter, long long* area_union, uint8_t* mask_out, int B, int H, int W,
-                        void* workspace, void* stream);
+int dfw_rthres_iou_hist(const uint8_t* pred_u8, int pred_is_mask, const uint8_t* gt, const uint8_t* ignore,
+                        float r_threshold, long long* area_inter, long long* area_union, uint8_t* mask_out, int B,
+                        int H, int W, void* workspace, void* stream);
 /* AverageMeter.update: buf[2, nclass] (int64) += counts[b, :] at column class_id[b].  ref: logger.py:35-37 */
 int dfw_iou_accumulate(const long long* area_inter, const long long* area_union, const long long* class_id,
                        long long* inter_buf, long long* union_buf, int B, int nclass, void* stream);

@@ -1,0 +1,153 @@
+"""GPU parity: the B200 engine against the CPU oracle on identical seeded inputs and identical random-init weights.
+
+Bars (BASELINE.md §4 / north_star): UNet output latent rel-L2 <= 1e-2 (bf16 tensor-core operands);
+binarised masks agree on >= 99.5 % of pixels; intersection/union counts bit-exact given identical masks.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+UNET_RTOL = 1e-2
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def small_models():
+    from oracle.sd21 import build_models
+    return build_models(0, (64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))
+
+
+@pytest.fixture(scope="module")
+def full_models():
+    from oracle.sd21 import build_models
+    return build_models(0)
+
+
+def _unet_pair(unet_o, lat, B, k, seed=1):
+    from diffews_b200.synthetic import prompt_embedding
+    from diffews_b200.unet import MyUNet2DConditionModel
+    g = torch.Generator().manual_seed(seed)
+    sup = torch.randn(B * k, 8, lat, lat, generator=g) * 0.8
+    qry = torch.randn(B, 4, lat, lat, generator=g) * 0.8
+    ehs = prompt_embedding()
+    unet_o.clear_attn_bank()
+    unet_o(sup, 1, ehs.repeat(B * k, 1, 1), is_target=False)
+    ref = unet_o(qry, 1, ehs.repeat(B, 1, 1))
+    unet_o.clear_attn_bank()
+    eng = MyUNet2DConditionModel.from_module(unet_o)
+    eng.clear_attn_bank()
+    eng(sup.cuda(), torch.tensor(1), ehs.repeat(B * k, 1, 1).cuda(), is_target=False)
+    out = eng(qry.cuda(), torch.tensor(1), ehs.repeat(B, 1, 1).cuda()).sample
+    eng.clear_attn_bank()
+    torch.cuda.synchronize()
+    return out, ref
+
+
+@pytest.mark.parametrize("B,k,lat", [(1, 1, 16), (2, 1, 8), (2, 3, 16)])
+def test_unet_small_width(small_models, B, k, lat):
+    out, ref = _unet_pair(small_models[0], lat, B, k)
+    e = rel_l2(out, ref)
+    print(f"small unet B{B} k{k} lat{lat}: rel-L2 {e:.3e}")
+    assert e <= UNET_RTOL
+
+
+@pytest.mark.parametrize("B,k,lat", [(1, 1, 16), (1, 1, 32), (1, 5, 16), (2, 1, 16)])
+def test_unet_full_width(full_models, B, k, lat):
+    """SD-2.1 widths (320..1280, heads 5..20), reduced latent so the CPU oracle finishes in seconds."""
+    out, ref = _unet_pair(full_models[0], lat, B, k)
+    e = rel_l2(out, ref)
+    print(f"full unet B{B} k{k} lat{lat}: rel-L2 {e:.3e}")
+    assert e <= UNET_RTOL
+
+
+def test_unet_batched_equals_singletons(small_models):
+    """B episodes batched == B singletons (episodes are independent; property from SURVEY §4)."""
+    from diffews_b200.synthetic import prompt_embedding
+    from diffews_b200.unet import MyUNet2DConditionModel
+    eng = MyUNet2DConditionModel.from_module(small_models[0])
+    g = torch.Generator().manual_seed(3)
+    B, k, lat = 3, 2, 8
+    sup = (torch.randn(B * k, 8, lat, lat, generator=g) * 0.8).cuda()
+    qry = (torch.randn(B, 4, lat, lat, generator=g) * 0.8).cuda()
+    e1 = prompt_embedding().cuda()
+
+    def run(s, q):
+        eng.clear_attn_bank()
+        eng(s, 1, e1.repeat(s.shape[0], 1, 1), is_target=False)
+        o = eng(q, 1, e1.repeat(q.shape[0], 1, 1)).sample
+        eng.clear_attn_bank()
+        return o
+    full = run(sup, qry)
+    for b in range(B):
+        one = run(sup[b * k:(b + 1) * k], qry[b:b + 1])
+        assert torch.equal(one[0], full[b]), f"episode {b}: batched result differs from singleton"
+
+
+@pytest.mark.parametrize("size", [64, 128])
+def test_vae_roundtrip_small_width(small_models, size):
+    from diffews_b200.vae import AutoencoderKL
+    from oracle.pipeline import SCALE, decode_seg, encode_rgb
+    vae_o = small_models[1]
+    eng = AutoencoderKL.from_module(vae_o)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, size, size, generator=g) * 2 - 1
+    ref_lat = encode_rgb(vae_o, x)
+    lat = eng.encode_mean(x.cuda(), scale=SCALE)
+    e = rel_l2(lat, ref_lat)
+    print(f"vae encode {size}: rel-L2 {e:.3e}")
+    assert e <= 1.5e-2
+    ref_dec = decode_seg(vae_o, ref_lat)
+    dec = eng.decode_rows(ref_lat.cuda(), in_scale=1.0 / SCALE).view(2, size, size, 3).permute(0, 3, 1, 2).clip(-1, 1)
+    e = rel_l2(dec, ref_dec)
+    print(f"vae decode {size}: rel-L2 {e:.3e}")
+    # The random-init decoder amplifies bf16 operand rounding to ~1.9e-2 (a CPU emulation that only rounds the
+    # tensor-core operands of the fp32 oracle gives the same figure); the acceptance bar for the decoder is the mask
+    # agreement >= 99.5 % checked in the pipeline tests below.
+    assert e <= 3e-2
+
+
+def _pipeline_parity(models, size, B, k, start=0):
+    from diffews_b200.evaluation import Evaluator
+    from diffews_b200.pipeline import MarigoldPipelineRGBLatentNoise
+    from diffews_b200.synthetic import make_batch, pipeline_inputs, prompt_embedding
+    from diffews_b200.unet import MyUNet2DConditionModel
+    from diffews_b200.vae import AutoencoderKL
+    from oracle.pipeline import evaluate_episode
+    unet_o, vae_o = models
+    pipe = MarigoldPipelineRGBLatentNoise(MyUNet2DConditionModel.from_module(unet_o), AutoencoderKL.from_module(vae_o),
+                                          text_embeds=prompt_embedding())
+    batch = make_batch(start, B, size, k)
+    out = pipe(pipeline_inputs(batch), denoising_steps=1, ensemble_size=1, processing_res=size, batch_size=B,
+               show_progress_bar=False, mode="seg", rgb_paths=[], seed=0, output_type="pt")
+    gbatch = {"query_mask": batch["query_mask"].cuda()}
+    inter, union, mask = Evaluator.rthres_classify(out.seg_u8, gbatch, 0.25, want_mask=True)
+    torch.cuda.synchronize()
+    agree, lat_err = [], []
+    for b in range(B):
+        one = {kk: v[b:b + 1] for kk, v in batch.items()}
+        o_inter, o_union, o_mask, o_u8, o_lat = evaluate_episode(unet_o, vae_o, prompt_embedding(), one)
+        lat_err.append(rel_l2(pipe._last_noise_pred[b], o_lat[0]))
+        agree.append((mask[b].cpu().float() == o_mask[0]).float().mean().item())
+        # counts must be bit-exact GIVEN IDENTICAL MASKS: recount the engine's own mask with the oracle
+        from oracle.metric import classify_prediction
+        ci, cu = classify_prediction(mask[b:b + 1].cpu().float(), {"query_mask": one["query_mask"]})
+        assert torch.equal(inter[b].cpu(), ci[:, 0].long()) and torch.equal(union[b].cpu(), cu[:, 0].long())
+    return agree, lat_err
+
+
+def test_pipeline_small_width(small_models):
+    agree, lat_err = _pipeline_parity(small_models, 64, 3, 2)
+    print("small pipeline: mask agreement", agree, "latent rel-L2", lat_err)
+    assert min(agree) >= 0.995 and max(lat_err) <= UNET_RTOL
+
+
+def test_pipeline_full_width_128(full_models):
+    """Full SD-2.1 widths at 128x128 images (16x16 latents): the complete path of BASELINE config 1 at reduced size."""
+    agree, lat_err = _pipeline_parity(full_models, 128, 2, 1)
+    print("full pipeline 128: mask agreement", agree, "latent rel-L2", lat_err)
+    assert min(agree) >= 0.995 and max(lat_err) <= UNET_RTOL
