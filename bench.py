@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true")
+    ap.add_argument("--vae-stream", default="half", choices=["half", "f32"], help="VAE residual-stream storage")
+    ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -193,7 +195,9 @@ def main():
     from oracle.sd21 import build_models          # weight source: deterministic random init (no checkpoints offline)
 
     unet_o, vae_o = build_models(0)
-    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding(), device=dev)
+    from diffews_b200.layers import Precision
+    vae_prec = Precision(stream_f32=(args.vae_stream == "f32"), mid_f32=False)
+    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding(), device=dev, vae_precision=vae_prec)
     runner = EpisodeRunner(pipe, "coco", img_size=args.size)
     B = args.batch
 
@@ -282,6 +286,14 @@ def main():
         summ = timer.summary()
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / (v["ms"] * 1e9), 1)
                        if v["ms"] > 0 else None, "share_of_step": round(v["ms"] / ms_total, 3)} for k, v in summ.items()}
+        if args.layer_table and rank == 0:
+            rows = sorted(timer.by_shape().items(), key=lambda kv: -kv[1]["ms"])
+            with open(args.layer_table, "w") as f:
+                f.write(f"# per-shape CUDA-event times over {args.steps} timed steps (B={B}/GPU); step total {ms_total:.1f} ms\n")
+                f.write("kind\tshape\tlaunches\tms_total\tshare\tTFLOP/s\n")
+                for (kind, shape), v in rows:
+                    tf = v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else 0.0
+                    f.write(f"{kind}\t{shape}\t{v['launches']}\t{v['ms']:.3f}\t{v['ms'] / ms_total:.4f}\t{tf:.1f}\n")
         ig = summ.get("igemm")
         if ig and ig["ms"] > 0:
             achieved = ig["flops"] / (ig["ms"] * 1e9)
@@ -304,13 +316,15 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{args.nshot}-shot {args.size}x{args.size} episodes, batch {B} per GPU, single-step "
                                    "SD-2.1 UNet (KV-bank attention) + VAE encode x3 / decode + rthres/IoU, random-init "
                                    "weights (BASELINE config 2)",
                        "episodes_per_step_per_gpu": B, "parallelism": f"dp{world}",
                        "l2_policy": "inputs + activations per step (>2 GB) exceed the 126 MB L2; 2 alternating batches",
-                       "precision": "bf16 tensor-core operands, fp32 accumulate / residual stream / statistics"},
+                       "precision": "fp16 tensor-core operands (the reference's own half mode), fp32 accumulate / softmax / "
+                                    f"statistics, UNet residual stream fp32, VAE stream {args.vae_stream}; an all-bf16 "
+                                    "operand mode exists (layers.PURE_BF16) but misses the 1e-2 latent bar (1.2e-2)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels,
             "frac_of_tensor_roofline_whole_path": round(value / world * FLOPS_PER_EPISODE_1SHOT_512 / (peak_tf * 1e12), 4)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdiffews_b200.so")
 
 DFW_OK, DFW_ERR_INVALID, DFW_ERR_CUDA, DFW_ERR_ARCH = 0, -1, -2, -3
-EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU = 1, 2, 4, 8
+EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU, EPI_F16 = 1, 2, 4, 8, 16
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -24,15 +24,15 @@ SIGNATURES = {
     "dfw_conv2d_igemm": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
-                                  _i, _f, _vp]),
-    "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp]),
+                                  _i, _f, _i, _vp]),
+    "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "dfw_groupnorm_workspace_bytes": (_ll, [_i, _i, _i, _i]),
-    "dfw_groupnorm_silu": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
-    "dfw_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "dfw_softmax_rows": (_i, [_vp, _vp, _i, _i, _f, _vp]),
-    "dfw_upsample2x_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "dfw_groupnorm_silu": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "dfw_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "dfw_softmax_rows": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
+    "dfw_upsample2x_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
-    "dfw_cast_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "dfw_cast_f32_to_16": (_i, [_vp, _vp, _i, _ll, _vp]),
     "dfw_conv3x3_small_cin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dfw_pointwise_small": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _f, _f, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
     "dfw_nhwc_f32_to_nchw_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp]),

@@ -26,11 +26,11 @@ bf16 = torch.bfloat16
 class MyAttention:
     """Prepared weights + bank state of one `attn1` (self-attention) module."""
 
-    def __init__(self, sd, prefix, device, heads: int):
+    def __init__(self, sd, prefix, device, heads: int, wdtype=bf16):
         self.heads = heads
         self.scale = 64 ** -0.5
-        self.to_qkv = FusedLinear(sd, [prefix + ".to_q", prefix + ".to_k", prefix + ".to_v"], device)
-        self.to_out = Linear(sd, prefix + ".to_out.0", device)
+        self.to_qkv = FusedLinear(sd, [prefix + ".to_q", prefix + ".to_k", prefix + ".to_v"], device, wdtype=wdtype)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wdtype)
         self.inner_dim = self.to_qkv.splits[0]
         assert self.inner_dim == heads * 64, "the flash kernel is specialised for head_dim 64"
         self.residual_connection = False
@@ -76,7 +76,7 @@ class MyXFormersAttnProcessor:
             raise NotImplementedError("the KV-bank processor is self-attention only (reference: attn1)")
         if scale != 1.0:
             raise NotImplementedError("LoRA scale is not part of the hot path")
-        assert hidden_states.ndim == 3 and hidden_states.dtype == bf16
+        assert hidden_states.ndim == 3 and hidden_states.dtype in (bf16, torch.float16)
         N, S, C = hidden_states.shape
         qkv = attn.to_qkv(hidden_states)                       # [N, S, 3C]  one GEMM
         D = attn.inner_dim

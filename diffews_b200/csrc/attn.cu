@@ -32,6 +32,8 @@ constexpr int ATT_THREADS = 256;
 constexpr int ATT_SMEM = TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * 2 * TILE_BYTES /*P x2*/ +
                          1024 + 256;
 constexpr int ATT_TMEM_COLS = 512;
+// All 16-bit tensors of a call (Q, K, V, P, O) share one format, bf16 or fp16: tcgen05 kind::f16 requires the A and B
+// operand of an MMA to have the same format (a bf16 x fp16 mix raises an illegal-instruction trap on sm_100).
 
 struct AttnMaps {
     CUtensorMap q, k_self, v_self, k_bank, v_bank;
@@ -40,9 +42,10 @@ struct AttnParams {
     int Lq, Ls, Lb;
     int n_self, n_bank;   // number of 128-key tiles per source
     float scale_log2;     // scale * log2(e)
-    __nv_bfloat16* o;
+    uint16_t* o;
     long long o_batch_stride;
     int o_row_stride;
+    int f16;              // 16-bit tensors are fp16 (else bf16)
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -115,8 +118,9 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_M, ATT_N, 0);   // S = Q K^T : B (=K) is K-major
-            constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_M, ATT_D, 1);   // O = P V   : B (=V) is MN-major
+            const uint32_t fmt = p.f16 ? 0u : 1u;
+            const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (=K) is K-major
+            const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);   // O = P V   : B (=V) is MN-major
             auto issue_s = [&](int j) {
                 const int s = j % KV_STAGES;
                 mbar_wait(kv_full(s), (j / KV_STAGES) & 1, 11);
@@ -212,10 +216,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     uint4 w;
-                    w.x = pack_bf16x2(pf[u * 8 + 0], pf[u * 8 + 1]);
-                    w.y = pack_bf16x2(pf[u * 8 + 2], pf[u * 8 + 3]);
-                    w.z = pack_bf16x2(pf[u * 8 + 4], pf[u * 8 + 5]);
-                    w.w = pack_bf16x2(pf[u * 8 + 6], pf[u * 8 + 7]);
+                    w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], p.f16);
+                    w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], p.f16);
+                    w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], p.f16);
+                    w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], p.f16);
                     const int unit = ((c & 1) * 4 + u) ^ (row & 7);
                     *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
                 }
@@ -231,15 +235,15 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         accumulate_o(ntiles - 1, alpha_pending);
         if (q0 + row < p.Lq) {
             const float inv = 1.0f / l_run;
-            __nv_bfloat16* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
+            uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
                                 static_cast<long long>(q0 + row) * p.o_row_stride + head * ATT_D;
 #pragma unroll
             for (int i = 0; i < ATT_D; i += 8) {
                 uint4 w;
-                w.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-                w.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-                w.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-                w.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+                w.x = pack_h2(o_acc[i] * inv, o_acc[i + 1] * inv, p.f16);
+                w.y = pack_h2(o_acc[i + 2] * inv, o_acc[i + 3] * inv, p.f16);
+                w.z = pack_h2(o_acc[i + 4] * inv, o_acc[i + 5] * inv, p.f16);
+                w.w = pack_h2(o_acc[i + 6] * inv, o_acc[i + 7] * inv, p.f16);
                 *reinterpret_cast<uint4*>(op + i) = w;
             }
         }
@@ -263,10 +267,15 @@ int make_seq_map(CUtensorMap* m, const void* base, int C, int L, int B, int row_
 // ---------------------------------------------------------------------------------------------------------
 // K2: cross attention to Lctx <= 128 prompt tokens. 8 lanes per (token, head); online softmax over the keys.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void cross_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                  const __nv_bfloat16* __restrict__ v, long long kv_batch_stride,
-                                  __nv_bfloat16* __restrict__ o, long long total_groups, int L, int heads, int Lctx,
-                                  float scale_log2) {
+__device__ __forceinline__ void unpack8(const uint4& u, int f16, float (&f)[8]) {
+    const float2 a = unpack_h2(u.x, f16), b = unpack_h2(u.y, f16), c = unpack_h2(u.z, f16), d = unpack_h2(u.w, f16);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__global__ void cross_attn_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                  const uint16_t* __restrict__ v, long long kv_batch_stride,
+                                  uint16_t* __restrict__ o, long long total_groups, int L, int heads, int Lctx,
+                                  float scale_log2, int f16) {
     const long long gid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
     const bool active = gid < total_groups;
@@ -277,16 +286,18 @@ __global__ void cross_attn_kernel(const __nv_bfloat16* __restrict__ q, const __n
     const int C = heads * 64;
     const long long qoff = tok * C + h * 64 + sub * 8;
     const uint4 qv = __ldg(reinterpret_cast<const uint4*>(q + qoff));
-    const float qf[8] = {bf16_lo(qv.x), bf16_hi(qv.x), bf16_lo(qv.y), bf16_hi(qv.y),
-                         bf16_lo(qv.z), bf16_hi(qv.z), bf16_lo(qv.w), bf16_hi(qv.w)};
+    float qf[8];
+    unpack8(qv, f16, qf);
     float m = -INFINITY, l = 0.f;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const __nv_bfloat16* kb = k + bidx * kv_batch_stride + h * 64 + sub * 8;
-    const __nv_bfloat16* vb = v + bidx * kv_batch_stride + h * 64 + sub * 8;
+    const uint16_t* kb = k + bidx * kv_batch_stride + h * 64 + sub * 8;
+    const uint16_t* vb = v + bidx * kv_batch_stride + h * 64 + sub * 8;
     for (int j = 0; j < Lctx; ++j) {
         const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * C));
-        float d = qf[0] * bf16_lo(kv.x) + qf[1] * bf16_hi(kv.x) + qf[2] * bf16_lo(kv.y) + qf[3] * bf16_hi(kv.y) +
-                  qf[4] * bf16_lo(kv.z) + qf[5] * bf16_hi(kv.z) + qf[6] * bf16_lo(kv.w) + qf[7] * bf16_hi(kv.w);
+        float kf[8];
+        unpack8(kv, f16, kf);
+        float d = qf[0] * kf[0] + qf[1] * kf[1] + qf[2] * kf[2] + qf[3] * kf[3] + qf[4] * kf[4] + qf[5] * kf[5] +
+                  qf[6] * kf[6] + qf[7] * kf[7];
         d += __shfl_xor_sync(0xffffffffu, d, 1);
         d += __shfl_xor_sync(0xffffffffu, d, 2);
         d += __shfl_xor_sync(0xffffffffu, d, 4);
@@ -296,8 +307,8 @@ __global__ void cross_attn_kernel(const __nv_bfloat16* __restrict__ q, const __n
         const float pj = exp2f(s - m_new);
         l = fmaf(l, alpha, pj);
         const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * C));
-        const float vf[8] = {bf16_lo(vv.x), bf16_hi(vv.x), bf16_lo(vv.y), bf16_hi(vv.y),
-                             bf16_lo(vv.z), bf16_hi(vv.z), bf16_lo(vv.w), bf16_hi(vv.w)};
+        float vf[8];
+        unpack8(vv, f16, vf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], alpha, pj * vf[i]);
         m = m_new;
@@ -305,10 +316,10 @@ __global__ void cross_attn_kernel(const __nv_bfloat16* __restrict__ q, const __n
     if (active) {
         const float inv = 1.0f / l;
         uint4 w;
-        w.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-        w.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-        w.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
-        w.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+        w.x = pack_h2(acc[0] * inv, acc[1] * inv, f16);
+        w.y = pack_h2(acc[2] * inv, acc[3] * inv, f16);
+        w.z = pack_h2(acc[4] * inv, acc[5] * inv, f16);
+        w.w = pack_h2(acc[6] * inv, acc[7] * inv, f16);
         *reinterpret_cast<uint4*>(o + qoff) = w;
     }
 }
@@ -322,7 +333,7 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
                          const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
                          const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
                          int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
-                         int heads, int Lq, int Ls, int Lb, float scale, void* stream_) {
+                         int heads, int Lq, int Ls, int Lb, float scale, int f16, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
@@ -355,7 +366,8 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     p.n_self = (Ls + ATT_N - 1) / ATT_N;
     p.n_bank = (Lb + ATT_N - 1) / ATT_N;
     p.scale_log2 = scale * 1.4426950408889634f;
-    p.o = reinterpret_cast<__nv_bfloat16*>(o);
+    p.o = reinterpret_cast<uint16_t*>(o);
+    p.f16 = f16;
     p.o_batch_stride = o_batch_stride;
     p.o_row_stride = o_row_stride;
     static bool attr_set = false;
@@ -371,7 +383,7 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
 }
 
 int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv_batch_stride, void* o, int B,
-                       int L, int heads, int Lctx, float scale, void* stream_) {
+                       int L, int heads, int Lctx, float scale, int f16, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
@@ -382,9 +394,9 @@ int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv
     const long long blocks = (threads + 255) / 256;
     DFW_REQUIRE(blocks < (1LL << 31));
     cross_attn_kernel<<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-        reinterpret_cast<const __nv_bfloat16*>(v), kv_batch_stride, reinterpret_cast<__nv_bfloat16*>(o), groups, L,
-        heads, Lctx, scale * 1.4426950408889634f);
+        reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(k),
+        reinterpret_cast<const uint16_t*>(v), kv_batch_stride, reinterpret_cast<uint16_t*>(o), groups, L,
+        heads, Lctx, scale * 1.4426950408889634f, f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -59,10 +59,11 @@ template <int BLOCK_N>
 struct IgemmCfg {
     static constexpr int B_TILE_BYTES = BLOCK_N * 128;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N > 128 ? 5 : (BLOCK_N == 128 ? 6 : 8));
+    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4 /*staging*/ + 128 * 16 /*row table*/;
     static constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
@@ -84,79 +85,136 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t) {
     return c;
 }
 
-template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, float (&f)[CH], int col_in0, int col_out0,
-                                               int img, long long pix, bool row_valid) {
-    // f: raw accumulators for weight rows [col_in0, col_in0+CH). Output columns [col_out0, col_out0+CH).
-    if (!row_valid || col_in0 >= p.Cout) return;
-    const int ncols = min(CH, p.Cout - col_in0);
-    if (p.bias != nullptr) {
-        const float* bp = p.bias + static_cast<long long>(img) * p.bias_sample_stride + col_in0;
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue.  tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per load).  Writing rows
+// straight to global would make every store instruction touch 32 different cache lines, so each warp transposes
+// its 32x32 chunk through a padded smem staging buffer: afterwards 8 consecutive lanes own one row's 32 columns
+// (4 columns each) and every global load/store instruction covers 4 complete rows of the chunk (4 x 128 B in fp32).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int STG_LD = 36;                       // staging row pitch in floats (pad 4: conflict-free float4 access)
+constexpr int STG_BYTES_PER_WARP = 32 * STG_LD * 4;
+
+struct EpiRow {                                  // per accumulator row, computed once per tile
+    long long pix;                               // output pixel index, -1 if the row is outside the tensor
+    int img;
+    int pad;
+};
+
+__device__ __forceinline__ void stage_rows(float* stg, int lane, const uint32_t (&v)[32]) {
+    float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD);
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-            if (j < ncols) f[j] += __ldg(bp + j);
-    }
-    if (p.out_scale != 1.0f) {
+    for (int j = 0; j < 8; ++j)
+        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+}
+
+// Raw residual values of one 32x32 chunk in the transposed ("8 lanes per row") layout, fetched BEFORE the chunk's
+// accumulators are read so that the global-load latency overlaps the TMEM load / smem transpose of the chunk and the
+// stores of the previous one (the loads must not be interleaved with the stores: out and residual may alias as far
+// as the compiler knows, and an in-order LDG -> FADD -> STG chain per row group serialises on DRAM latency).
+struct ResChunk {
+    uint4 raw[8];      // fp32 residual: 4 floats; 16-bit residual: .x/.y hold 4 halves
+};
+
+__device__ __forceinline__ void prefetch_residual(const IgemmParams& p, const EpiRow* rows, int lane, int col_in0,
+                                                  int col_out0, int NC, ResChunk& rc) {
+    if (p.residual == nullptr) return;
+    const int cq = (lane & 7) * 4, sub = lane >> 3;
+    const int ncols = min(NC, p.Cout - col_in0);
+    const bool vec = (p.out_ch % 4 == 0) && (ncols > 0) && (ncols % 4 == 0);
+    if (!vec || cq >= ncols) return;     // the scalar tail path loads inline
 #pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] *= p.out_scale;
-    }
-    if (p.flags & DFW_EPI_SILU) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] = silu(f[j]);
-    }
-    const long long off = pix * p.out_ch + col_out0;
-    const bool vec_ok = (ncols == CH) && (p.out_ch % 8 == 0);
-    if (p.residual != nullptr) {
+    for (int i = 0; i < 8; ++i) {
+        const long long pix = rows[4 * i + sub].pix;
+        rc.raw[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (pix < 0) continue;
+        const long long off = pix * p.out_ch + col_out0 + cq;
         if (p.flags & DFW_EPI_RES_F32) {
-            const float* rp = reinterpret_cast<const float*>(p.residual) + off;
-            if (vec_ok) {
-#pragma unroll
-                for (int j = 0; j < CH; j += 4) {
-                    float4 r = *reinterpret_cast<const float4*>(rp + j);
-                    f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-                }
-            } else {
-                for (int j = 0; j < ncols; ++j) f[j] += rp[j];
-            }
+            rc.raw[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + off));
         } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + off;
-            if (vec_ok) {
-#pragma unroll
-                for (int j = 0; j < CH; j += 8) {
-                    uint4 r = *reinterpret_cast<const uint4*>(rp + j);
-                    f[j] += bf16_lo(r.x); f[j + 1] += bf16_hi(r.x);
-                    f[j + 2] += bf16_lo(r.y); f[j + 3] += bf16_hi(r.y);
-                    f[j + 4] += bf16_lo(r.z); f[j + 5] += bf16_hi(r.z);
-                    f[j + 6] += bf16_lo(r.w); f[j + 7] += bf16_hi(r.w);
-                }
-            } else {
-                for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(rp[j]);
-            }
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + off));
+            rc.raw[i].x = t.x; rc.raw[i].y = t.y;
         }
     }
-    if (p.flags & DFW_EPI_OUT_F32) {
-        float* op = reinterpret_cast<float*>(p.out) + off;
-        if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-            for (int j = 0; j < ncols; ++j) op[j] = f[j];
+}
+
+// Processes one staged chunk of NC (<= 32) columns starting at weight row `col_in0`, output column `col_out0`.
+__device__ __forceinline__ void epilogue_store_chunk(const IgemmParams& p, const float* stg, const EpiRow* rows,
+                                                     int lane, int col_in0, int col_out0, int NC, const ResChunk& rc) {
+    const int cq = (lane & 7) * 4;               // this lane's 4 columns inside the chunk
+    const int sub = lane >> 3;                   // row within a group of 4
+    const int f16 = p.flags & DFW_EPI_F16;       // 16-bit tensors are fp16 (else bf16)
+    const int ncols = min(NC, p.Cout - col_in0); // valid columns in this chunk
+    if (ncols <= 0) return;
+    const bool vec = (p.out_ch % 4 == 0) && (ncols % 4 == 0);
+    const bool lane_has_cols = cq < ncols;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool shared_bias = (p.bias != nullptr) && (p.bias_sample_stride == 0);
+    if (shared_bias && lane_has_cols) {
+        if (vec) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0 + cq));
+        else {
+            const float* bp = p.bias + col_in0 + cq;
+            bias4.x = __ldg(bp);
+            if (cq + 1 < ncols) bias4.y = __ldg(bp + 1);
+            if (cq + 2 < ncols) bias4.z = __ldg(bp + 2);
+            if (cq + 3 < ncols) bias4.w = __ldg(bp + 3);
         }
-    } else {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-        if (vec_ok) {
+    }
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(f[j], f[j + 1]);
-                o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(op + j) = o;
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + sub;
+        const EpiRow row = rows[r];
+        if (row.pix < 0 || !lane_has_cols) continue;
+        float4 f = *reinterpret_cast<const float4*>(stg + r * STG_LD + cq);
+        if (p.bias != nullptr) {
+            if (shared_bias) { f.x += bias4.x; f.y += bias4.y; f.z += bias4.z; f.w += bias4.w; }
+            else {
+                const float* bp = p.bias + static_cast<long long>(row.img) * p.bias_sample_stride + col_in0 + cq;
+                if (vec) { const float4 b = __ldg(reinterpret_cast<const float4*>(bp)); f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w; }
+                else {
+                    f.x += __ldg(bp);
+                    if (cq + 1 < ncols) f.y += __ldg(bp + 1);
+                    if (cq + 2 < ncols) f.z += __ldg(bp + 2);
+                    if (cq + 3 < ncols) f.w += __ldg(bp + 3);
+                }
+            }
+        }
+        if (p.out_scale != 1.0f) { f.x *= p.out_scale; f.y *= p.out_scale; f.z *= p.out_scale; f.w *= p.out_scale; }
+        if (p.flags & DFW_EPI_SILU) { f.x = silu(f.x); f.y = silu(f.y); f.z = silu(f.z); f.w = silu(f.w); }
+        const long long off = row.pix * p.out_ch + col_out0 + cq;
+        if (vec) {
+            if (p.residual != nullptr) {
+                if (p.flags & DFW_EPI_RES_F32) {
+                    f.x += __uint_as_float(rc.raw[i].x); f.y += __uint_as_float(rc.raw[i].y);
+                    f.z += __uint_as_float(rc.raw[i].z); f.w += __uint_as_float(rc.raw[i].w);
+                } else {
+                    const float2 r0 = unpack_h2(rc.raw[i].x, f16), r1 = unpack_h2(rc.raw[i].y, f16);
+                    f.x += r0.x; f.y += r0.y; f.z += r1.x; f.w += r1.y;
+                }
+            }
+            if (p.flags & DFW_EPI_OUT_F32) {
+                __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off), f);
+            } else {
+                uint2 o;
+                o.x = pack_h2(f.x, f.y, f16);
+                o.y = pack_h2(f.z, f.w, f16);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + off) = o;
             }
         } else {
-            for (int j = 0; j < ncols; ++j) op[j] = __float2bfloat16_rn(f[j]);
+            const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (cq + j >= ncols) break;
+                float val = fv[j];
+                if (p.residual != nullptr) {
+                    if (p.flags & DFW_EPI_RES_F32) val += reinterpret_cast<const float*>(p.residual)[off + j];
+                    else if (f16) val += __half2float(reinterpret_cast<const __half*>(p.residual)[off + j]);
+                    else val += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[off + j]);
+                }
+                if (p.flags & DFW_EPI_OUT_F32) reinterpret_cast<float*>(p.out)[off + j] = val;
+                else if (f16) reinterpret_cast<__half*>(p.out)[off + j] = __float2half_rn(val);
+                else reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16_rn(val);
+            }
         }
     }
 }
@@ -169,7 +227,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;          // staging + row table
+    const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
     auto sA = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto sB = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -179,6 +238,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+    uint8_t* epi_generic = smem_raw + (epi_base - smem_raw_u32);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -232,7 +292,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0);
+            const uint32_t fmt = (p.flags & DFW_EPI_F16) ? 0u : 1u;       // A and B must share one 16-bit format
+            const uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N, fmt, fmt, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -264,77 +325,97 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const int rem = row % (p.TH * p.TW);
         const int th = rem / p.TW;
         const int tw = rem % p.TW;
+        float* stg = reinterpret_cast<float*>(epi_generic + q * STG_BYTES_PER_WARP);
+        EpiRow* rows = reinterpret_cast<EpiRow*>(epi_generic + 4 * STG_BYTES_PER_WARP) + q * 32;
+        const bool geglu = (BLOCK_N == 256) && (p.flags & DFW_EPI_GEGLU);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t);
-            const int img = tc.n0 + tn, hh = tc.h0 + th, ww = tc.w0 + tw;
-            const bool row_valid = (img < p.N) && (hh < p.H) && (ww < p.W);
-            const long long pix = (static_cast<long long>(img) * p.H + hh) * p.W + ww;
+            {
+                const int img = tc.n0 + tn, hh = tc.h0 + th, ww = tc.w0 + tw;
+                const bool ok = (img < p.N) && (hh < p.H) && (ww < p.W);
+                EpiRow er;
+                er.pix = ok ? (static_cast<long long>(img) * p.H + hh) * p.W + ww : -1;
+                er.img = img;
+                er.pad = 0;
+                __syncwarp();
+                rows[lane] = er;
+                __syncwarp();
+            }
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-            if constexpr (BLOCK_N == 256) {
-                if (p.flags & DFW_EPI_GEGLU) {
+            if (geglu) {
+                if constexpr (BLOCK_N == 256) {
+                    const int cq = (lane & 7) * 4, sub = lane >> 3;
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
-                        uint32_t v[32], g[32];
+                        uint32_t v[32];
+                        float4 val[8];
+                        const int cv = tc.n_tile * 256 + c * 32 + cq;             // permuted weight row of this lane's values
                         tmem_ld_32x32(taddr + c * 32, v);
-                        tmem_ld_32x32(taddr + 128 + c * 32, g);
                         tmem_ld_wait();
-                        if (row_valid) {
-                            float f[32];
-                            const int cv = tc.n_tile * 256 + c * 32;
-                            const float* bv = p.bias ? p.bias + cv : nullptr;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float val = __uint_as_float(v[j]);
-                                float gate = __uint_as_float(g[j]);
-                                if (bv) { val += __ldg(bv + j); gate += __ldg(bv + 128 + j); }
-                                f[j] = val * gelu_erf(gate);
-                            }
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ch +
-                                                tc.n_tile * 128 + c * 32;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint4 o;
-                                o.x = pack_bf16x2(f[j], f[j + 1]);
-                                o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                                o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                                o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                                *reinterpret_cast<uint4*>(op + j) = o;
-                            }
+                        stage_rows(stg, lane, v);
+                        __syncwarp();
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+                        if (p.bias) {
+                            bv = __ldg(reinterpret_cast<const float4*>(p.bias + cv));
+                            bg = __ldg(reinterpret_cast<const float4*>(p.bias + cv + 128));
                         }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) val[i] = *reinterpret_cast<const float4*>(stg + (4 * i + sub) * STG_LD + cq);
+                        __syncwarp();
+                        tmem_ld_32x32(taddr + 128 + c * 32, v);
+                        tmem_ld_wait();
+                        stage_rows(stg, lane, v);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 4 * i + sub;
+                            const long long pix = rows[r].pix;
+                            if (pix < 0) continue;
+                            const float4 g = *reinterpret_cast<const float4*>(stg + r * STG_LD + cq);
+                            uint2 o;
+                            const int f16 = p.flags & DFW_EPI_F16;
+                            o.x = pack_h2((val[i].x + bv.x) * gelu_erf(g.x + bg.x), (val[i].y + bv.y) * gelu_erf(g.y + bg.y), f16);
+                            o.y = pack_h2((val[i].z + bv.z) * gelu_erf(g.z + bg.z), (val[i].w + bv.w) * gelu_erf(g.w + bg.w), f16);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.out_ch +
+                                                      tc.n_tile * 128 + c * 32 + cq) = o;
+                        }
+                        __syncwarp();
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
-                    continue;
                 }
-            }
-            if constexpr (BLOCK_N >= 32) {
+            } else if constexpr (BLOCK_N >= 32) {
+                ResChunk rc_next;
+                prefetch_residual(p, rows, lane, tc.n_tile * BLOCK_N, tc.n_tile * BLOCK_N, 32, rc_next);
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    const ResChunk rc = rc_next;
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + c * 32, v);
                     tmem_ld_wait();
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    stage_rows(stg, lane, v);
+                    __syncwarp();
                     const int col0 = tc.n_tile * BLOCK_N + c * 32;
-                    epilogue_chunk<32>(p, f, col0, col0, img, pix, row_valid);
+                    if (c + 1 < BLOCK_N / 32) prefetch_residual(p, rows, lane, col0 + 32, col0 + 32, 32, rc_next);
+                    epilogue_store_chunk(p, stg, rows, lane, col0, col0, 32, rc);
+                    __syncwarp();
                 }
             } else {
-                uint32_t v[16];
-                tmem_ld_32x16(taddr, v);
+                uint32_t v[32];
+                uint32_t v16[16];
+                tmem_ld_32x16(taddr, v16);
                 tmem_ld_wait();
-                float f[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+                stage_rows(stg, lane, v);
+                __syncwarp();
                 const int col0 = tc.n_tile * BLOCK_N;
-                epilogue_chunk<16>(p, f, col0, col0, img, pix, row_valid);
+                ResChunk rc;
+                prefetch_residual(p, rows, lane, col0, col0, 16, rc);
+                epilogue_store_chunk(p, stg, rows, lane, col0, col0, 16, rc);
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

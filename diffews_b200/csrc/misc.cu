@@ -34,7 +34,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 
 // same, fp32 input -> bf16 output (fuses the fp32 residual-stream -> bf16 MMA-operand cast)
 __global__ void upsample2x_f32_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long total_vecs, int H,
-                                      int W, int V) {
+                                      int W, int V, int y_f16) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vecs; i += stride) {
         const int vc = static_cast<int>(i % V);
@@ -45,8 +45,8 @@ __global__ void upsample2x_f32_kernel(const float4* __restrict__ x, uint4* __res
         const long long n = pix / H;
         const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
         uint4 v;
-        v.x = pack_bf16x2(a.x, a.y); v.y = pack_bf16x2(a.z, a.w);
-        v.z = pack_bf16x2(b.x, b.y); v.w = pack_bf16x2(b.z, b.w);
+        v.x = pack_h2(a.x, a.y, y_f16); v.y = pack_h2(a.z, a.w, y_f16);
+        v.z = pack_h2(b.x, b.y, y_f16); v.w = pack_h2(b.z, b.w, y_f16);
         const long long W2 = 2LL * W;
         const long long o = ((n * 2 * H + 2 * h) * W2 + 2 * w) * V + vc;
         y[o] = v;
@@ -56,13 +56,13 @@ __global__ void upsample2x_f32_kernel(const float4* __restrict__ x, uint4* __res
     }
 }
 
-__global__ void cast_f32_bf16_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long nvec) {
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long nvec, int y_f16) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
         uint4 v;
-        v.x = pack_bf16x2(a.x, a.y); v.y = pack_bf16x2(a.z, a.w);
-        v.z = pack_bf16x2(b.x, b.y); v.w = pack_bf16x2(b.z, b.w);
+        v.x = pack_h2(a.x, a.y, y_f16); v.y = pack_h2(a.z, a.w, y_f16);
+        v.z = pack_h2(b.x, b.y, y_f16); v.w = pack_h2(b.z, b.w, y_f16);
         y[i] = v;
     }
 }
@@ -88,7 +88,7 @@ constexpr int SC_PIX = 32;
 constexpr int SC_ROWS = 8;
 __global__ void __launch_bounds__(256)
 conv3x3_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                         void* __restrict__ y_, int y_f32, int H, int W, int Cin, int Cout) {
+                         void* __restrict__ y_, int y_dtype, int H, int W, int Cin, int Cout) {
     extern __shared__ float smf[];
     // layout: wsm [9*Cin][Cout] (k-major so that 8 consecutive couts are contiguous), patch [Cin][3][SC_PIX+2]
     float* wsm = smf;
@@ -147,15 +147,16 @@ conv3x3_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ 
                 }
             }
             if (valid) {
-                if (y_f32) {
+                if (y_dtype == 1) {
                     float* y = reinterpret_cast<float*>(y_) + out_row + co;
                     *reinterpret_cast<float4*>(y) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                     *reinterpret_cast<float4*>(y + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 } else {
                     uint4 o;
-                    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-                    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_) + out_row + co) = o;
+                    const int hf = (y_dtype == 2);
+                    o.x = pack_h2(acc[0], acc[1], hf); o.y = pack_h2(acc[2], acc[3], hf);
+                    o.z = pack_h2(acc[4], acc[5], hf); o.w = pack_h2(acc[6], acc[7], hf);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y_) + out_row + co) = o;
                 }
             }
         }
@@ -242,7 +243,7 @@ int grid_for(long long total, int threads) {
 
 extern "C" {
 
-int dfw_upsample2x_nhwc(const void* x, int x_f32, void* y, int N, int H, int W, int C, void* stream_) {
+int dfw_upsample2x_nhwc(const void* x, int x_f32, void* y, int y_f16, int N, int H, int W, int C, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
@@ -251,7 +252,7 @@ int dfw_upsample2x_nhwc(const void* x, int x_f32, void* y, int N, int H, int W, 
     const long long total = static_cast<long long>(N) * H * W * V;
     if (x_f32)
         upsample2x_f32_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-            reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), total, H, W, V);
+            reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), total, H, W, V, y_f16);
     else
         upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
             reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), total, H, W, V);
@@ -277,20 +278,20 @@ int dfw_concat_channels(const void* a, const void* b, void* y, long long rows, i
     return DFW_OK;
 }
 
-int dfw_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream_) {
+int dfw_cast_f32_to_16(const float* x, void* y, int y_f16, long long n, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(x && y && n > 0 && n % 8 == 0);
     cast_f32_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), n / 8);
+        reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), n / 8, y_f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }
 
-int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int y_f32, int N, int H, int W,
-                          int Cin, int Cout, void* stream_) {
+int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int y_dtype, int N, int H,
+                          int W, int Cin, int Cout, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
@@ -308,7 +309,7 @@ int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, voi
     const long long blocks = static_cast<long long>(N) * ((H + SC_ROWS - 1) / SC_ROWS) * tiles_w;
     DFW_REQUIRE(blocks < (1LL << 31));
     conv3x3_small_cin_kernel<<<static_cast<int>(blocks), 256, smem, static_cast<cudaStream_t>(stream_)>>>(
-        x, w, bias, y, y_f32, H, W, Cin, Cout);
+        x, w, bias, y, y_dtype, H, W, Cin, Cout);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -13,31 +13,38 @@ namespace {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-// load 8 consecutive channels as fp32
-template <bool F32>
+// load 8 consecutive channels as fp32.  XD: 0 = bf16, 1 = fp32, 2 = fp16 storage
+template <int XD>
 __device__ __forceinline__ void load8(const void* base, long long elem_off, float (&v)[8]) {
-    if constexpr (F32) {
+    if constexpr (XD == 1) {
         const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
         float4 a = __ldg(p), b = __ldg(p + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
-        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + elem_off));
+        const float2 a = unpack_h2(u.x, XD == 2), b = unpack_h2(u.y, XD == 2), c = unpack_h2(u.z, XD == 2),
+                     d = unpack_h2(u.w, XD == 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
     }
 }
-__device__ __forceinline__ void store8_bf16(void* base, long long elem_off, const float (&v)[8]) {
+// store 8 consecutive channels as bf16 (f16 == 0) or fp16 (f16 != 0); both are 2-byte tensor-core operand formats
+__device__ __forceinline__ void store8_16(void* base, long long elem_off, const float (&v)[8], int f16) {
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = o;
+    if (f16) {
+        o.x = pack_f16x2(v[0], v[1]); o.y = pack_f16x2(v[2], v[3]);
+        o.z = pack_f16x2(v[4], v[5]); o.w = pack_f16x2(v[6], v[7]);
+    } else {
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + elem_off) = o;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // GroupNorm stage 1: per (image, row-chunk) partial sums per group.  blockDim = V * RPI (V = C/8).
 // partial layout: [N, nchunks, groups, 2]
 // ---------------------------------------------------------------------------------------------------------
-template <bool F32>
+template <int XD>
 __global__ void gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
                                 int rows_per_chunk, int RPI) {
     extern __shared__ float sm[];  // [RPI][C][2]
@@ -52,7 +59,7 @@ __global__ void gn_stats_kernel(const void* __restrict__ x, float* __restrict__ 
     const long long img_off = static_cast<long long>(n) * HW * C;
     for (int row = row0 + r; row < row1; row += RPI) {
         float v[8];
-        load8<F32>(x, img_off + static_cast<long long>(row) * C + vc * 8, v);
+        load8<XD>(x, img_off + static_cast<long long>(row) * C + vc * 8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
     }
@@ -102,9 +109,10 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const floa
 }
 
 // stage 3: y = [silu](x * scale + shift)
-template <bool F32>
+template <int XD>
 __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restrict__ scale_shift,
-                                void* __restrict__ y, long long total_vecs, int HW, int C, int apply_silu) {
+                                void* __restrict__ y, long long total_vecs, int HW, int C, int apply_silu,
+                                int y_f16) {
     const int V = C / 8;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vecs; i += stride) {
@@ -112,7 +120,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restr
         const long long rowg = i / V;
         const int n = static_cast<int>(rowg / HW);
         float v[8];
-        load8<F32>(x, i * 8, v);
+        load8<XD>(x, i * 8, v);
         const float4* sp = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + vc * 8) * 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -122,16 +130,17 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restr
             if (apply_silu) { a = silu_f(a); b = silu_f(b); }
             v[2 * j] = a; v[2 * j + 1] = b;
         }
-        store8_bf16(y, i * 8, v);
+        store8_16(y, i * 8, v, y_f16);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 2048), exact two-pass statistics.
 // ---------------------------------------------------------------------------------------------------------
-template <bool F32>
+template <int XD>
 __global__ void layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, void* __restrict__ y, int M, int C, float eps) {
+                                 const float* __restrict__ beta, void* __restrict__ y, int M, int C, float eps,
+                                 int y_f16) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
@@ -143,7 +152,7 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
     for (int k = 0; k < 8; ++k) {
         const int vc = lane + 32 * k;
         if (vc < V) {
-            load8<F32>(x, row_off + vc * 8, v[k]);
+            load8<XD>(x, row_off + vc * 8, v[k]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += v[k][j];
         }
@@ -175,7 +184,7 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
             o[2] = (v[k][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[k][3] - mean) * rstd * g0.w + b0.w;
             o[4] = (v[k][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[k][5] - mean) * rstd * g1.y + b1.y;
             o[6] = (v[k][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[k][7] - mean) * rstd * g1.w + b1.w;
-            store8_bf16(y, row_off + vc * 8, o);
+            store8_16(y, row_off + vc * 8, o, y_f16);
         }
     }
 }
@@ -183,10 +192,11 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
 // ---------------------------------------------------------------------------------------------------------
 // Row softmax (fp32 logits -> bf16 probabilities), one CTA per row.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int L, float scale) {
+__global__ void softmax_rows_kernel(const float* __restrict__ s, uint16_t* __restrict__ p, int L, float scale,
+                                    int y_f16) {
     __shared__ float red[32];
     const float* row = s + static_cast<long long>(blockIdx.x) * L;
-    __nv_bfloat16* out = p + static_cast<long long>(blockIdx.x) * L;
+    uint16_t* out = p + static_cast<long long>(blockIdx.x) * L;
     const int nvec = L / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float m = -INFINITY;
@@ -219,8 +229,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* 
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
         uint2 o;
-        o.x = pack_bf16x2(exp2f(fmaf(v.x, c, -mc)) * inv, exp2f(fmaf(v.y, c, -mc)) * inv);
-        o.y = pack_bf16x2(exp2f(fmaf(v.z, c, -mc)) * inv, exp2f(fmaf(v.w, c, -mc)) * inv);
+        o.x = pack_h2(exp2f(fmaf(v.x, c, -mc)) * inv, exp2f(fmaf(v.y, c, -mc)) * inv, y_f16);
+        o.y = pack_h2(exp2f(fmaf(v.z, c, -mc)) * inv, exp2f(fmaf(v.w, c, -mc)) * inv, y_f16);
         *reinterpret_cast<uint2*>(out + 4 * i) = o;
     }
 }
@@ -259,12 +269,13 @@ long long dfw_groupnorm_workspace_bytes(int N, int HW, int C, int groups) {
     return (partial + ss) * static_cast<long long>(sizeof(float)) + 256;
 }
 
-int dfw_groupnorm_silu(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int N, int HW,
-                       int C, int groups, float eps, int apply_silu, void* workspace, void* stream_) {
+int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int N,
+                       int HW, int C, int groups, float eps, int apply_silu, void* workspace, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(x && gamma && beta && y && workspace);
+    DFW_REQUIRE(x_dtype >= 0 && x_dtype <= 2);
     DFW_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0);
     DFW_REQUIRE(C / 8 <= 1024);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -274,60 +285,51 @@ int dfw_groupnorm_silu(const void* x, int x_f32, const float* gamma, const float
     partial_elems = (partial_elems + 63) / 64 * 64;
     float* scale_shift = partial + partial_elems;
     dim3 grid(pl.nchunks, N);
-    if (pl.smem > 48 * 1024) {
-        static bool set0 = false, set1 = false;
-        if (x_f32 && !set1) {
-            DFW_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            set1 = true;
-        }
-        if (!x_f32 && !set0) {
-            DFW_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            set0 = true;
-        }
-    }
-    if (x_f32)
-        gn_stats_kernel<true><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI);
-    else
-        gn_stats_kernel<false><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI);
-    gn_finalize_kernel<<<N, 256, 0, stream>>>(partial, gamma, beta, scale_shift, HW, C, groups, pl.nchunks, eps);
+    DFW_REQUIRE(pl.smem <= 48 * 1024);
     const long long total_vecs = static_cast<long long>(N) * HW * (C / 8);
     long long blocks = (total_vecs + 255) / 256;
     const long long cap = static_cast<long long>(sm_count()) * 16;
     if (blocks > cap) blocks = cap;
-    if (x_f32)
-        gn_apply_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(x, scale_shift, y, total_vecs, HW, C, apply_silu);
-    else
-        gn_apply_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(x, scale_shift, y, total_vecs, HW, C, apply_silu);
+    const int ab = static_cast<int>(blocks);
+#define DFW_GN_LAUNCH(XD)                                                                                          \
+    gn_stats_kernel<XD><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI); \
+    gn_finalize_kernel<<<N, 256, 0, stream>>>(partial, gamma, beta, scale_shift, HW, C, groups, pl.nchunks, eps);  \
+    gn_apply_kernel<XD><<<ab, 256, 0, stream>>>(x, scale_shift, y, total_vecs, HW, C, apply_silu, y_f16);
+    if (x_dtype == 1) { DFW_GN_LAUNCH(1) } else if (x_dtype == 2) { DFW_GN_LAUNCH(2) } else { DFW_GN_LAUNCH(0) }
+#undef DFW_GN_LAUNCH
     g_launches.fetch_add(3);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }
 
-int dfw_layernorm(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int M, int C, float eps,
-                  void* stream_) {
+int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int M, int C,
+                  float eps, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(x && gamma && beta && y && M > 0 && C > 0 && C % 8 == 0 && C <= 2048);
+    DFW_REQUIRE(x_dtype >= 0 && x_dtype <= 2);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int warps_per_block = 8;
     const int blocks = (M + warps_per_block - 1) / warps_per_block;
-    if (x_f32)
-        layernorm_kernel<true><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+    if (x_dtype == 1)
+        layernorm_kernel<1><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
+    else if (x_dtype == 2)
+        layernorm_kernel<2><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
     else
-        layernorm_kernel<false><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps);
+        layernorm_kernel<0><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }
 
-int dfw_softmax_rows(const float* s, void* p, int M, int L, float scale, void* stream_) {
+int dfw_softmax_rows(const float* s, void* p, int y_f16, int M, int L, float scale, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(s && p && M > 0 && L > 0 && L % 4 == 0);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    softmax_rows_kernel<<<M, 256, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(p), L, scale);
+    softmax_rows_kernel<<<M, 256, 0, stream>>>(s, reinterpret_cast<uint16_t*>(p), L, scale, y_f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 
 namespace dfw {
@@ -148,15 +149,20 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64
         : "memory");
 }
 
-// Instruction descriptor, kind::f16, A/B = bf16, D = fp32, A K-major; B K-major (b_mn_major=0) or MN-major (1).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major) {
+// Instruction descriptor, kind::f16, D = fp32, A K-major; B K-major (b_mn_major=0) or MN-major (1).
+// a_fmt / b_fmt: 0 = fp16, 1 = bf16 (the two operands may differ: both are 16-bit, the MMA converts per operand).
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt,
+                                                  uint32_t b_mn_major) {
     return (1u << 4)                 // c_format  = F32
-           | (1u << 7)               // a_format  = BF16
-           | (1u << 10)              // b_format  = BF16
+           | (a_fmt << 7)            // a_format
+           | (b_fmt << 10)           // b_format
            | (0u << 15)              // a_major   = K
            | (b_mn_major << 16)      // b_major
            | ((N >> 3) << 17)        // n_dim
            | ((M >> 4) << 24);       // m_dim
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major) {
+    return umma_idesc(M, N, 1u, 1u, b_mn_major);
 }
 
 // Shared-memory matrix descriptor for a SWIZZLE_128B tile whose rows are 128 bytes (64 bf16) wide and whose
@@ -206,6 +212,18 @@ __device__ __forceinline__ void tmem_ld_wait() {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// generic 16-bit pair helpers: f16 != 0 -> IEEE fp16, else bf16
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int f16) {
+    return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }

@@ -1,12 +1,7 @@
 """Prepared-weight layer objects shared by the UNet and VAE engines.
 
 Each object owns device copies of one diffusers module's parameters in the layout the kernels want
-(bf16 [Cout, taps*Cin] GEMM weights, fp32 biases / norm affine) and drives `ops.*`.  No torch math on the data path.
-
-Precision policy (DESIGN.md §"Numerics"): every tensor-core operand is bf16; tensors that are only read by a
-normalisation kernel or a residual add may be kept in fp32 (`Precision.stream_f32` for the residual stream,
-`Precision.mid_f32` for conv -> GroupNorm intermediates).  With random-init SD-2.1 weights the all-bf16 policy gives
-a UNet-latent rel-L2 of ~1.15e-2 against the fp32 oracle, the fp32-stream policy ~0.7e-2 (bar: 1e-2).
+(16-bit [Cout, taps*Cin] GEMM weights, fp32 biases / norm affine) and drives `ops.*`.  No torch math on the data path.
 """
 from __future__ import annotations
 
@@ -22,8 +17,25 @@ bf16 = torch.bfloat16
 
 @dataclass(frozen=True)
 class Precision:
-    stream_f32: bool = True   # residual stream / skip connections in fp32
-    mid_f32: bool = True      # conv1 -> norm2 intermediates in fp32
+    """Numerics policy (DESIGN.md "Numerics").
+
+    half        the 16-bit format of every tensor-core operand (weights and activations) and of every 16-bit
+                activation tensor: torch.float16 (default) or torch.bfloat16.  tcgen05 kind::f16 runs both at the same
+                rate but needs A and B in the SAME format.  fp16 is also the reference's own half-precision mode
+                (evaluation_util/main_oss.py:332-336 `--half_precision` -> torch.float16; training runs fp16 autocast,
+                scripts/train_*_v3.sh).  Accumulation, softmax, statistics are always fp32.
+    stream_f32  keep the residual stream / skip connections in fp32 (they only feed norm kernels and residual adds).
+    mid_f32     keep conv1 -> norm2 intermediates in fp32.
+
+    Measured, UNet latent rel-L2 vs the fp32 oracle on the 1-shot pipeline with random-init SD-2.1 weights (identical
+    UNet inputs; bar 1e-2): bf16 operands 1.2e-2 .. 1.4e-2 (fails), fp16 operands ~1.3e-3.
+    """
+    half: torch.dtype = torch.float16
+    stream_f32: bool = True
+    mid_f32: bool = True
+
+
+PURE_BF16 = Precision(half=torch.bfloat16)
 
 
 def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
@@ -33,11 +45,11 @@ def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
 class Conv:
     """3x3 / 1x1 convolution on the tcgen05 implicit-GEMM kernel."""
 
-    def __init__(self, sd, prefix, device, stride=1, pad_mode=0, cout_pad=None):
+    def __init__(self, sd, prefix, device, stride=1, pad_mode=0, wdtype=bf16):
         w = sd[prefix + ".weight"]
         self.cout, self.cin, self.ksize, _ = w.shape
         self.stride, self.pad_mode = stride, pad_mode
-        self.w = _dev(conv_weight_to_gemm(w), device, bf16)
+        self.w = _dev(conv_weight_to_gemm(w), device, wdtype)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
 
     def __call__(self, x, *, bias=None, bias_per_sample=False, residual=None, out_f32=False, out_scale=1.0):
@@ -47,13 +59,13 @@ class Conv:
 
 
 class Linear:
-    def __init__(self, sd, prefix, device, geglu=False):
+    def __init__(self, sd, prefix, device, geglu=False, wdtype=bf16):
         w = sd[prefix + ".weight"]
         b = sd.get(prefix + ".bias")
         self.geglu = geglu
         if geglu:
             w, b = geglu_permute(w, b)
-        self.w = _dev(w, device, bf16)
+        self.w = _dev(w, device, wdtype)
         self.b = _dev(b, device, torch.float32) if b is not None else None
 
     def __call__(self, x, *, residual=None, out_f32=False):
@@ -63,10 +75,10 @@ class Linear:
 class FusedLinear:
     """Several bias-free Linears on the same input, one GEMM (rows of the weights concatenated)."""
 
-    def __init__(self, sd, prefixes, device):
+    def __init__(self, sd, prefixes, device, wdtype=bf16):
         ws = [sd[p + ".weight"] for p in prefixes]
         self.splits = [w.shape[0] for w in ws]
-        self.w = _dev(torch.cat(ws, 0), device, bf16)
+        self.w = _dev(torch.cat(ws, 0), device, wdtype)
         bs = [sd.get(p + ".bias") for p in prefixes]
         self.b = _dev(torch.cat(bs, 0), device, torch.float32) if bs[0] is not None else None
 
@@ -75,23 +87,23 @@ class FusedLinear:
 
 
 class GroupNorm:
-    def __init__(self, sd, prefix, device, eps, groups=32):
+    def __init__(self, sd, prefix, device, eps, groups=32, out_dtype=bf16):
         self.g = _dev(sd[prefix + ".weight"], device, torch.float32)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
-        self.eps, self.groups = eps, groups
+        self.eps, self.groups, self.out_dtype = eps, groups, out_dtype
 
     def __call__(self, x, silu):
-        return ops.groupnorm(x, self.g, self.b, groups=self.groups, eps=self.eps, silu=silu)
+        return ops.groupnorm(x, self.g, self.b, groups=self.groups, eps=self.eps, silu=silu, out_dtype=self.out_dtype)
 
 
 class LayerNorm:
-    def __init__(self, sd, prefix, device, eps=1e-5):
+    def __init__(self, sd, prefix, device, eps=1e-5, out_dtype=bf16):
         self.g = _dev(sd[prefix + ".weight"], device, torch.float32)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
-        self.eps = eps
+        self.eps, self.out_dtype = eps, out_dtype
 
     def __call__(self, x):
-        return ops.layernorm(x, self.g, self.b, self.eps)
+        return ops.layernorm(x, self.g, self.b, self.eps, out_dtype=self.out_dtype)
 
 
 class Resnet:
@@ -99,11 +111,13 @@ class Resnet:
 
     def __init__(self, sd, prefix, device, eps, prec: Precision, has_temb: bool):
         self.prec = prec
-        self.norm1 = GroupNorm(sd, prefix + ".norm1", device, eps)
-        self.conv1 = Conv(sd, prefix + ".conv1", device)
-        self.norm2 = GroupNorm(sd, prefix + ".norm2", device, eps)
-        self.conv2 = Conv(sd, prefix + ".conv2", device)
-        self.shortcut = Conv(sd, prefix + ".conv_shortcut", device) if (prefix + ".conv_shortcut.weight") in sd else None
+        wd = nd = prec.half
+        self.norm1 = GroupNorm(sd, prefix + ".norm1", device, eps, out_dtype=nd)
+        self.conv1 = Conv(sd, prefix + ".conv1", device, wdtype=wd)
+        self.norm2 = GroupNorm(sd, prefix + ".norm2", device, eps, out_dtype=nd)
+        self.conv2 = Conv(sd, prefix + ".conv2", device, wdtype=wd)
+        self.shortcut = (Conv(sd, prefix + ".conv_shortcut", device, wdtype=wd)
+                         if (prefix + ".conv_shortcut.weight") in sd else None)
         # time-embedding projection is folded into conv1's bias per timestep (fp32, host): see UNet._temb_biases
         self.temb_w = sd[prefix + ".time_emb_proj.weight"].detach().float().cpu() if has_temb else None
         self.temb_b = sd[prefix + ".time_emb_proj.bias"].detach().float().cpu() if has_temb else None
@@ -114,5 +128,5 @@ class Resnet:
         a = self.norm1(h, silu=True)
         t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32)
         c = self.norm2(t, silu=True)
-        s = h if self.shortcut is None else self.shortcut(ops.cast_bf16(h), out_f32=p.stream_f32)
+        s = h if self.shortcut is None else self.shortcut(ops.cast16(h, p.half), out_f32=p.stream_f32)
         return self.conv2(c, residual=s, out_f32=p.stream_f32)

@@ -8,9 +8,16 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import EPI_GEGLU, EPI_OUT_F32, EPI_RES_F32, EPI_SILU, check, lib
+from ._lib import EPI_F16, EPI_GEGLU, EPI_OUT_F32, EPI_RES_F32, EPI_SILU, check, lib
 
 bf16 = torch.bfloat16
+f16 = torch.float16
+OPERAND_DTYPES = (bf16, f16)      # 16-bit tensor-core operand formats; one format per call (A and B must match)
+
+
+def _xd(t) -> int:
+    """x_dtype code of the C ABI: 0 = bf16, 1 = fp32, 2 = fp16."""
+    return {bf16: 0, torch.float32: 1, f16: 2}[t.dtype]
 
 
 def _stream() -> int:
@@ -42,12 +49,19 @@ class KernelTimer:
     def __init__(self):
         self.records = []   # (kind, flops, ev0, ev1)
 
-    def add(self, kind, flops, ev0, ev1):
-        self.records.append((kind, flops, ev0, ev1))
+    def add(self, kind, flops, ev0, ev1, shape=None):
+        self.records.append((kind, flops, ev0, ev1, shape))
+
+    def by_shape(self):
+        out = {}
+        for kind, flops, e0, e1, shape in self.records:
+            d = out.setdefault((kind, shape), {"launches": 0, "flops": 0.0, "ms": 0.0})
+            d["launches"] += 1; d["flops"] += flops; d["ms"] += e0.elapsed_time(e1)
+        return out
 
     def summary(self):
         out = {}
-        for kind, flops, e0, e1 in self.records:
+        for kind, flops, e0, e1, _ in self.records:
             ms = e0.elapsed_time(e1)
             d = out.setdefault(kind, {"launches": 0, "flops": 0.0, "ms": 0.0})
             d["launches"] += 1; d["flops"] += flops; d["ms"] += ms
@@ -63,8 +77,8 @@ def set_timer(t):
 
 
 class _Timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, shape=None):
+        self.kind, self.flops, self.shape = kind, flops, shape
 
     def __enter__(self):
         if _timer is not None:
@@ -75,7 +89,7 @@ class _Timed:
     def __exit__(self, *a):
         if _timer is not None:
             self.e1.record()
-            _timer.add(self.kind, self.flops, self.e0, self.e1)
+            _timer.add(self.kind, self.flops, self.e0, self.e1, self.shape)
         return False
 
 
@@ -83,17 +97,19 @@ class _Timed:
 def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_scale=1.0, out_f32=False,
            silu=False, geglu=False, bias_per_sample=False):
     """x bf16 [N,H,W,Cin]; w bf16 [Cout, ks*ks*Cin]; bias fp32 [Cout] or [N,Cout]; returns [N,H/s,W/s,Cout_eff]."""
-    _req(x, bf16, "x"); _req(w, bf16, "w")
+    assert x.dtype in OPERAND_DTYPES and w.dtype == x.dtype, (x.dtype, w.dtype)
+    _req(x, x.dtype, "x"); _req(w, w.dtype, "w")
+    h16 = x.dtype
     N, H, W, Cin = x.shape
     Cout = w.shape[0]
     assert w.numel() == Cout * ksize * ksize * Cin, (w.shape, Cin, ksize)
-    flags = 0
+    flags = EPI_F16 if h16 == f16 else 0
     if out_f32: flags |= EPI_OUT_F32
     if silu: flags |= EPI_SILU
     if geglu: flags |= EPI_GEGLU
     cout_eff = Cout // 2 if geglu else Cout
     Ho, Wo = H // stride, W // stride
-    y = torch.empty((N, Ho, Wo, cout_eff), device=x.device, dtype=torch.float32 if out_f32 else bf16)
+    y = torch.empty((N, Ho, Wo, cout_eff), device=x.device, dtype=torch.float32 if out_f32 else h16)
     bss = 0
     if bias is not None:
         _req(bias, torch.float32, "bias")
@@ -103,8 +119,9 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
     if residual is not None:
         assert residual.shape == y.shape and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
-        else: assert residual.dtype == bf16
-    with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin):
+        else: assert residual.dtype == h16
+    with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin,
+                f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags}"):
         check(lib.dfw_conv2d_igemm(x.data_ptr(), w.data_ptr(), _ptr(bias), bss, _ptr(residual), y.data_ptr(), N, H, W,
                                    Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale), _stream()),
               "dfw_conv2d_igemm")
@@ -113,17 +130,19 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
 
 def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu=False, geglu=False, out=None):
     """x bf16 [..., K]; w bf16 [Nout, K]; returns [..., Nout_eff] (written into `out` if given)."""
-    _req(x, bf16, "x"); _req(w, bf16, "w")
+    assert x.dtype in OPERAND_DTYPES and w.dtype == x.dtype, (x.dtype, w.dtype)
+    _req(x, x.dtype, "x"); _req(w, w.dtype, "w")
+    h16 = x.dtype
     K = x.shape[-1]
     M = x.numel() // K
     Nout = w.shape[0]
     assert w.shape[1] == K
-    flags = 0
+    flags = EPI_F16 if h16 == f16 else 0
     if out_f32: flags |= EPI_OUT_F32
     if silu: flags |= EPI_SILU
     if geglu: flags |= EPI_GEGLU
     nout_eff = Nout // 2 if geglu else Nout
-    odt = torch.float32 if out_f32 else bf16
+    odt = torch.float32 if out_f32 else h16
     if out is None:
         y = torch.empty(x.shape[:-1] + (nout_eff,), device=x.device, dtype=odt)
     else:
@@ -133,8 +152,8 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
     if residual is not None:
         assert residual.numel() == y.numel() and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
-        else: assert residual.dtype == bf16
-    with _Timed("igemm", 2.0 * M * K * Nout):
+        else: assert residual.dtype == h16
+    with _Timed("igemm", 2.0 * M * K * Nout, f"linear M{M} K{K} N{Nout} f{flags}"):
         check(lib.dfw_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, K, Nout, flags,
                              float(out_scale), _stream()), "dfw_linear")
     return y
@@ -145,43 +164,48 @@ def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
     (e.g. fused QKV) buffer: only the last dim must be unit-stride."""
     B, Lq, C = q.shape
     assert C == heads * 64
+    h16 = q.dtype
+    assert h16 in OPERAND_DTYPES
     for t in (q, k_self, v_self):
-        assert t.dtype == bf16 and t.is_cuda and t.stride(2) == 1
+        assert t.dtype == h16 and t.is_cuda and t.stride(2) == 1
     Ls = k_self.shape[1]
     assert k_self.stride() == v_self.stride()
-    o = torch.empty((B, Lq, C), device=q.device, dtype=bf16)
+    o = torch.empty((B, Lq, C), device=q.device, dtype=h16)
     if k_bank is not None:
         Lb = k_bank.shape[1]
         assert k_bank.shape[0] == B and k_bank.stride() == v_bank.stride() and k_bank.stride(2) == 1
+        assert k_bank.dtype == h16 and v_bank.dtype == h16
         kb, vb, kbs, krs = k_bank.data_ptr(), v_bank.data_ptr(), k_bank.stride(0), k_bank.stride(1)
     else:
         Lb, kb, vb, kbs, krs = 0, 0, 0, 0, 0
-    with _Timed("attn", 4.0 * B * heads * Lq * (Ls + Lb) * 64):
+    with _Timed("attn", 4.0 * B * heads * Lq * (Ls + Lb) * 64, f"attn B{B} h{heads} Lq{Lq} Lk{Ls + Lb}"):
         check(lib.dfw_attn_kvfused_fwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
                                        k_self.stride(0), k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0),
-                                       o.stride(1), B, heads, Lq, Ls, Lb, float(scale), _stream()),
+                                       o.stride(1), B, heads, Lq, Ls, Lb, float(scale), int(h16 == f16), _stream()),
               "dfw_attn_kvfused_fwd")
     return o
 
 
 def cross_attn(q, k, v, heads, scale):
     """q [B,L,C] bf16; k,v [Bk,Lctx,C] with Bk in {1,B}."""
-    _req(q, bf16, "q"); _req(k, bf16, "k"); _req(v, bf16, "v")
+    h16 = q.dtype
+    assert h16 in OPERAND_DTYPES
+    _req(q, h16, "q"); _req(k, h16, "k"); _req(v, h16, "v")
     B, L, C = q.shape
     Lctx = k.shape[1]
     kvs = 0 if k.shape[0] == 1 else Lctx * C
     o = torch.empty_like(q)
     check(lib.dfw_cross_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), kvs, o.data_ptr(), B, L, heads, Lctx,
-                                 float(scale), _stream()), "dfw_cross_attn_fwd")
+                                 float(scale), int(h16 == f16), _stream()), "dfw_cross_attn_fwd")
     return o
 
 
 _gn_ws = {}
 
 
-def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False):
-    """x bf16|fp32 [N, ..., C] channels-last; returns bf16 of the same shape."""
-    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, torch.float32)
+def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=bf16):
+    """x bf16|fp16|fp32 [N, ..., C] channels-last; returns bf16 (or fp16) of the same shape."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, f16, torch.float32)
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     need = int(lib.dfw_groupnorm_workspace_bytes(N, HW, C, groups))
@@ -190,45 +214,49 @@ def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False):
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 1 << 20), device=x.device, dtype=torch.uint8)
         _gn_ws[key] = ws
-    y = torch.empty(x.shape, device=x.device, dtype=bf16)
-    check(lib.dfw_groupnorm_silu(x.data_ptr(), int(x.dtype == torch.float32), gamma.data_ptr(), beta.data_ptr(),
-                                 y.data_ptr(), N, HW, C, groups, float(eps), int(silu), ws.data_ptr(), _stream()),
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib.dfw_groupnorm_silu(x.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
+                                 y.data_ptr(), int(out_dtype == f16), N, HW, C, groups, float(eps), int(silu),
+                                 ws.data_ptr(), _stream()),
           "dfw_groupnorm_silu")
     return y
 
 
-def layernorm(x, gamma, beta, eps=1e-5):
-    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, torch.float32)
+def layernorm(x, gamma, beta, eps=1e-5, out_dtype=bf16):
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, f16, torch.float32)
     C = x.shape[-1]
     M = x.numel() // C
-    y = torch.empty(x.shape, device=x.device, dtype=bf16)
-    check(lib.dfw_layernorm(x.data_ptr(), int(x.dtype == torch.float32), gamma.data_ptr(), beta.data_ptr(),
-                            y.data_ptr(), M, C, float(eps), _stream()), "dfw_layernorm")
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib.dfw_layernorm(x.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
+                            y.data_ptr(), int(out_dtype == f16), M, C, float(eps), _stream()), "dfw_layernorm")
     return y
 
 
-def softmax_rows(s, scale):
+def softmax_rows(s, scale, out_dtype=bf16):
     _req(s, torch.float32, "s")
     L = s.shape[-1]
     M = s.numel() // L
-    p = torch.empty(s.shape, device=s.device, dtype=bf16)
-    check(lib.dfw_softmax_rows(s.data_ptr(), p.data_ptr(), M, L, float(scale), _stream()), "dfw_softmax_rows")
+    p = torch.empty(s.shape, device=s.device, dtype=out_dtype)
+    check(lib.dfw_softmax_rows(s.data_ptr(), p.data_ptr(), int(out_dtype == f16), M, L, float(scale), _stream()),
+          "dfw_softmax_rows")
     return p
 
 
-def upsample2x(x):
-    """x bf16|fp32 [N,H,W,C] -> bf16 [N,2H,2W,C]."""
-    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, torch.float32)
+def upsample2x(x, out_dtype=bf16):
+    """x 16-bit|fp32 [N,H,W,C] -> 16-bit [N,2H,2W,C] (fp32 input is cast to `out_dtype`)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, f16, torch.float32)
+    if x.dtype != torch.float32:
+        out_dtype = x.dtype
     N, H, W, Cc = x.shape
-    y = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=bf16)
-    check(lib.dfw_upsample2x_nhwc(x.data_ptr(), int(x.dtype == torch.float32), y.data_ptr(), N, H, W, Cc,
-                                  _stream()), "dfw_upsample2x_nhwc")
+    y = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=out_dtype)
+    check(lib.dfw_upsample2x_nhwc(x.data_ptr(), int(x.dtype == torch.float32), y.data_ptr(), int(out_dtype == f16),
+                                  N, H, W, Cc, _stream()), "dfw_upsample2x_nhwc")
     return y
 
 
 def concat_channels(a, b):
     assert a.is_cuda and a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype
-    assert a.dtype in (bf16, torch.float32) and a.shape[:-1] == b.shape[:-1]
+    assert a.dtype in (bf16, f16, torch.float32) and a.shape[:-1] == b.shape[:-1]
     Ca, Cb = a.shape[-1], b.shape[-1]
     rows = a.numel() // Ca
     y = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=a.dtype)
@@ -237,23 +265,28 @@ def concat_channels(a, b):
     return y
 
 
-def cast_bf16(x):
-    """fp32 -> bf16 (no-op for bf16 input)."""
-    if x.dtype == bf16:
+def cast16(x, dtype=bf16):
+    """fp32 -> bf16 / fp16 (no-op for an input that already has `dtype`)."""
+    if x.dtype == dtype:
         return x
     _req(x, torch.float32, "x")
-    y = torch.empty(x.shape, device=x.device, dtype=bf16)
-    check(lib.dfw_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "dfw_cast_f32_to_bf16")
+    y = torch.empty(x.shape, device=x.device, dtype=dtype)
+    check(lib.dfw_cast_f32_to_16(x.data_ptr(), y.data_ptr(), int(dtype == f16), x.numel(), _stream()),
+          "dfw_cast_f32_to_16")
     return y
 
 
-def conv3x3_small_cin(x_nchw, w, bias, out_f32=False):
-    """x fp32 NCHW [N,Cin<=8,H,W]; w fp32 [Cout,3,3,Cin]; returns bf16 (or fp32) NHWC [N,H,W,Cout]."""
+def cast_bf16(x):
+    return cast16(x, bf16)
+
+
+def conv3x3_small_cin(x_nchw, w, bias, out_dtype=bf16):
+    """x fp32 NCHW [N,Cin<=8,H,W]; w fp32 [Cout,3,3,Cin]; returns NHWC [N,H,W,Cout] in bf16 / fp16 / fp32."""
     _req(x_nchw, torch.float32, "x"); _req(w, torch.float32, "w")
     N, Cin, H, W = x_nchw.shape
     Cout = w.shape[0]
-    y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=torch.float32 if out_f32 else bf16)
-    check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), int(out_f32), N, H, W,
+    y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=out_dtype)
+    check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), _xd(y), N, H, W,
                                     Cin, Cout, _stream()), "dfw_conv3x3_small_cin")
     return y
 

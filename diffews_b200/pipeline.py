@@ -133,6 +133,7 @@ class MarigoldPipelineRGBLatentNoise:
         H, W = rgb_in_tag.shape[-2:]
         seg_f32, seg_u8 = ops.seg_post(rows, H, W, want_f32=True, want_u8=_want_u8)
         self._last_noise_pred = noise_pred
+        self._last_unet_inputs = (latents_rgb_cond_ref, depth_latent)
         return (seg_f32, seg_u8) if _want_u8 else seg_f32
 
     # ------------------------------------------------------------------------------------------------------------

@@ -26,14 +26,15 @@ class VaeAttention:
 
     def __init__(self, sd, prefix, device, prec: Precision):
         self.prec = prec
-        self.norm = GroupNorm(sd, prefix + ".group_norm", device, eps=1e-6)
-        self.to_q = Linear(sd, prefix + ".to_q", device)
-        self.to_k = Linear(sd, prefix + ".to_k", device)
+        wd = prec.half
+        self.norm = GroupNorm(sd, prefix + ".group_norm", device, eps=1e-6, out_dtype=prec.half)
+        self.to_q = Linear(sd, prefix + ".to_q", device, wdtype=wd)
+        self.to_k = Linear(sd, prefix + ".to_k", device, wdtype=wd)
         # V^T = W_v X^T is produced directly ([C, L] per image, the K-major B operand of P V); its bias is added
         # after the P V product instead (softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T).
-        self.wv = _dev(sd[prefix + ".to_v.weight"], device, bf16)
+        self.wv = _dev(sd[prefix + ".to_v.weight"], device, wd)
         self.bv = _dev(sd[prefix + ".to_v.bias"], device, torch.float32)
-        self.to_out = Linear(sd, prefix + ".to_out.0", device)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wd)
         self.C = self.wv.shape[0]
         self.scale = self.C ** -0.5
 
@@ -43,11 +44,11 @@ class VaeAttention:
         xn = self.norm(h, silu=False).view(N, L, C)
         q = self.to_q(xn)
         k = self.to_k(xn)
-        o = torch.empty((N, L, C), device=h.device, dtype=bf16)
+        o = torch.empty((N, L, C), device=h.device, dtype=self.prec.half)
         for n in range(N):
             vt = ops.linear(self.wv, xn[n])                               # [C, L] = W_v @ X_n^T
             s = ops.linear(q[n], k[n], out_f32=True)                      # [L, L] fp32 logits
-            p = ops.softmax_rows(s, self.scale)                           # bf16
+            p = ops.softmax_rows(s, self.scale, out_dtype=self.prec.half)
             ops.linear(p, vt, self.bv, out=o[n])                          # P V + b_v
         y = self.to_out(o, residual=h.view(N, L, C), out_f32=self.prec.stream_f32)
         return y.view(N, H, W, C)
@@ -68,7 +69,10 @@ class AutoencoderKL:
                  precision: Optional[Precision] = None):
         sd = state_dict
         self.device = dev = torch.device(device)
-        self.prec = prec = precision or Precision(stream_f32=True, mid_f32=False)
+        # default: every VAE activation in the 16-bit format (the decoder's 512^2 x 128-channel tensors make the VAE
+        # bandwidth-sensitive; with fp16 operands the decoded mask still agrees with the fp32 oracle on > 99.9 %)
+        self.prec = prec = precision or Precision(stream_f32=False, mid_f32=False)
+        self._sdt = torch.float32 if prec.stream_f32 else prec.half
         self.dtype = torch.float32
         c = tuple(block_out_channels)
         self.config = SimpleNamespace(block_out_channels=c, latent_channels=4, scaling_factor=0.18215)
@@ -79,11 +83,12 @@ class AutoencoderKL:
         for i in range(4):
             blk = SimpleNamespace(
                 resnets=[Resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(2)],
-                down=Conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", dev, stride=2, pad_mode=1) if i < 3 else None)
+                down=Conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", dev, stride=2, pad_mode=1,
+                          wdtype=prec.half) if i < 3 else None)
             self.enc_down.append(blk)
         self.enc_mid = _Mid(sd, "encoder.mid_block", dev, prec)
-        self.enc_norm_out = GroupNorm(sd, "encoder.conv_norm_out", dev, eps=1e-6)
-        self.enc_conv_out = Conv(sd, "encoder.conv_out", dev)
+        self.enc_norm_out = GroupNorm(sd, "encoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half)
+        self.enc_conv_out = Conv(sd, "encoder.conv_out", dev, wdtype=prec.half)
         # quant_conv (1x1, 8->8): only the 4 `mean` channels are consumed (pipeline:858-860); host-side constants
         self.quant_w = sd["quant_conv.weight"].detach().float().cpu()[:4, :, 0, 0].contiguous()
         self.quant_b = sd["quant_conv.bias"].detach().float().cpu()[:4].contiguous()
@@ -97,10 +102,10 @@ class AutoencoderKL:
         for i in range(4):
             blk = SimpleNamespace(
                 resnets=[Resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(3)],
-                up=Conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev) if i < 3 else None)
+                up=Conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half) if i < 3 else None)
             self.dec_up.append(blk)
-        self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6)
-        self.dec_conv_out = Conv(sd, "decoder.conv_out", dev)
+        self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half)
+        self.dec_conv_out = Conv(sd, "decoder.conv_out", dev, wdtype=prec.half)
 
     @classmethod
     def from_module(cls, module: torch.nn.Module, device="cuda", **kw):
@@ -123,12 +128,12 @@ class AutoencoderKL:
         if H % 8 or W % 8:
             raise ValueError("image height/width must be multiples of 8")
         f32 = self.prec.stream_f32
-        h = ops.conv3x3_small_cin(x, self.enc_conv_in_w, self.enc_conv_in_b, out_f32=f32)
+        h = ops.conv3x3_small_cin(x, self.enc_conv_in_w, self.enc_conv_in_b, out_dtype=self._sdt)
         for blk in self.enc_down:
             for r in blk.resnets:
                 h = r(h)
             if blk.down is not None:
-                h = blk.down(ops.cast_bf16(h), out_f32=f32)
+                h = blk.down(ops.cast16(h, self.prec.half), out_f32=f32)
         h = self.enc_mid(h)
         h = self.enc_norm_out(h, silu=True)
         m = self.enc_conv_out(h, out_f32=True)                                   # [N,h,w,8] fp32 moments
@@ -149,13 +154,13 @@ class AutoencoderKL:
         zq = torch.empty_like(z)
         ops.pointwise_small(z, (Cz * hh * ww, 1, hh * ww), self.post_quant_w, self.post_quant_b, zq,
                             (Cz * hh * ww, 1, hh * ww), N, hh * ww, in_scale=in_scale, out_scale=1.0)
-        h = ops.conv3x3_small_cin(zq, self.dec_conv_in_w, self.dec_conv_in_b, out_f32=f32)
+        h = ops.conv3x3_small_cin(zq, self.dec_conv_in_w, self.dec_conv_in_b, out_dtype=self._sdt)
         h = self.dec_mid(h)
         for blk in self.dec_up:
             for r in blk.resnets:
                 h = r(h)
             if blk.up is not None:
-                h = blk.up(ops.upsample2x(h), out_f32=f32)
+                h = blk.up(ops.upsample2x(h, self.prec.half), out_f32=f32)
         h = self.dec_norm_out(h, silu=True)
         y = self.dec_conv_out(h, out_f32=True)                                   # [N,H,W,3] fp32
         return y.view(N, y.shape[1] * y.shape[2], 3)

@@ -28,11 +28,13 @@ extern "C" {
 #define DFW_ERR_ARCH (-3)    /* device is not sm_100 (B200) — no fallback by design           */
 
 /* epilogue flags for dfw_conv2d_igemm / dfw_linear */
-#define DFW_EPI_OUT_F32 1   /* y is fp32 (default bf16)                                               */
-#define DFW_EPI_RES_F32 2   /* residual is fp32 (default bf16)                                        */
+#define DFW_EPI_OUT_F32 1   /* y is fp32 (default: 16-bit, bf16 or fp16 per DFW_EPI_F16)              */
+#define DFW_EPI_RES_F32 2   /* residual is fp32 (default: 16-bit)                                     */
 #define DFW_EPI_GEGLU 4     /* weight rows are [128 value | 128 gate] interleaved per 256-row block;  */
                             /* y[:, j] = (v+bv) * gelu_erf(g+bg), y has Cout/2 channels               */
 #define DFW_EPI_SILU 8      /* y = silu(acc + bias) (time-embedding MLP)                              */
+#define DFW_EPI_F16 16      /* every 16-bit tensor of the call (x, w, 16-bit y / residual) is IEEE fp16 instead of  */
+                            /* bf16.  tcgen05 kind::f16 needs A and B in the SAME format (mixing traps on sm_100).  */
 
 /* ABI version: bump on any signature change. */
 int dfw_version(void);
@@ -69,64 +71,69 @@ int dfw_linear(const void* x, const void* w, const float* bias, const void* resi
  * ref: diffews/models/attention_processor.py:251-271 (MyXFormersAttnProcessor: key = cat([key_self, bank_folded]),
  *      xformers.ops.memory_efficient_attention(q,k,v,scale)); :351-365 (SDPA variant).
  *  The concatenation is never materialised: keys/values stream from two sources (self, then bank).
- *   q       bf16, element (b, l, h, d) at q[b*q_batch_stride + l*q_row_stride + h*64 + d],   l < Lq
+ *   (16-bit tensors are bf16, or fp16 when f16 != 0 — one format per call)
+ *   q       16-bit, element (b, l, h, d) at q[b*q_batch_stride + l*q_row_stride + h*64 + d],   l < Lq
  *   k_self / v_self  same addressing with kv_self_* strides, l < Ls
  *   k_bank / v_bank  same addressing with kv_bank_* strides, l < Lb (Lb = k_shots * S, shot-major; may be 0/NULL)
- *   o       bf16 [B, Lq, heads*64] (row stride o_row_stride)
+ *   o       16-bit [B, Lq, heads*64] (row stride o_row_stride)
  *  softmax(q k^T * scale) v over the Ls + Lb keys, fp32 softmax, fp32 accumulation.
  * ------------------------------------------------------------------------------------------------------------ */
 int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
                          const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
                          const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
                          int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
-                         int heads, int Lq, int Ls, int Lb, float scale, void* stream);
+                         int heads, int Lq, int Ls, int Lb, float scale, int f16, void* stream);
 
 /* K2  cross-attention to a short prompt embedding (Lctx <= 128 keys, head_dim 64), CUDA cores.
  * ref: BasicTransformerBlock.attn2 (upstream) reached from unet_2d_condition.py:1161; Lctx = 2 at eval
  *      (marigold_pipeline_rgb_latent_noise.py:591-601).
- *   q bf16 [B, L, heads*64]; k,v bf16 [B, Lctx, heads*64] (kv_batch_stride elements, 0 = shared); o like q. */
+ *   q 16-bit [B, L, heads*64]; k,v [B, Lctx, heads*64] (kv_batch_stride elements, 0 = shared); o like q;
+ *   f16 != 0: fp16 tensors, else bf16. */
 int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv_batch_stride, void* o, int B,
-                       int L, int heads, int Lctx, float scale, void* stream);
+                       int L, int heads, int Lctx, float scale, int f16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K4  GroupNorm(32 groups) (+SiLU), NHWC, fp32 statistics, deterministic two-stage reduction.
  * ref: nn.GroupNorm(+SiLU) in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out
  *      (diffews/models/unet_2d_condition.py:1246-1248; upstream blocks).
- *   x bf16 (or fp32 if x_f32) [N, HW, C]; gamma/beta fp32 [C]; y bf16 [N, HW, C].  C % 8 == 0, C % groups == 0.
+ *   x [N, HW, C] with x_dtype 0 = bf16, 1 = fp32, 2 = fp16; gamma/beta fp32 [C]; y bf16 (fp16 if y_f16: normalised activations are
+ *   bounded, and fp16 carries 3 more mantissa bits into the tensor core) [N, HW, C].  C % 8 == 0, C % groups == 0.
  *   workspace: fp32, dfw_groupnorm_workspace_bytes(N, HW, C) bytes.
  * ------------------------------------------------------------------------------------------------------------ */
 long long dfw_groupnorm_workspace_bytes(int N, int HW, int C, int groups);
-int dfw_groupnorm_silu(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int N, int HW,
-                       int C, int groups, float eps, int apply_silu, void* workspace, void* stream);
+int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int N,
+                       int HW, int C, int groups, float eps, int apply_silu, void* workspace, void* stream);
 
-/* K7  LayerNorm over the last dim. x bf16/fp32 [M, C] -> y bf16 [M, C].  C % 8 == 0, C <= 2048.
+/* K7  LayerNorm over the last dim. x [M, C] (x_dtype 0 bf16 / 1 fp32 / 2 fp16) -> y bf16 (fp16 if y_f16) [M, C].
+ * C % 8 == 0, C <= 2048.
  * ref: BasicTransformerBlock.norm1/2/3 (upstream). */
-int dfw_layernorm(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int M, int C, float eps,
-                  void* stream);
+int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int M, int C,
+                  float eps, void* stream);
 
-/* Row softmax for the VAE mid-block attention (single head, d=512): s fp32 [M, L] -> p bf16 [M, L],
+/* Row softmax for the VAE mid-block attention (single head, d=512): s fp32 [M, L] -> p bf16 (fp16 if y_f16) [M, L],
  * p = softmax(s * scale).  ref: AutoencoderKL mid_block Attention (upstream), pipeline:852,901. */
-int dfw_softmax_rows(const float* s, void* p, int M, int L, float scale, void* stream);
+int dfw_softmax_rows(const float* s, void* p, int y_f16, int M, int L, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Layout / small-channel helpers (CUDA cores, bandwidth-bound).
  * ------------------------------------------------------------------------------------------------------------ */
-/* nearest 2x upsample NHWC [N,H,W,C] (bf16, or fp32 if x_f32) -> bf16 [N,2H,2W,C].  C % 8 == 0.
+/* nearest 2x upsample NHWC [N,H,W,C] (16-bit copied as is, or fp32 if x_f32 -> bf16 / fp16 per y_f16)
+ * -> 16-bit [N,2H,2W,C].  C % 8 == 0.
  * ref: Upsample2D F.interpolate(scale 2, nearest) (upstream) */
-int dfw_upsample2x_nhwc(const void* x, int x_f32, void* y, int N, int H, int W, int C, void* stream);
+int dfw_upsample2x_nhwc(const void* x, int x_f32, void* y, int y_f16, int N, int H, int W, int C, void* stream);
 /* channel concat: y[rows,Ca+Cb] = cat(a[rows,Ca], b[rows,Cb]), elem_bytes 2 (bf16) or 4 (fp32).
  * ref: torch.cat([hidden_states, res_hidden_states], dim=1) in the UNet up blocks (upstream, unet:1226) */
 int dfw_concat_channels(const void* a, const void* b, void* y, long long rows, int Ca, int Cb, int elem_bytes,
                         void* stream);
-/* fp32 -> bf16 cast (n % 8 == 0): the fp32 residual stream becomes an MMA operand (shortcut / downsample convs). */
-int dfw_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+/* fp32 -> bf16 / fp16 cast (n % 8 == 0): the fp32 residual stream becomes an MMA operand (shortcut / downsample). */
+int dfw_cast_f32_to_16(const float* x, void* y, int y_f16, long long n, void* stream);
 /* 3x3 / stride 1 / pad 1 convolution with a tiny input channel count (Cin <= 8), CUDA cores:
  *   x  fp32 NCHW [N,Cin,H,W] (the reference's image / latent layout);  w fp32 [Cout,3,3,Cin]; bias fp32 [Cout]
- *   y  bf16 (or fp32 if y_f32) NHWC [N,H,W,Cout], Cout % 64 == 0, Cout <= 512.
+ *   y  NHWC [N,H,W,Cout] with y_dtype 0 = bf16, 1 = fp32, 2 = fp16; Cout % 64 == 0, Cout <= 512.
  * ref: UNet conv_in / conv_in_ref (unet_2d_condition.py:301-306,1118-1121), VAE encoder conv_in (3->128),
  *      VAE decoder conv_in (4->512) (upstream). */
-int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int y_f32, int N, int H, int W,
-                          int Cin, int Cout, void* stream);
+int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int y_dtype, int N, int H,
+                          int W, int Cin, int Cout, void* stream);
 /* 1x1 conv on <= 8 channels, fp32 math, arbitrary element strides (so it also converts NHWC <-> NCHW):
  *   y[n,p,co] = (sum_ci w[co,ci] * (x[n,p,ci] * in_scale) + b[co]) * out_scale
  *   x element (n,p,ci) at x[n*x_ns + p*x_ps + ci*x_cs]; y likewise.  w [Cout,Cin] and b [Cout] are HOST pointers

@@ -47,6 +47,63 @@ def linear_basic():
 
 
 @case
+def linear_fp16_operands():
+    """The 16-bit format is a per-call choice (bf16 or fp16); A and B must share it (a mix is rejected on the host:
+    tcgen05 kind::f16 traps with an illegal instruction when a_format != b_format)."""
+    import torch
+    from diffews_b200 import ops
+    M, K, N = 777, 640, 640
+    xf = _mk((M, K), 1.0, 1); wf = _mk((N, K), K ** -0.5, 2); b = _mk((N,), 1.0, 3)
+    for dt in (torch.bfloat16, torch.float16):
+        x, w = xf.to(dt), wf.to(dt)
+        y = ops.linear(x, w, b, out_f32=True)
+        ref = x.float() @ w.float().t() + b
+        e = rel(y, ref)
+        print(f"linear {dt} f32 out: rel {e:.3e}")
+        assert e < 1e-4
+        r = _mk((M, N), 1, 5).to(dt)
+        y = ops.linear(x, w, b, residual=r)
+        assert y.dtype == dt
+        e = rel(y, ref + r.float()); print(f"linear {dt} 16-bit out + res: rel {e:.3e}")
+        assert e < (6e-3 if dt == torch.bfloat16 else 8e-4)
+    try:
+        ops.linear(xf.bfloat16(), wf.half())
+        raise SystemExit("mixed operand formats must be rejected")
+    except AssertionError:
+        pass
+    from diffews_b200.weights import conv_weight_to_gemm
+    x = _mk((2, 16, 16, 128), 1, 1).half(); w = _mk((256, 128, 3, 3), (128 * 9) ** -0.5, 2).half(); bb = _mk((256,), 1, 3)
+    y = ops.conv2d(x, conv_weight_to_gemm(w), bb, ksize=3, out_f32=True)
+    e = rel(y, _conv_ref(x, w, bb)); print("conv fp16:", e); assert e < 1e-3
+    g = _mk((128,), 1, 2); be = _mk((128,), 1, 3); xx = _mk((2, 256, 128), 2, 1)
+    import torch.nn.functional as F
+    for xin in (xx, xx.half(), xx.bfloat16()):
+        yn = ops.groupnorm(xin, g, be, eps=1e-6, silu=True, out_dtype=torch.float16)
+        refn = F.silu(F.group_norm(xin.float().transpose(1, 2), 32, g, be, 1e-6).transpose(1, 2))
+        assert yn.dtype == torch.float16 and rel(yn, refn) < 6e-4, rel(yn, refn)
+        yl = ops.layernorm(xin, g, be, out_dtype=torch.float16)
+        assert yl.dtype == torch.float16 and rel(yl, F.layer_norm(xin.float(), (128,), g, be, 1e-5)) < 6e-4
+    print("gn/ln fp16 ok")
+    # fp16 attention + cross attention
+    B, h, L = 2, 5, 256; C = 320
+    q = _mk((B, L, C), 1.5, 1).half(); k = _mk((B, L, C), 1.5, 2).half(); v = _mk((B, L, C), 1, 3).half()
+    o = ops.attn_kvfused(q, k, v, k, v, h, 0.125)
+    ref = _attn_ref(q, torch.cat([k, k], 1), torch.cat([v, v], 1), h, 0.125)
+    assert o.dtype == torch.float16
+    e = rel(o, ref); print("attn fp16:", e); assert e < 1.5e-3
+    kk = _mk((1, 2, C), 1, 2).half(); vv = _mk((1, 2, C), 1, 3).half()
+    o = ops.cross_attn(q, kk, vv, h, 0.125)
+    e = rel(o, _attn_ref(q, kk.expand(B, -1, -1), vv.expand(B, -1, -1), h, 0.125)); print("cross fp16:", e); assert e < 1e-3
+    xs = _mk((2, 4, 4, 64), 1, 1)
+    assert torch.equal(ops.upsample2x(xs, torch.float16).float(),
+                       F.interpolate(xs.half().float().permute(0, 3, 1, 2), scale_factor=2.0).permute(0, 2, 3, 1))
+    assert torch.equal(ops.cast16(xs, torch.float16), xs.half())
+    s_ = _mk((64, 256), 10, 1)
+    e = rel(ops.softmax_rows(s_, 0.1, out_dtype=torch.float16), torch.softmax(s_ * 0.1, -1)); assert e < 6e-4, e
+    print("fp16 misc ok")
+
+
+@case
 def linear_geglu():
     import torch
     from diffews_b200 import ops

@@ -1,0 +1,103 @@
+"""Standalone launches of the hot kernels at BASELINE config-2 shapes (B = 16, 512^2), timed with CUDA events.
+Used (a) for quick kernel iteration and (b) as the short command profiled under `ncu --set full`.
+  python scripts/profile_kernels.py [conv128|conv256|conv512|conv320|conv1280|lin|geglu|attn|gn|all] [--iters N]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from diffews_b200 import ops  # noqa: E402
+from diffews_b200.weights import conv_weight_to_gemm  # noqa: E402
+
+bf16 = torch.bfloat16
+
+
+def timeit(fn, iters, flush):
+    fn(); fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()                      # > L2-size write between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def conv_case(N, H, C_in, C_out, ks=3, out_f32=False, res=None):
+    x = torch.randn(N, H, H, C_in, device="cuda").to(bf16)
+    w = conv_weight_to_gemm(torch.randn(C_out, C_in, ks, ks, device="cuda") * (C_in * ks * ks) ** -0.5).to(bf16)
+    b = torch.randn(C_out, device="cuda")
+    r = None
+    if res is not None:
+        r = torch.randn(N, H, H, C_out, device="cuda").to(res)
+    flops = 2.0 * N * H * H * C_out * C_in * ks * ks
+    return (lambda: ops.conv2d(x, w, b, ksize=ks, out_f32=out_f32, residual=r)), flops, None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["all"])
+    ap.add_argument("--iters", type=int, default=5)
+    args = ap.parse_args()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    cases = {
+        "conv128": lambda: conv_case(16, 512, 128, 128),
+        "conv128_f32res": lambda: conv_case(16, 512, 128, 128, out_f32=True, res=torch.float32),
+        "conv128_h16res": lambda: conv_case(16, 512, 128, 128, res=bf16),
+        "conv256_f32res": lambda: conv_case(16, 256, 256, 256, out_f32=True, res=torch.float32),
+        "conv256": lambda: conv_case(16, 256, 256, 256),
+        "conv512": lambda: conv_case(16, 128, 512, 512),
+        "conv512s": lambda: conv_case(16, 64, 512, 512),
+        "conv320": lambda: conv_case(16, 64, 320, 320),
+        "conv640": lambda: conv_case(16, 32, 640, 640),
+        "conv1280": lambda: conv_case(16, 16, 1280, 1280),
+        "conv1280s": lambda: conv_case(16, 8, 1280, 1280),
+    }
+
+    def lin_res():
+        x = torch.randn(16 * 4096, 320, device="cuda").to(bf16); w = (torch.randn(320, 320, device="cuda") * 0.05).to(bf16)
+        r = torch.randn(16 * 4096, 320, device="cuda"); b = torch.randn(320, device="cuda")
+        return (lambda: ops.linear(x, w, b, residual=r, out_f32=True)), 2.0 * 16 * 4096 * 320 * 320, None
+
+    def lin():
+        x = torch.randn(16 * 4096, 320, device="cuda").to(bf16); w = (torch.randn(960, 320, device="cuda") * 0.05).to(bf16)
+        return (lambda: ops.linear(x, w)), 2.0 * 16 * 4096 * 320 * 960, None
+
+    def geglu():
+        x = torch.randn(16 * 4096, 320, device="cuda").to(bf16); w = (torch.randn(2560, 320, device="cuda") * 0.05).to(bf16)
+        b = torch.randn(2560, device="cuda")
+        return (lambda: ops.linear(x, w, b, geglu=True)), 2.0 * 16 * 4096 * 320 * 2560, None
+
+    def attn():
+        B, h, L = 16, 5, 4096
+        qkv = torch.randn(B, L, 3 * 320, device="cuda").to(bf16)
+        bank = torch.randn(B, L, 3 * 320, device="cuda").to(bf16)
+        q, k, v = qkv[..., :320], qkv[..., 320:640], qkv[..., 640:]
+        kb, vb = bank[..., 320:640], bank[..., 640:]
+        return (lambda: ops.attn_kvfused(q, k, v, kb, vb, h, 0.125)), 4.0 * B * h * L * 2 * L * 64, None
+
+    def gn():
+        x = torch.randn(16, 512 * 512, 128, device="cuda")
+        g = torch.ones(128, device="cuda"); b = torch.zeros(128, device="cuda")
+        nbytes = x.numel() * (4 + 2)          # algorithmic: read fp32 once, write bf16 once
+        return (lambda: ops.groupnorm(x, g, b, eps=1e-6, silu=True)), None, nbytes
+    cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, gn=gn)
+    which = list(cases) if args.which == ["all"] else args.which
+    for name in which:
+        fn, flops, nbytes = cases[name]()
+        ms = timeit(fn, args.iters, flush)
+        if flops:
+            print(f"{name:10s} {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
+        else:
+            print(f"{name:10s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s (algorithmic bytes)")
+        del fn
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""CPU tests of the host-side logic: weight re-layouts, synthetic episodes, scheduler, sharding, gloo all-reduce."""
+import os
+
+import pytest
+import torch
+
+from diffews_b200.weights import conv_weight_to_gemm, geglu_permute
+
+
+def test_conv_weight_layout():
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    g = conv_weight_to_gemm(w)
+    assert g.shape == (2, 27)
+    # K index = (kh*3 + kw)*Cin + c
+    for co in range(2):
+        for kh in range(3):
+            for kw in range(3):
+                for c in range(3):
+                    assert g[co, (kh * 3 + kw) * 3 + c] == w[co, c, kh, kw]
+
+
+def test_geglu_permutation_roundtrip():
+    C = 64
+    w = torch.randn(8 * C, C)
+    b = torch.randn(8 * C)
+    wp, bp = geglu_permute(w, b)
+    x = torch.randn(5, C)
+    h = x @ w.t() + b
+    ref = h[:, :4 * C] * torch.nn.functional.gelu(h[:, 4 * C:])
+    hp = x @ wp.t() + bp
+    out = torch.empty(5, 4 * C)
+    for t in range(8 * C // 256):           # what the DFW_EPI_GEGLU epilogue does per 256-column tile
+        v, gte = hp[:, t * 256:t * 256 + 128], hp[:, t * 256 + 128:(t + 1) * 256]
+        out[:, t * 128:(t + 1) * 128] = v * torch.nn.functional.gelu(gte)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_synthetic_episode_layout_and_determinism():
+    from diffews_b200.synthetic import make_batch, pipeline_inputs
+    b1, b2 = make_batch(3, 2, 64, 2), make_batch(3, 2, 64, 2)
+    for k in b1:
+        assert torch.equal(b1[k], b2[k])
+    assert b1["query_img"].shape == (2, 3, 64, 64) and b1["support_imgs"].shape == (2, 2, 3, 64, 64)
+    assert b1["support_masks"].shape == (2, 2, 64, 64) and b1["query_mask"].shape == (2, 64, 64)
+    assert set(b1["query_mask"].unique().tolist()) <= {0.0, 1.0}
+    frac = b1["query_mask"].mean().item()
+    assert 0.01 < frac < 0.9
+    si, q, sm = pipeline_inputs(b1)               # main_oss.py:99-110
+    assert si.shape == (4, 3, 64, 64) and sm.shape == (4, 3, 64, 64) and q.shape == (2, 3, 64, 64)
+    assert set(sm.unique().tolist()) <= {-1.0, 1.0}
+    assert -1 <= si.min() and si.max() <= 1
+
+
+def test_shard_episodes_partition():
+    from diffews_b200.runner import shard_episodes
+    for n, world in [(1000, 8), (17, 4), (5, 8)]:
+        seen = []
+        for r in range(world):
+            seen += list(shard_episodes(n, r, world))
+        assert sorted(seen) == list(range(n))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffews_b200.evaluation import AverageMeter
+    from diffews_b200.runner import shard_episodes
+    m = AverageMeter(benchmark="coco", class_ids=range(80), device="cpu")
+    g = torch.Generator().manual_seed(0)
+    inter = torch.randint(0, 1000, (40, 2), generator=g)
+    union = inter + torch.randint(1, 1000, (40, 2), generator=g)
+    cls = torch.randint(0, 80, (40,), generator=g)
+    for i in shard_episodes(40, rank, world):      # host stand-in for the accumulation kernel (no GPU here)
+        m.intersection_buf[:, cls[i]] += inter[i]
+        m.union_buf[:, cls[i]] += union[i]
+    m.all_reduce()
+    miou, fb, _ = m.compute_iou()
+    q.put((rank, m.intersection_buf.clone(), m.union_buf.clone(), float(miou), float(fb)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_data_parallel_counts_equal_single_process():
+    """world_size-2 gloo: all-reduced int64 [2,nclass] buffers == single-process accumulation over the same episodes."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=30)
+    g = torch.Generator().manual_seed(0)
+    inter = torch.randint(0, 1000, (40, 2), generator=g)
+    union = inter + torch.randint(1, 1000, (40, 2), generator=g)
+    cls = torch.randint(0, 80, (40,), generator=g)
+    ib = torch.zeros(2, 80, dtype=torch.int64); ub = torch.zeros(2, 80, dtype=torch.int64)
+    for i in range(40):
+        ib[:, cls[i]] += inter[i]; ub[:, cls[i]] += union[i]
+    for rank, i_buf, u_buf, miou, fb in res:
+        assert torch.equal(i_buf, ib) and torch.equal(u_buf, ub)
+    assert res[0][3] == res[1][3] and res[0][4] == res[1][4]
