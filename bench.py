@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true")
     ap.add_argument("--vae-stream", default="half", choices=["half", "f32"], help="VAE residual-stream storage")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -216,11 +217,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device leg: inputs resident in HBM ------------------------------------------------------------
+    use_graph = not args.no_graph
+    if use_graph:
+        runner.enable_cuda_graph(dev_batches[0])
     for i in range(args.warmup):
         runner.step(dev_batches[i % pool])
     barrier()
-    timer = None if args.no_kernel_timer else ops.KernelTimer()
-    ops.set_timer(timer)
+    n_before = ops.launch_count()
+    runner.step(dev_batches[0])
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - n_before           # 0 in graph mode: replays do not pass through the C ABI
+    if use_graph:
+        launches_per_step = runner.launches_in_graph
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -234,9 +242,8 @@ def main():
         runner.meter.all_reduce()
     ev1.record()
     barrier()
-    launches = ops.launch_count() - n0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    ops.set_timer(None)
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -253,9 +260,7 @@ def main():
         host_out = torch.empty((2, B, 2), dtype=torch.int64).pin_memory()
 
         def e2e_step(i):
-            hb = host_batches[i % pool]
-            db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-            inter, union = runner.step(db)
+            inter, union = runner.step(host_batches[i % pool])     # pinned host tensors: H2D happens inside step()
             host_out[0].copy_(inter, non_blocking=True)
             host_out[1].copy_(union, non_blocking=True)
             torch.cuda.current_stream().synchronize()         # the caller reads the counts every step
@@ -279,28 +284,46 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
     # ---------------- roofline of the dominant kernel family ----------------------------------------------------------
+    # Per-launch CUDA events cannot be recorded inside a graph replay, so the tensor-core launches are timed in an
+    # instrumented pass of the same steps launched eagerly (same kernels, same shapes, same stream) right after.
     peak_tf, peak_gbs, peak_kind = _peaks()
     roofline = None
     kernels = None
+    timer = None if args.no_kernel_timer else ops.KernelTimer()
+    if timer is not None:
+        runner_graph, runner._graph = getattr(runner, "_graph", None), None
+        runner.step(dev_batches[0])
+        barrier()
+        ops.set_timer(timer)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(args.steps):
+            runner.step(dev_batches[i % pool])
+        t1e.record()
+        barrier()
+        ops.set_timer(None)
+        runner._graph = runner_graph
+        ms_total_instr = t0e.elapsed_time(t1e)
     if timer is not None:
         summ = timer.summary()
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / (v["ms"] * 1e9), 1)
-                       if v["ms"] > 0 else None, "share_of_step": round(v["ms"] / ms_total, 3)} for k, v in summ.items()}
+                       if v["ms"] > 0 else None, "share_of_step": round(v["ms"] / ms_total_instr, 3)} for k, v in summ.items()}
         if args.layer_table and rank == 0:
             rows = sorted(timer.by_shape().items(), key=lambda kv: -kv[1]["ms"])
             with open(args.layer_table, "w") as f:
-                f.write(f"# per-shape CUDA-event times over {args.steps} timed steps (B={B}/GPU); step total {ms_total:.1f} ms\n")
+                f.write(f"# per-shape CUDA-event times over {args.steps} instrumented eager steps (B={B}/GPU); total {ms_total_instr:.1f} ms\n")
                 f.write("kind\tshape\tlaunches\tms_total\tshare\tTFLOP/s\n")
                 for (kind, shape), v in rows:
                     tf = v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else 0.0
-                    f.write(f"{kind}\t{shape}\t{v['launches']}\t{v['ms']:.3f}\t{v['ms'] / ms_total:.4f}\t{tf:.1f}\n")
+                    f.write(f"{kind}\t{shape}\t{v['launches']}\t{v['ms']:.3f}\t{v['ms'] / ms_total_instr:.4f}\t{tf:.1f}\n")
         ig = summ.get("igemm")
         if ig and ig["ms"] > 0:
             achieved = ig["flops"] / (ig["ms"] * 1e9)
             roofline = {"bound": "tensor", "kernel": "igemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear)",
                         "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": f"{peak_kind} sustained bf16",
-                        "launches": ig["launches"], "share_of_step": round(ig["ms"] / ms_total, 3)}
+                        "launches": ig["launches"], "share_of_step": round(ig["ms"] / ms_total_instr, 3),
+                        "timed_in": "instrumented eager pass of the same steps (events around every launch)"}
 
     # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------------------
     cpu = None
@@ -321,6 +344,7 @@ def main():
                                    "SD-2.1 UNet (KV-bank attention) + VAE encode x3 / decode + rthres/IoU, random-init "
                                    "weights (BASELINE config 2)",
                        "episodes_per_step_per_gpu": B, "parallelism": f"dp{world}",
+                       "launch": "one CUDA graph per step" if use_graph else "eager",
                        "l2_policy": "inputs + activations per step (>2 GB) exceed the 126 MB L2; 2 alternating batches",
                        "precision": "fp16 tensor-core operands (the reference's own half mode), fp32 accumulate / softmax / "
                                     f"statistics, UNet residual stream fp32, VAE stream {args.vae_stream}; an all-bf16 "

@@ -37,6 +37,11 @@ static PFN_encodeTiled get_encode() {
 
 int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap(out, base, 2, 128, rank, dims, strides_bytes, box);
+}
+
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         fprintf(stderr, "[dfw] cuTensorMapEncodeTiled entry point unavailable\n");
@@ -52,8 +57,12 @@ int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const u
         estr[i] = 1;
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                     gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUtensorMapDataType dt = (elem_bytes == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    const CUtensorMapSwizzle sw = (swizzle_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (swizzle_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : (swizzle_bytes == 32) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                     gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fprintf(stderr, "[dfw] cuTensorMapEncodeTiled failed (%d): rank %d dims", static_cast<int>(r), rank);

@@ -35,6 +35,10 @@ int require_sm100();
 // dims[0] is the contiguous dimension. strides_bytes[i] is the stride of dims[i+1].
 int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box);
+// General form: elem_bytes 2|4, swizzle_bytes 0|32|64|128 (inner box extent * elem_bytes must equal the swizzle span
+// when swizzling).  Used for the epilogue's TMA stores / residual loads.
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box);
 
 inline int sm_count() {
     static int n = 0;

@@ -32,6 +32,8 @@ constexpr int MAX_TAPS = 9;
 struct IgemmMaps {
     CUtensorMap a[4];
     CUtensorMap b;
+    CUtensorMap out;   // TMA-store epilogue: y   as [out_ch, W, H, N], box [64 B, TW, TH, TN], SWIZZLE_64B
+    CUtensorMap res;   //                     residual, same geometry
 };
 
 struct IgemmParams {
@@ -53,6 +55,8 @@ struct IgemmParams {
     int out_ch;       // channels of y
     float out_scale;
     int flags;
+    int tma_epi;      // 1: epilogue stages 64-byte-wide column chunks in smem and uses TMA stores / residual TMA loads
+    int has_res;
 };
 
 template <int BLOCK_N>
@@ -60,7 +64,9 @@ struct IgemmCfg {
     static constexpr int B_TILE_BYTES = BLOCK_N * 128;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N > 128 ? 5 : (BLOCK_N == 128 ? 6 : 8));
-    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4 /*staging*/ + 128 * 16 /*row table*/;
+    // epilogue smem, shared by the two epilogue flavours: TMA path 2 x 8 KiB out + 2 x 8 KiB residual chunk buffers;
+    // direct path 4 x 4.5 KiB transpose staging + 2 KiB row table
+    static constexpr int EPI_BYTES = 4 * 8192;
     static constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -235,10 +241,18 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
+    auto res_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
     uint8_t* epi_generic = smem_raw + (epi_base - smem_raw_u32);
+    auto out_buf = [&](int b) { return epi_base + 8192u * b; };
+    auto res_buf = [&](int b) { return epi_base + 16384u + 8192u * b; };
+    // TMA-epilogue chunk geometry: 64 bytes of output per row -> 32 columns (16-bit y) or 16 columns (fp32 y)
+    const int CW = (p.flags & DFW_EPI_OUT_F32) ? 16 : 32;
+    const int out_cols_per_tile = (p.flags & DFW_EPI_GEGLU) ? BLOCK_N / 2 : BLOCK_N;
+    const int chunks_per_tile = out_cols_per_tile / CW;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -246,6 +260,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
         tma_prefetch_desc(&maps.b);
+        if (p.tma_epi) {
+            tma_prefetch_desc(&maps.out);
+            if (p.has_res) tma_prefetch_desc(&maps.res);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -255,6 +273,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 4);
+            mbar_init(res_full(a), 1);
+            mbar_init(res_empty(a), 4);
         }
         fence_mbar_init();
     }
@@ -318,6 +338,153 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
+    } else if (warp == 3) {
+        // residual loader for the TMA epilogue: one 8 KiB chunk (128 rows x 64 B) per epilogue chunk, 2-deep ring
+        if (lane == 0 && p.tma_epi && p.has_res) {
+            uint32_t g = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                for (int c = 0; c < chunks_per_tile; ++c, ++g) {
+                    const int b = g & 1;
+                    mbar_wait(res_empty(b), ((g >> 1) & 1) ^ 1u, 5);
+                    mbar_arrive_expect_tx(res_full(b), 8192);
+                    tma_load_4d(res_buf(b), &maps.res, res_full(b), tc.n_tile * out_cols_per_tile + c * CW, tc.w0,
+                                tc.h0, tc.n0);
+                }
+            }
+        }
+    } else if (warp >= 4 && p.tma_epi) {
+        // ---------------- TMA epilogue: thread = accumulator row; 64-byte chunks through swizzled smem ----------------
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        const int f16 = p.flags & DFW_EPI_F16;
+        const bool out_f32 = (p.flags & DFW_EPI_OUT_F32) != 0;
+        const bool geglu = (BLOCK_N == 256) && (p.flags & DFW_EPI_GEGLU);
+        const bool issuer = (threadIdx.x == 128);
+        const uint32_t row_off = static_cast<uint32_t>(row) * 64u;
+        const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);          // SWIZZLE_64B: unit ^= (row/2) % 4
+        int acc = 0;
+        uint32_t acc_phase = 0, g = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t);
+            mbar_wait(tfull_bar(acc), acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < chunks_per_tile; ++c, ++g) {
+                const int b = g & 1;
+                float f[32];
+                const int col_out0 = tc.n_tile * out_cols_per_tile + c * CW;
+                if (geglu) {
+                    if constexpr (BLOCK_N == 256) {
+                        uint32_t v[32], gt[32];
+                        tmem_ld_32x32(taddr + c * 32, v);
+                        tmem_ld_32x32(taddr + 128 + c * 32, gt);
+                        tmem_ld_wait();
+                        const float* bp = p.bias ? p.bias + tc.n_tile * 256 + c * 32 : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+                            if (bp) { bv = __ldg(reinterpret_cast<const float4*>(bp + j)); bg = __ldg(reinterpret_cast<const float4*>(bp + 128 + j)); }
+                            f[j] = (__uint_as_float(v[j]) + bv.x) * gelu_erf(__uint_as_float(gt[j]) + bg.x);
+                            f[j + 1] = (__uint_as_float(v[j + 1]) + bv.y) * gelu_erf(__uint_as_float(gt[j + 1]) + bg.y);
+                            f[j + 2] = (__uint_as_float(v[j + 2]) + bv.z) * gelu_erf(__uint_as_float(gt[j + 2]) + bg.z);
+                            f[j + 3] = (__uint_as_float(v[j + 3]) + bv.w) * gelu_erf(__uint_as_float(gt[j + 3]) + bg.w);
+                        }
+                    }
+                } else {
+                    const int col_in0 = tc.n_tile * BLOCK_N + c * CW;
+                    if (out_f32) {
+                        uint32_t v[16];
+                        tmem_ld_32x16(taddr + c * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                    } else {
+                        if constexpr (BLOCK_N >= 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(taddr + c * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        }
+                    }
+                    if (p.bias != nullptr) {
+                        if (col_in0 + CW <= p.Cout) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (j < CW) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0 + j));
+                                    f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < CW && col_in0 + j < p.Cout) f[j] += __ldg(p.bias + col_in0 + j);
+                        }
+                    }
+                    if (p.out_scale != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+                    }
+                    if (p.flags & DFW_EPI_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
+                    }
+                }
+                if (p.has_res) {
+                    mbar_wait(res_full(b), (g >> 1) & 1, 6);
+                    const uint32_t rb = res_buf(b) + row_off;
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        uint4 r;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(rb + ((u ^ sw) << 4)));
+                        if (out_f32) {
+                            f[4 * u] += __uint_as_float(r.x); f[4 * u + 1] += __uint_as_float(r.y);
+                            f[4 * u + 2] += __uint_as_float(r.z); f[4 * u + 3] += __uint_as_float(r.w);
+                        } else {
+                            const float2 a0 = unpack_h2(r.x, f16), a1 = unpack_h2(r.y, f16), a2 = unpack_h2(r.z, f16),
+                                         a3 = unpack_h2(r.w, f16);
+                            f[8 * u] += a0.x; f[8 * u + 1] += a0.y; f[8 * u + 2] += a1.x; f[8 * u + 3] += a1.y;
+                            f[8 * u + 4] += a2.x; f[8 * u + 5] += a2.y; f[8 * u + 6] += a3.x; f[8 * u + 7] += a3.y;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(res_empty(b));
+                }
+                // the store issued two chunks ago (same buffer) must have finished reading smem
+                if (issuer) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
+                const uint32_t ob = out_buf(b) + row_off;
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    uint4 w;
+                    if (out_f32) {
+                        w.x = __float_as_uint(f[4 * u]); w.y = __float_as_uint(f[4 * u + 1]);
+                        w.z = __float_as_uint(f[4 * u + 2]); w.w = __float_as_uint(f[4 * u + 3]);
+                    } else {
+                        w.x = pack_h2(f[8 * u], f[8 * u + 1], f16); w.y = pack_h2(f[8 * u + 2], f[8 * u + 3], f16);
+                        w.z = pack_h2(f[8 * u + 4], f[8 * u + 5], f16); w.w = pack_h2(f[8 * u + 6], f[8 * u + 7], f16);
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                                 ::"r"(ob + ((u ^ sw) << 4)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    tma_store_4d(&maps.out, out_buf(b), col_out0, tc.w0, tc.h0, tc.n0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (issuer) tma_store_wait_all<0>();
     } else if (warp >= 4) {
         const int q = warp - 4;
         const int row = q * 32 + lane;
@@ -556,6 +723,35 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
         const uint32_t bbox[2] = {BLOCK_K, static_cast<uint32_t>(block_n)};
         rc = encode_tmap_bf16_sw128(&maps.b, w, 2, dims, strides, bbox);
         if (rc != DFW_OK) return rc;
+    }
+    // TMA-store epilogue whenever the output (and residual) rows are TMA-addressable and of one element size
+    {
+        const bool out_f32 = (flags & DFW_EPI_OUT_F32) != 0, res_f32 = (flags & DFW_EPI_RES_F32) != 0;
+        const uint64_t oesz = out_f32 ? 4 : 2;
+        const bool ok = block_n != 16 && bias_sample_stride == 0 && (p.out_ch * oesz) % 16 == 0 &&
+                        (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                        (residual == nullptr || (res_f32 == out_f32 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
+        p.tma_epi = ok ? 1 : 0;
+        p.has_res = (ok && residual != nullptr) ? 1 : 0;
+        if (ok) {
+            const uint64_t dims[4] = {static_cast<uint64_t>(p.out_ch), static_cast<uint64_t>(Wout),
+                                      static_cast<uint64_t>(Hout), static_cast<uint64_t>(N)};
+            const uint64_t strides[3] = {p.out_ch * oesz, static_cast<uint64_t>(Wout) * p.out_ch * oesz,
+                                         static_cast<uint64_t>(Hout) * Wout * p.out_ch * oesz};
+            const uint32_t obox[4] = {static_cast<uint32_t>(64 / oesz), static_cast<uint32_t>(p.TW),
+                                      static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+            rc = encode_tmap(&maps.out, y, static_cast<int>(oesz), 64, 4, dims, strides, obox);
+            if (rc != DFW_OK) return rc;
+            if (residual != nullptr) {
+                rc = encode_tmap(&maps.res, residual, static_cast<int>(oesz), 64, 4, dims, strides, obox);
+                if (rc != DFW_OK) return rc;
+            } else {
+                maps.res = maps.out;
+            }
+        } else {
+            maps.out = maps.b;
+            maps.res = maps.b;
+        }
     }
     switch (block_n) {
         case 16: return launch_igemm<16>(maps, p, stream);
