@@ -23,15 +23,17 @@ namespace dfw {
 extern std::atomic<long long> g_launches;
 namespace {
 
-constexpr int ATT_M = 128;       // query rows per CTA
+constexpr int ATT_M = 128;       // query rows per tile (one tcgen05 M)
+constexpr int ATT_QT = 2;        // query tiles per CTA (ping-pong: softmax of one overlaps the MMAs of the other)
 constexpr int ATT_N = 128;       // keys per tile
 constexpr int ATT_D = 64;        // head dim
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * 128;             // 128 rows x 128 B
-constexpr int ATT_THREADS = 256;
-constexpr int ATT_SMEM = TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * 2 * TILE_BYTES /*P x2*/ +
-                         1024 + 256;
-constexpr int ATT_TMEM_COLS = 512;
+constexpr int ATT_THREADS = 384;                  // 4 control warps + 2 x 4 softmax warps
+constexpr int ATT_SMEM = ATT_QT * TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ +
+                         ATT_QT * 2 * TILE_BYTES /*P*/ + 1024 + 256;
+constexpr int ATT_TMEM_COLS = 512;                // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+constexpr float ATT_RESCALE_TAU = 8.0f;           // lazy rescale threshold in the log2 domain (P <= 2^8)
 // All 16-bit tensors of a call (Q, K, V, P, O) share one format, bf16 or fp16: tcgen05 kind::f16 requires the A and B
 // operand of an MMA to have the same format (a bf16 x fp16 mix raises an illegal-instruction trap on sm_100).
 
@@ -48,31 +50,44 @@ struct AttnParams {
     int f16;              // 16-bit tensors are fp16 (else bf16)
 };
 
+// CTA = 256 query rows (two 128-row tiles A, B) of one (episode, head).
+//   warp 0      TMA producer: Q_A, Q_B once; (K_j, V_j) 128-key tiles through a 3-stage ring, from two tensor maps
+//               (self keys first, then the support bank) — the concatenation is never materialised
+//   warp 1      MMA issuer: S_X(j) = Q_X K_j^T into TMEM (128x128x64), O_X += P_X(j) V_j accumulated IN TMEM
+//               (128x64x128, V consumed MN-major straight from the TMA tile); schedule A,B interleaved
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax of tile A, warps 8-11 softmax of tile B: one thread per query row (= TMEM lane); running max
+//               and sum in the log2 domain; O is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row of
+//               the warp raises its max by more than 2^TAU, so the common case never touches O; P -> 16-bit ->
+//               128B-swizzled smem (the K-major A operand of the PV MMA)
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
-    const uint32_t sQ = base;
-    auto sK = [&](int s) { return base + TILE_BYTES + s * 2 * TILE_BYTES; };
-    auto sV = [&](int s) { return base + TILE_BYTES + s * 2 * TILE_BYTES + TILE_BYTES; };
-    auto sP = [&](int b) { return base + TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + b * 2 * TILE_BYTES; };
-    const uint32_t bar_base = base + TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 4 * TILE_BYTES;
+    auto sQ = [&](int x) { return base + x * TILE_BYTES; };
+    const uint32_t kv_base = base + ATT_QT * TILE_BYTES;
+    auto sK = [&](int s) { return kv_base + s * 2 * TILE_BYTES; };
+    auto sV = [&](int s) { return kv_base + s * 2 * TILE_BYTES + TILE_BYTES; };
+    const uint32_t p_base = kv_base + KV_STAGES * 2 * TILE_BYTES;
+    auto sP = [&](int x) { return p_base + x * 2 * TILE_BYTES; };
+    const uint32_t bar_base = p_base + ATT_QT * 2 * TILE_BYTES;
     const uint32_t q_full = bar_base;
     auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
     auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KV_STAGES + s); };
-    auto s_full = [&](int b) { return bar_base + 8u * (1 + 2 * KV_STAGES + b); };
-    auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * KV_STAGES + b); };
-    auto pv_done = [&](int b) { return bar_base + 8u * (5 + 2 * KV_STAGES + b); };
+    auto s_full = [&](int x) { return bar_base + 8u * (1 + 2 * KV_STAGES + x); };
+    auto p_full = [&](int x) { return bar_base + 8u * (3 + 2 * KV_STAGES + x); };
+    auto pv_done = [&](int x) { return bar_base + 8u * (5 + 2 * KV_STAGES + x); };
     const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * KV_STAGES);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
-    uint8_t* sP_generic = smem_raw + (sP(0) - raw_u32);
+    uint8_t* sP_generic = smem_raw + (p_base - raw_u32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * ATT_M;
+    const int q0 = blockIdx.x * ATT_M * ATT_QT;
     const int head = blockIdx.y;
     const int b = blockIdx.z;
     const int ntiles = p.n_self + p.n_bank;
+    const bool has_b = (q0 + ATT_M) < p.Lq;          // second query tile holds at least one valid row
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.q);
@@ -83,7 +98,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 128); mbar_init(pv_done(i), 1); }
+        for (int x = 0; x < ATT_QT; ++x) { mbar_init(s_full(x), 1); mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -94,13 +109,14 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    auto tS = [&](int i) { return tmem_base + i * 128; };
-    auto tO = [&](int i) { return tmem_base + 256 + i * 64; };
+    auto tS = [&](int x) { return tmem_base + x * 128; };
+    auto tO = [&](int x) { return tmem_base + 256 + x * 64; };
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, TILE_BYTES);
-            tma_load_3d(sQ, &maps.q, q_full, head * ATT_D, q0, b);
+            mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+            tma_load_3d(sQ(0), &maps.q, q_full, head * ATT_D, q0, b);
+            if (has_b) tma_load_3d(sQ(1), &maps.q, q_full, head * ATT_D, q0 + ATT_M, b);
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
                 const uint32_t ph = (j / KV_STAGES) & 1;
@@ -121,130 +137,151 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             const uint32_t fmt = p.f16 ? 0u : 1u;
             const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (=K) is K-major
             const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);   // O = P V   : B (=V) is MN-major
-            auto issue_s = [&](int j) {
+            const int nq = has_b ? 2 : 1;
+            auto issue_s = [&](int x, int j) {                                // needs K_j landed, S_X free
                 const int s = j % KV_STAGES;
-                mbar_wait(kv_full(s), (j / KV_STAGES) & 1, 11);
-                tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(sQ);
+                const uint64_t adesc = umma_desc_sw128(sQ(x));
                 const uint64_t bdesc = umma_desc_sw128(sK(s));
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_ss(tS(j & 1), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-                tc_commit(s_full(j & 1));
+                    umma_ss(tS(x), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                tc_commit(s_full(x));
             };
             mbar_wait(q_full, 0, 12);
-            issue_s(0);
+            mbar_wait(kv_full(0), 0, 11);
+            tc_fence_after();
+            for (int x = 0; x < nq; ++x) issue_s(x, 0);
             for (int j = 0; j < ntiles; ++j) {
-                if (j + 1 < ntiles) issue_s(j + 1);
-                mbar_wait(p_full(j & 1), (j >> 1) & 1, 13);
-                tc_fence_after();
                 const int s = j % KV_STAGES;
-#pragma unroll
-                for (int ks = 0; ks < ATT_N / 16; ++ks) {
-                    const uint64_t adesc = umma_desc_sw128(sP(j & 1) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
-                    const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
-                    umma_ss(tO(j & 1), adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+                if (j + 1 < ntiles) {
+                    mbar_wait(kv_full((j + 1) % KV_STAGES), ((j + 1) / KV_STAGES) & 1, 11);
+                    tc_fence_after();
                 }
-                tc_commit(kv_empty(s));
-                tc_commit(pv_done(j & 1));
+                for (int x = 0; x < nq; ++x) {
+                    mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, S_X consumed, O_X rescaled
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < ATT_N / 16; ++ks) {
+                        const uint64_t adesc = umma_desc_sw128(sP(x) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
+                        const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
+                        umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(pv_done(x));
+                    if (j + 1 < ntiles) issue_s(x, j + 1);
+                }
+                tc_commit(kv_empty(s));                                        // K_j / V_j fully consumed by both tiles
             }
         }
     } else if (warp >= 4) {
-        const int qd = warp - 4;
+        const int x = (warp - 4) >> 2;                // query tile of this softmax group
+        const int qd = (warp - 4) & 3;                // TMEM lane quadrant
         const int row = qd * 32 + lane;
-        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f, alpha_pending = 0.f;
-        float o_acc[ATT_D];
+        const int qrow0 = q0 + x * ATT_M;
+        if (x == 0 || has_b) {
+            const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+            const uint32_t ts = tS(x) + lane_off;
+            const uint32_t to = tO(x) + lane_off;
+            float m_used = -INFINITY, l_run = 0.f;
+            uint8_t* pbuf = sP_generic + x * 2 * TILE_BYTES;
+            for (int j = 0; j < ntiles; ++j) {
+                int valid;
+                if (j < p.n_self) valid = min(ATT_N, p.Ls - j * ATT_N);
+                else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
+                mbar_wait(s_full(x), j & 1, 15);
+                tc_fence_after();
+                // pass 1: row max of the scaled logits
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(ts + c * 32, v);
+                    tmem_ld_wait();
+                    if (valid == ATT_N) {
 #pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
-
-        auto accumulate_o = [&](int j, float alpha) {
-            mbar_wait(pv_done(j & 1), (j >> 1) & 1, 14);
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    }
+                }
+                const float m_new = fmaxf(m_used, mx * p.scale_log2);
+                // lazy rescale: only when some row of the warp moved its max by more than 2^TAU (warp-uniform branch,
+                // tcgen05.ld/st are warp-collective)
+                if (__any_sync(0xffffffffu, m_new > m_used + ATT_RESCALE_TAU)) {
+                    const float alpha = exp2f(m_used - m_new);        // 0 on the first tile
+                    if (j > 0) {
+                        mbar_wait(pv_done(x), (j - 1) & 1, 14);       // O_X holds tiles < j
+                        tc_fence_after();
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(to + c * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            tmem_st_32x32(to + c * 32, v);
+                        }
+                        tmem_st_wait();
+                    }
+                    l_run *= alpha;
+                    m_used = m_new;
+                }
+                // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile
+                float psum = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(ts + c * 32, v);
+                    tmem_ld_wait();
+                    float pf[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used));
+                        if (valid != ATT_N && c * 32 + i >= valid) e = 0.f;
+                        pf[i] = e;
+                        psum += e;
+                    }
+                    uint8_t* chunk = pbuf + (c >> 1) * TILE_BYTES + row * 128;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w;
+                        w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], p.f16);
+                        w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], p.f16);
+                        w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], p.f16);
+                        w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], p.f16);
+                        const int unit = ((c & 1) * 4 + u) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
+                    }
+                }
+                l_run += psum;
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(p_full(x));
+            }
+            // epilogue: O_X / l
+            mbar_wait(pv_done(x), (ntiles - 1) & 1, 16);
             tc_fence_after();
+            const float inv = 1.0f / l_run;
+            const bool row_ok = (qrow0 + row) < p.Lq;
+            uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
+                           static_cast<long long>(qrow0 + row) * p.o_row_stride + head * ATT_D;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld_32x32(tO(j & 1) + lane_off + c * 32, v);
+                tmem_ld_32x32(to + c * 32, v);
                 tmem_ld_wait();
+                if (row_ok) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(v[i]));
-            }
-        };
-
-        for (int j = 0; j < ntiles; ++j) {
-            int valid;
-            if (j < p.n_self) valid = min(ATT_N, p.Ls - j * ATT_N);
-            else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
-            mbar_wait(s_full(j & 1), (j >> 1) & 1, 15);
-            tc_fence_after();
-            const uint32_t ts = tS(j & 1) + lane_off;
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(ts + c * 32, v);
-                tmem_ld_wait();
-                if (valid == ATT_N) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 w;
+                        w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, p.f16);
+                        w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, p.f16);
+                        w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, p.f16);
+                        w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, p.f16);
+                        *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+                    }
                 }
-            }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);   // first tile: exp2(-inf) = 0
-            float psum = 0.f;
-            // pass 2: p = exp2(s*c - m), bf16, swizzled store into the K-major P tile
-            uint8_t* pbuf = sP_generic + (j & 1) * 2 * TILE_BYTES;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(ts + c * 32, v);
-                tmem_ld_wait();
-                float pf[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-                    if (valid != ATT_N && c * 32 + i >= valid) e = 0.f;
-                    pf[i] = e;
-                    psum += e;
-                }
-                uint8_t* chunk = pbuf + (c >> 1) * TILE_BYTES + row * 128;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 w;
-                    w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], p.f16);
-                    w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], p.f16);
-                    w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], p.f16);
-                    w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], p.f16);
-                    const int unit = ((c & 1) * 4 + u) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
-                }
-            }
-            l_run = fmaf(l_run, alpha, psum);
-            m_run = m_new;
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(p_full(j & 1));
-            if (j >= 1) accumulate_o(j - 1, alpha_pending);
-            alpha_pending = alpha;
-        }
-        accumulate_o(ntiles - 1, alpha_pending);
-        if (q0 + row < p.Lq) {
-            const float inv = 1.0f / l_run;
-            uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
-                                static_cast<long long>(q0 + row) * p.o_row_stride + head * ATT_D;
-#pragma unroll
-            for (int i = 0; i < ATT_D; i += 8) {
-                uint4 w;
-                w.x = pack_h2(o_acc[i] * inv, o_acc[i + 1] * inv, p.f16);
-                w.y = pack_h2(o_acc[i + 2] * inv, o_acc[i + 3] * inv, p.f16);
-                w.z = pack_h2(o_acc[i + 4] * inv, o_acc[i + 5] * inv, p.f16);
-                w.w = pack_h2(o_acc[i + 6] * inv, o_acc[i + 7] * inv, p.f16);
-                *reinterpret_cast<uint4*>(op + i) = w;
             }
         }
     }
@@ -375,7 +412,7 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
-    dim3 grid((Lq + ATT_M - 1) / ATT_M, heads, B);
+    dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
     attn_kvfused_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_)>>>(maps, p);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());

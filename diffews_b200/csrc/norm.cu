@@ -11,7 +11,14 @@ namespace dfw {
 extern std::atomic<long long> g_launches;
 namespace {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU op (tanh.approx.f32, max rel. error 2^-11 — the same
+// order as the fp16 / bf16 rounding of the stored result) instead of ex2 + rcp.
+__device__ __forceinline__ float silu_f(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
 
 // load 8 consecutive channels as fp32.  XD: 0 = bf16, 1 = fp32, 2 = fp16 storage
 template <int XD>
@@ -56,10 +63,23 @@ __global__ void gn_stats_kernel(const void* __restrict__ x, float* __restrict__ 
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-    const long long img_off = static_cast<long long>(n) * HW * C;
-    for (int row = row0 + r; row < row1; row += RPI) {
+    const long long img_off = static_cast<long long>(n) * HW * C + vc * 8;
+    int row = row0 + r;
+    for (; row + 3 * RPI < row1; row += 4 * RPI) {          // 4 independent 16-byte loads in flight per thread
+        float v0[8], v1[8], v2[8], v3[8];
+        load8<XD>(x, img_off + static_cast<long long>(row) * C, v0);
+        load8<XD>(x, img_off + static_cast<long long>(row + RPI) * C, v1);
+        load8<XD>(x, img_off + static_cast<long long>(row + 2 * RPI) * C, v2);
+        load8<XD>(x, img_off + static_cast<long long>(row + 3 * RPI) * C, v3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+            ss[j] = fmaf(v0[j], v0[j], fmaf(v1[j], v1[j], fmaf(v2[j], v2[j], fmaf(v3[j], v3[j], ss[j]))));
+        }
+    }
+    for (; row < row1; row += RPI) {
         float v[8];
-        load8<XD>(x, img_off + static_cast<long long>(row) * C + vc * 8, v);
+        load8<XD>(x, img_off + static_cast<long long>(row) * C, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
     }
@@ -108,29 +128,49 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const floa
     }
 }
 
-// stage 3: y = [silu](x * scale + shift)
+// stage 3: y = [silu](x * scale + shift).  Same (row-chunk, image) decomposition as stage 1: a thread owns 8 fixed
+// channels (scale / shift live in registers) and walks rows, so there is no per-vector index arithmetic.
 template <int XD>
 __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restrict__ scale_shift,
-                                void* __restrict__ y, long long total_vecs, int HW, int C, int apply_silu,
+                                void* __restrict__ y, int HW, int C, int rows_per_chunk, int RPI, int apply_silu,
                                 int y_f16) {
     const int V = C / 8;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vecs; i += stride) {
-        const int vc = static_cast<int>(i % V);
-        const long long rowg = i / V;
-        const int n = static_cast<int>(rowg / HW);
-        float v[8];
-        load8<XD>(x, i * 8, v);
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int vc = threadIdx.x % V, r = threadIdx.x / V;
+    const int row0 = chunk * rows_per_chunk;
+    const int row1 = min(HW, row0 + rows_per_chunk);
+    float sc[8], sh[8];
+    {
         const float4* sp = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + vc * 8) * 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float4 q = __ldg(sp + j);  // (scale, shift, scale, shift)
-            float a = fmaf(v[2 * j], q.x, q.y);
-            float b = fmaf(v[2 * j + 1], q.z, q.w);
-            if (apply_silu) { a = silu_f(a); b = silu_f(b); }
-            v[2 * j] = a; v[2 * j + 1] = b;
+            const float4 q = __ldg(sp + j);           // (scale, shift, scale, shift)
+            sc[2 * j] = q.x; sh[2 * j] = q.y; sc[2 * j + 1] = q.z; sh[2 * j + 1] = q.w;
         }
-        store8_16(y, i * 8, v, y_f16);
+    }
+    const long long img_off = static_cast<long long>(n) * HW * C + vc * 8;
+    auto finish = [&](float (&v)[8], long long off) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = fmaf(v[j], sc[j], sh[j]);
+            if (apply_silu) a = silu_f(a);
+            v[j] = a;
+        }
+        store8_16(y, off, v, y_f16);
+    };
+    int row = row0 + r;
+    for (; row + 3 * RPI < row1; row += 4 * RPI) {
+        float v0[8], v1[8], v2[8], v3[8];
+        const long long o0 = img_off + static_cast<long long>(row) * C, o1 = o0 + static_cast<long long>(RPI) * C,
+                        o2 = o1 + static_cast<long long>(RPI) * C, o3 = o2 + static_cast<long long>(RPI) * C;
+        load8<XD>(x, o0, v0); load8<XD>(x, o1, v1); load8<XD>(x, o2, v2); load8<XD>(x, o3, v3);
+        finish(v0, o0); finish(v1, o1); finish(v2, o2); finish(v3, o3);
+    }
+    for (; row < row1; row += RPI) {
+        float v[8];
+        const long long o = img_off + static_cast<long long>(row) * C;
+        load8<XD>(x, o, v);
+        finish(v, o);
     }
 }
 
@@ -245,8 +285,8 @@ GnPlan gn_plan(int N, int HW, int C) {
     pl.RPI = pl.V >= 256 ? 1 : 256 / pl.V;
     if (pl.RPI > HW) pl.RPI = HW;
     pl.threads = pl.V * pl.RPI;
-    int want = (4 * 148 + N - 1) / N;                 // ~4 CTAs per SM over the whole batch
-    int max_chunks = (HW + pl.RPI * 8 - 1) / (pl.RPI * 8);  // at least 8 rows per thread
+    int want = (8 * 148 + N - 1) / N;                 // ~8 CTAs per SM over the whole batch
+    int max_chunks = (HW + pl.RPI * 16 - 1) / (pl.RPI * 16);  // at least 16 rows per thread
     if (max_chunks < 1) max_chunks = 1;
     pl.nchunks = want < max_chunks ? want : max_chunks;
     if (pl.nchunks < 1) pl.nchunks = 1;
@@ -286,15 +326,11 @@ int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const flo
     float* scale_shift = partial + partial_elems;
     dim3 grid(pl.nchunks, N);
     DFW_REQUIRE(pl.smem <= 48 * 1024);
-    const long long total_vecs = static_cast<long long>(N) * HW * (C / 8);
-    long long blocks = (total_vecs + 255) / 256;
-    const long long cap = static_cast<long long>(sm_count()) * 16;
-    if (blocks > cap) blocks = cap;
-    const int ab = static_cast<int>(blocks);
 #define DFW_GN_LAUNCH(XD)                                                                                          \
     gn_stats_kernel<XD><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI); \
     gn_finalize_kernel<<<N, 256, 0, stream>>>(partial, gamma, beta, scale_shift, HW, C, groups, pl.nchunks, eps);  \
-    gn_apply_kernel<XD><<<ab, 256, 0, stream>>>(x, scale_shift, y, total_vecs, HW, C, apply_silu, y_f16);
+    gn_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, scale_shift, y, HW, C, pl.rows_per_chunk, pl.RPI,         \
+                                                          apply_silu, y_f16);
     if (x_dtype == 1) { DFW_GN_LAUNCH(1) } else if (x_dtype == 2) { DFW_GN_LAUNCH(2) } else { DFW_GN_LAUNCH(0) }
 #undef DFW_GN_LAUNCH
     g_launches.fetch_add(3);
