@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true")
     ap.add_argument("--vae-stream", default="half", choices=["half", "f32"], help="VAE residual-stream storage")
+    ap.add_argument("--unet-stream", default="f32", choices=["half", "f32"], help="UNet residual-stream storage")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
     args = ap.parse_args()
@@ -198,7 +199,9 @@ def main():
     unet_o, vae_o = build_models(0)
     from diffews_b200.layers import Precision
     vae_prec = Precision(stream_f32=(args.vae_stream == "f32"), mid_f32=False)
-    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding(), device=dev, vae_precision=vae_prec)
+    unet_prec = Precision(stream_f32=(args.unet_stream == "f32"), mid_f32=(args.unet_stream == "f32"))
+    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding(), device=dev, vae_precision=vae_prec,
+                                     unet_precision=unet_prec)
     runner = EpisodeRunner(pipe, "coco", img_size=args.size)
     B = args.batch
 
@@ -347,7 +350,7 @@ def main():
                        "launch": "one CUDA graph per step" if use_graph else "eager",
                        "l2_policy": "inputs + activations per step (>2 GB) exceed the 126 MB L2; 2 alternating batches",
                        "precision": "fp16 tensor-core operands (the reference's own half mode), fp32 accumulate / softmax / "
-                                    f"statistics, UNet residual stream fp32, VAE stream {args.vae_stream}; an all-bf16 "
+                                    f"statistics, UNet residual stream {args.unet_stream}, VAE stream {args.vae_stream}; an all-bf16 "
                                     "operand mode exists (layers.PURE_BF16) but misses the 1e-2 latent bar (1.2e-2)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels,

@@ -23,6 +23,7 @@ SIGNATURES = {
     "dfw_launch_count": (_ll, []),
     "dfw_conv2d_igemm": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "dfw_bmm_nt": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
                                   _i, _f, _i, _vp]),
     "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _i, _vp]),
@@ -33,6 +34,7 @@ SIGNATURES = {
     "dfw_upsample2x_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "dfw_cast_f32_to_16": (_i, [_vp, _vp, _i, _ll, _vp]),
+    "dfw_im2col3x3_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dfw_conv3x3_small_cin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dfw_pointwise_small": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _f, _f, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
     "dfw_nhwc_f32_to_nchw_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp]),

@@ -55,20 +55,26 @@ struct IgemmParams {
     int out_ch;       // channels of y
     float out_scale;
     int flags;
+    int w_batched;    // 1: per-image weights (batched GEMM): the B tensor map's 3rd coordinate is the image index
     int tma_epi;      // 1: epilogue stages 64-byte-wide column chunks in smem and uses TMA stores / residual TMA loads
     int has_res;
 };
 
-template <int BLOCK_N>
+// TPU = output tiles per work unit.  TPU = 2 ("paired tiles", only when the layer has a single Cout tile) lets two
+// consecutive 128-pixel tiles share every weight tile: 48 KiB of operands per 2 x (128x128x64) MMAs instead of
+// 2 x 32 KiB, which is what bounds the Cout = 128 layers (L2 -> smem operand traffic, not the tensor pipe).
+template <int BLOCK_N, int TPU = 1>
 struct IgemmCfg {
     static constexpr int B_TILE_BYTES = BLOCK_N * 128;
-    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N > 128 ? 5 : (BLOCK_N == 128 ? 6 : 8));
+    static constexpr int STAGE_BYTES = TPU * A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int STAGES = (STAGE_BYTES >= 48 * 1024) ? 4 : (STAGE_BYTES > 32 * 1024 ? 5 : (STAGE_BYTES == 32 * 1024 ? 6 : 8));
     // epilogue smem, shared by the two epilogue flavours: TMA path 2 x 8 KiB out + 2 x 8 KiB residual chunk buffers;
     // direct path 4 x 4.5 KiB transpose staging + 2 KiB row table
     static constexpr int EPI_BYTES = 4 * 8192;
-    static constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+    static constexpr int SUB_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+    static constexpr int ACC_COLS = TPU * SUB_COLS;          // TMEM columns of one work unit's accumulators
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
+    static_assert(TMEM_COLS <= 512, "TMEM budget");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(SMEM_BYTES <= 232448, "smem budget");
@@ -225,18 +231,19 @@ __device__ __forceinline__ void epilogue_store_chunk(const IgemmParams& p, const
     }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int TPU>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmParams p) {
-    using Cfg = IgemmCfg<BLOCK_N>;
+    using Cfg = IgemmCfg<BLOCK_N, TPU>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
     const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;          // staging + row table
     const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
-    auto sA = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
-    auto sB = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
+    auto sA = [&](int s, int sub) { return smem_base + s * Cfg::STAGE_BYTES + sub * A_TILE_BYTES; };
+    auto sB = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + TPU * A_TILE_BYTES; };
+    const int units = (p.total_tiles + TPU - 1) / TPU;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -293,18 +300,24 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t);
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int t0 = u * TPU;
+                const int nsub = min(TPU, p.total_tiles - t0);
+                TileCoord tc[TPU];
+#pragma unroll
+                for (int sub = 0; sub < TPU; ++sub) tc[sub] = decode_tile(p, min(t0 + sub, p.total_tiles - 1));
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     const CUtensorMap* am = &maps.a[p.tap_map[tap]];
-                    const int hh = tc.h0 + p.tap_dh[tap];
-                    const int ww = tc.w0 + p.tap_dw[tap];
                     for (int kb = 0; kb < p.kb_per_tap; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-                        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                        tma_load_4d(sA(stage), am, full_bar(stage), kb * BLOCK_K, ww, hh, tc.n0);
-                        tma_load_2d(sB(stage), &maps.b, full_bar(stage), (tap * p.kb_per_tap + kb) * BLOCK_K,
-                                    tc.n_tile * BLOCK_N);
+                        mbar_arrive_expect_tx(full_bar(stage), nsub * A_TILE_BYTES + Cfg::B_TILE_BYTES);
+#pragma unroll
+                        for (int sub = 0; sub < TPU; ++sub)
+                            if (sub < nsub)
+                                tma_load_4d(sA(stage, sub), am, full_bar(stage), kb * BLOCK_K,
+                                            tc[sub].w0 + p.tap_dw[tap], tc[sub].h0 + p.tap_dh[tap], tc[sub].n0);
+                        tma_load_3d(sB(stage), &maps.b, full_bar(stage), (tap * p.kb_per_tap + kb) * BLOCK_K,
+                                    tc[0].n_tile * BLOCK_N, p.w_batched ? tc[0].n0 : 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -318,18 +331,25 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int nsub = min(TPU, p.total_tiles - u * TPU);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
                 for (int kbi = 0; kbi < kblocks; ++kbi) {
                     mbar_wait(full_bar(stage), phase, 3);
                     tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128(sA(stage));
                     const uint64_t bdesc = umma_desc_sw128(sB(stage));
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k)
-                        umma_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kbi > 0 || k > 0) ? 1u : 0u);
+                    for (int sub = 0; sub < TPU; ++sub) {
+                        if (sub < nsub) {
+                            const uint64_t adesc = umma_desc_sw128(sA(stage, sub));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_ss(d_tmem + sub * Cfg::SUB_COLS, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                        (kbi > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
                     tc_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -342,7 +362,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         // residual loader for the TMA epilogue: one 8 KiB chunk (128 rows x 64 B) per epilogue chunk, 2-deep ring
         if (lane == 0 && p.tma_epi && p.has_res) {
             uint32_t g = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < units; u += gridDim.x)
+            for (int t = u * TPU; t < min(u * TPU + TPU, p.total_tiles); ++t) {
                 const TileCoord tc = decode_tile(p, t);
                 for (int c = 0; c < chunks_per_tile; ++c, ++g) {
                     const int b = g & 1;
@@ -365,11 +386,13 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);          // SWIZZLE_64B: unit ^= (row/2) % 4
         int acc = 0;
         uint32_t acc_phase = 0, g = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(p, t);
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+          for (int t = u * TPU; t < min(u * TPU + TPU, p.total_tiles); ++t) {
+            const TileCoord tc = decode_tile(p, t);
+            const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (t - u * TPU) * Cfg::SUB_COLS +
+                                   (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < chunks_per_tile; ++c, ++g) {
                 const int b = g & 1;
@@ -478,6 +501,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     tma_store_commit();
                 }
             }
+          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -497,7 +521,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const bool geglu = (BLOCK_N == 256) && (p.flags & DFW_EPI_GEGLU);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            mbar_wait(tfull_bar(acc), acc_phase, 4);
+            tc_fence_after();
+          for (int t = u * TPU; t < min(u * TPU + TPU, p.total_tiles); ++t) {
             const TileCoord tc = decode_tile(p, t);
             {
                 const int img = tc.n0 + tn, hh = tc.h0 + th, ww = tc.w0 + tw;
@@ -510,9 +537,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 rows[lane] = er;
                 __syncwarp();
             }
-            mbar_wait(tfull_bar(acc), acc_phase, 4);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (t - u * TPU) * Cfg::SUB_COLS +
+                                   (static_cast<uint32_t>(q * 32) << 16);
             if (geglu) {
                 if constexpr (BLOCK_N == 256) {
                     const int cq = (lane & 7) * 4, sub = lane >> 3;
@@ -584,6 +610,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 epilogue_store_chunk(p, stg, rows, lane, col0, col0, 16, rc);
                 __syncwarp();
             }
+          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -617,19 +644,20 @@ void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
     (void)N;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int TPU = 1>
 int launch_igemm(const IgemmMaps& maps, IgemmParams& p, cudaStream_t stream) {
-    using Cfg = IgemmCfg<BLOCK_N>;
+    using Cfg = IgemmCfg<BLOCK_N, TPU>;
     static bool attr_set = false;
     if (!attr_set) {
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, TPU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES));
         attr_set = true;
     }
     p.n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_nimg * p.n_tiles;
-    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    const int units = (p.total_tiles + TPU - 1) / TPU;
+    const int grid = units < sm_count() ? units : sm_count();
+    igemm_kernel<BLOCK_N, TPU><<<grid, IGEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
@@ -637,7 +665,8 @@ int launch_igemm(const IgemmMaps& maps, IgemmParams& p, cudaStream_t stream) {
 
 int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sample_stride, const void* residual,
                    void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode,
-                   int flags, float out_scale, cudaStream_t stream) {
+                   int flags, float out_scale, cudaStream_t stream, long long w_row_stride = 0,
+                   long long w_batch_stride = 0) {
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(x && w && y);
@@ -658,6 +687,10 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     p.kb_per_tap = Cin / BLOCK_K;
     p.ntaps = ksize * ksize;
     choose_tile(Wout, Hout, N, p.TW, p.TH, p.TN);
+    if (w_batch_stride > 0 && p.TN != 1) {       // per-image weights: a tile must not straddle images
+        p.TN = 1;
+        if (Hout == 1) { p.TW = 128; p.TH = 1; } else { p.TH = 128 / p.TW; }
+    }
     p.tiles_w = (Wout + p.TW - 1) / p.TW;
     p.tiles_h = (Hout + p.TH - 1) / p.TH;
     p.tiles_nimg = (N + p.TN - 1) / p.TN;
@@ -718,10 +751,14 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     else block_n = 128;
     {
         const uint64_t Kt = static_cast<uint64_t>(p.ntaps) * Cin;
-        const uint64_t dims[2] = {Kt, static_cast<uint64_t>(Cout)};
-        const uint64_t strides[1] = {Kt * esz};
-        const uint32_t bbox[2] = {BLOCK_K, static_cast<uint32_t>(block_n)};
-        rc = encode_tmap_bf16_sw128(&maps.b, w, 2, dims, strides, bbox);
+        const uint64_t row = w_row_stride > 0 ? static_cast<uint64_t>(w_row_stride) : Kt;
+        p.w_batched = w_batch_stride > 0 ? 1 : 0;
+        if (p.w_batched) DFW_REQUIRE(p.TN == 1 && (w_batch_stride * esz) % 16 == 0);   // one image per tile
+        DFW_REQUIRE((row * esz) % 16 == 0);
+        const uint64_t dims[3] = {Kt, static_cast<uint64_t>(Cout), static_cast<uint64_t>(p.w_batched ? N : 1)};
+        const uint64_t strides[2] = {row * esz, (p.w_batched ? static_cast<uint64_t>(w_batch_stride) : row * Cout) * esz};
+        const uint32_t bbox[3] = {BLOCK_K, static_cast<uint32_t>(block_n), 1};
+        rc = encode_tmap_bf16_sw128(&maps.b, w, 3, dims, strides, bbox);
         if (rc != DFW_OK) return rc;
     }
     // TMA-store epilogue whenever the output (and residual) rows are TMA-addressable and of one element size
@@ -755,7 +792,12 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     }
     switch (block_n) {
         case 16: return launch_igemm<16>(maps, p, stream);
-        case 128: return launch_igemm<128>(maps, p, stream);
+        case 128: {
+            // paired tiles when there is a single Cout tile and enough work to keep every SM busy with pairs
+            const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_nimg;
+            if (Cout <= 128 && m_tiles >= 4LL * sm_count()) return launch_igemm<128, 2>(maps, p, stream);
+            return launch_igemm<128>(maps, p, stream);
+        }
         case 160: return launch_igemm<160>(maps, p, stream);
         default: return launch_igemm<256>(maps, p, stream);
     }
@@ -771,6 +813,13 @@ int dfw_conv2d_igemm(const void* x, const void* w, const float* bias, int bias_s
                      int flags, float out_scale, void* stream) {
     return dfw::igemm_dispatch(x, w, bias, bias_sample_stride, residual, y, N, Hin, Win, Cin, Cout, ksize, stride,
                                pad_mode, flags, out_scale, static_cast<cudaStream_t>(stream));
+}
+
+int dfw_bmm_nt(const void* x, const void* w, long long w_row_stride, long long w_batch_stride, const float* bias,
+               void* y, int B, int M, int K, int Nout, int flags, float out_scale, void* stream) {
+    // y[b] (M x Nout) = x[b] (M x K) @ w[b]^T, w[b] element (n, k) at w[b*w_batch_stride + n*w_row_stride + k]
+    return dfw::igemm_dispatch(x, w, bias, 0, nullptr, y, B, 1, M, K, Nout, 1, 1, 0, flags, out_scale,
+                               static_cast<cudaStream_t>(stream), w_row_stride, w_batch_stride);
 }
 
 int dfw_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,

@@ -164,6 +164,42 @@ conv3x3_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// im2col for 3x3 / stride 1 / pad 1 convolutions with a tiny input channel count: fp32 NCHW -> 16-bit rows
+// [N*H*W, Kpad], k = (kh*3 + kw)*Cin + c, zero-padded to Kpad (multiple of 64) so the convolution becomes one
+// tcgen05 GEMM with K = Kpad.  8 lanes cover one pixel's row (16 B each), so a warp writes 4 complete rows.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void im2col3x3_small_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, long long total_vecs,
+                                       int H, int W, int Cin, int Kpad, int y_f16) {
+    const int VPR = Kpad / 8;                     // 16-byte vectors per output row
+    const int K = 9 * Cin;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vecs; i += stride) {
+        const int v = static_cast<int>(i % VPR);
+        long long pix = i / VPR;
+        const int w = static_cast<int>(pix % W);
+        const long long t = pix / W;
+        const int h = static_cast<int>(t % H);
+        const long long n = t / H;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = v * 8 + j;
+            float val = 0.f;
+            if (k < K) {
+                const int tap = k / Cin, c = k - tap * Cin;
+                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + ((n * Cin + c) * H + hh) * W + ww);
+            }
+            f[j] = val;
+        }
+        uint4 o;
+        o.x = pack_h2(f[0], f[1], y_f16); o.y = pack_h2(f[2], f[3], y_f16);
+        o.z = pack_h2(f[4], f[5], y_f16); o.w = pack_h2(f[6], f[7], y_f16);
+        *reinterpret_cast<uint4*>(y + i * 8) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // 1x1 conv on <= 8 channels with arbitrary element strides (NCHW <-> NHWC), fp32.
 // ---------------------------------------------------------------------------------------------------------
 struct PwParams {
@@ -285,6 +321,20 @@ int dfw_cast_f32_to_16(const float* x, void* y, int y_f16, long long n, void* st
     DFW_REQUIRE(x && y && n > 0 && n % 8 == 0);
     cast_f32_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), n / 8, y_f16);
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_im2col3x3_small(const float* x, void* y, int y_f16, int N, int H, int W, int Cin, int Kpad, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 16);
+    DFW_REQUIRE(Kpad % 64 == 0 && Kpad >= 9 * Cin);
+    const long long total = static_cast<long long>(N) * H * W * (Kpad / 8);
+    im2col3x3_small_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, reinterpret_cast<uint16_t*>(y), total, H, W, Cin, Kpad, y_f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -99,54 +99,55 @@ __global__ void gn_stats_kernel(const void* __restrict__ x, float* __restrict__ 
     }
 }
 
-// stage 2: fold partials (fixed order, double), emit per-(image, channel) scale / shift.
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale_shift, int HW, int C,
-                                   int groups, int nchunks, float eps) {
-    __shared__ float s_mean[64], s_rstd[64];
-    const int n = blockIdx.x;
-    const int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double s = 0.0, ss = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-            const float* p = partial + ((static_cast<size_t>(n) * nchunks + c) * groups + g) * 2;
-            s += p[0]; ss += p[1];
-        }
-        const double cnt = static_cast<double>(HW) * cpg;
-        const double mean = s / cnt;
-        double var = ss / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = static_cast<float>(mean);
-        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float sc = s_rstd[g] * gamma[c];
-        scale_shift[(static_cast<size_t>(n) * C + c) * 2] = sc;
-        scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 1] = beta[c] - s_mean[g] * sc;
-    }
-}
-
-// stage 3: y = [silu](x * scale + shift).  Same (row-chunk, image) decomposition as stage 1: a thread owns 8 fixed
-// channels (scale / shift live in registers) and walks rows, so there is no per-vector index arithmetic.
+// stage 2: y = [silu](x * scale + shift).  Same (row-chunk, image) decomposition as stage 1: a thread owns 8 fixed
+// channels and walks rows, so there is no per-vector index arithmetic.  Every CTA first folds the stage-1 partials of
+// its image (fixed order -> deterministic; a few KB from L2) into mean / rstd per group — no separate finalize launch.
 template <int XD>
-__global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restrict__ scale_shift,
-                                void* __restrict__ y, int HW, int C, int rows_per_chunk, int RPI, int apply_silu,
-                                int y_f16) {
+__global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restrict__ partial,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                void* __restrict__ y, int HW, int C, int groups, int nchunks, float eps,
+                                int rows_per_chunk, int RPI, int apply_silu, int y_f16) {
+    __shared__ float s_red[8][64][2];
+    __shared__ float s_mean[64], s_rstd[64];
     const int V = C / 8;
     const int n = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / groups;
+    {
+        // 8 slices x groups threads (first 8*groups threads of the CTA; blockDim >= 128 whenever C >= 128*... else loop)
+        const int nthr = blockDim.x;
+        for (int idx = threadIdx.x; idx < 8 * groups; idx += nthr) {
+            const int g = idx % groups, sl = idx / groups;
+            float s = 0.f, ss = 0.f;
+            for (int c = sl; c < nchunks; c += 8) {
+                const float* pp = partial + ((static_cast<size_t>(n) * nchunks + c) * groups + g) * 2;
+                s += __ldg(pp); ss += __ldg(pp + 1);
+            }
+            s_red[sl][g][0] = s; s_red[sl][g][1] = ss;
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < groups; g += nthr) {
+            double s = 0.0, ss = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) { s += s_red[sl][g][0]; ss += s_red[sl][g][1]; }
+            const double cnt = static_cast<double>(HW) * cpg;
+            const double mean = s / cnt;
+            double var = ss / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[g] = static_cast<float>(mean);
+            s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        }
+        __syncthreads();
+    }
     const int vc = threadIdx.x % V, r = threadIdx.x / V;
     const int row0 = chunk * rows_per_chunk;
     const int row1 = min(HW, row0 + rows_per_chunk);
     float sc[8], sh[8];
-    {
-        const float4* sp = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + vc * 8) * 2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = __ldg(sp + j);           // (scale, shift, scale, shift)
-            sc[2 * j] = q.x; sh[2 * j] = q.y; sc[2 * j + 1] = q.z; sh[2 * j + 1] = q.w;
-        }
+    for (int j = 0; j < 8; ++j) {
+        const int c = vc * 8 + j;
+        const int g = c / cpg;
+        sc[j] = s_rstd[g] * __ldg(gamma + c);
+        sh[j] = __ldg(beta + c) - s_mean[g] * sc[j];
     }
     const long long img_off = static_cast<long long>(n) * HW * C + vc * 8;
     auto finish = [&](float (&v)[8], long long off) {
@@ -323,17 +324,16 @@ int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const flo
     float* partial = reinterpret_cast<float*>(workspace);
     size_t partial_elems = static_cast<size_t>(N) * pl.nchunks * groups * 2;
     partial_elems = (partial_elems + 63) / 64 * 64;
-    float* scale_shift = partial + partial_elems;
+    (void)partial_elems;
     dim3 grid(pl.nchunks, N);
     DFW_REQUIRE(pl.smem <= 48 * 1024);
 #define DFW_GN_LAUNCH(XD)                                                                                          \
     gn_stats_kernel<XD><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI); \
-    gn_finalize_kernel<<<N, 256, 0, stream>>>(partial, gamma, beta, scale_shift, HW, C, groups, pl.nchunks, eps);  \
-    gn_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, scale_shift, y, HW, C, pl.rows_per_chunk, pl.RPI,         \
-                                                          apply_silu, y_f16);
+    gn_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, partial, gamma, beta, y, HW, C, groups, pl.nchunks, eps,  \
+                                                          pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
     if (x_dtype == 1) { DFW_GN_LAUNCH(1) } else if (x_dtype == 2) { DFW_GN_LAUNCH(2) } else { DFW_GN_LAUNCH(0) }
 #undef DFW_GN_LAUNCH
-    g_launches.fetch_add(3);
+    g_launches.fetch_add(2);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }

@@ -58,6 +58,27 @@ class Conv:
                           bias_per_sample=bias_per_sample)
 
 
+class SmallCinConv:
+    """3x3 / pad 1 conv with Cin <= 16 reading the reference's NCHW fp32 tensor: im2col (K = 9*Cin padded to a multiple
+    of 64) + one tcgen05 GEMM.  conv_in / conv_in_ref of the UNet, conv_in of the VAE encoder / decoder."""
+
+    def __init__(self, sd, prefix, device, wdtype=bf16):
+        w = sd[prefix + ".weight"]
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        k = 9 * self.cin
+        self.kpad = (k + 63) // 64 * 64
+        wg = torch.zeros(self.cout, self.kpad, dtype=torch.float32)
+        wg[:, :k] = conv_weight_to_gemm(w.detach().float().cpu())
+        self.w = _dev(wg, device, wdtype)
+        self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
+        self.half = wdtype
+
+    def __call__(self, x_nchw, out_f32):
+        cols = ops.im2col3x3_small(x_nchw, self.kpad, self.half)
+        N, H, W, _ = cols.shape
+        return ops.linear(cols.view(N * H * W, self.kpad), self.w, self.b, out_f32=out_f32).view(N, H, W, self.cout)
+
+
 class Linear:
     def __init__(self, sd, prefix, device, geglu=False, wdtype=bf16):
         w = sd[prefix + ".weight"]

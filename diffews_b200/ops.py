@@ -159,6 +159,22 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
     return y
 
 
+def bmm_nt(x, w, bias=None, *, out_f32=False, out_scale=1.0):
+    """y[b] = x[b] @ w[b]^T (+ bias).  x [B, M, K] contiguous; w [B, Nout, K] with unit stride on K and arbitrary
+    row / batch strides (so a column slice of a wider buffer works)."""
+    assert x.dtype in OPERAND_DTYPES and w.dtype == x.dtype and x.is_cuda and x.is_contiguous()
+    B, M, K = x.shape
+    assert w.shape[0] == B and w.shape[2] == K and w.stride(2) == 1
+    Nout = w.shape[1]
+    flags = (EPI_F16 if x.dtype == f16 else 0) | (EPI_OUT_F32 if out_f32 else 0)
+    y = torch.empty((B, M, Nout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
+    if bias is not None: _req(bias, torch.float32, "bias")
+    with _Timed("igemm", 2.0 * B * M * K * Nout, f"bmm B{B} M{M} K{K} N{Nout} f{flags}"):
+        check(lib.dfw_bmm_nt(x.data_ptr(), w.data_ptr(), w.stride(1), w.stride(0), _ptr(bias), y.data_ptr(), B, M, K,
+                             Nout, flags, float(out_scale), _stream()), "dfw_bmm_nt")
+    return y
+
+
 def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
     """q [B,Lq,C]; k_self/v_self [B,Ls,C]; k_bank/v_bank [B,Lb,C] or None.  Tensors may be column slices of a wider
     (e.g. fused QKV) buffer: only the last dim must be unit-stride."""
@@ -288,6 +304,16 @@ def conv3x3_small_cin(x_nchw, w, bias, out_dtype=bf16):
     y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=out_dtype)
     check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), _xd(y), N, H, W,
                                     Cin, Cout, _stream()), "dfw_conv3x3_small_cin")
+    return y
+
+
+def im2col3x3_small(x_nchw, kpad, dtype=bf16):
+    """x fp32 NCHW [N,Cin,H,W] -> 16-bit [N,H,W,kpad] im2col rows (k = tap*Cin + c, zero padded)."""
+    _req(x_nchw, torch.float32, "x")
+    N, Cin, H, W = x_nchw.shape
+    y = torch.empty((N, H, W, kpad), device=x_nchw.device, dtype=dtype)
+    check(lib.dfw_im2col3x3_small(x_nchw.data_ptr(), y.data_ptr(), int(dtype == f16), N, H, W, Cin, kpad, _stream()),
+          "dfw_im2col3x3_small")
     return y
 
 

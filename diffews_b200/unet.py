@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 from .attention_processor import MyAttention
-from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, _dev
+from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, SmallCinConv, _dev
 
 bf16 = torch.bfloat16
 
@@ -99,11 +99,9 @@ class MyUNet2DConditionModel:
                                       attention_head_dim=tuple(heads), cross_attention_dim=cross_attention_dim,
                                       layers_per_block=2, norm_num_groups=32, norm_eps=1e-5, sample_size=96)
         self.dtype = torch.float32
-        # small-Cin input convs run on the direct kernel with fp32 weights [Cout,3,3,Cin]
-        self.conv_in_w = _dev(sd["conv_in.weight"].permute(0, 2, 3, 1), dev, torch.float32)
-        self.conv_in_b = _dev(sd["conv_in.bias"], dev, torch.float32)
-        self.conv_in_ref_w = _dev(sd["conv_in_ref.weight"].permute(0, 2, 3, 1), dev, torch.float32)
-        self.conv_in_ref_b = _dev(sd["conv_in_ref.bias"], dev, torch.float32)
+        # small-Cin input convs: im2col + tensor-core GEMM straight from the NCHW fp32 latents
+        self.conv_in = SmallCinConv(sd, "conv_in", dev, prec.half)
+        self.conv_in_ref = SmallCinConv(sd, "conv_in_ref", dev, prec.half)
         # time embedding: evaluated on the host in fp32 once per distinct timestep and folded into conv1 biases
         self._te = {k: sd[f"time_embedding.{k}"].detach().float().cpu()
                     for k in ("linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias")}
@@ -255,10 +253,10 @@ class MyUNet2DConditionModel:
 
         if is_target:                                                            # unet_2d_condition.py:1118-1121
             assert Cin == self.config.in_channels
-            h = ops.conv3x3_small_cin(x, self.conv_in_w, self.conv_in_b, out_dtype=sdt)
+            h = self.conv_in(x, out_f32=f32)
         else:
             assert Cin == self.config.in_channels_ref
-            h = ops.conv3x3_small_cin(x, self.conv_in_ref_w, self.conv_in_ref_b, out_dtype=sdt)
+            h = self.conv_in_ref(x, out_f32=f32)
 
         skips = [h]
         for blk in self.down:                                                    # :1154-1175

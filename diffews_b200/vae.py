@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .layers import Conv, GroupNorm, Linear, Precision, Resnet, _dev
+from .layers import Conv, GroupNorm, Linear, Precision, Resnet, SmallCinConv, _dev
 
 bf16 = torch.bfloat16
 
@@ -44,12 +44,11 @@ class VaeAttention:
         xn = self.norm(h, silu=False).view(N, L, C)
         q = self.to_q(xn)
         k = self.to_k(xn)
-        o = torch.empty((N, L, C), device=h.device, dtype=self.prec.half)
-        for n in range(N):
-            vt = ops.linear(self.wv, xn[n])                               # [C, L] = W_v @ X_n^T
-            s = ops.linear(q[n], k[n], out_f32=True)                      # [L, L] fp32 logits
-            p = ops.softmax_rows(s, self.scale, out_dtype=self.prec.half)
-            ops.linear(p, vt, self.bv, out=o[n])                          # P V + b_v
+        vt = ops.linear(self.wv, xn.view(N * L, C))                       # [C, N*L]: V^T of every image, side by side
+        vt = vt.view(C, N, L).permute(1, 0, 2)                            # [N, C, L] view (row stride N*L)
+        s = ops.bmm_nt(q, k, out_f32=True)                                # [N, L, L] fp32 logits, one launch
+        p = ops.softmax_rows(s, self.scale, out_dtype=self.prec.half)
+        o = ops.bmm_nt(p, vt, self.bv)                                    # P V + b_v, one launch
         y = self.to_out(o, residual=h.view(N, L, C), out_f32=self.prec.stream_f32)
         return y.view(N, H, W, C)
 
@@ -77,8 +76,7 @@ class AutoencoderKL:
         c = tuple(block_out_channels)
         self.config = SimpleNamespace(block_out_channels=c, latent_channels=4, scaling_factor=0.18215)
         # ---- encoder
-        self.enc_conv_in_w = _dev(sd["encoder.conv_in.weight"].permute(0, 2, 3, 1), dev, torch.float32)
-        self.enc_conv_in_b = _dev(sd["encoder.conv_in.bias"], dev, torch.float32)
+        self.enc_conv_in = SmallCinConv(sd, "encoder.conv_in", dev, prec.half)
         self.enc_down = []
         for i in range(4):
             blk = SimpleNamespace(
@@ -95,8 +93,7 @@ class AutoencoderKL:
         # ---- decoder
         self.post_quant_w = sd["post_quant_conv.weight"].detach().float().cpu()[:, :, 0, 0].contiguous()
         self.post_quant_b = sd["post_quant_conv.bias"].detach().float().cpu().contiguous()
-        self.dec_conv_in_w = _dev(sd["decoder.conv_in.weight"].permute(0, 2, 3, 1), dev, torch.float32)
-        self.dec_conv_in_b = _dev(sd["decoder.conv_in.bias"], dev, torch.float32)
+        self.dec_conv_in = SmallCinConv(sd, "decoder.conv_in", dev, prec.half)
         self.dec_mid = _Mid(sd, "decoder.mid_block", dev, prec)
         self.dec_up = []
         for i in range(4):
@@ -128,7 +125,7 @@ class AutoencoderKL:
         if H % 8 or W % 8:
             raise ValueError("image height/width must be multiples of 8")
         f32 = self.prec.stream_f32
-        h = ops.conv3x3_small_cin(x, self.enc_conv_in_w, self.enc_conv_in_b, out_dtype=self._sdt)
+        h = self.enc_conv_in(x, out_f32=f32)
         for blk in self.enc_down:
             for r in blk.resnets:
                 h = r(h)
@@ -154,7 +151,7 @@ class AutoencoderKL:
         zq = torch.empty_like(z)
         ops.pointwise_small(z, (Cz * hh * ww, 1, hh * ww), self.post_quant_w, self.post_quant_b, zq,
                             (Cz * hh * ww, 1, hh * ww), N, hh * ww, in_scale=in_scale, out_scale=1.0)
-        h = ops.conv3x3_small_cin(zq, self.dec_conv_in_w, self.dec_conv_in_b, out_dtype=self._sdt)
+        h = self.dec_conv_in(zq, out_f32=f32)
         h = self.dec_mid(h)
         for blk in self.dec_up:
             for r in blk.resnets:

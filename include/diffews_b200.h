@@ -66,6 +66,13 @@ int dfw_conv2d_igemm(const void* x, const void* w, const float* bias, int bias_s
 int dfw_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,
                int Nout, int flags, float out_scale, void* stream);
 
+/* Batched GEMM with per-batch "weights": y[b] (M x Nout) = epi(x[b] (M x K) @ w[b]^T + bias), w[b] element (n, k) at
+ * w[b*w_batch_stride + n*w_row_stride + k] (strides in elements, multiples of 8).  M >= 128, K % 64 == 0.
+ * ref: the single-head d=512 attention of the VAE mid block (diffusers Attention + AttnProcessor2_0, upstream),
+ *      reached from pipeline:852 / :901 — Q K^T (fp32 logits) and P V per image. */
+int dfw_bmm_nt(const void* x, const void* w, long long w_row_stride, long long w_batch_stride, const float* bias,
+               void* y, int B, int M, int K, int Nout, int flags, float out_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K1  KV-fused flash attention forward, head_dim 64, tcgen05 + TMEM + TMA.
  * ref: diffews/models/attention_processor.py:251-271 (MyXFormersAttnProcessor: key = cat([key_self, bank_folded]),
@@ -134,6 +141,10 @@ int dfw_cast_f32_to_16(const float* x, void* y, int y_f16, long long n, void* st
  *      VAE decoder conv_in (4->512) (upstream). */
 int dfw_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int y_dtype, int N, int H,
                           int W, int Cin, int Cout, void* stream);
+/* im2col for the same tiny-Cin 3x3 convolutions (Cin <= 16): x fp32 NCHW -> y 16-bit rows [N*H*W, Kpad],
+ * k = (kh*3+kw)*Cin + c, zero padded to Kpad (% 64 == 0); the convolution then is dfw_linear with K = Kpad and the
+ * weight matrix [Cout, Kpad] in the same k order (tensor cores instead of CUDA cores for the 3 -> 128 @ 512^2 layer). */
+int dfw_im2col3x3_small(const float* x, void* y, int y_f16, int N, int H, int W, int Cin, int Kpad, void* stream);
 /* 1x1 conv on <= 8 channels, fp32 math, arbitrary element strides (so it also converts NHWC <-> NCHW):
  *   y[n,p,co] = (sum_ci w[co,ci] * (x[n,p,ci] * in_scale) + b[co]) * out_scale
  *   x element (n,p,ci) at x[n*x_ns + p*x_ps + ci*x_cs]; y likewise.  w [Cout,Cin] and b [Cout] are HOST pointers

@@ -134,7 +134,8 @@ def conv_s1():
     from diffews_b200.weights import conv_weight_to_gemm
     for (N, H, W, Ci, Co, ks) in [(2, 16, 16, 128, 128, 3), (3, 8, 8, 64, 320, 3), (1, 64, 64, 320, 320, 3),
                                   (2, 32, 32, 640, 1280, 1), (1, 24, 40, 128, 256, 3), (2, 12, 12, 64, 128, 3),
-                                  (1, 128, 128, 128, 128, 3), (5, 8, 8, 1280, 1280, 3)]:
+                                  (1, 128, 128, 128, 128, 3), (5, 8, 8, 1280, 1280, 3),
+                                  (4, 256, 256, 128, 128, 3), (1, 593, 128, 64, 128, 3), (3, 200, 128, 128, 64, 1)]:
         x = _mk((N, H, W, Ci), 1, 1).bfloat16(); w = _mk((Co, Ci, ks, ks), (Ci * ks * ks) ** -0.5, 2).bfloat16()
         b = _mk((Co,), 1, 3)
         y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=ks)
@@ -149,6 +150,14 @@ def conv_s1():
     y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=3, residual=r, bias_per_sample=True)
     ref = _conv_ref(x, w, None) + b[:, None, None, :] + r.float()
     print("conv per-sample bias + res:", rel(y, ref)); assert rel(y, ref) < 6e-3
+    # paired-tile path (single Cout tile, many pixel tiles) with residual, 16-bit and fp32
+    N, H, W, Ci, Co = 2, 300, 256, 128, 128
+    x = _mk((N, H, W, Ci), 1, 1).bfloat16(); w = _mk((Co, Ci, 3, 3), (Ci * 9) ** -0.5, 2).bfloat16(); b = _mk((Co,), 1, 3)
+    r = _mk((N, H, W, Co), 1, 4)
+    y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=3, residual=r.bfloat16())
+    e = rel(y, _conv_ref(x, w, b) + r.bfloat16().float()); print("paired conv + bf16 res:", e); assert e < 6e-3
+    y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=3, residual=r, out_f32=True)
+    e = rel(y, _conv_ref(x, w, b) + r); print("paired conv + f32 res:", e); assert e < 1e-3
 
 
 @case
@@ -288,6 +297,34 @@ def misc():
     assert torch.equal(u, ref.clip(0, 255).to(torch.uint8)); print("seg_post ok")
     t = ops.nhwc_f32_to_nchw(dec, 4, 8, 8, scale=2.0)
     assert torch.equal(t, (dec[..., :4] * 2.0).permute(0, 2, 1).reshape(2, 4, 8, 8)); print("nhwc->nchw ok")
+
+
+@case
+def bmm_and_im2col():
+    import torch
+    import torch.nn.functional as F
+    from diffews_b200 import ops
+    B, M, K, N = 3, 512, 256, 384
+    x = _mk((B, M, K), 1, 1).half(); w = _mk((B, N, K), K ** -0.5, 2).half(); b = _mk((N,), 1, 3)
+    y = ops.bmm_nt(x, w, b, out_f32=True)
+    ref = torch.bmm(x.float(), w.float().transpose(1, 2)) + b
+    e = rel(y, ref); print("bmm_nt:", e); assert e < 1e-4
+    # strided per-batch weights: w[b] = big[:, b*N:(b+1)*N]^T slices of a [K2, B*L] buffer (the V^T layout of the VAE attention)
+    C, L = 128, 256
+    big = _mk((C, B * L), 1, 4).half()                      # [C, B*L]
+    vt = big.view(C, B, L).permute(1, 0, 2)                 # [B, C, L], row stride B*L
+    p = _mk((B, 384, L), 1, 5).half()
+    y = ops.bmm_nt(p, vt)
+    ref = torch.bmm(p.float(), vt.float().transpose(1, 2))
+    e = rel(y, ref); print("bmm_nt strided w:", e); assert e < 1.5e-3
+    from diffews_b200.layers import SmallCinConv
+    for (Nn, Ci, H, W, Co) in [(2, 3, 40, 72, 128), (2, 4, 16, 16, 320), (1, 8, 64, 64, 320), (2, 4, 24, 24, 512)]:
+        conv = torch.nn.Conv2d(Ci, Co, 3, padding=1)
+        xx = _mk((Nn, Ci, H, W), 1, 1)
+        layer = SmallCinConv({"c.weight": conv.weight.data, "c.bias": conv.bias.data}, "c", "cuda", torch.float16)
+        y = layer(xx, out_f32=True)
+        ref = F.conv2d(xx.cpu(), conv.weight.data, conv.bias.data, padding=1).permute(0, 2, 3, 1)
+        e = rel(y.cpu(), ref); print(f"im2col conv {Ci}->{Co}: {e:.2e}"); assert e < 1.5e-3
 
 
 @case

@@ -121,7 +121,7 @@ def test_vae_roundtrip_small_width(small_models, size):
     assert e <= 3e-2
 
 
-def _pipeline_parity(models, size, B, k, start=0):
+def _pipeline_parity(models, size, B, k, start=0, unet_precision=None):
     """Runs B episodes through the engine pipeline and each of them (bsz=1) through the oracle.
     Returns per episode: end-to-end mask agreement, end-to-end UNet-latent rel-L2 (inputs = images, i.e. including the
     bf16 VAE encoders) and the UNet-only rel-L2 (oracle UNet fed the engine's own latents = identical UNet inputs)."""
@@ -133,8 +133,8 @@ def _pipeline_parity(models, size, B, k, start=0):
     from oracle.metric import classify_prediction
     from oracle.pipeline import evaluate_episode
     unet_o, vae_o = models
-    pipe = MarigoldPipelineRGBLatentNoise(MyUNet2DConditionModel.from_module(unet_o), AutoencoderKL.from_module(vae_o),
-                                          text_embeds=prompt_embedding())
+    pipe = MarigoldPipelineRGBLatentNoise(MyUNet2DConditionModel.from_module(unet_o, precision=unet_precision),
+                                          AutoencoderKL.from_module(vae_o), text_embeds=prompt_embedding())
     batch = make_batch(start, B, size, k)
     out = pipe(pipeline_inputs(batch), denoising_steps=1, ensemble_size=1, processing_res=size, batch_size=B,
                show_progress_bar=False, mode="seg", rgb_paths=[], seed=0, output_type="pt")
@@ -189,3 +189,62 @@ def test_pipeline_full_size_512(full_models):
     agree, e2e_err, unet_err = _pipeline_parity(full_models, 512, 1, 1, start=3)
     print("full pipeline 512: mask agreement", agree, "e2e latent", e2e_err, "unet-only latent", unet_err)
     assert min(agree) >= 0.995 and max(unet_err) <= UNET_RTOL and max(e2e_err) <= 2e-2
+
+
+def test_pipeline_full_width_half_stream_128(full_models):
+    """Optional policy: UNet residual stream and conv->norm intermediates in fp16 as well (everything 16-bit)."""
+    from diffews_b200.layers import Precision
+    agree, e2e_err, unet_err = _pipeline_parity(full_models, 128, 2, 1, unet_precision=Precision(stream_f32=False, mid_f32=False))
+    print("full pipeline 128 (fp16 UNet stream): mask agreement", agree, "e2e latent", e2e_err, "unet-only latent", unet_err)
+    assert min(agree) >= 0.995 and max(unet_err) <= UNET_RTOL and max(e2e_err) <= 2e-2
+
+
+def test_runner_cuda_graph_equals_eager(small_models):
+    """EpisodeRunner: a graph replay gives the same per-episode counts and meter buffers as eager launches."""
+    from diffews_b200.runner import EpisodeRunner, build_engine_from_modules
+    from diffews_b200.synthetic import make_batch, prompt_embedding
+    pipe = build_engine_from_modules(small_models[0], small_models[1], prompt_embedding())
+    b0 = {k: v.cuda() for k, v in make_batch(0, 2, 64, 1).items()}
+    b1 = {k: v.cuda() for k, v in make_batch(2, 2, 64, 1).items()}
+    eager = EpisodeRunner(pipe, "coco", img_size=64)
+    e0 = [t.clone() for t in eager.step(b0)]
+    e1 = [t.clone() for t in eager.step(b1)]
+    graphed = EpisodeRunner(pipe, "coco", img_size=64)
+    graphed.enable_cuda_graph(b0)
+    g0 = [t.clone() for t in graphed.step(b0)]
+    g1 = [t.clone() for t in graphed.step(b1)]
+    torch.cuda.synchronize()
+    for a, b in zip(e0 + e1, g0 + g1):
+        assert torch.equal(a, b)
+    assert torch.equal(eager.meter.intersection_buf, graphed.meter.intersection_buf)
+    assert torch.equal(eager.meter.union_buf, graphed.meter.union_buf)
+    assert int(graphed.meter.union_buf.sum()) > 0
+    miou, fb, _ = graphed.finish()
+    assert 0.0 <= float(miou) <= 100.0 and 0.0 <= float(fb) <= 100.0
+
+
+def test_evaluator_dropin_matches_oracle():
+    """Evaluator.classify_prediction (reference signature, float masks, PASCAL ignore) == oracle, bit-exact."""
+    from diffews_b200.evaluation import AverageMeter, Evaluator
+    from oracle import metric as om
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 4, 96, 64
+    pred = (torch.rand(B, H, W, generator=g) > 0.5).float()
+    gt = (torch.rand(B, H, W, generator=g) > 0.7).float()
+    ign = ((torch.rand(B, H, W, generator=g) > 0.9) & (gt == 0)).float()
+    cls = torch.randint(0, 20, (B,), generator=g)
+    for ignore in (None, ign):
+        batch = {"query_mask": gt.clone()}
+        gbatch = {"query_mask": gt.cuda()}
+        if ignore is not None:
+            batch["query_ignore_idx"] = ignore.clone(); gbatch["query_ignore_idx"] = ignore.cuda()
+        oi, ou = om.classify_prediction(pred.clone(), batch)
+        gi, gu = Evaluator.classify_prediction(pred.cuda(), gbatch)
+        assert gi.dtype == torch.float32 and gi.shape == (2, B)
+        assert torch.equal(gi.cpu(), oi) and torch.equal(gu.cpu(), ou)
+    m = AverageMeter(benchmark="pascal", class_ids=range(20))
+    mo = om.AverageMeter("pascal", range(20), exact=True)
+    m.update(gi, gu, cls.cuda()); mo.update(oi, ou, cls)
+    assert torch.equal(m.intersection_buf.cpu(), mo.intersection_buf) and torch.equal(m.union_buf.cpu(), mo.union_buf)
+    a, b = m.compute_iou()[:2], mo.compute_iou()[:2]
+    assert abs(float(a[0]) - float(b[0])) < 1e-4 and abs(float(a[1]) - float(b[1])) < 1e-4
