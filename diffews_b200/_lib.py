@@ -23,6 +23,7 @@ SIGNATURES = {
     "dfw_launch_count": (_ll, []),
     "dfw_conv2d_igemm": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "dfw_upconv2x_igemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dfw_bmm_nt": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
                                   _i, _f, _i, _vp]),

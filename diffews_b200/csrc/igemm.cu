@@ -666,7 +666,10 @@ int launch_igemm(const IgemmMaps& maps, IgemmParams& p, cudaStream_t stream) {
 int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sample_stride, const void* residual,
                    void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode,
                    int flags, float out_scale, cudaStream_t stream, long long w_row_stride = 0,
-                   long long w_batch_stride = 0) {
+                   long long w_batch_stride = 0, int up_phase = -1) {
+    // up_phase >= 0: this launch computes output phase (ph, pw) = (up_phase / 2, up_phase % 2) of a
+    // "nearest-2x upsample -> 3x3 conv": a 2x2-tap convolution over the LOW-resolution input x (weights pre-summed
+    // on the host, K order = (a*2 + b)*Cin + c), written to y[:, ph::2, pw::2, :] of the [N, 2H, 2W, Cout] output.
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(x && w && y);
@@ -685,7 +688,8 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     const int Hout = Hin / stride, Wout = Win / stride;
     p.N = N; p.H = Hout; p.W = Wout; p.Cout = Cout;
     p.kb_per_tap = Cin / BLOCK_K;
-    p.ntaps = ksize * ksize;
+    p.ntaps = (up_phase >= 0) ? 4 : ksize * ksize;
+    if (up_phase >= 0) DFW_REQUIRE(ksize == 3 && stride == 1 && pad_mode == 0 && residual == nullptr);
     choose_tile(Wout, Hout, N, p.TW, p.TH, p.TN);
     if (w_batch_stride > 0 && p.TN != 1) {       // per-image weights: a tile must not straddle images
         p.TN = 1;
@@ -711,11 +715,20 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
         if (rc != DFW_OK) return rc;
         for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
         const int pad = (ksize - 1) / 2;
-        for (int kh = 0; kh < ksize; ++kh)
-            for (int kw = 0; kw < ksize; ++kw) {
-                const int t = kh * ksize + kw;
-                p.tap_map[t] = 0; p.tap_dh[t] = kh - pad; p.tap_dw[t] = kw - pad;
-            }
+        if (up_phase >= 0) {
+            const int ph = up_phase >> 1, pw = up_phase & 1;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    const int t = a * 2 + b;
+                    p.tap_map[t] = 0; p.tap_dh[t] = a + ph - 1; p.tap_dw[t] = b + pw - 1;
+                }
+        } else {
+            for (int kh = 0; kh < ksize; ++kh)
+                for (int kw = 0; kw < ksize; ++kw) {
+                    const int t = kh * ksize + kw;
+                    p.tap_map[t] = 0; p.tap_dh[t] = kh - pad; p.tap_dw[t] = kw - pad;
+                }
+        }
     } else {
         // stride 2: four phase views x[:, ph::2, pw::2, :] of the input, each a plain stride-1 TMA tensor.
         const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win / 2),
@@ -770,7 +783,20 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
                         (residual == nullptr || (res_f32 == out_f32 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
         p.tma_epi = ok ? 1 : 0;
         p.has_res = (ok && residual != nullptr) ? 1 : 0;
-        if (ok) {
+        if (up_phase >= 0) DFW_REQUIRE(ok);          // the strided phase view is only reachable through the TMA store
+        if (ok && up_phase >= 0) {
+            const int ph = up_phase >> 1, pw = up_phase & 1;
+            const uint64_t W2 = 2ull * Wout, H2 = 2ull * Hout;
+            const uint64_t dims[4] = {static_cast<uint64_t>(p.out_ch), static_cast<uint64_t>(Wout),
+                                      static_cast<uint64_t>(Hout), static_cast<uint64_t>(N)};
+            const uint64_t strides[3] = {2 * p.out_ch * oesz, 2 * W2 * p.out_ch * oesz, H2 * W2 * p.out_ch * oesz};
+            const uint32_t obox[4] = {static_cast<uint32_t>(64 / oesz), static_cast<uint32_t>(p.TW),
+                                      static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+            uint8_t* base = reinterpret_cast<uint8_t*>(y) + (static_cast<uint64_t>(ph) * W2 + pw) * p.out_ch * oesz;
+            rc = encode_tmap(&maps.out, base, static_cast<int>(oesz), 64, 4, dims, strides, obox);
+            if (rc != DFW_OK) return rc;
+            maps.res = maps.out;
+        } else if (ok) {
             const uint64_t dims[4] = {static_cast<uint64_t>(p.out_ch), static_cast<uint64_t>(Wout),
                                       static_cast<uint64_t>(Hout), static_cast<uint64_t>(N)};
             const uint64_t strides[3] = {p.out_ch * oesz, static_cast<uint64_t>(Wout) * p.out_ch * oesz,
@@ -813,6 +839,19 @@ int dfw_conv2d_igemm(const void* x, const void* w, const float* bias, int bias_s
                      int flags, float out_scale, void* stream) {
     return dfw::igemm_dispatch(x, w, bias, bias_sample_stride, residual, y, N, Hin, Win, Cin, Cout, ksize, stride,
                                pad_mode, flags, out_scale, static_cast<cudaStream_t>(stream));
+}
+
+int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y, int N, int Hin, int Win, int Cin,
+                       int Cout, int flags, void* stream) {
+    // four phase convolutions (2x2 taps each) = nearest-2x upsample followed by a 3x3 / pad 1 convolution
+    const size_t esz = 2;
+    for (int phase = 0; phase < 4; ++phase) {
+        const uint8_t* wp = reinterpret_cast<const uint8_t*>(w4) + static_cast<size_t>(phase) * Cout * 4 * Cin * esz;
+        int rc = dfw::igemm_dispatch(x, wp, bias, 0, nullptr, y, N, Hin, Win, Cin, Cout, 3, 1, 0, flags, 1.0f,
+                                     static_cast<cudaStream_t>(stream), 0, 0, phase);
+        if (rc != DFW_OK) return rc;
+    }
+    return DFW_OK;
 }
 
 int dfw_bmm_nt(const void* x, const void* w, long long w_row_stride, long long w_batch_stride, const float* bias,

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import torch
 
 from . import ops
-from .weights import conv_weight_to_gemm, geglu_permute
+from .weights import conv_weight_to_gemm, geglu_permute, upconv_phase_weights
 
 bf16 = torch.bfloat16
 
@@ -56,6 +56,18 @@ class Conv:
         return ops.conv2d(x, self.w, self.b if bias is None else bias, ksize=self.ksize, stride=self.stride,
                           pad_mode=self.pad_mode, residual=residual, out_f32=out_f32, out_scale=out_scale,
                           bias_per_sample=bias_per_sample)
+
+
+class UpsampleConv:
+    """diffusers Upsample2D (nearest 2x + 3x3 conv) as four 2x2-tap phase convolutions (weights.upconv_phase_weights)."""
+
+    def __init__(self, sd, prefix, device, wdtype=bf16):
+        self.w4 = _dev(upconv_phase_weights(sd[prefix + ".weight"]), device, wdtype)
+        self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
+        self.half = wdtype
+
+    def __call__(self, h, out_f32):
+        return ops.upconv2x(ops.cast16(h, self.half), self.w4, self.b, out_f32=out_f32)
 
 
 class SmallCinConv:

@@ -159,6 +159,22 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
     return y
 
 
+def upconv2x(x, w4, bias=None, *, out_f32=False):
+    """nearest-2x upsample + 3x3 conv, fused: x 16-bit [N,H,W,Cin]; w4 [4,Cout,4*Cin] -> [N,2H,2W,Cout]."""
+    assert x.dtype in OPERAND_DTYPES and w4.dtype == x.dtype
+    _req(x, x.dtype, "x"); _req(w4, w4.dtype, "w4")
+    N, H, W, Cin = x.shape
+    Cout = w4.shape[1]
+    assert w4.shape == (4, Cout, 4 * Cin)
+    flags = (EPI_F16 if x.dtype == f16 else 0) | (EPI_OUT_F32 if out_f32 else 0)
+    y = torch.empty((N, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
+    if bias is not None: _req(bias, torch.float32, "bias")
+    with _Timed("igemm", 2.0 * N * H * W * 16 * Cin * Cout, f"upconv N{N} {H}x{W} {Cin}->{Cout} f{flags}"):
+        check(lib.dfw_upconv2x_igemm(x.data_ptr(), w4.data_ptr(), _ptr(bias), y.data_ptr(), N, H, W, Cin, Cout,
+                                     flags, _stream()), "dfw_upconv2x_igemm")
+    return y
+
+
 def bmm_nt(x, w, bias=None, *, out_f32=False, out_scale=1.0):
     """y[b] = x[b] @ w[b]^T (+ bias).  x [B, M, K] contiguous; w [B, Nout, K] with unit stride on K and arbitrary
     row / batch strides (so a column slice of a wider buffer works)."""

@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 from .attention_processor import MyAttention
-from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, SmallCinConv, _dev
+from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, SmallCinConv, UpsampleConv, _dev
 
 bf16 = torch.bfloat16
 
@@ -144,7 +144,7 @@ class MyUNet2DConditionModel:
                 if i > 0:
                     blk.attns.append(tfm(f"up_blocks.{i}.attentions.{j}", rh[i]))
             if i < 3:
-                blk.up = Conv(sd, f"up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half)
+                blk.up = UpsampleConv(sd, f"up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half)
             self.up.append(blk)
         self.conv_norm_out = GroupNorm(sd, "conv_norm_out", dev, eps=1e-5, out_dtype=prec.half)
         self.conv_out = Conv(sd, "conv_out", dev, wdtype=prec.half)
@@ -277,7 +277,7 @@ class MyUNet2DConditionModel:
                 if blk.attns:
                     h = blk.attns[j](h, next(kvs))
             if blk.up is not None:
-                h = blk.up(ops.upsample2x(h, half), out_f32=f32)
+                h = blk.up(h, out_f32=f32)
         h = self.conv_norm_out(h, silu=True)                                     # :1246-1249
         y = self.conv_out(h, out_f32=True)                                       # [N,H,W,4] fp32
         out = ops.nhwc_f32_to_nchw(y.view(N, H * W, 4), 4, H, W)

@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .layers import Conv, GroupNorm, Linear, Precision, Resnet, SmallCinConv, _dev
+from .layers import Conv, GroupNorm, Linear, Precision, Resnet, SmallCinConv, UpsampleConv, _dev
 
 bf16 = torch.bfloat16
 
@@ -99,7 +99,7 @@ class AutoencoderKL:
         for i in range(4):
             blk = SimpleNamespace(
                 resnets=[Resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(3)],
-                up=Conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half) if i < 3 else None)
+                up=UpsampleConv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half) if i < 3 else None)
             self.dec_up.append(blk)
         self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half)
         self.dec_conv_out = Conv(sd, "decoder.conv_out", dev, wdtype=prec.half)
@@ -157,7 +157,7 @@ class AutoencoderKL:
             for r in blk.resnets:
                 h = r(h)
             if blk.up is not None:
-                h = blk.up(ops.upsample2x(h, self.prec.half), out_f32=f32)
+                h = blk.up(h, out_f32=f32)
         h = self.dec_norm_out(h, silu=True)
         y = self.dec_conv_out(h, out_f32=True)                                   # [N,H,W,3] fp32
         return y.view(N, y.shape[1] * y.shape[2], 3)

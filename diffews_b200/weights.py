@@ -23,3 +23,23 @@ def geglu_permute(w: torch.Tensor, b: torch.Tensor | None, block: int = 128):
     wp = w.index_select(0, idx).contiguous()
     bp = b.index_select(0, idx).contiguous() if b is not None else None
     return wp, bp
+
+
+def upconv_phase_weights(w_oihw: torch.Tensor) -> torch.Tensor:
+    """Weights of `nearest-2x upsample -> 3x3 conv (pad 1)` collapsed per output phase.
+
+    For output row 2i+ph the three kernel rows read input rows {i-1, i, i} (ph = 0) or {i, i, i+1} (ph = 1), so along
+    each axis the 3 taps fold into 2:  ph = 0 -> [W0, W1+W2] at input offsets (-1, 0);  ph = 1 -> [W0+W1, W2] at
+    offsets (0, +1).  Returns fp32 [4, Cout, 4*Cin] with phase = ph*2+pw and K index = (a*2+b)*Cin + c."""
+    w = w_oihw.detach().float()
+    co, ci = w.shape[0], w.shape[1]
+
+    def fold(t, phase, dim):
+        a, b, c = t.unbind(dim)
+        return torch.stack([a, b + c], dim) if phase == 0 else torch.stack([a + b, c], dim)
+    out = []
+    for ph in range(2):
+        for pw in range(2):
+            f = fold(fold(w, ph, 2), pw, 3)                      # [co, ci, 2, 2]
+            out.append(f.permute(0, 2, 3, 1).reshape(co, 4 * ci))
+    return torch.stack(out, 0).contiguous()

@@ -66,6 +66,16 @@ int dfw_conv2d_igemm(const void* x, const void* w, const float* bias, int bias_s
 int dfw_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,
                int Nout, int flags, float out_scale, void* stream);
 
+/* Nearest-2x upsample fused with the 3x3 / pad 1 convolution that follows it (diffusers Upsample2D: F.interpolate(
+ * scale_factor=2, "nearest") -> conv, upstream; UNet up blocks unet_2d_condition.py:1226, VAE decoder pipeline:901).
+ * Each output phase (oh%2, ow%2) only ever sees 2x2 distinct input pixels, so the 9 taps collapse into 4 with
+ * pre-summed weights: 2.25x fewer FLOPs and the 4x larger upsampled tensor is never written.
+ *   x  16-bit [N, Hin, Win, Cin];  y 16-bit / fp32 [N, 2Hin, 2Win, Cout]  (Cout*elem % 16 == 0)
+ *   w4 16-bit [4 phases (ph*2+pw)][Cout][(a*2+b)*Cin + c] with, per axis, phase 0: {W[0], W[1]+W[2]},
+ *      phase 1: {W[0]+W[1], W[2]} (see diffews_b200/weights.py::upconv_phase_weights). */
+int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y, int N, int Hin, int Win, int Cin,
+                       int Cout, int flags, void* stream);
+
 /* Batched GEMM with per-batch "weights": y[b] (M x Nout) = epi(x[b] (M x K) @ w[b]^T + bias), w[b] element (n, k) at
  * w[b*w_batch_stride + n*w_row_stride + k] (strides in elements, multiples of 8).  M >= 128, K % 64 == 0.
  * ref: the single-head d=512 attention of the VAE mid block (diffusers Attention + AttnProcessor2_0, upstream),

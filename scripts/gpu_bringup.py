@@ -328,6 +328,22 @@ def bmm_and_im2col():
 
 
 @case
+def upconv():
+    import torch
+    import torch.nn.functional as F
+    from diffews_b200 import ops
+    from diffews_b200.weights import upconv_phase_weights
+    for (N, H, W, Ci, Co, dt, f32) in [(2, 16, 16, 128, 128, torch.float16, False), (1, 24, 40, 256, 256, torch.bfloat16, False),
+                                       (3, 8, 8, 1280, 1280, torch.float16, True), (2, 64, 64, 512, 512, torch.float16, False)]:
+        x = _mk((N, H, W, Ci), 1, 1).to(dt); w = _mk((Co, Ci, 3, 3), (Ci * 9) ** -0.5, 2).to(dt); b = _mk((Co,), 1, 3)
+        y = ops.upconv2x(x, upconv_phase_weights(w).cuda().to(dt), b, out_f32=f32)
+        ref = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), w.float(), b,
+                       padding=1).permute(0, 2, 3, 1)
+        e = rel(y, ref); print(f"upconv N{N} {H}x{W} {Ci}->{Co} {dt}: rel {e:.3e}")
+        assert y.shape == ref.shape and e < (6e-3 if dt == torch.bfloat16 else 1.5e-3)
+
+
+@case
 def rthres():
     import torch
     from diffews_b200 import ops
