@@ -189,13 +189,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
                 mbar_wait(s_full(x), j & 1, 15);
                 tc_fence_after();
-                // pass 1: row max of the scaled logits
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(ts + c * 32, v);
-                    tmem_ld_wait();
+                // The TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is
+                // processed (tcgen05.wait::ld waits for everything outstanding, so it is placed after the compute).
+                uint32_t va[32], vb[32];
+                auto chunk_max = [&](const uint32_t (&v)[32], int c, float& mx) {
                     if (valid == ATT_N) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
@@ -204,7 +201,23 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                         for (int i = 0; i < 32; ++i)
                             if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
                     }
-                }
+                };
+                // pass 1: row max of the scaled logits
+                float mx = -INFINITY;
+                tmem_ld_32x32(ts, va);
+                tmem_ld_wait(); tmem_regs_ready(va);
+                tmem_ld_32x32(ts + 32, vb);
+                chunk_max(va, 0, mx);
+                tmem_ld_wait(); tmem_regs_ready(vb);
+                tmem_ld_32x32(ts + 64, va);
+                chunk_max(vb, 1, mx);
+                tmem_ld_wait(); tmem_regs_ready(va);
+                tmem_ld_32x32(ts + 96, vb);
+                chunk_max(va, 2, mx);
+                tmem_ld_wait(); tmem_regs_ready(vb);
+                tmem_ld_32x32(ts, va);                               // chunk 0 again, for pass 2
+                chunk_max(vb, 3, mx);
+                tmem_ld_wait(); tmem_regs_ready(va);
                 const float m_new = fmaxf(m_used, mx * p.scale_log2);
                 // lazy rescale: only when some row of the warp moved its max by more than 2^TAU (warp-uniform branch,
                 // tcgen05.ld/st are warp-collective)
@@ -229,11 +242,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 }
                 // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile
                 float psum = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(ts + c * 32, v);
-                    tmem_ld_wait();
+                auto chunk_p = [&](const uint32_t (&v)[32], int c) {
                     float pf[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -253,7 +262,17 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                         const int unit = ((c & 1) * 4 + u) ^ (row & 7);
                         *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
                     }
-                }
+                };
+                tmem_ld_32x32(ts + 32, vb);
+                chunk_p(va, 0);
+                tmem_ld_wait(); tmem_regs_ready(vb);
+                tmem_ld_32x32(ts + 64, va);
+                chunk_p(vb, 1);
+                tmem_ld_wait(); tmem_regs_ready(va);
+                tmem_ld_32x32(ts + 96, vb);
+                chunk_p(va, 2);
+                tmem_ld_wait(); tmem_regs_ready(vb);
+                chunk_p(vb, 3);
                 l_run += psum;
                 fence_proxy_async_smem();
                 tc_fence_before();

@@ -56,6 +56,9 @@ struct IgemmParams {
     float out_scale;
     int flags;
     int w_batched;    // 1: per-image weights (batched GEMM): the B tensor map's 3rd coordinate is the image index
+    float* gn_partial; // optional: per-(image, CTA, group) partial (sum, sumsq) of y for the GroupNorm that consumes y
+    int gn_cpg;        // channels per group of that GroupNorm (must divide the chunk width; TN == 1)
+    long long gn_img_stride;   // floats between consecutive images in gn_partial (slot of this CTA: + blockIdx.x * 64)
     int tma_epi;      // 1: epilogue stages 64-byte-wide column chunks in smem and uses TMA stores / residual TMA loads
     int has_res;
 };
@@ -75,13 +78,59 @@ struct IgemmCfg {
     static constexpr int ACC_COLS = TPU * SUB_COLS;          // TMEM columns of one work unit's accumulators
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS <= 512, "TMEM budget");
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int GN_BYTES = 4 * 64 * 4;      // per-epilogue-warp GroupNorm partial sums (32 groups x 2)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + GN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// Butterfly reduce-scatter over the warp: on return v[0] of lane l holds the sum over all 32 lanes of element
+// (l >> (5 - log2 NV)) of the input vectors.  NV + ... shuffles instead of 5 * NV for NV independent all-reduces.
+template <int NV>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[NV], int lane) {
+    int bit = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half /= 2, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    float r = v[0];
+    for (; bit >= 1; bit >>= 1) r += __shfl_xor_sync(0xffffffffu, r, bit);
+    return r;
+}
+
+// GroupNorm partial statistics of one epilogue chunk: f[0..CW) are the final output values of this thread's row for
+// channels [col0, col0 + CW); CPG channels per group.  Each warp owns 64 floats of smem (32 groups x (sum, sumsq)).
+template <int CPG, int CW>
+__device__ __forceinline__ void gn_chunk_stats(const float (&f)[32], bool row_valid, int col0, int lane, float* wacc) {
+    constexpr int G = CW / CPG;
+    constexpr int NV = 2 * G;
+    float v[NV];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPG; ++i) { const float x = f[g * CPG + i]; s += x; ss = fmaf(x, x, ss); }
+        v[g] = row_valid ? s : 0.f;
+        v[G + g] = row_valid ? ss : 0.f;
+    }
+    const float r = warp_reduce_scatter<NV>(v, lane);
+    constexpr int LPV = 32 / NV;                       // lanes holding the same element
+    if ((lane & (LPV - 1)) == 0) {
+        const int idx = lane / LPV;                    // 0..NV-1 : [0,G) sums, [G,2G) sums of squares
+        const int g = idx % G, k = idx / G;
+        float* slot = wacc + ((col0 / CPG + g) * 2 + k);
+        *slot += r;
+    }
+}
 
 struct TileCoord {
     int n_tile, n0, h0, w0;
@@ -240,7 +289,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const uint32_t smem_raw_u32 = smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
     const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;          // staging + row table
-    const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+    const uint32_t gn_base = epi_base + Cfg::EPI_BYTES;
+    const uint32_t bar_base = gn_base + Cfg::GN_BYTES;
     auto sA = [&](int s, int sub) { return smem_base + s * Cfg::STAGE_BYTES + sub * A_TILE_BYTES; };
     auto sB = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + TPU * A_TILE_BYTES; };
     const int units = (p.total_tiles + TPU - 1) / TPU;
@@ -384,6 +434,27 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const bool issuer = (threadIdx.x == 128);
         const uint32_t row_off = static_cast<uint32_t>(row) * 64u;
         const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);          // SWIZZLE_64B: unit ^= (row/2) % 4
+        // fused GroupNorm statistics of the output (consumed by the next layer's GroupNorm): per-warp smem partials,
+        // flushed to gn_partial[image][cta][group][2] whenever the CTA moves on to another image (TN == 1)
+        float* wacc_all = reinterpret_cast<float*>(smem_raw + (gn_base - smem_raw_u32));
+        float* wacc = wacc_all + q * 64;
+        const int gn_th = row / p.TW, gn_tw = row % p.TW;
+        int gn_img = -1;
+        auto gn_flush = [&](int img) {
+            named_bar_sync(1, 128);
+            const int e = threadIdx.x - 128;
+            if (e < 64) {
+                const float tot = (wacc_all[e] + wacc_all[64 + e]) + (wacc_all[128 + e] + wacc_all[192 + e]);
+                p.gn_partial[static_cast<size_t>(img) * p.gn_img_stride + blockIdx.x * 64 + e] = tot;
+            }
+            named_bar_sync(1, 128);
+            if (lane < 32) { wacc[lane] = 0.f; wacc[32 + lane] = 0.f; }
+            __syncwarp();
+        };
+        if (p.gn_partial != nullptr) {          // (the host zero-fills gn_partial: CTAs write only the images they touch)
+            wacc[lane] = 0.f; wacc[32 + lane] = 0.f;
+            __syncwarp();
+        }
         int acc = 0;
         uint32_t acc_phase = 0, g = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -391,6 +462,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             tc_fence_after();
           for (int t = u * TPU; t < min(u * TPU + TPU, p.total_tiles); ++t) {
             const TileCoord tc = decode_tile(p, t);
+            bool gn_row_valid = false;
+            if (p.gn_partial != nullptr) {
+                if (tc.n0 != gn_img) {
+                    if (gn_img >= 0) gn_flush(gn_img);
+                    gn_img = tc.n0;
+                }
+                gn_row_valid = (tc.h0 + gn_th < p.H) && (tc.w0 + gn_tw < p.W);
+            }
             const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + (t - u * TPU) * Cfg::SUB_COLS +
                                    (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
@@ -477,6 +556,17 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     __syncwarp();
                     if (lane == 0) mbar_arrive(res_empty(b));
                 }
+                if (p.gn_partial != nullptr && col_out0 < p.out_ch) {
+                    if (out_f32) {
+                        if (p.gn_cpg == 4) gn_chunk_stats<4, 16>(f, gn_row_valid, col_out0, lane, wacc);
+                        else if (p.gn_cpg == 8) gn_chunk_stats<8, 16>(f, gn_row_valid, col_out0, lane, wacc);
+                        else gn_chunk_stats<16, 16>(f, gn_row_valid, col_out0, lane, wacc);
+                    } else {
+                        if (p.gn_cpg == 4) gn_chunk_stats<4, 32>(f, gn_row_valid, col_out0, lane, wacc);
+                        else if (p.gn_cpg == 8) gn_chunk_stats<8, 32>(f, gn_row_valid, col_out0, lane, wacc);
+                        else gn_chunk_stats<16, 32>(f, gn_row_valid, col_out0, lane, wacc);
+                    }
+                }
                 // the store issued two chunks ago (same buffer) must have finished reading smem
                 if (issuer) tma_store_wait_read<1>();
                 named_bar_sync(1, 128);
@@ -508,6 +598,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if (p.gn_partial != nullptr && gn_img >= 0) gn_flush(gn_img);
         if (issuer) tma_store_wait_all<0>();
     } else if (warp >= 4) {
         const int q = warp - 4;
@@ -666,7 +757,8 @@ int launch_igemm(const IgemmMaps& maps, IgemmParams& p, cudaStream_t stream) {
 int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sample_stride, const void* residual,
                    void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode,
                    int flags, float out_scale, cudaStream_t stream, long long w_row_stride = 0,
-                   long long w_batch_stride = 0, int up_phase = -1) {
+                   long long w_batch_stride = 0, int up_phase = -1, float* gn_partial = nullptr, int gn_groups = 0,
+                   long long gn_img_stride = 0) {
     // up_phase >= 0: this launch computes output phase (ph, pw) = (up_phase / 2, up_phase % 2) of a
     // "nearest-2x upsample -> 3x3 conv": a 2x2-tap convolution over the LOW-resolution input x (weights pre-summed
     // on the host, K order = (a*2 + b)*Cin + c), written to y[:, ph::2, pw::2, :] of the [N, 2H, 2W, Cout] output.
@@ -783,6 +875,17 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
                         (residual == nullptr || (res_f32 == out_f32 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0));
         p.tma_epi = ok ? 1 : 0;
         p.has_res = (ok && residual != nullptr) ? 1 : 0;
+        p.gn_partial = nullptr;
+        p.gn_cpg = 0;
+        if (gn_partial != nullptr) {
+            // fused GroupNorm statistics: TMA epilogue, one image per tile, channels-per-group in {4, 8, 16}
+            DFW_REQUIRE(ok && p.TN == 1 && gn_groups == 32 && p.out_ch % 32 == 0 && !geglu);
+            const int cpg = p.out_ch / 32;
+            DFW_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16);
+            p.gn_partial = gn_partial;
+            p.gn_cpg = cpg;
+            p.gn_img_stride = gn_img_stride > 0 ? gn_img_stride : static_cast<long long>(sm_count()) * 64;
+        }
         if (up_phase >= 0) DFW_REQUIRE(ok);          // the strided phase view is only reachable through the TMA store
         if (ok && up_phase >= 0) {
             const int ph = up_phase >> 1, pw = up_phase & 1;
@@ -842,16 +945,45 @@ int dfw_conv2d_igemm(const void* x, const void* w, const float* bias, int bias_s
 }
 
 int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y, int N, int Hin, int Win, int Cin,
-                       int Cout, int flags, void* stream) {
+                       int Cout, int flags, float* gn_partial, void* stream) {
     // four phase convolutions (2x2 taps each) = nearest-2x upsample followed by a 3x3 / pad 1 convolution
     const size_t esz = 2;
+    // partial layout [N][4 phases x #SMs][32][2]: each phase launch owns a slice of #SMs slots inside every image
+    const long long slots = 4LL * dfw::sm_count();
+    if (gn_partial) {
+        if (cudaMemsetAsync(gn_partial, 0, static_cast<size_t>(N) * slots * 64 * sizeof(float),
+                            static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
+    }
     for (int phase = 0; phase < 4; ++phase) {
         const uint8_t* wp = reinterpret_cast<const uint8_t*>(w4) + static_cast<size_t>(phase) * Cout * 4 * Cin * esz;
         int rc = dfw::igemm_dispatch(x, wp, bias, 0, nullptr, y, N, Hin, Win, Cin, Cout, 3, 1, 0, flags, 1.0f,
-                                     static_cast<cudaStream_t>(stream), 0, 0, phase);
+                                     static_cast<cudaStream_t>(stream), 0, 0, phase,
+                                     gn_partial ? gn_partial + static_cast<size_t>(phase) * dfw::sm_count() * 64 : nullptr,
+                                     gn_partial ? 32 : 0, slots * 64);
         if (rc != DFW_OK) return rc;
     }
     return DFW_OK;
+}
+
+int dfw_conv_gnstats_supported(int N, int Hout, int Wout, int Cout) {
+    if (N <= 0 || Hout <= 0 || Wout <= 0 || Cout % 32 != 0) return 0;
+    const int cpg = Cout / 32;
+    if (cpg != 4 && cpg != 8 && cpg != 16) return 0;
+    int TW, TH, TN;
+    dfw::choose_tile(Wout, Hout, N, TW, TH, TN);
+    return TN == 1 ? 1 : 0;
+}
+
+long long dfw_gn_partial_floats(int N) { return N > 0 ? static_cast<long long>(N) * dfw::sm_count() * 64 : -1; }
+
+int dfw_conv2d_igemm_gnstats(const void* x, const void* w, const float* bias, const void* residual, void* y, int N,
+                             int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode, int flags,
+                             float out_scale, float* gn_partial, void* stream) {
+    if (gn_partial == nullptr) return DFW_ERR_INVALID;
+    if (cudaMemsetAsync(gn_partial, 0, static_cast<size_t>(N) * dfw::sm_count() * 64 * sizeof(float),
+                        static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
+    return dfw::igemm_dispatch(x, w, bias, 0, residual, y, N, Hin, Win, Cin, Cout, ksize, stride, pad_mode, flags,
+                               out_scale, static_cast<cudaStream_t>(stream), 0, 0, -1, gn_partial, 32);
 }
 
 int dfw_bmm_nt(const void* x, const void* w, long long w_row_stride, long long w_batch_stride, const float* bias,

@@ -338,6 +338,28 @@ int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const flo
     return DFW_OK;
 }
 
+int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial, int nchunks, const float* gamma,
+                               const float* beta, void* y, int y_f16, int N, int HW, int C, int groups, float eps,
+                               int apply_silu, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(x && partial && gamma && beta && y && nchunks > 0);
+    DFW_REQUIRE(x_dtype >= 0 && x_dtype <= 2);
+    DFW_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0 && C / 8 <= 1024);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    GnPlan pl = gn_plan(N, HW, C);
+    dim3 grid(pl.nchunks, N);
+#define DFW_GN_APPLY(XD)                                                                                            \
+    gn_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, partial, gamma, beta, y, HW, C, groups, nchunks, eps,      \
+                                                          pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
+    if (x_dtype == 1) { DFW_GN_APPLY(1) } else if (x_dtype == 2) { DFW_GN_APPLY(2) } else { DFW_GN_APPLY(0) }
+#undef DFW_GN_APPLY
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
 int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int M, int C,
                   float eps, void* stream_) {
     using namespace dfw;

@@ -221,6 +221,17 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+// Compiler-level fence for software-pipelined TMEM loads: an empty volatile asm that "redefines" the 32 destination
+// registers.  Placed right after tcgen05.wait::ld it keeps nvcc from scheduling arithmetic on those registers above
+// the wait (volatile asms keep their relative order; plain register arithmetic otherwise may move across them).
+__device__ __forceinline__ void tmem_regs_ready(uint32_t (&v)[32]) {
+    asm volatile(""
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+          "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+          "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+          "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
+}
 // registers -> TMEM, 32 lanes x 32 columns
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(

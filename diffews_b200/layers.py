@@ -52,10 +52,11 @@ class Conv:
         self.w = _dev(conv_weight_to_gemm(w), device, wdtype)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
 
-    def __call__(self, x, *, bias=None, bias_per_sample=False, residual=None, out_f32=False, out_scale=1.0):
+    def __call__(self, x, *, bias=None, bias_per_sample=False, residual=None, out_f32=False, out_scale=1.0,
+                 gn_stats=False):
         return ops.conv2d(x, self.w, self.b if bias is None else bias, ksize=self.ksize, stride=self.stride,
                           pad_mode=self.pad_mode, residual=residual, out_f32=out_f32, out_scale=out_scale,
-                          bias_per_sample=bias_per_sample)
+                          bias_per_sample=bias_per_sample, gn_stats=gn_stats)
 
 
 class UpsampleConv:
@@ -66,8 +67,8 @@ class UpsampleConv:
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
         self.half = wdtype
 
-    def __call__(self, h, out_f32):
-        return ops.upconv2x(ops.cast16(h, self.half), self.w4, self.b, out_f32=out_f32)
+    def __call__(self, h, out_f32, gn_stats=False):
+        return ops.upconv2x(ops.cast16(h, self.half), self.w4, self.b, out_f32=out_f32, gn_stats=gn_stats)
 
 
 class SmallCinConv:
@@ -85,10 +86,9 @@ class SmallCinConv:
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
         self.half = wdtype
 
-    def __call__(self, x_nchw, out_f32):
-        cols = ops.im2col3x3_small(x_nchw, self.kpad, self.half)
-        N, H, W, _ = cols.shape
-        return ops.linear(cols.view(N * H * W, self.kpad), self.w, self.b, out_f32=out_f32).view(N, H, W, self.cout)
+    def __call__(self, x_nchw, out_f32, gn_stats=False):
+        cols = ops.im2col3x3_small(x_nchw, self.kpad, self.half)      # [N,H,W,Kpad]: a 1x1 convolution from here on
+        return ops.conv2d(cols, self.w, self.b, ksize=1, out_f32=out_f32, gn_stats=gn_stats)
 
 
 class Linear:
@@ -156,10 +156,13 @@ class Resnet:
         self.temb_b = sd[prefix + ".time_emb_proj.bias"].detach().float().cpu() if has_temb else None
         self.conv1_bias_host = sd[prefix + ".conv1.bias"].detach().float().cpu()
 
-    def __call__(self, h, conv1_bias=None):
+    def __call__(self, h, conv1_bias=None, gn_stats_out=False):
+        """`gn_stats_out`: the block's output feeds another GroupNorm — let conv2's epilogue emit its statistics.
+        conv1's output always feeds norm2, so conv1 always tries to (ops.conv2d falls back silently when the shape
+        is not supported, e.g. the UNet's 10/20/40-channel groups)."""
         p = self.prec
         a = self.norm1(h, silu=True)
-        t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32)
+        t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32, gn_stats=True)
         c = self.norm2(t, silu=True)
         s = h if self.shortcut is None else self.shortcut(ops.cast16(h, p.half), out_f32=p.stream_f32)
-        return self.conv2(c, residual=s, out_f32=p.stream_f32)
+        return self.conv2(c, residual=s, out_f32=p.stream_f32, gn_stats=gn_stats_out)

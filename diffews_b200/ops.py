@@ -94,8 +94,28 @@ class _Timed:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+_sm_count = {}
+
+
+def _sms(device) -> int:
+    n = _sm_count.get(device)
+    if n is None:
+        n = torch.cuda.get_device_properties(device).multi_processor_count
+        _sm_count[device] = n
+    return n
+
+
+def gn_stats_supported(N, Ho, Wo, Cout, out_f32, residual, bias_per_sample) -> bool:
+    """Can the conv epilogue emit the GroupNorm(32) statistics of its output (dfw_conv2d_igemm_gnstats)?"""
+    if bias_per_sample or (Cout * (4 if out_f32 else 2)) % 16:
+        return False
+    if residual is not None and (residual.dtype == torch.float32) != out_f32:
+        return False
+    return bool(lib.dfw_conv_gnstats_supported(N, Ho, Wo, Cout))      # group width in {4,8,16}, one image per tile
+
+
 def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_scale=1.0, out_f32=False,
-           silu=False, geglu=False, bias_per_sample=False):
+           silu=False, geglu=False, bias_per_sample=False, gn_stats=False):
     """x bf16 [N,H,W,Cin]; w bf16 [Cout, ks*ks*Cin]; bias fp32 [Cout] or [N,Cout]; returns [N,H/s,W/s,Cout_eff]."""
     assert x.dtype in OPERAND_DTYPES and w.dtype == x.dtype, (x.dtype, w.dtype)
     _req(x, x.dtype, "x"); _req(w, w.dtype, "w")
@@ -120,6 +140,15 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
         assert residual.shape == y.shape and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
         else: assert residual.dtype == h16
+    if gn_stats and not (silu or geglu) and gn_stats_supported(N, Ho, Wo, Cout, out_f32, residual, bias_per_sample):
+        partial = torch.empty(int(lib.dfw_gn_partial_floats(N)), device=x.device, dtype=torch.float32)
+        with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin,
+                    f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags} +gn"):
+            check(lib.dfw_conv2d_igemm_gnstats(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), N,
+                                               H, W, Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale),
+                                               partial.data_ptr(), _stream()), "dfw_conv2d_igemm_gnstats")
+        y._gn_partial = (partial, _sms(x.device))
+        return y
     with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin,
                 f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags}"):
         check(lib.dfw_conv2d_igemm(x.data_ptr(), w.data_ptr(), _ptr(bias), bss, _ptr(residual), y.data_ptr(), N, H, W,
@@ -159,7 +188,7 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
     return y
 
 
-def upconv2x(x, w4, bias=None, *, out_f32=False):
+def upconv2x(x, w4, bias=None, *, out_f32=False, gn_stats=False):
     """nearest-2x upsample + 3x3 conv, fused: x 16-bit [N,H,W,Cin]; w4 [4,Cout,4*Cin] -> [N,2H,2W,Cout]."""
     assert x.dtype in OPERAND_DTYPES and w4.dtype == x.dtype
     _req(x, x.dtype, "x"); _req(w4, w4.dtype, "w4")
@@ -169,9 +198,14 @@ def upconv2x(x, w4, bias=None, *, out_f32=False):
     flags = (EPI_F16 if x.dtype == f16 else 0) | (EPI_OUT_F32 if out_f32 else 0)
     y = torch.empty((N, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
     if bias is not None: _req(bias, torch.float32, "bias")
+    partial = None
+    if gn_stats and gn_stats_supported(N, H, W, Cout, out_f32, None, False):
+        partial = torch.empty(4 * int(lib.dfw_gn_partial_floats(N)), device=x.device, dtype=torch.float32)
     with _Timed("igemm", 2.0 * N * H * W * 16 * Cin * Cout, f"upconv N{N} {H}x{W} {Cin}->{Cout} f{flags}"):
         check(lib.dfw_upconv2x_igemm(x.data_ptr(), w4.data_ptr(), _ptr(bias), y.data_ptr(), N, H, W, Cin, Cout,
-                                     flags, _stream()), "dfw_upconv2x_igemm")
+                                     flags, _ptr(partial), _stream()), "dfw_upconv2x_igemm")
+    if partial is not None:
+        y._gn_partial = (partial, 4 * _sms(x.device))
     return y
 
 
@@ -240,6 +274,15 @@ def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=bf16
     assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, f16, torch.float32)
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
+    pre = getattr(x, "_gn_partial", None)
+    if pre is not None and groups == 32:
+        # the producing convolution already reduced the statistics in its epilogue: normalise-and-store pass only
+        partial, nchunks = pre
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        check(lib.dfw_groupnorm_from_partial(x.data_ptr(), _xd(x), partial.data_ptr(), nchunks, gamma.data_ptr(),
+                                             beta.data_ptr(), y.data_ptr(), int(out_dtype == f16), N, HW, C, groups,
+                                             float(eps), int(silu), _stream()), "dfw_groupnorm_from_partial")
+        return y
     need = int(lib.dfw_groupnorm_workspace_bytes(N, HW, C, groups))
     key = (x.device, torch.cuda.current_stream().cuda_stream)
     ws = _gn_ws.get(key)

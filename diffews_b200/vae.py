@@ -59,8 +59,9 @@ class _Mid:
         self.attn = VaeAttention(sd, prefix + ".attentions.0", device, prec)
         self.res1 = Resnet(sd, prefix + ".resnets.1", device, 1e-6, prec, has_temb=False)
 
-    def __call__(self, h):
-        return self.res1(self.attn(self.res0(h)))
+    def __call__(self, h, gn_stats_out=True):
+        # res0's output feeds the attention's GroupNorm through a .view (statistics attribute is dropped there)
+        return self.res1(self.attn(self.res0(h, gn_stats_out=True)), gn_stats_out=gn_stats_out)
 
 
 class AutoencoderKL:
@@ -125,12 +126,13 @@ class AutoencoderKL:
         if H % 8 or W % 8:
             raise ValueError("image height/width must be multiples of 8")
         f32 = self.prec.stream_f32
-        h = self.enc_conv_in(x, out_f32=f32)
+        # every tensor below is consumed by a GroupNorm next: the producing conv emits its statistics (gn_stats)
+        h = self.enc_conv_in(x, out_f32=f32, gn_stats=True)
         for blk in self.enc_down:
-            for r in blk.resnets:
-                h = r(h)
+            for j, r in enumerate(blk.resnets):
+                h = r(h, gn_stats_out=not (blk.down is not None and j == len(blk.resnets) - 1))
             if blk.down is not None:
-                h = blk.down(ops.cast16(h, self.prec.half), out_f32=f32)
+                h = blk.down(ops.cast16(h, self.prec.half), out_f32=f32, gn_stats=True)
         h = self.enc_mid(h)
         h = self.enc_norm_out(h, silu=True)
         m = self.enc_conv_out(h, out_f32=True)                                   # [N,h,w,8] fp32 moments
@@ -151,13 +153,13 @@ class AutoencoderKL:
         zq = torch.empty_like(z)
         ops.pointwise_small(z, (Cz * hh * ww, 1, hh * ww), self.post_quant_w, self.post_quant_b, zq,
                             (Cz * hh * ww, 1, hh * ww), N, hh * ww, in_scale=in_scale, out_scale=1.0)
-        h = self.dec_conv_in(zq, out_f32=f32)
+        h = self.dec_conv_in(zq, out_f32=f32, gn_stats=True)
         h = self.dec_mid(h)
         for blk in self.dec_up:
-            for r in blk.resnets:
-                h = r(h)
+            for j, r in enumerate(blk.resnets):
+                h = r(h, gn_stats_out=not (blk.up is not None and j == len(blk.resnets) - 1))
             if blk.up is not None:
-                h = blk.up(h, out_f32=f32)
+                h = blk.up(h, out_f32=f32, gn_stats=True)
         h = self.dec_norm_out(h, silu=True)
         y = self.dec_conv_out(h, out_f32=True)                                   # [N,H,W,3] fp32
         return y.view(N, y.shape[1] * y.shape[2], 3)

@@ -74,7 +74,21 @@ int dfw_linear(const void* x, const void* w, const float* bias, const void* resi
  *   w4 16-bit [4 phases (ph*2+pw)][Cout][(a*2+b)*Cin + c] with, per axis, phase 0: {W[0], W[1]+W[2]},
  *      phase 1: {W[0]+W[1], W[2]} (see diffews_b200/weights.py::upconv_phase_weights). */
 int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y, int N, int Hin, int Win, int Cin,
-                       int Cout, int flags, void* stream);
+                       int Cout, int flags, float* gn_partial /* NULL or 4 * dfw_gn_partial_floats(N) floats */,
+                       void* stream);
+
+/* Convolution that also emits the GroupNorm(32) statistics of its OUTPUT (the tensor the next layer normalises), so
+ * the consumer can skip its statistics pass (one full read of the tensor): every epilogue thread reduces its row's
+ * channel groups, warps reduce-scatter with shuffles, and each CTA writes one partial (sum, sum of squares) per
+ * (image, group): gn_partial[N][#SMs][32][2] fp32, dfw_gn_partial_floats(N) floats.  Requires Cout/32 in {4, 8, 16},
+ * >= 128 output pixels per image row block (one image per tile) and the TMA epilogue (Cout*elem % 16 == 0, residual
+ * of the output's element size).  Consumed by dfw_groupnorm_from_partial(nchunks = dfw_gn_partial_floats(N)/(N*64)).
+ * ref: the GroupNorm at the head of every diffusers ResnetBlock2D / Attention block of the VAE (upstream). */
+long long dfw_gn_partial_floats(int N);
+int dfw_conv_gnstats_supported(int N, int Hout, int Wout, int Cout);   /* 1 if the fused statistics apply */
+int dfw_conv2d_igemm_gnstats(const void* x, const void* w, const float* bias, const void* residual, void* y, int N,
+                             int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode, int flags,
+                             float out_scale, float* gn_partial, void* stream);
 
 /* Batched GEMM with per-batch "weights": y[b] (M x Nout) = epi(x[b] (M x K) @ w[b]^T + bias), w[b] element (n, k) at
  * w[b*w_batch_stride + n*w_row_stride + k] (strides in elements, multiples of 8).  M >= 128, K % 64 == 0.
@@ -120,6 +134,12 @@ int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv
 long long dfw_groupnorm_workspace_bytes(int N, int HW, int C, int groups);
 int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int N,
                        int HW, int C, int groups, float eps, int apply_silu, void* workspace, void* stream);
+
+/* GroupNorm (+SiLU) whose statistics were already produced as partial sums (by dfw_conv2d_igemm_gnstats / dfw_upconv2x_igemm
+ * or by any producer with the layout partial[N][nchunks][groups][2]): only the normalise-and-store pass runs. */
+int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial, int nchunks, const float* gamma,
+                               const float* beta, void* y, int y_f16, int N, int HW, int C, int groups, float eps,
+                               int apply_silu, void* stream);
 
 /* K7  LayerNorm over the last dim. x [M, C] (x_dtype 0 bf16 / 1 fp32 / 2 fp16) -> y bf16 (fp16 if y_f16) [M, C].
  * C % 8 == 0, C <= 2048.

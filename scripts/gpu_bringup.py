@@ -344,6 +344,38 @@ def upconv():
 
 
 @case
+def gn_fused_stats():
+    """conv epilogue emits the GroupNorm statistics of its output; groupnorm() then skips its statistics pass."""
+    import torch
+    import torch.nn.functional as F
+    from diffews_b200 import ops
+    from diffews_b200.weights import conv_weight_to_gemm, upconv_phase_weights
+    for (N, H, W, Ci, Co, res, f32) in [(3, 32, 32, 128, 128, False, False), (2, 40, 24, 128, 256, True, False),
+                                         (2, 16, 16, 256, 512, True, True), (16, 64, 64, 128, 128, True, False),
+                                         (5, 300, 256, 64, 128, False, False)]:
+        x = _mk((N, H, W, Ci), 1, 1).half(); w = _mk((Co, Ci, 3, 3), (Ci * 9) ** -0.5, 2).half(); b = _mk((Co,), 1, 3)
+        r = (_mk((N, H, W, Co), 1, 4) if f32 else _mk((N, H, W, Co), 1, 4).half()) if res else None
+        g = _mk((Co,), 1, 5); be = _mk((Co,), 1, 6)
+        y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=3, residual=r, out_f32=f32, gn_stats=True)
+        fused = hasattr(y, "_gn_partial")
+        yn = ops.groupnorm(y, g, be, eps=1e-6, silu=True, out_dtype=torch.float16)
+        y_plain = y.clone()                                  # clone drops the attribute -> two-pass path
+        yn_ref_kernel = ops.groupnorm(y_plain, g, be, eps=1e-6, silu=True, out_dtype=torch.float16)
+        ref = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, g, be, 1e-6)).permute(0, 2, 3, 1)
+        e1, e2 = rel(yn, ref), rel(yn_ref_kernel, ref)
+        print(f"gn fused N{N} {H}x{W} {Ci}->{Co} res={res} f32={f32}: fused={fused} rel {e1:.2e} (two-pass {e2:.2e})")
+        assert e1 < 1e-3 and e2 < 1e-3
+        assert fused == bool(ops.lib.dfw_conv_gnstats_supported(N, H, W, Co))
+    x = _mk((2, 32, 32, 256), 1, 1).half(); w = _mk((256, 256, 3, 3), (256 * 9) ** -0.5, 2).half(); b = _mk((256,), 1, 3)
+    g = _mk((256,), 1, 5); be = _mk((256,), 1, 6)
+    y = ops.upconv2x(x, upconv_phase_weights(w).cuda().half(), b, gn_stats=True)
+    assert hasattr(y, "_gn_partial")
+    yn = ops.groupnorm(y, g, be, eps=1e-6, silu=False, out_dtype=torch.float16)
+    ref = F.group_norm(y.float().permute(0, 3, 1, 2), 32, g, be, 1e-6).permute(0, 2, 3, 1)
+    e = rel(yn, ref); print("gn fused after upconv:", e); assert e < 1e-3
+
+
+@case
 def rthres():
     import torch
     from diffews_b200 import ops

@@ -86,7 +86,12 @@ def main():
         g = torch.ones(128, device="cuda"); b = torch.zeros(128, device="cuda")
         nbytes = x.numel() * (4 + 2)          # algorithmic: read fp32 once, write bf16 once
         return (lambda: ops.groupnorm(x, g, b, eps=1e-6, silu=True)), None, nbytes
-    cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, gn=gn)
+    def gn16():
+        x = torch.randn(16, 512 * 512, 128, device="cuda").half()
+        g = torch.ones(128, device="cuda"); b = torch.zeros(128, device="cuda")
+        nbytes = x.numel() * (2 + 2)          # algorithmic: read fp16 once, write fp16 once
+        return (lambda: ops.groupnorm(x, g, b, eps=1e-6, silu=True, out_dtype=torch.float16)), None, nbytes
+    cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, gn=gn, gn16=gn16)
     which = list(cases) if args.which == ["all"] else args.which
     for name in which:
         fn, flops, nbytes = cases[name]()
