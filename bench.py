@@ -187,6 +187,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     if args.warmup < 3:
         args.warmup = 3

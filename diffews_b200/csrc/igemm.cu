@@ -14,6 +14,7 @@
 // (ref: diffews/models/unet_2d_condition.py:1118-1121,1161,1191,1226,1249 and the diffusers-0.25 blocks they
 //  reach; diffews/marigold_pipeline_rgb_latent_noise.py:852-853,901-902 for the VAE).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -59,6 +60,7 @@ struct IgemmParams {
     float* gn_partial; // optional: per-(image, CTA, group) partial (sum, sumsq) of y for the GroupNorm that consumes y
     int gn_cpg;        // channels per group of that GroupNorm (must divide the chunk width; TN == 1)
     long long gn_img_stride;   // floats between consecutive images in gn_partial (slot of this CTA: + blockIdx.x * 64)
+    int halo;         // 1: 3x3 stride-1 "halo" mainloop (vertical taps reuse one (TH+2) x TW patch per horizontal offset)
     int tma_epi;      // 1: epilogue stages 64-byte-wide column chunks in smem and uses TMA stores / residual TMA loads
     int has_res;
 };
@@ -79,7 +81,15 @@ struct IgemmCfg {
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS <= 512, "TMEM budget");
     static constexpr int GN_BYTES = 4 * 64 * 4;      // per-epilogue-warp GroupNorm partial sums (32 groups x 2)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + GN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // "halo" mainloop for 3x3 / stride-1 convolutions (tile = 8 rows x 16 cols): the operand area is split into an
+    // A ring of (8+2) x 16-pixel patches (one per horizontal filter offset; the 3 vertical taps read the SAME patch at
+    // row offsets 0 / 16 / 32, which stay 1024-byte aligned, so the SWIZZLE_128B phase is preserved) and a B ring.
+    static constexpr int PATCH_BYTES = (8 + 2) * 16 * 128;              // 20 KiB
+    static constexpr int HALO_A_SLOTS = (TPU == 2) ? 2 : ((BLOCK_N >= 160) ? 3 : 4);
+    static constexpr int HALO_B_RAW = (STAGES * STAGE_BYTES - HALO_A_SLOTS * TPU * PATCH_BYTES) / B_TILE_BYTES;
+    static constexpr int HALO_B_SLOTS = HALO_B_RAW > 8 ? 8 : HALO_B_RAW;
+    static_assert(HALO_B_SLOTS >= 3, "halo ring sizing");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + GN_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
     static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
@@ -301,6 +311,13 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
     auto res_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
+    const uint32_t hbar = bar_base + 8u * (2 * STAGES + 9);
+    auto ha_full = [&](int i) { return hbar + 8u * i; };
+    auto ha_empty = [&](int i) { return hbar + 8u * (4 + i); };
+    auto hb_full = [&](int i) { return hbar + 8u * (8 + i); };
+    auto hb_empty = [&](int i) { return hbar + 8u * (16 + i); };
+    auto hA = [&](int slot, int sub) { return smem_base + (slot * TPU + sub) * Cfg::PATCH_BYTES; };
+    auto hB = [&](int slot) { return smem_base + Cfg::HALO_A_SLOTS * TPU * Cfg::PATCH_BYTES + slot * Cfg::B_TILE_BYTES; };
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
     uint8_t* epi_generic = smem_raw + (epi_base - smem_raw_u32);
@@ -333,6 +350,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             mbar_init(res_full(a), 1);
             mbar_init(res_empty(a), 4);
         }
+        for (int i = 0; i < 4; ++i) { mbar_init(ha_full(i), 1); mbar_init(ha_empty(i), 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(hb_full(i), 1); mbar_init(hb_empty(i), 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -346,7 +365,39 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 
     const int kblocks = p.ntaps * p.kb_per_tap;
 
-    if (warp == 0) {
+    if (warp == 0 && p.halo) {
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int t0 = u * TPU;
+                const int nsub = min(TPU, p.total_tiles - t0);
+                TileCoord tc[TPU];
+#pragma unroll
+                for (int sub = 0; sub < TPU; ++sub) tc[sub] = decode_tile(p, min(t0 + sub, p.total_tiles - 1));
+                for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                    for (int dw = -1; dw <= 1; ++dw) {
+                        mbar_wait(ha_empty(as), aph ^ 1u, 7);
+                        mbar_arrive_expect_tx(ha_full(as), nsub * Cfg::PATCH_BYTES);
+#pragma unroll
+                        for (int sub = 0; sub < TPU; ++sub)
+                            if (sub < nsub)
+                                tma_load_4d(hA(as, sub), &maps.a[1], ha_full(as), kb * BLOCK_K, tc[sub].w0 + dw,
+                                            tc[sub].h0 - 1, tc[sub].n0);
+                        if (++as == Cfg::HALO_A_SLOTS) { as = 0; aph ^= 1u; }
+                        for (int dh = -1; dh <= 1; ++dh) {
+                            const int tap = (dh + 1) * 3 + (dw + 1);
+                            mbar_wait(hb_empty(bs), bph ^ 1u, 8);
+                            mbar_arrive_expect_tx(hb_full(bs), Cfg::B_TILE_BYTES);
+                            tma_load_3d(hB(bs), &maps.b, hb_full(bs), (tap * p.kb_per_tap + kb) * BLOCK_K,
+                                        tc[0].n_tile * BLOCK_N, 0);
+                            if (++bs == Cfg::HALO_B_SLOTS) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -371,6 +422,51 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
+            }
+        }
+    } else if (warp == 1 && p.halo) {
+        if (lane == 0) {
+            const uint32_t fmt = (p.flags & DFW_EPI_F16) ? 0u : 1u;
+            const uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N, fmt, fmt, 0);
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int nsub = min(TPU, p.total_tiles - u * TPU);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+                bool first = true;
+                for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                    for (int dw = 0; dw < 3; ++dw) {
+                        mbar_wait(ha_full(as), aph, 9);
+                        for (int dh = 0; dh < 3; ++dh) {
+                            mbar_wait(hb_full(bs), bph, 3);
+                            tc_fence_after();
+                            const uint64_t bdesc = umma_desc_sw128(hB(bs));
+#pragma unroll
+                            for (int sub = 0; sub < TPU; ++sub) {
+                                if (sub < nsub) {
+                                    // vertical tap dh reads patch rows [16*dh, 16*dh + 128): + dh * 2048 bytes
+                                    const uint64_t adesc = umma_desc_sw128(hA(as, sub) + dh * 16 * 128);
+#pragma unroll
+                                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                                        umma_ss(d_tmem + sub * Cfg::SUB_COLS, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                                (!first || k > 0) ? 1u : 0u);
+                                }
+                            }
+                            first = false;
+                            tc_commit(hb_empty(bs));
+                            if (++bs == Cfg::HALO_B_SLOTS) { bs = 0; bph ^= 1u; }
+                        }
+                        tc_commit(ha_empty(as));
+                        if (++as == Cfg::HALO_A_SLOTS) { as = 0; aph ^= 1u; }
+                    }
+                }
+                tc_commit(tfull_bar(acc));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
             }
         }
     } else if (warp == 1) {
@@ -783,6 +879,11 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     p.ntaps = (up_phase >= 0) ? 4 : ksize * ksize;
     if (up_phase >= 0) DFW_REQUIRE(ksize == 3 && stride == 1 && pad_mode == 0 && residual == nullptr);
     choose_tile(Wout, Hout, N, p.TW, p.TH, p.TN);
+    // halo mainloop: 3x3 / stride 1 on images that tile exactly into 8 x 16 output patches
+    static const bool halo_enabled = [] { const char* e = getenv("DFW_HALO"); return !(e && e[0] == '0'); }();
+    p.halo = (halo_enabled && ksize == 3 && stride == 1 && up_phase < 0 && w_batch_stride == 0 && Wout % 16 == 0 &&
+              Hout % 8 == 0 && Cout > 16) ? 1 : 0;
+    if (p.halo) { p.TW = 16; p.TH = 8; p.TN = 1; }
     if (w_batch_stride > 0 && p.TN != 1) {       // per-image weights: a tile must not straddle images
         p.TN = 1;
         if (Hout == 1) { p.TW = 128; p.TH = 1; } else { p.TH = 128 / p.TW; }
@@ -806,6 +907,11 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
         rc = encode_tmap_bf16_sw128(&maps.a[0], x, 4, dims, strides, box);
         if (rc != DFW_OK) return rc;
         for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+        if (p.halo) {       // a[1]: (TH+2) x TW patch box for the halo mainloop
+            const uint32_t pbox[4] = {BLOCK_K, 16, 10, 1};
+            rc = encode_tmap_bf16_sw128(&maps.a[1], x, 4, dims, strides, pbox);
+            if (rc != DFW_OK) return rc;
+        }
         const int pad = (ksize - 1) / 2;
         if (up_phase >= 0) {
             const int ph = up_phase >> 1, pw = up_phase & 1;

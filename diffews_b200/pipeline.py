@@ -58,6 +58,8 @@ class MarigoldPipelineRGBLatentNoise:
         self.dtype = torch.float32
         self._embed_cache = {}
         self.validate_inputs = True     # the reference asserts the [-1,1] input range (pipeline:309)
+        if hasattr(unet, "skip_support_tail"):
+            unet.skip_support_tail = True   # single_infer discards the support pass's output (pipeline:719-720)
 
     def to(self, *a, **k):
         return self

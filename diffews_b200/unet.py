@@ -84,6 +84,16 @@ class Transformer2D:
         x = self.block(x, kv)
         return self.proj_out(x, residual=h.view(N, H * W, C), out_f32=self.prec.stream_f32).view(N, H, W, C)
 
+    def fill_bank_only(self, h):
+        """Support pass, last transformer of the network: only its attn1 K/V bank is ever consumed (the support
+        pass's output is discarded, pipeline:719-720), so stop after the fused QKV projection."""
+        N, H, W, C = h.shape
+        x = self.proj_in(self.norm(h, silu=False).view(N, H * W, C), out_f32=self.prec.stream_f32)
+        a = self.block.attn1
+        qkv = a.to_qkv(self.block.norm1(x))
+        D = a.inner_dim
+        a.k_bank, a.v_bank = qkv[..., D:2 * D], qkv[..., 2 * D:]
+
 
 class MyUNet2DConditionModel:
     """B200 engine behind the reference's UNet interface."""
@@ -107,6 +117,9 @@ class MyUNet2DConditionModel:
                     for k in ("linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias")}
         self._temb_cache = {}
         self._kv_cache = {}
+        # The reference computes the support pass to the end and throws its output away (pipeline:719-720).  When the
+        # caller opts in, the support pass stops after the last K/V bank is filled and returns sample=None.
+        self.skip_support_tail = False
 
         self.resnets = []          # all resnets in execution order (for the temb bias table)
         self.transformers = []     # all Transformer2D in execution order (for the cross-attn K/V table)
@@ -271,10 +284,13 @@ class MyUNet2DConditionModel:
         h = self.mid.res0(h, next(biases))                                       # :1189-1200
         h = self.mid.attn(h, next(kvs))
         h = self.mid.res1(h, next(biases))
-        for blk in self.up:                                                      # :1214-1243
+        for bi, blk in enumerate(self.up):                                       # :1214-1243
             for j, r in enumerate(blk.resnets):
                 h = r(ops.concat_channels(h, skips.pop()), next(biases))
                 if blk.attns:
+                    if (not is_target) and self.skip_support_tail and bi == 3 and j == 2:
+                        blk.attns[j].fill_bank_only(h)
+                        return UNet2DConditionOutput(sample=None) if return_dict else (None,)
                     h = blk.attns[j](h, next(kvs))
             if blk.up is not None:
                 h = blk.up(h, out_f32=f32)
