@@ -27,7 +27,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int IGEMM_THREADS = 256;
+constexpr int IGEMM_THREADS = 384;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 residual loader, 4-11 two epilogue groups
+constexpr int GN_SLOTS_PER_CTA = 2;     // one GroupNorm partial slot per epilogue group
 constexpr int MAX_TAPS = 9;
 
 struct IgemmMaps {
@@ -80,7 +81,7 @@ struct IgemmCfg {
     static constexpr int ACC_COLS = TPU * SUB_COLS;          // TMEM columns of one work unit's accumulators
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS <= 512, "TMEM budget");
-    static constexpr int GN_BYTES = 4 * 64 * 4;      // per-epilogue-warp GroupNorm partial sums (32 groups x 2)
+    static constexpr int GN_BYTES = 8 * 64 * 4;      // per-epilogue-warp GroupNorm partial sums (32 groups x 2)
     // "halo" mainloop for 3x3 / stride-1 convolutions (tile = 8 rows x 16 cols): the operand area is split into an
     // A ring of (8+2) x 16-pixel patches (one per horizontal filter offset; the 3 vertical taps read the SAME patch at
     // row offsets 0 / 16 / 32, which stay 1024-byte aligned, so the SWIZZLE_128B phase is preserved) and a B ring.
@@ -89,7 +90,10 @@ struct IgemmCfg {
     static constexpr int HALO_B_RAW = (STAGES * STAGE_BYTES - HALO_A_SLOTS * TPU * PATCH_BYTES) / B_TILE_BYTES;
     static constexpr int HALO_B_SLOTS = HALO_B_RAW > 8 ? 8 : HALO_B_RAW;
     static_assert(HALO_B_SLOTS >= 3, "halo ring sizing");
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + GN_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+    // the dynamic smem array is declared __align__(1024); 512 B of slack remain and the kernel traps if the base ever
+    // needs more than that to reach the 1024-byte alignment SWIZZLE_128B wants
+    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + EPI_BYTES + GN_BYTES + 512 /*barriers*/;
+    static constexpr int SMEM_BYTES = SMEM_USED + 512 /*align slack*/;
     static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
@@ -295,9 +299,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmParams p) {
     using Cfg = IgemmCfg<BLOCK_N, TPU>;
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+    if (smem_base - smem_raw_u32 > static_cast<uint32_t>(Cfg::SMEM_BYTES - Cfg::SMEM_USED)) __trap();
     const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;          // staging + row table
     const uint32_t gn_base = epi_base + Cfg::EPI_BYTES;
     const uint32_t bar_base = gn_base + Cfg::GN_BYTES;
@@ -308,10 +313,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
-    auto res_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
-    const uint32_t hbar = bar_base + 8u * (2 * STAGES + 9);
+    auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };     // 4 epilogue chunk buffers
+    auto buf_free = [&](int b) { return bar_base + 8u * (2 * STAGES + 8 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 12);
+    const uint32_t hbar = bar_base + 8u * (2 * STAGES + 13);
     auto ha_full = [&](int i) { return hbar + 8u * i; };
     auto ha_empty = [&](int i) { return hbar + 8u * (4 + i); };
     auto hb_full = [&](int i) { return hbar + 8u * (8 + i); };
@@ -321,8 +326,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
     uint8_t* epi_generic = smem_raw + (epi_base - smem_raw_u32);
-    auto out_buf = [&](int b) { return epi_base + 8192u * b; };
-    auto res_buf = [&](int b) { return epi_base + 16384u + 8192u * b; };
+    // TMA epilogue: 4 chunk buffers of 8 KiB used IN PLACE — the residual chunk is TMA-loaded into a buffer, every
+    // thread adds its accumulator row to its own row of the buffer and writes the result back, then the same buffer
+    // is TMA-stored; a buffer is recycled when its store has finished reading it (4-deep ring for loads and stores).
+    auto epi_buf = [&](int b) { return epi_base + 8192u * b; };
     // TMA-epilogue chunk geometry: 64 bytes of output per row -> 32 columns (16-bit y) or 16 columns (fp32 y)
     const int CW = (p.flags & DFW_EPI_OUT_F32) ? 16 : 32;
     const int out_cols_per_tile = (p.flags & DFW_EPI_GEGLU) ? BLOCK_N / 2 : BLOCK_N;
@@ -346,9 +353,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);
+            mbar_init(tempty_bar(a), p.tma_epi ? 8 : 4);
+        }
+        for (int a = 0; a < 4; ++a) {
             mbar_init(res_full(a), 1);
-            mbar_init(res_empty(a), 4);
+            mbar_init(buf_free(a), 1);
         }
         for (int i = 0; i < 4; ++i) { mbar_init(ha_full(i), 1); mbar_init(ha_empty(i), 1); }
         for (int i = 0; i < 8; ++i) { mbar_init(hb_full(i), 1); mbar_init(hb_empty(i), 1); }
@@ -505,49 +514,61 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             }
         }
     } else if (warp == 3) {
-        // residual loader for the TMA epilogue: one 8 KiB chunk (128 rows x 64 B) per epilogue chunk, 2-deep ring
+        // residual loader for the TMA epilogue: one 8 KiB chunk (128 rows x 64 B) per epilogue chunk, 4-deep ring
         if (lane == 0 && p.tma_epi && p.has_res) {
             uint32_t g = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x)
             for (int t = u * TPU; t < min(u * TPU + TPU, p.total_tiles); ++t) {
                 const TileCoord tc = decode_tile(p, t);
                 for (int c = 0; c < chunks_per_tile; ++c, ++g) {
-                    const int b = g & 1;
-                    mbar_wait(res_empty(b), ((g >> 1) & 1) ^ 1u, 5);
+                    const int b = g & 3;
+                    mbar_wait(buf_free(b), ((g >> 2) & 1) ^ 1u, 5);       // the store that last used this buffer is done
                     mbar_arrive_expect_tx(res_full(b), 8192);
-                    tma_load_4d(res_buf(b), &maps.res, res_full(b), tc.n_tile * out_cols_per_tile + c * CW, tc.w0,
+                    tma_load_4d(epi_buf(b), &maps.res, res_full(b), tc.n_tile * out_cols_per_tile + c * CW, tc.w0,
                                 tc.h0, tc.n0);
                 }
             }
         }
     } else if (warp >= 4 && p.tma_epi) {
         // ---------------- TMA epilogue: thread = accumulator row; 64-byte chunks through swizzled smem ----------------
-        const int q = warp - 4;
+        // Two groups of four warps (one warp of each group per SM sub-partition, so the sub-partition's scheduler has a
+        // second warp to issue from while the first waits on TMEM / smem / a barrier); group eg takes the chunks with
+        // (global chunk index & 1) == eg and owns chunk buffers {eg, eg + 2}, named barrier 1 + eg and its own stores.
+        const int eg = (warp - 4) >> 2;
+        const int q = (warp - 4) & 3;                 // TMEM lane quarter = warp % 4
         const int row = q * 32 + lane;
         const int f16 = p.flags & DFW_EPI_F16;
         const bool out_f32 = (p.flags & DFW_EPI_OUT_F32) != 0;
         const bool geglu = (BLOCK_N == 256) && (p.flags & DFW_EPI_GEGLU);
-        const bool issuer = (threadIdx.x == 128);
+        const bool issuer = (q == 0 && lane == 0);
+        const bool has_res = p.has_res != 0;
+        const bool has_bias = p.bias != nullptr;
+        const bool has_gn = p.gn_partial != nullptr;
+        const int epi_flags = p.flags;
+        const float out_scale = p.out_scale;
+        const int gn_cpg = p.gn_cpg;
+        const int bar_id = 1 + eg;
         const uint32_t row_off = static_cast<uint32_t>(row) * 64u;
         const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);          // SWIZZLE_64B: unit ^= (row/2) % 4
         // fused GroupNorm statistics of the output (consumed by the next layer's GroupNorm): per-warp smem partials,
         // flushed to gn_partial[image][cta][group][2] whenever the CTA moves on to another image (TN == 1)
         float* wacc_all = reinterpret_cast<float*>(smem_raw + (gn_base - smem_raw_u32));
-        float* wacc = wacc_all + q * 64;
+        float* wacc = wacc_all + (eg * 4 + q) * 64;
         const int gn_th = row / p.TW, gn_tw = row % p.TW;
         int gn_img = -1;
         auto gn_flush = [&](int img) {
-            named_bar_sync(1, 128);
-            const int e = threadIdx.x - 128;
+            named_bar_sync(bar_id, 128);
+            const int e = q * 32 + lane;
             if (e < 64) {
-                const float tot = (wacc_all[e] + wacc_all[64 + e]) + (wacc_all[128 + e] + wacc_all[192 + e]);
-                p.gn_partial[static_cast<size_t>(img) * p.gn_img_stride + blockIdx.x * 64 + e] = tot;
+                const float* wg = wacc_all + eg * 256;
+                const float tot = (wg[e] + wg[64 + e]) + (wg[128 + e] + wg[192 + e]);
+                p.gn_partial[static_cast<size_t>(img) * p.gn_img_stride + (blockIdx.x * GN_SLOTS_PER_CTA + eg) * 64 + e] = tot;
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(bar_id, 128);
             if (lane < 32) { wacc[lane] = 0.f; wacc[32 + lane] = 0.f; }
             __syncwarp();
         };
-        if (p.gn_partial != nullptr) {          // (the host zero-fills gn_partial: CTAs write only the images they touch)
+        if (has_gn) {          // (the host zero-fills gn_partial: CTAs write only the images they touch)
             wacc[lane] = 0.f; wacc[32 + lane] = 0.f;
             __syncwarp();
         }
@@ -559,7 +580,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           for (int t = u * TPU; t < min(u * TPU + TPU, p.total_tiles); ++t) {
             const TileCoord tc = decode_tile(p, t);
             bool gn_row_valid = false;
-            if (p.gn_partial != nullptr) {
+            if (has_gn) {
                 if (tc.n0 != gn_img) {
                     if (gn_img >= 0) gn_flush(gn_img);
                     gn_img = tc.n0;
@@ -570,7 +591,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                                    (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < chunks_per_tile; ++c, ++g) {
-                const int b = g & 1;
+                if ((g & 1u) != static_cast<uint32_t>(eg)) continue;
+                const int b = g & 3;
                 float f[32];
                 const int col_out0 = tc.n_tile * out_cols_per_tile + c * CW;
                 if (geglu) {
@@ -592,48 +614,61 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     }
                 } else {
                     const int col_in0 = tc.n_tile * BLOCK_N + c * CW;
+                    const bool bias_vec = has_bias && (col_in0 + CW <= p.Cout);
                     if (out_f32) {
                         uint32_t v[16];
                         tmem_ld_32x16(taddr + c * 16, v);
+                        float4 bb[4];                             // bias loads overlap the TMEM read
+                        if (bias_vec) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0) + j);
+                        }
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                        if (bias_vec) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[4 * j] += bb[j].x; f[4 * j + 1] += bb[j].y; f[4 * j + 2] += bb[j].z; f[4 * j + 3] += bb[j].w;
+                            }
+                        }
                     } else {
                         if constexpr (BLOCK_N >= 32) {
                             uint32_t v[32];
                             tmem_ld_32x32(taddr + c * 32, v);
+                            float4 bb[8];
+                            if (bias_vec) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0) + j);
+                            }
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        }
-                    }
-                    if (p.bias != nullptr) {
-                        if (col_in0 + CW <= p.Cout) {
+                            if (bias_vec) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (j < CW) {
-                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0 + j));
-                                    f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+                                for (int j = 0; j < 8; ++j) {
+                                    f[4 * j] += bb[j].x; f[4 * j + 1] += bb[j].y; f[4 * j + 2] += bb[j].z; f[4 * j + 3] += bb[j].w;
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < CW && col_in0 + j < p.Cout) f[j] += __ldg(p.bias + col_in0 + j);
                         }
                     }
-                    if (p.out_scale != 1.0f) {
+                    if (has_bias && !bias_vec) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+                        for (int j = 0; j < 32; ++j)
+                            if (j < CW && col_in0 + j < p.Cout) f[j] += __ldg(p.bias + col_in0 + j);
                     }
-                    if (p.flags & DFW_EPI_SILU) {
+                    if (out_scale != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] *= out_scale;
+                    }
+                    if (epi_flags & DFW_EPI_SILU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = silu(f[j]);
                     }
                 }
-                if (p.has_res) {
-                    mbar_wait(res_full(b), (g >> 1) & 1, 6);
-                    const uint32_t rb = res_buf(b) + row_off;
+                if (has_res) {
+                    mbar_wait(res_full(b), (g >> 2) & 1, 6);
+                    const uint32_t rb = epi_buf(b) + row_off;
 #pragma unroll
                     for (uint32_t u = 0; u < 4; ++u) {
                         uint4 r;
@@ -649,24 +684,24 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                             f[8 * u + 4] += a2.x; f[8 * u + 5] += a2.y; f[8 * u + 6] += a3.x; f[8 * u + 7] += a3.y;
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(res_empty(b));
                 }
-                if (p.gn_partial != nullptr && col_out0 < p.out_ch) {
+                if (has_gn && col_out0 < p.out_ch) {
                     if (out_f32) {
-                        if (p.gn_cpg == 4) gn_chunk_stats<4, 16>(f, gn_row_valid, col_out0, lane, wacc);
-                        else if (p.gn_cpg == 8) gn_chunk_stats<8, 16>(f, gn_row_valid, col_out0, lane, wacc);
+                        if (gn_cpg == 4) gn_chunk_stats<4, 16>(f, gn_row_valid, col_out0, lane, wacc);
+                        else if (gn_cpg == 8) gn_chunk_stats<8, 16>(f, gn_row_valid, col_out0, lane, wacc);
                         else gn_chunk_stats<16, 16>(f, gn_row_valid, col_out0, lane, wacc);
                     } else {
-                        if (p.gn_cpg == 4) gn_chunk_stats<4, 32>(f, gn_row_valid, col_out0, lane, wacc);
-                        else if (p.gn_cpg == 8) gn_chunk_stats<8, 32>(f, gn_row_valid, col_out0, lane, wacc);
+                        if (gn_cpg == 4) gn_chunk_stats<4, 32>(f, gn_row_valid, col_out0, lane, wacc);
+                        else if (gn_cpg == 8) gn_chunk_stats<8, 32>(f, gn_row_valid, col_out0, lane, wacc);
                         else gn_chunk_stats<16, 32>(f, gn_row_valid, col_out0, lane, wacc);
                     }
                 }
-                // the store issued two chunks ago (same buffer) must have finished reading smem
-                if (issuer) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
-                const uint32_t ob = out_buf(b) + row_off;
+                if (!has_res) {
+                    // no loader in the loop: this group's store two chunks ago (same buffer) must have finished reading
+                    if (issuer) tma_store_wait_read<1>();
+                    named_bar_sync(bar_id, 128);
+                }
+                const uint32_t ob = epi_buf(b) + row_off;
 #pragma unroll
                 for (uint32_t u = 0; u < 4; ++u) {
                     uint4 w;
@@ -681,10 +716,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                                  ::"r"(ob + ((u ^ sw) << 4)), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);
+                named_bar_sync(bar_id, 128);
                 if (issuer) {
-                    tma_store_4d(&maps.out, out_buf(b), col_out0, tc.w0, tc.h0, tc.n0);
+                    tma_store_4d(&maps.out, epi_buf(b), col_out0, tc.w0, tc.h0, tc.n0);
                     tma_store_commit();
+                    if (has_res && g >= 2) {
+                        tma_store_wait_read<1>();                    // this group's previous store (chunk g-2) has drained
+                        mbar_arrive(buf_free((g - 2) & 3));          // its buffer: hand it back to the residual loader
+                    }
                 }
             }
           }
@@ -694,9 +733,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (p.gn_partial != nullptr && gn_img >= 0) gn_flush(gn_img);
+        if (has_gn && gn_img >= 0) gn_flush(gn_img);
         if (issuer) tma_store_wait_all<0>();
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         const int q = warp - 4;
         const int row = q * 32 + lane;
         const int tn = row / (p.TH * p.TW);
@@ -882,7 +921,7 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     // halo mainloop: 3x3 / stride 1 on images that tile exactly into 8 x 16 output patches
     static const bool halo_enabled = [] { const char* e = getenv("DFW_HALO"); return !(e && e[0] == '0'); }();
     p.halo = (halo_enabled && ksize == 3 && stride == 1 && up_phase < 0 && w_batch_stride == 0 && Wout % 16 == 0 &&
-              Hout % 8 == 0 && Cout > 16) ? 1 : 0;
+              Hout % 8 == 0) ? 1 : 0;
     if (p.halo) { p.TW = 16; p.TH = 8; p.TN = 1; }
     if (w_batch_stride > 0 && p.TN != 1) {       // per-image weights: a tile must not straddle images
         p.TN = 1;
@@ -954,12 +993,28 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
             }
     }
 
+    // Cout tile width: among the widths that divide Cout, the one with the cheapest schedule on this many SMs
+    // (rounds of the persistent loop x per-tile cost) -- e.g. 1280 channels on 32 pixel tiles: 256 -> 160 tiles = 2 rounds
+    // of 256 columns, 160 -> 256 tiles = 2 rounds of 160 columns; on 8 pixel tiles 128 -> 80 tiles = 1 round of 128.
     int block_n;
     if (geglu) block_n = 256;
     else if (Cout <= 16) block_n = 16;
-    else if (Cout % 256 == 0) block_n = 256;
-    else if (Cout % 160 == 0) block_n = 160;
-    else block_n = 128;
+    else {
+        const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_nimg;
+        const int cand[3] = {256, 160, 128};
+        double best = 0.0;
+        block_n = 0;
+        for (int i = 0; i < 3; ++i) {
+            const int bn = cand[i];
+            if (Cout % bn != 0 && !(bn == 128 && block_n == 0)) continue;     // 128 is the ragged-Cout fallback
+            const long long tiles = m_tiles * ((Cout + bn - 1) / bn);
+            const long long rounds = (tiles + sm_count() - 1) / sm_count();
+            // per-tile cost in accumulator columns: + fixed pipeline fill / drain; N = 128 MMAs run ~15 % below the
+            // N = 256 rate per column (measured)
+            const double cost = static_cast<double>(rounds) * (bn + 24) * (bn == 128 ? 1.15 : 1.0);
+            if (block_n == 0 || cost < best - 1e-9) { best = cost; block_n = bn; }
+        }
+    }
     {
         const uint64_t Kt = static_cast<uint64_t>(p.ntaps) * Cin;
         const uint64_t row = w_row_stride > 0 ? static_cast<uint64_t>(w_row_stride) : Kt;
@@ -990,7 +1045,7 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
             DFW_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16);
             p.gn_partial = gn_partial;
             p.gn_cpg = cpg;
-            p.gn_img_stride = gn_img_stride > 0 ? gn_img_stride : static_cast<long long>(sm_count()) * 64;
+            p.gn_img_stride = gn_img_stride > 0 ? gn_img_stride : static_cast<long long>(sm_count()) * GN_SLOTS_PER_CTA * 64;
         }
         if (up_phase >= 0) DFW_REQUIRE(ok);          // the strided phase view is only reachable through the TMA store
         if (ok && up_phase >= 0) {
@@ -1055,7 +1110,7 @@ int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y
     // four phase convolutions (2x2 taps each) = nearest-2x upsample followed by a 3x3 / pad 1 convolution
     const size_t esz = 2;
     // partial layout [N][4 phases x #SMs][32][2]: each phase launch owns a slice of #SMs slots inside every image
-    const long long slots = 4LL * dfw::sm_count();
+    const long long slots = 4LL * dfw::sm_count() * dfw::GN_SLOTS_PER_CTA;
     if (gn_partial) {
         if (cudaMemsetAsync(gn_partial, 0, static_cast<size_t>(N) * slots * 64 * sizeof(float),
                             static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
@@ -1064,7 +1119,7 @@ int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y
         const uint8_t* wp = reinterpret_cast<const uint8_t*>(w4) + static_cast<size_t>(phase) * Cout * 4 * Cin * esz;
         int rc = dfw::igemm_dispatch(x, wp, bias, 0, nullptr, y, N, Hin, Win, Cin, Cout, 3, 1, 0, flags, 1.0f,
                                      static_cast<cudaStream_t>(stream), 0, 0, phase,
-                                     gn_partial ? gn_partial + static_cast<size_t>(phase) * dfw::sm_count() * 64 : nullptr,
+                                     gn_partial ? gn_partial + static_cast<size_t>(phase) * dfw::sm_count() * dfw::GN_SLOTS_PER_CTA * 64 : nullptr,
                                      gn_partial ? 32 : 0, slots * 64);
         if (rc != DFW_OK) return rc;
     }
@@ -1080,13 +1135,15 @@ int dfw_conv_gnstats_supported(int N, int Hout, int Wout, int Cout) {
     return TN == 1 ? 1 : 0;
 }
 
-long long dfw_gn_partial_floats(int N) { return N > 0 ? static_cast<long long>(N) * dfw::sm_count() * 64 : -1; }
+long long dfw_gn_partial_floats(int N) {
+    return N > 0 ? static_cast<long long>(N) * dfw::sm_count() * dfw::GN_SLOTS_PER_CTA * 64 : -1;
+}
 
 int dfw_conv2d_igemm_gnstats(const void* x, const void* w, const float* bias, const void* residual, void* y, int N,
                              int Hin, int Win, int Cin, int Cout, int ksize, int stride, int pad_mode, int flags,
                              float out_scale, float* gn_partial, void* stream) {
     if (gn_partial == nullptr) return DFW_ERR_INVALID;
-    if (cudaMemsetAsync(gn_partial, 0, static_cast<size_t>(N) * dfw::sm_count() * 64 * sizeof(float),
+    if (cudaMemsetAsync(gn_partial, 0, static_cast<size_t>(dfw_gn_partial_floats(N)) * sizeof(float),
                         static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
     return dfw::igemm_dispatch(x, w, bias, 0, residual, y, N, Hin, Win, Cin, Cout, ksize, stride, pad_mode, flags,
                                out_scale, static_cast<cudaStream_t>(stream), 0, 0, -1, gn_partial, 32);

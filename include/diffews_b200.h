@@ -80,7 +80,7 @@ int dfw_upconv2x_igemm(const void* x, const void* w4, const float* bias, void* y
 /* Convolution that also emits the GroupNorm(32) statistics of its OUTPUT (the tensor the next layer normalises), so
  * the consumer can skip its statistics pass (one full read of the tensor): every epilogue thread reduces its row's
  * channel groups, warps reduce-scatter with shuffles, and each CTA writes one partial (sum, sum of squares) per
- * (image, group): gn_partial[N][#SMs][32][2] fp32, dfw_gn_partial_floats(N) floats.  Requires Cout/32 in {4, 8, 16},
+ * (image, group): gn_partial[N][2 x #SMs][32][2] fp32 (one slot per epilogue warp group), dfw_gn_partial_floats(N) floats.  Requires Cout/32 in {4, 8, 16},
  * >= 128 output pixels per image row block (one image per tile) and the TMA epilogue (Cout*elem % 16 == 0, residual
  * of the output's element size).  Consumed by dfw_groupnorm_from_partial(nchunks = dfw_gn_partial_floats(N)/(N*64)).
  * ref: the GroupNorm at the head of every diffusers ResnetBlock2D / Attention block of the VAE (upstream). */

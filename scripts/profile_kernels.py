@@ -28,7 +28,7 @@ def timeit(fn, iters, flush):
     return ts[len(ts) // 2]
 
 
-def conv_case(N, H, C_in, C_out, ks=3, out_f32=False, res=None):
+def conv_case(N, H, C_in, C_out, ks=3, out_f32=False, res=None, gn=False):
     x = torch.randn(N, H, H, C_in, device="cuda").to(bf16)
     w = conv_weight_to_gemm(torch.randn(C_out, C_in, ks, ks, device="cuda") * (C_in * ks * ks) ** -0.5).to(bf16)
     b = torch.randn(C_out, device="cuda")
@@ -36,7 +36,7 @@ def conv_case(N, H, C_in, C_out, ks=3, out_f32=False, res=None):
     if res is not None:
         r = torch.randn(N, H, H, C_out, device="cuda").to(res)
     flops = 2.0 * N * H * H * C_out * C_in * ks * ks
-    return (lambda: ops.conv2d(x, w, b, ksize=ks, out_f32=out_f32, residual=r)), flops, None
+    return (lambda: ops.conv2d(x, w, b, ksize=ks, out_f32=out_f32, residual=r, gn_stats=gn)), flops, None
 
 
 def main():
@@ -57,6 +57,10 @@ def main():
         "conv640": lambda: conv_case(16, 32, 640, 640),
         "conv1280": lambda: conv_case(16, 16, 1280, 1280),
         "conv1280s": lambda: conv_case(16, 8, 1280, 1280),
+        "conv128to3": lambda: conv_case(16, 512, 128, 3),
+        "conv64k1": lambda: conv_case(16, 512, 64, 128, ks=1),
+        "conv64k1_gn": lambda: conv_case(16, 512, 64, 128, ks=1, gn=True),
+        "conv128_gn": lambda: conv_case(16, 512, 128, 128, gn=True),
     }
 
     def lin_res():
