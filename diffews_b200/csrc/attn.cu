@@ -82,7 +82,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
     uint8_t* sP_generic = smem_raw + (p_base - raw_u32);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index via shuffle = provably warp-uniform; role loops run on all lanes, TMA / tcgen05 issue sits in
+    // elect_one() regions (see igemm.cu: `if (lane == 0)` around the loop costs an ELECT/BRA.U.ANY loop per instruction)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * ATT_M * ATT_QT;
     const int head = blockIdx.y;
     const int b = blockIdx.z;
@@ -113,32 +116,38 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     auto tO = [&](int x) { return tmem_base + 256 + x * 64; };
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
-            tma_load_3d(sQ(0), &maps.q, q_full, head * ATT_D, q0, b);
-            if (has_b) tma_load_3d(sQ(1), &maps.q, q_full, head * ATT_D, q0 + ATT_M, b);
+        {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+                tma_load_3d(sQ(0), &maps.q, q_full, head * ATT_D, q0, b);
+                if (has_b) tma_load_3d(sQ(1), &maps.q, q_full, head * ATT_D, q0 + ATT_M, b);
+            }
+            __syncwarp();
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
                 const uint32_t ph = (j / KV_STAGES) & 1;
                 mbar_wait(kv_empty(s), ph ^ 1u, 10);
-                mbar_arrive_expect_tx(kv_full(s), 2 * TILE_BYTES);
-                if (j < p.n_self) {
-                    tma_load_3d(sK(s), &maps.k_self, kv_full(s), head * ATT_D, j * ATT_N, b);
-                    tma_load_3d(sV(s), &maps.v_self, kv_full(s), head * ATT_D, j * ATT_N, b);
-                } else {
-                    const int jb = j - p.n_self;
-                    tma_load_3d(sK(s), &maps.k_bank, kv_full(s), head * ATT_D, jb * ATT_N, b);
-                    tma_load_3d(sV(s), &maps.v_bank, kv_full(s), head * ATT_D, jb * ATT_N, b);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(kv_full(s), 2 * TILE_BYTES);
+                    if (j < p.n_self) {
+                        tma_load_3d(sK(s), &maps.k_self, kv_full(s), head * ATT_D, j * ATT_N, b);
+                        tma_load_3d(sV(s), &maps.v_self, kv_full(s), head * ATT_D, j * ATT_N, b);
+                    } else {
+                        const int jb = j - p.n_self;
+                        tma_load_3d(sK(s), &maps.k_bank, kv_full(s), head * ATT_D, jb * ATT_N, b);
+                        tma_load_3d(sV(s), &maps.v_bank, kv_full(s), head * ATT_D, jb * ATT_N, b);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t fmt = p.f16 ? 0u : 1u;
             const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (=K) is K-major
             const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);   // O = P V   : B (=V) is MN-major
             const int nq = has_b ? 2 : 1;
-            auto issue_s = [&](int x, int j) {                                // needs K_j landed, S_X free
+            auto issue_s = [&](int x, int j) {          // needs K_j landed, S_X free; called by the elected lane
                 const int s = j % KV_STAGES;
                 const uint64_t adesc = umma_desc_sw128(sQ(x));
                 const uint64_t bdesc = umma_desc_sw128(sK(s));
@@ -150,7 +159,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             mbar_wait(q_full, 0, 12);
             mbar_wait(kv_full(0), 0, 11);
             tc_fence_after();
-            for (int x = 0; x < nq; ++x) issue_s(x, 0);
+            if (elect_one()) {
+                for (int x = 0; x < nq; ++x) issue_s(x, 0);
+            }
+            __syncwarp();
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
                 if (j + 1 < ntiles) {
@@ -160,16 +172,19 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 for (int x = 0; x < nq; ++x) {
                     mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, S_X consumed, O_X rescaled
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < ATT_N / 16; ++ks) {
-                        const uint64_t adesc = umma_desc_sw128(sP(x) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
-                        const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
-                        umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < ATT_N / 16; ++ks) {
+                            const uint64_t adesc = umma_desc_sw128(sP(x) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
+                            const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
+                            umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        tc_commit(pv_done(x));
+                        if (j + 1 < ntiles) issue_s(x, j + 1);
+                        if (x == nq - 1) tc_commit(kv_empty(s));              // K_j / V_j fully consumed by both tiles
                     }
-                    tc_commit(pv_done(x));
-                    if (j + 1 < ntiles) issue_s(x, j + 1);
+                    __syncwarp();
                 }
-                tc_commit(kv_empty(s));                                        // K_j / V_j fully consumed by both tiles
             }
         }
     } else if (warp >= 4) {

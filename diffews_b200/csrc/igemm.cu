@@ -335,7 +335,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const int out_cols_per_tile = (p.flags & DFW_EPI_GEGLU) ? BLOCK_N / 2 : BLOCK_N;
     const int chunks_per_tile = out_cols_per_tile / CW;
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle so the compiler knows it is warp-uniform: the role loops below run on all 32 lanes
+    // and only the tcgen05 / TMA instructions sit inside elect_one() regions (a plain `if (lane == 0)` around a whole
+    // loop makes ptxas wrap every uniform-datapath instruction in an ELECT / BRA.U.ANY serialisation loop, which made
+    // the issue of an N = 128 MMA slower than the MMA itself)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -375,7 +379,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const int kblocks = p.ntaps * p.kb_per_tap;
 
     if (warp == 0 && p.halo) {
-        if (lane == 0) {
+        {
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -387,19 +391,25 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 for (int kb = 0; kb < p.kb_per_tap; ++kb) {
                     for (int dw = -1; dw <= 1; ++dw) {
                         mbar_wait(ha_empty(as), aph ^ 1u, 7);
-                        mbar_arrive_expect_tx(ha_full(as), nsub * Cfg::PATCH_BYTES);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(ha_full(as), nsub * Cfg::PATCH_BYTES);
 #pragma unroll
-                        for (int sub = 0; sub < TPU; ++sub)
-                            if (sub < nsub)
-                                tma_load_4d(hA(as, sub), &maps.a[1], ha_full(as), kb * BLOCK_K, tc[sub].w0 + dw,
-                                            tc[sub].h0 - 1, tc[sub].n0);
+                            for (int sub = 0; sub < TPU; ++sub)
+                                if (sub < nsub)
+                                    tma_load_4d(hA(as, sub), &maps.a[1], ha_full(as), kb * BLOCK_K, tc[sub].w0 + dw,
+                                                tc[sub].h0 - 1, tc[sub].n0);
+                        }
+                        __syncwarp();
                         if (++as == Cfg::HALO_A_SLOTS) { as = 0; aph ^= 1u; }
                         for (int dh = -1; dh <= 1; ++dh) {
                             const int tap = (dh + 1) * 3 + (dw + 1);
                             mbar_wait(hb_empty(bs), bph ^ 1u, 8);
-                            mbar_arrive_expect_tx(hb_full(bs), Cfg::B_TILE_BYTES);
-                            tma_load_3d(hB(bs), &maps.b, hb_full(bs), (tap * p.kb_per_tap + kb) * BLOCK_K,
-                                        tc[0].n_tile * BLOCK_N, 0);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(hb_full(bs), Cfg::B_TILE_BYTES);
+                                tma_load_3d(hB(bs), &maps.b, hb_full(bs), (tap * p.kb_per_tap + kb) * BLOCK_K,
+                                            tc[0].n_tile * BLOCK_N, 0);
+                            }
+                            __syncwarp();
                             if (++bs == Cfg::HALO_B_SLOTS) { bs = 0; bph ^= 1u; }
                         }
                     }
@@ -407,7 +417,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             }
         }
     } else if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -420,21 +430,24 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     const CUtensorMap* am = &maps.a[p.tap_map[tap]];
                     for (int kb = 0; kb < p.kb_per_tap; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-                        mbar_arrive_expect_tx(full_bar(stage), nsub * A_TILE_BYTES + Cfg::B_TILE_BYTES);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(full_bar(stage), nsub * A_TILE_BYTES + Cfg::B_TILE_BYTES);
 #pragma unroll
-                        for (int sub = 0; sub < TPU; ++sub)
-                            if (sub < nsub)
-                                tma_load_4d(sA(stage, sub), am, full_bar(stage), kb * BLOCK_K,
-                                            tc[sub].w0 + p.tap_dw[tap], tc[sub].h0 + p.tap_dh[tap], tc[sub].n0);
-                        tma_load_3d(sB(stage), &maps.b, full_bar(stage), (tap * p.kb_per_tap + kb) * BLOCK_K,
-                                    tc[0].n_tile * BLOCK_N, p.w_batched ? tc[0].n0 : 0);
+                            for (int sub = 0; sub < TPU; ++sub)
+                                if (sub < nsub)
+                                    tma_load_4d(sA(stage, sub), am, full_bar(stage), kb * BLOCK_K,
+                                                tc[sub].w0 + p.tap_dw[tap], tc[sub].h0 + p.tap_dh[tap], tc[sub].n0);
+                            tma_load_3d(sB(stage), &maps.b, full_bar(stage), (tap * p.kb_per_tap + kb) * BLOCK_K,
+                                        tc[0].n_tile * BLOCK_N, p.w_batched ? tc[0].n0 : 0);
+                        }
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1 && p.halo) {
-        if (lane == 0) {
+        {
             const uint32_t fmt = (p.flags & DFW_EPI_F16) ? 0u : 1u;
             const uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N, fmt, fmt, 0);
             int as = 0, bs = 0;
@@ -453,33 +466,36 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                         for (int dh = 0; dh < 3; ++dh) {
                             mbar_wait(hb_full(bs), bph, 3);
                             tc_fence_after();
-                            const uint64_t bdesc = umma_desc_sw128(hB(bs));
+                            if (elect_one()) {
+                                const uint64_t bdesc = umma_desc_sw128(hB(bs));
 #pragma unroll
-                            for (int sub = 0; sub < TPU; ++sub) {
-                                if (sub < nsub) {
-                                    // vertical tap dh reads patch rows [16*dh, 16*dh + 128): + dh * 2048 bytes
-                                    const uint64_t adesc = umma_desc_sw128(hA(as, sub) + dh * 16 * 128);
+                                for (int sub = 0; sub < TPU; ++sub) {
+                                    if (sub < nsub) {
+                                        // vertical tap dh reads patch rows [16*dh, 16*dh + 128): + dh * 2048 bytes
+                                        const uint64_t adesc = umma_desc_sw128(hA(as, sub) + dh * 16 * 128);
 #pragma unroll
-                                    for (int k = 0; k < BLOCK_K / 16; ++k)
-                                        umma_ss(d_tmem + sub * Cfg::SUB_COLS, adesc + 2u * k, bdesc + 2u * k, idesc,
-                                                (!first || k > 0) ? 1u : 0u);
+                                        for (int k = 0; k < BLOCK_K / 16; ++k)
+                                            umma_ss(d_tmem + sub * Cfg::SUB_COLS, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                                    (!first || k > 0) ? 1u : 0u);
+                                    }
                                 }
+                                tc_commit(hb_empty(bs));
+                                if (dh == 2) tc_commit(ha_empty(as));
+                                if (dh == 2 && dw == 2 && kb == p.kb_per_tap - 1) tc_commit(tfull_bar(acc));
                             }
+                            __syncwarp();
                             first = false;
-                            tc_commit(hb_empty(bs));
                             if (++bs == Cfg::HALO_B_SLOTS) { bs = 0; bph ^= 1u; }
                         }
-                        tc_commit(ha_empty(as));
                         if (++as == Cfg::HALO_A_SLOTS) { as = 0; aph ^= 1u; }
                     }
                 }
-                tc_commit(tfull_bar(acc));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t fmt = (p.flags & DFW_EPI_F16) ? 0u : 1u;       // A and B must share one 16-bit format
             const uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N, fmt, fmt, 0);
             int stage = 0;
@@ -494,21 +510,24 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 for (int kbi = 0; kbi < kblocks; ++kbi) {
                     mbar_wait(full_bar(stage), phase, 3);
                     tc_fence_after();
-                    const uint64_t bdesc = umma_desc_sw128(sB(stage));
+                    if (elect_one()) {
+                        const uint64_t bdesc = umma_desc_sw128(sB(stage));
 #pragma unroll
-                    for (int sub = 0; sub < TPU; ++sub) {
-                        if (sub < nsub) {
-                            const uint64_t adesc = umma_desc_sw128(sA(stage, sub));
+                        for (int sub = 0; sub < TPU; ++sub) {
+                            if (sub < nsub) {
+                                const uint64_t adesc = umma_desc_sw128(sA(stage, sub));
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; ++k)
-                                umma_ss(d_tmem + sub * Cfg::SUB_COLS, adesc + 2u * k, bdesc + 2u * k, idesc,
-                                        (kbi > 0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < BLOCK_K / 16; ++k)
+                                    umma_ss(d_tmem + sub * Cfg::SUB_COLS, adesc + 2u * k, bdesc + 2u * k, idesc,
+                                            (kbi > 0 || k > 0) ? 1u : 0u);
+                            }
                         }
+                        tc_commit(empty_bar(stage));
+                        if (kbi == kblocks - 1) tc_commit(tfull_bar(acc));
                     }
-                    tc_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(acc));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
