@@ -311,16 +311,22 @@ def main():
         ms_total_instr = t0e.elapsed_time(t1e)
     if timer is not None:
         summ = timer.summary()
-        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / (v["ms"] * 1e9), 1)
-                       if v["ms"] > 0 else None, "share_of_step": round(v["ms"] / ms_total_instr, 3)} for k, v in summ.items()}
+        kernels = {}
+        for k, v in summ.items():
+            rate = (v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else None)          # TFLOP/s, or (memory kinds) TB/s
+            d = {"launches": v["launches"], "ms": round(v["ms"], 3), "share_of_step": round(v["ms"] / ms_total_instr, 3)}
+            if k in ops.MEM_KINDS: d["gb_per_s"] = round(rate * 1e3, 1) if rate else None   # algorithmic bytes
+            else: d["tflops"] = round(rate, 1) if rate else None
+            kernels[k] = d
         if args.layer_table and rank == 0:
             rows = sorted(timer.by_shape().items(), key=lambda kv: -kv[1]["ms"])
             with open(args.layer_table, "w") as f:
                 f.write(f"# per-shape CUDA-event times over {args.steps} instrumented eager steps (B={B}/GPU); total {ms_total_instr:.1f} ms\n")
-                f.write("kind\tshape\tlaunches\tms_total\tshare\tTFLOP/s\n")
+                f.write("kind\tshape\tlaunches\tms_total\tshare\tTFLOP/s (igemm, attn) | TB/s of algorithmic bytes (others)\n")
                 for (kind, shape), v in rows:
                     tf = v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else 0.0
-                    f.write(f"{kind}\t{shape}\t{v['launches']}\t{v['ms']:.3f}\t{v['ms'] / ms_total_instr:.4f}\t{tf:.1f}\n")
+                    f.write(f"{kind}\t{shape}\t{v['launches']}\t{v['ms']:.3f}\t{v['ms'] / ms_total_instr:.4f}\t"
+                            + (f"{tf:.2f}" if kind in ops.MEM_KINDS else f"{tf:.1f}") + "\n")
         ig = summ.get("igemm")
         if ig and ig["ms"] > 0:
             achieved = ig["flops"] / (ig["ms"] * 1e9)

@@ -93,6 +93,14 @@ class _Timed:
         return False
 
 
+def _nb(*ts) -> float:
+    """algorithmic bytes of the HBM-bound kernels: every operand read or written once"""
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+MEM_KINDS = ("groupnorm", "layernorm", "softmax", "elementwise", "im2col", "cross_attn", "metric")   # work = bytes
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 _sm_count = {}
 
@@ -261,8 +269,9 @@ def cross_attn(q, k, v, heads, scale):
     Lctx = k.shape[1]
     kvs = 0 if k.shape[0] == 1 else Lctx * C
     o = torch.empty_like(q)
-    check(lib.dfw_cross_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), kvs, o.data_ptr(), B, L, heads, Lctx,
-                                 float(scale), int(h16 == f16), _stream()), "dfw_cross_attn_fwd")
+    with _Timed("cross_attn", _nb(q, o), f"cross_attn B{B} L{L} h{heads} ctx{Lctx}"):
+        check(lib.dfw_cross_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), kvs, o.data_ptr(), B, L, heads, Lctx,
+                                     float(scale), int(h16 == f16), _stream()), "dfw_cross_attn_fwd")
     return o
 
 
@@ -279,9 +288,10 @@ def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=bf16
         # the producing convolution already reduced the statistics in its epilogue: normalise-and-store pass only
         partial, nchunks = pre
         y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-        check(lib.dfw_groupnorm_from_partial(x.data_ptr(), _xd(x), partial.data_ptr(), nchunks, gamma.data_ptr(),
-                                             beta.data_ptr(), y.data_ptr(), int(out_dtype == f16), N, HW, C, groups,
-                                             float(eps), int(silu), _stream()), "dfw_groupnorm_from_partial")
+        with _Timed("groupnorm", _nb(x, y), f"gn-apply N{N} HW{HW} C{C} {x.dtype}".replace("torch.", "")):
+            check(lib.dfw_groupnorm_from_partial(x.data_ptr(), _xd(x), partial.data_ptr(), nchunks, gamma.data_ptr(),
+                                                 beta.data_ptr(), y.data_ptr(), int(out_dtype == f16), N, HW, C, groups,
+                                                 float(eps), int(silu), _stream()), "dfw_groupnorm_from_partial")
         return y
     need = int(lib.dfw_groupnorm_workspace_bytes(N, HW, C, groups))
     key = (x.device, torch.cuda.current_stream().cuda_stream)
@@ -290,10 +300,11 @@ def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=bf16
         ws = torch.empty(max(need, 1 << 20), device=x.device, dtype=torch.uint8)
         _gn_ws[key] = ws
     y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    check(lib.dfw_groupnorm_silu(x.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
-                                 y.data_ptr(), int(out_dtype == f16), N, HW, C, groups, float(eps), int(silu),
-                                 ws.data_ptr(), _stream()),
-          "dfw_groupnorm_silu")
+    with _Timed("groupnorm", _nb(x, y), f"gn-full N{N} HW{HW} C{C} {x.dtype}".replace("torch.", "")):
+        check(lib.dfw_groupnorm_silu(x.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
+                                     y.data_ptr(), int(out_dtype == f16), N, HW, C, groups, float(eps), int(silu),
+                                     ws.data_ptr(), _stream()),
+              "dfw_groupnorm_silu")
     return y
 
 
@@ -302,8 +313,9 @@ def layernorm(x, gamma, beta, eps=1e-5, out_dtype=bf16):
     C = x.shape[-1]
     M = x.numel() // C
     y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    check(lib.dfw_layernorm(x.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
-                            y.data_ptr(), int(out_dtype == f16), M, C, float(eps), _stream()), "dfw_layernorm")
+    with _Timed("layernorm", _nb(x, y), f"ln M{M} C{C}"):
+        check(lib.dfw_layernorm(x.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
+                                y.data_ptr(), int(out_dtype == f16), M, C, float(eps), _stream()), "dfw_layernorm")
     return y
 
 
@@ -312,8 +324,9 @@ def softmax_rows(s, scale, out_dtype=bf16):
     L = s.shape[-1]
     M = s.numel() // L
     p = torch.empty(s.shape, device=s.device, dtype=out_dtype)
-    check(lib.dfw_softmax_rows(s.data_ptr(), p.data_ptr(), int(out_dtype == f16), M, L, float(scale), _stream()),
-          "dfw_softmax_rows")
+    with _Timed("softmax", _nb(s, p), f"softmax M{M} L{L}"):
+        check(lib.dfw_softmax_rows(s.data_ptr(), p.data_ptr(), int(out_dtype == f16), M, L, float(scale), _stream()),
+              "dfw_softmax_rows")
     return p
 
 
@@ -324,8 +337,9 @@ def upsample2x(x, out_dtype=bf16):
         out_dtype = x.dtype
     N, H, W, Cc = x.shape
     y = torch.empty((N, 2 * H, 2 * W, Cc), device=x.device, dtype=out_dtype)
-    check(lib.dfw_upsample2x_nhwc(x.data_ptr(), int(x.dtype == torch.float32), y.data_ptr(), int(out_dtype == f16),
-                                  N, H, W, Cc, _stream()), "dfw_upsample2x_nhwc")
+    with _Timed("elementwise", _nb(x, y), f"upsample2x N{N} {H}x{W} C{Cc}"):
+        check(lib.dfw_upsample2x_nhwc(x.data_ptr(), int(x.dtype == torch.float32), y.data_ptr(), int(out_dtype == f16),
+                                      N, H, W, Cc, _stream()), "dfw_upsample2x_nhwc")
     return y
 
 
@@ -335,8 +349,9 @@ def concat_channels(a, b):
     Ca, Cb = a.shape[-1], b.shape[-1]
     rows = a.numel() // Ca
     y = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=a.dtype)
-    check(lib.dfw_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), rows, Ca, Cb, a.element_size(),
-                                  _stream()), "dfw_concat_channels")
+    with _Timed("elementwise", 2 * _nb(y), f"concat rows{rows} {Ca}+{Cb} x{a.element_size()}B"):
+        check(lib.dfw_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), rows, Ca, Cb, a.element_size(),
+                                      _stream()), "dfw_concat_channels")
     return y
 
 
@@ -346,8 +361,9 @@ def cast16(x, dtype=bf16):
         return x
     _req(x, torch.float32, "x")
     y = torch.empty(x.shape, device=x.device, dtype=dtype)
-    check(lib.dfw_cast_f32_to_16(x.data_ptr(), y.data_ptr(), int(dtype == f16), x.numel(), _stream()),
-          "dfw_cast_f32_to_16")
+    with _Timed("elementwise", _nb(x, y), f"cast16 n{x.numel()}"):
+        check(lib.dfw_cast_f32_to_16(x.data_ptr(), y.data_ptr(), int(dtype == f16), x.numel(), _stream()),
+              "dfw_cast_f32_to_16")
     return y
 
 
@@ -361,8 +377,9 @@ def conv3x3_small_cin(x_nchw, w, bias, out_dtype=bf16):
     N, Cin, H, W = x_nchw.shape
     Cout = w.shape[0]
     y = torch.empty((N, H, W, Cout), device=x_nchw.device, dtype=out_dtype)
-    check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), _xd(y), N, H, W,
-                                    Cin, Cout, _stream()), "dfw_conv3x3_small_cin")
+    with _Timed("elementwise", _nb(x_nchw, y), f"conv3x3_small N{N} {H}x{W} {Cin}->{Cout}"):
+        check(lib.dfw_conv3x3_small_cin(x_nchw.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), _xd(y), N, H, W,
+                                        Cin, Cout, _stream()), "dfw_conv3x3_small_cin")
     return y
 
 
@@ -371,8 +388,9 @@ def im2col3x3_small(x_nchw, kpad, dtype=bf16):
     _req(x_nchw, torch.float32, "x")
     N, Cin, H, W = x_nchw.shape
     y = torch.empty((N, H, W, kpad), device=x_nchw.device, dtype=dtype)
-    check(lib.dfw_im2col3x3_small(x_nchw.data_ptr(), y.data_ptr(), int(dtype == f16), N, H, W, Cin, kpad, _stream()),
-          "dfw_im2col3x3_small")
+    with _Timed("im2col", _nb(x_nchw, y), f"im2col N{N} {H}x{W} Cin{Cin} K{kpad}"):
+        check(lib.dfw_im2col3x3_small(x_nchw.data_ptr(), y.data_ptr(), int(dtype == f16), N, H, W, Cin, kpad, _stream()),
+              "dfw_im2col3x3_small")
     return y
 
 
@@ -384,9 +402,10 @@ def pointwise_small(x, x_strides, w_host, b_host, y, y_strides, N, HW, in_scale=
     if b_host is not None:
         assert b_host.device.type == "cpu" and b_host.dtype == torch.float32
         bptr = b_host.data_ptr()
-    check(lib.dfw_pointwise_small(x.data_ptr(), *x_strides, w_host.data_ptr(), bptr, float(in_scale),
-                                  float(out_scale), y.data_ptr(), *y_strides, N, HW, Cin, Cout, _stream()),
-          "dfw_pointwise_small")
+    with _Timed("elementwise", float(N) * HW * (Cin + Cout) * 4, f"pointwise N{N} HW{HW} {Cin}->{Cout}"):
+        check(lib.dfw_pointwise_small(x.data_ptr(), *x_strides, w_host.data_ptr(), bptr, float(in_scale),
+                                      float(out_scale), y.data_ptr(), *y_strides, N, HW, Cin, Cout, _stream()),
+              "dfw_pointwise_small")
     return y
 
 
@@ -396,8 +415,9 @@ def nhwc_f32_to_nchw(x, C, H, W, scale=1.0, shift=0.0, lo=-3.0e38, hi=3.0e38):
     N = x.shape[0]
     row_stride = x.shape[-1]
     y = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
-    check(lib.dfw_nhwc_f32_to_nchw_f32(x.data_ptr(), row_stride, y.data_ptr(), N, C, H * W, float(scale),
-                                       float(shift), float(lo), float(hi), _stream()), "dfw_nhwc_f32_to_nchw_f32")
+    with _Timed("elementwise", 2 * _nb(y), f"nhwc->nchw N{N} C{C} {H}x{W}"):
+        check(lib.dfw_nhwc_f32_to_nchw_f32(x.data_ptr(), row_stride, y.data_ptr(), N, C, H * W, float(scale),
+                                           float(shift), float(lo), float(hi), _stream()), "dfw_nhwc_f32_to_nchw_f32")
     return y
 
 
@@ -408,7 +428,8 @@ def seg_post(dec, H, W, want_f32=True, want_u8=True):
     rs = dec.shape[-1]
     f = torch.empty((N, 3, H, W), device=dec.device, dtype=torch.float32) if want_f32 else None
     u = torch.empty((N, 3, H, W), device=dec.device, dtype=torch.uint8) if want_u8 else None
-    check(lib.dfw_seg_post(dec.data_ptr(), rs, _ptr(f), _ptr(u), N, H * W, _stream()), "dfw_seg_post")
+    with _Timed("elementwise", float(N) * H * W * 3 * 4 + _nb(f, u), f"seg_post N{N} {H}x{W}"):
+        check(lib.dfw_seg_post(dec.data_ptr(), rs, _ptr(f), _ptr(u), N, H * W, _stream()), "dfw_seg_post")
     return f, u
 
 
@@ -425,9 +446,10 @@ def rthres_iou_hist(pred_u8, gt_u8, ignore_u8=None, r_threshold=0.25, want_mask=
     mask = torch.empty((B, H, W), device=dev, dtype=torch.uint8) if want_mask else None
     ws = torch.empty(int(lib.dfw_rthres_workspace_bytes(B)), device=dev, dtype=torch.uint8)
     if ignore_u8 is not None: _req(ignore_u8, torch.uint8, "ignore")
-    check(lib.dfw_rthres_iou_hist(pred_u8.data_ptr(), int(is_mask), gt_u8.data_ptr(), _ptr(ignore_u8), float(r_threshold),
-                                  inter.data_ptr(), union.data_ptr(), _ptr(mask), B, H, W, ws.data_ptr(), _stream()),
-          "dfw_rthres_iou_hist")
+    with _Timed("metric", _nb(pred_u8, gt_u8, mask), f"rthres B{B} {H}x{W}"):
+        check(lib.dfw_rthres_iou_hist(pred_u8.data_ptr(), int(is_mask), gt_u8.data_ptr(), _ptr(ignore_u8), float(r_threshold),
+                                      inter.data_ptr(), union.data_ptr(), _ptr(mask), B, H, W, ws.data_ptr(), _stream()),
+              "dfw_rthres_iou_hist")
     return inter, union, mask
 
 

@@ -76,7 +76,8 @@ def _gloo_worker(rank, world, port, q):
         m.union_buf[:, cls[i]] += union[i]
     m.all_reduce()
     miou, fb, _ = m.compute_iou()
-    q.put((rank, m.intersection_buf.clone(), m.union_buf.clone(), float(miou), float(fb)))
+    # plain lists, not tensors: a tensor in a Queue travels as a shared-memory handle that dies with this process
+    q.put((rank, m.intersection_buf.tolist(), m.union_buf.tolist(), float(miou), float(fb)))
     dist.destroy_process_group()
 
 
@@ -86,7 +87,10 @@ def test_data_parallel_counts_equal_single_process():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:                     # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -101,5 +105,5 @@ def test_data_parallel_counts_equal_single_process():
     for i in range(40):
         ib[:, cls[i]] += inter[i]; ub[:, cls[i]] += union[i]
     for rank, i_buf, u_buf, miou, fb in res:
-        assert torch.equal(i_buf, ib) and torch.equal(u_buf, ub)
+        assert i_buf == ib.tolist() and u_buf == ub.tolist()
     assert res[0][3] == res[1][3] and res[0][4] == res[1][4]
