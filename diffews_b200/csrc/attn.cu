@@ -16,6 +16,8 @@
 //              swizzled smem, O accumulated in registers with the per-tile rescale (no TMEM read-modify-write).
 #include <atomic>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -206,88 +208,98 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 tc_fence_after();
                 // The TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is
                 // processed (tcgen05.wait::ld waits for everything outstanding, so it is placed after the compute).
-                uint32_t va[32], vb[32];
-                auto chunk_max = [&](const uint32_t (&v)[32], int c, float& mx) {
-                    if (valid == ATT_N) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    }
-                };
-                // pass 1: row max of the scaled logits
-                float mx = -INFINITY;
-                tmem_ld_32x32(ts, va);
-                tmem_ld_wait(); tmem_regs_ready(va);
-                tmem_ld_32x32(ts + 32, vb);
-                chunk_max(va, 0, mx);
-                tmem_ld_wait(); tmem_regs_ready(vb);
-                tmem_ld_32x32(ts + 64, va);
-                chunk_max(vb, 1, mx);
-                tmem_ld_wait(); tmem_regs_ready(va);
-                tmem_ld_32x32(ts + 96, vb);
-                chunk_max(va, 2, mx);
-                tmem_ld_wait(); tmem_regs_ready(vb);
-                tmem_ld_32x32(ts, va);                               // chunk 0 again, for pass 2
-                chunk_max(vb, 3, mx);
-                tmem_ld_wait(); tmem_regs_ready(va);
-                const float m_new = fmaxf(m_used, mx * p.scale_log2);
-                // lazy rescale: only when some row of the warp moved its max by more than 2^TAU (warp-uniform branch,
-                // tcgen05.ld/st are warp-collective)
-                if (__any_sync(0xffffffffu, m_new > m_used + ATT_RESCALE_TAU)) {
-                    const float alpha = exp2f(m_used - m_new);        // 0 on the first tile
-                    if (j > 0) {
-                        mbar_wait(pv_done(x), (j - 1) & 1, 14);       // O_X holds tiles < j
-                        tc_fence_after();
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(to + c * 32, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                            tmem_st_32x32(to + c * 32, v);
-                        }
-                        tmem_st_wait();
-                    }
-                    l_run *= alpha;
-                    m_used = m_new;
-                }
-                // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile
+                // The whole tile body is instantiated twice (full tile / ragged last tile) so the common full-tile path
+                // carries no per-element masking; exp2 is one MUFU (ex2.approx.ftz), the row max uses 3-input max.
                 float psum = 0.f;
-                auto chunk_p = [&](const uint32_t (&v)[32], int c) {
-                    float pf[32];
+                auto run_tile = [&](auto full_tag) {
+                    constexpr bool FULL = decltype(full_tag)::value;
+                    uint32_t va[32], vb[32];
+                    auto chunk_max = [&](const uint32_t (&v)[32], int c, float& mx) {
+                        if constexpr (FULL) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used));
-                        if (valid != ATT_N && c * 32 + i >= valid) e = 0.f;
-                        pf[i] = e;
-                        psum += e;
-                    }
-                    uint8_t* chunk = pbuf + (c >> 1) * TILE_BYTES + row * 128;
+                            for (int i = 0; i < 32; i += 2)
+                                mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                        } else {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w;
-                        w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], p.f16);
-                        w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], p.f16);
-                        w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], p.f16);
-                        w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], p.f16);
-                        const int unit = ((c & 1) * 4 + u) ^ (row & 7);
-                        *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
+                            for (int i = 0; i < 32; ++i)
+                                if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        }
+                    };
+                    // pass 1: row max of the scaled logits
+                    float mx = -INFINITY;
+                    tmem_ld_32x32(ts, va);
+                    tmem_ld_wait(); tmem_regs_ready(va);
+                    tmem_ld_32x32(ts + 32, vb);
+                    chunk_max(va, 0, mx);
+                    tmem_ld_wait(); tmem_regs_ready(vb);
+                    tmem_ld_32x32(ts + 64, va);
+                    chunk_max(vb, 1, mx);
+                    tmem_ld_wait(); tmem_regs_ready(va);
+                    tmem_ld_32x32(ts + 96, vb);
+                    chunk_max(va, 2, mx);
+                    tmem_ld_wait(); tmem_regs_ready(vb);
+                    tmem_ld_32x32(ts, va);                               // chunk 0 again, for pass 2
+                    chunk_max(vb, 3, mx);
+                    tmem_ld_wait(); tmem_regs_ready(va);
+                    const float m_new = fmaxf(m_used, mx * p.scale_log2);
+                    // lazy rescale: only when some row of the warp moved its max by more than 2^TAU (warp-uniform
+                    // branch, tcgen05.ld/st are warp-collective)
+                    if (__any_sync(0xffffffffu, m_new > m_used + ATT_RESCALE_TAU)) {
+                        const float alpha = ex2_approx(m_used - m_new);   // 0 on the first tile
+                        if (j > 0) {
+                            mbar_wait(pv_done(x), (j - 1) & 1, 14);       // O_X holds tiles < j
+                            tc_fence_after();
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                uint32_t v[32];
+                                tmem_ld_32x32(to + c * 32, v);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                                tmem_st_32x32(to + c * 32, v);
+                            }
+                            tmem_st_wait();
+                        }
+                        l_run *= alpha;
+                        m_used = m_new;
                     }
+                    // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile
+                    const float sc = p.scale_log2, mu = m_used;
+                    auto chunk_p = [&](const uint32_t (&v)[32], int c) {
+                        float pf[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float e = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mu));
+                            if constexpr (!FULL) { if (c * 32 + i >= valid) e = 0.f; }
+                            pf[i] = e;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) psum += (pf[i] + pf[i + 1]) + (pf[i + 2] + pf[i + 3]);
+                        uint8_t* chunk = pbuf + (c >> 1) * TILE_BYTES + row * 128;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint4 w;
+                            w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], p.f16);
+                            w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], p.f16);
+                            w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], p.f16);
+                            w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], p.f16);
+                            const int unit = ((c & 1) * 4 + u) ^ (row & 7);
+                            *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
+                        }
+                    };
+                    tmem_ld_32x32(ts + 32, vb);
+                    chunk_p(va, 0);
+                    tmem_ld_wait(); tmem_regs_ready(vb);
+                    tmem_ld_32x32(ts + 64, va);
+                    chunk_p(vb, 1);
+                    tmem_ld_wait(); tmem_regs_ready(va);
+                    tmem_ld_32x32(ts + 96, vb);
+                    chunk_p(va, 2);
+                    tmem_ld_wait(); tmem_regs_ready(vb);
+                    chunk_p(vb, 3);
                 };
-                tmem_ld_32x32(ts + 32, vb);
-                chunk_p(va, 0);
-                tmem_ld_wait(); tmem_regs_ready(vb);
-                tmem_ld_32x32(ts + 64, va);
-                chunk_p(vb, 1);
-                tmem_ld_wait(); tmem_regs_ready(va);
-                tmem_ld_32x32(ts + 96, vb);
-                chunk_p(va, 2);
-                tmem_ld_wait(); tmem_regs_ready(vb);
-                chunk_p(vb, 3);
+                if (valid == ATT_N) run_tile(std::true_type{});
+                else run_tile(std::false_type{});
                 l_run += psum;
                 fence_proxy_async_smem();
                 tc_fence_before();

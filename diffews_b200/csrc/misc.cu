@@ -199,6 +199,53 @@ __global__ void im2col3x3_small_kernel(const float* __restrict__ x, uint16_t* __
     }
 }
 
+// Compile-time (Cin, Kpad) flavour used by every layer on the path (3->128, 4->320, 4->512: Kpad 64; 8->320: Kpad 128):
+// grid = (pixel blocks of a row, H, N), so no 64-bit index divisions, and tap / channel come from constant divisors.
+constexpr int IM2COL_ROWS = 8;
+template <int CIN, int KPAD>
+__global__ void __launch_bounds__(256) im2col3x3_small_t_kernel(const float* __restrict__ x, uint16_t* __restrict__ y,
+                                                                int H, int W, int y_f16) {
+    constexpr int VPR = KPAD / 8;                 // 16-byte vectors per output row
+    constexpr int PIX = 256 / VPR;                // pixels per CTA
+    constexpr int K = 9 * CIN;
+    const int v = threadIdx.x % VPR;
+    const int w = blockIdx.x * PIX + threadIdx.x / VPR;
+    const int n = blockIdx.z;
+    if (w >= W) return;
+    const float* xn = x + static_cast<size_t>(n) * CIN * H * W;
+    // IM2COL_ROWS image rows per thread: the loads of several rows are in flight together (the kernel is latency-,
+    // not bandwidth-limited with one 16-byte store per thread) and vertically adjacent taps hit in L1
+#pragma unroll 4
+    for (int r = 0; r < IM2COL_ROWS; ++r) {
+        const int h = blockIdx.y * IM2COL_ROWS + r;
+        if (h >= H) break;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = v * 8 + j;
+            float val = 0.f;
+            if (k < K) {
+                const int tap = k / CIN, c = k - tap * CIN;
+                const int dh = tap / 3;
+                const int hh = h + dh - 1, ww = w + (tap - dh * 3) - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(xn + (static_cast<size_t>(c) * H + hh) * W + ww);
+            }
+            f[j] = val;
+        }
+        uint4 o;
+        o.x = pack_h2(f[0], f[1], y_f16); o.y = pack_h2(f[2], f[3], y_f16);
+        o.z = pack_h2(f[4], f[5], y_f16); o.w = pack_h2(f[6], f[7], y_f16);
+        *reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * H + h) * W + w) * KPAD + v * 8) = o;
+    }
+}
+
+template <int CIN, int KPAD>
+static void launch_im2col_t(const float* x, uint16_t* y, int N, int H, int W, int y_f16, cudaStream_t st) {
+    constexpr int PIX = 256 / (KPAD / 8);
+    const dim3 grid((W + PIX - 1) / PIX, (H + IM2COL_ROWS - 1) / IM2COL_ROWS, N);
+    im2col3x3_small_t_kernel<CIN, KPAD><<<grid, 256, 0, st>>>(x, y, H, W, y_f16);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 1x1 conv on <= 8 channels with arbitrary element strides (NCHW <-> NHWC), fp32.
 // ---------------------------------------------------------------------------------------------------------
@@ -333,8 +380,14 @@ int dfw_im2col3x3_small(const float* x, void* y, int y_f16, int N, int H, int W,
     DFW_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 16);
     DFW_REQUIRE(Kpad % 64 == 0 && Kpad >= 9 * Cin);
     const long long total = static_cast<long long>(N) * H * W * (Kpad / 8);
-    im2col3x3_small_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        x, reinterpret_cast<uint16_t*>(y), total, H, W, Cin, Kpad, y_f16);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    uint16_t* y16 = reinterpret_cast<uint16_t*>(y);
+    const bool grid_ok = H <= 65535 && N <= 65535;
+    if (grid_ok && Cin == 3 && Kpad == 64) launch_im2col_t<3, 64>(x, y16, N, H, W, y_f16, st);
+    else if (grid_ok && Cin == 4 && Kpad == 64) launch_im2col_t<4, 64>(x, y16, N, H, W, y_f16, st);
+    else if (grid_ok && Cin == 8 && Kpad == 128) launch_im2col_t<8, 128>(x, y16, N, H, W, y_f16, st);
+    else
+        im2col3x3_small_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y16, total, H, W, Cin, Kpad, y_f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -230,6 +230,77 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
     }
 }
 
+// Same arithmetic (exact two-pass statistics on the register-resident row), laid out for bandwidth: 4-element vectors
+// (a warp instruction covers 512 contiguous bytes of an fp32 row) and NV = ceil(C / 128) compile-time steps, so the
+// 320 / 640 / 1280-channel rows of the UNet keep all lanes busy and every load of a row is in flight at once.
+template <int XD>
+__device__ __forceinline__ float4 ln_load4(const void* x, long long off) {
+    if constexpr (XD == 1) {
+        return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + off));
+    } else {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + off));
+        const float2 a = unpack_h2(r.x, XD == 2), b = unpack_h2(r.y, XD == 2);
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+template <int XD, int NV>
+__global__ void __launch_bounds__(256) layernorm_v4_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, void* __restrict__ y, int M,
+                                                           int C, float eps, int y_f16) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const int V = C / 4;
+    const long long row_off = static_cast<long long>(warp) * C;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int vc = lane + 32 * k;
+        v[k] = (vc < V) ? ln_load4<XD>(x, row_off + vc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (lane + 32 * k < V) {
+            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+            ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c, c, ss); ss = fmaf(d, d, ss);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / C + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int vc = lane + 32 * k;
+        if (vc < V) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + vc);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + vc);
+            uint2 o;
+            o.x = pack_h2((v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y, y_f16);
+            o.y = pack_h2((v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w, y_f16);
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + row_off + vc * 4) = o;
+        }
+    }
+}
+template <int XD>
+static bool launch_layernorm_v4(const void* x, const float* gamma, const float* beta, void* y, int M, int C, float eps,
+                                int y_f16, cudaStream_t stream) {
+    const int nv = (C / 4 + 31) / 32;
+    const int blocks = (M + 7) / 8;
+    if (nv <= 3) layernorm_v4_kernel<XD, 3><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
+    else if (nv <= 5) layernorm_v4_kernel<XD, 5><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
+    else if (nv <= 10) layernorm_v4_kernel<XD, 10><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
+    else if (nv <= 16) layernorm_v4_kernel<XD, 16><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
+    else return false;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Row softmax (fp32 logits -> bf16 probabilities), one CTA per row.
 // ---------------------------------------------------------------------------------------------------------
@@ -370,7 +441,11 @@ int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* b
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int warps_per_block = 8;
     const int blocks = (M + warps_per_block - 1) / warps_per_block;
-    if (x_dtype == 1)
+    if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (x_dtype == 1 ? launch_layernorm_v4<1>(x, gamma, beta, y, M, C, eps, y_f16, stream)
+         : x_dtype == 2 ? launch_layernorm_v4<2>(x, gamma, beta, y, M, C, eps, y_f16, stream)
+                        : launch_layernorm_v4<0>(x, gamma, beta, y, M, C, eps, y_f16, stream))) {
+    } else if (x_dtype == 1)
         layernorm_kernel<1><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
     else if (x_dtype == 2)
         layernorm_kernel<2><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
