@@ -34,7 +34,9 @@ constexpr int TILE_BYTES = 128 * 128;             // 128 rows x 128 B
 constexpr int ATT_THREADS = 384;                  // 4 control warps + 2 x 4 softmax warps
 constexpr int ATT_SMEM = ATT_QT * TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ +
                          ATT_QT * 2 * TILE_BYTES /*P*/ + 1024 + 256;
-constexpr int ATT_TMEM_COLS = 512;                // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+constexpr int ATT_SBUF = 3;                       // S accumulators rotate over 3 TMEM buffers: the MMA warp computes
+                                                  // S_X(j+1) while the softmax group of X still reads S_X(j)
+constexpr int ATT_TMEM_COLS = 512;                // S buffers [0,128) [128,256) [256,384); O_A [384,448) O_B [448,512)
 constexpr float ATT_RESCALE_TAU = 8.0f;           // lazy rescale threshold in the log2 domain (P <= 2^8)
 // All 16-bit tensors of a call (Q, K, V, P, O) share one format, bf16 or fp16: tcgen05 kind::f16 requires the A and B
 // operand of an MMA to have the same format (a bf16 x fp16 mix raises an illegal-instruction trap on sm_100).
@@ -62,6 +64,7 @@ struct AttnParams {
 //               and sum in the log2 domain; O is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row of
 //               the warp raises its max by more than 2^TAU, so the common case never touches O; P -> 16-bit ->
 //               128B-swizzled smem (the K-major A operand of the PV MMA)
+template <bool F16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -77,10 +80,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     const uint32_t q_full = bar_base;
     auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
     auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KV_STAGES + s); };
-    auto s_full = [&](int x) { return bar_base + 8u * (1 + 2 * KV_STAGES + x); };
-    auto p_full = [&](int x) { return bar_base + 8u * (3 + 2 * KV_STAGES + x); };
-    auto pv_done = [&](int x) { return bar_base + 8u * (5 + 2 * KV_STAGES + x); };
-    const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * KV_STAGES);
+    auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * KV_STAGES + buf); };      // one per S buffer
+    auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KV_STAGES + x); };
+    auto pv_done = [&](int x) { return bar_base + 8u * (6 + 2 * KV_STAGES + x); };
+    const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * KV_STAGES);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
     uint8_t* sP_generic = smem_raw + (p_base - raw_u32);
 
@@ -103,7 +106,8 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-        for (int x = 0; x < ATT_QT; ++x) { mbar_init(s_full(x), 1); mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1); }
+        for (int x = 0; x < ATT_SBUF; ++x) mbar_init(s_full(x), 1);
+        for (int x = 0; x < ATT_QT; ++x) { mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -114,8 +118,8 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    auto tS = [&](int x) { return tmem_base + x * 128; };
-    auto tO = [&](int x) { return tmem_base + 256 + x * 64; };
+    auto tS = [&](int buf) { return tmem_base + buf * 128; };
+    auto tO = [&](int x) { return tmem_base + ATT_SBUF * 128 + x * 64; };
 
     if (warp == 0) {
         {
@@ -145,18 +149,21 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         }
     } else if (warp == 1) {
         {
-            const uint32_t fmt = p.f16 ? 0u : 1u;
+            const uint32_t fmt = F16 ? 0u : 1u;
             const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (=K) is K-major
             const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);   // O = P V   : B (=V) is MN-major
             const int nq = has_b ? 2 : 1;
-            auto issue_s = [&](int x, int j) {          // needs K_j landed, S_X free; called by the elected lane
+            // S tiles are numbered in issue order, seq = nq * j + x, and live in TMEM buffer seq % 3.  S(seq) may be
+            // issued once K_j has landed and the softmax of S(seq - 3) has finished (its p_full was waited two PVs ago).
+            auto issue_s = [&](int x, int j) {          // called by the elected lane
                 const int s = j % KV_STAGES;
+                const int buf = (nq * j + x) % ATT_SBUF;
                 const uint64_t adesc = umma_desc_sw128(sQ(x));
                 const uint64_t bdesc = umma_desc_sw128(sK(s));
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_ss(tS(x), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-                tc_commit(s_full(x));
+                    umma_ss(tS(buf), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                tc_commit(s_full(buf));
             };
             mbar_wait(q_full, 0, 12);
             mbar_wait(kv_full(0), 0, 11);
@@ -172,7 +179,13 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                     tc_fence_after();
                 }
                 for (int x = 0; x < nq; ++x) {
-                    mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, S_X consumed, O_X rescaled
+                    // run ahead: S_X(j+1) goes to the tensor pipe before P_X(j) is waited for (its buffer, last used by
+                    // S(seq - 3), was released by a p_full wait of an earlier step)
+                    if (j + 1 < ntiles) {
+                        if (elect_one()) issue_s(x, j + 1);
+                        __syncwarp();
+                    }
+                    mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, S_X(j) consumed, O_X rescaled
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
@@ -182,7 +195,6 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                             umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
                         }
                         tc_commit(pv_done(x));
-                        if (j + 1 < ntiles) issue_s(x, j + 1);
                         if (x == nq - 1) tc_commit(kv_empty(s));              // K_j / V_j fully consumed by both tiles
                     }
                     __syncwarp();
@@ -196,7 +208,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         const int qrow0 = q0 + x * ATT_M;
         if (x == 0 || has_b) {
             const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-            const uint32_t ts = tS(x) + lane_off;
+            const int nq = has_b ? 2 : 1;
             const uint32_t to = tO(x) + lane_off;
             float m_used = -INFINITY, l_run = 0.f;
             uint8_t* pbuf = sP_generic + x * 2 * TILE_BYTES;
@@ -204,7 +216,9 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 int valid;
                 if (j < p.n_self) valid = min(ATT_N, p.Ls - j * ATT_N);
                 else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
-                mbar_wait(s_full(x), j & 1, 15);
+                const int seq = nq * j + x, sbuf = seq % ATT_SBUF;
+                const uint32_t ts = tS(sbuf) + lane_off;
+                mbar_wait(s_full(sbuf), (seq / ATT_SBUF) & 1, 15);
                 tc_fence_after();
                 // The TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is
                 // processed (tcgen05.wait::ld waits for everything outstanding, so it is placed after the compute).
@@ -263,7 +277,9 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                         l_run *= alpha;
                         m_used = m_new;
                     }
-                    // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile
+                    // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile.  The P buffer is still being
+                    // read by the PV MMA of tile j-1 until pv_done (S no longer orders this: it is computed ahead).
+                    if (j > 0) mbar_wait(pv_done(x), (j - 1) & 1, 17);
                     const float sc = p.scale_log2, mu = m_used;
                     auto chunk_p = [&](const uint32_t (&v)[32], int c) {
                         float pf[32];
@@ -279,10 +295,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             uint4 w;
-                            w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], p.f16);
-                            w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], p.f16);
-                            w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], p.f16);
-                            w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], p.f16);
+                            w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], F16);
+                            w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], F16);
+                            w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], F16);
+                            w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], F16);
                             const int unit = ((c & 1) * 4 + u) ^ (row & 7);
                             *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
                         }
@@ -321,10 +337,10 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
                         uint4 w;
-                        w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, p.f16);
-                        w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, p.f16);
-                        w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, p.f16);
-                        w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, p.f16);
+                        w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, F16);
+                        w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, F16);
+                        w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, F16);
+                        w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, F16);
                         *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
                     }
                 }
@@ -455,11 +471,13 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     p.o_row_stride = o_row_stride;
     static bool attr_set = false;
     if (!attr_set) {
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
     dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
-    attn_kvfused_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_)>>>(maps, p);
+    if (f16) attn_kvfused_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_)>>>(maps, p);
+    else attn_kvfused_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_)>>>(maps, p);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -201,7 +201,7 @@ __global__ void im2col3x3_small_kernel(const float* __restrict__ x, uint16_t* __
 
 // Compile-time (Cin, Kpad) flavour used by every layer on the path (3->128, 4->320, 4->512: Kpad 64; 8->320: Kpad 128):
 // grid = (pixel blocks of a row, H, N), so no 64-bit index divisions, and tap / channel come from constant divisors.
-constexpr int IM2COL_ROWS = 8;
+constexpr int IM2COL_ROWS = 16;
 template <int CIN, int KPAD>
 __global__ void __launch_bounds__(256) im2col3x3_small_t_kernel(const float* __restrict__ x, uint16_t* __restrict__ y,
                                                                 int H, int W, int y_f16) {
@@ -213,29 +213,36 @@ __global__ void __launch_bounds__(256) im2col3x3_small_t_kernel(const float* __r
     const int n = blockIdx.z;
     if (w >= W) return;
     const float* xn = x + static_cast<size_t>(n) * CIN * H * W;
-    // IM2COL_ROWS image rows per thread: the loads of several rows are in flight together (the kernel is latency-,
-    // not bandwidth-limited with one 16-byte store per thread) and vertically adjacent taps hit in L1
+    // Everything that does not depend on the image row is computed once per thread: for each of the 8 elements of this
+    // thread's 16-byte vector the offset of its tap relative to the pixel, and a 3-bit mask saying which vertical tap
+    // (top / centre / bottom) it reads (0 = padding column of K, or a horizontal tap outside the image).
+    int off[8];
+    int rmask[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = v * 8 + j;
+        const int tap = k / CIN, c = k - tap * CIN;
+        const int dh = tap / 3, dw = tap - dh * 3;
+        const int ww = w + dw - 1;
+        off[j] = c * H * W + (dh - 1) * W + (dw - 1);
+        rmask[j] = (k < K && ww >= 0 && ww < W) ? (1 << dh) : 0;
+    }
+    // IM2COL_ROWS image rows per thread: the loads of several rows are in flight together and vertically adjacent
+    // taps hit in L1
 #pragma unroll 4
     for (int r = 0; r < IM2COL_ROWS; ++r) {
         const int h = blockIdx.y * IM2COL_ROWS + r;
-        if (h >= H) break;
-        float f[8];
+        if (h < H) {
+            const int base = h * W + w;
+            const int rows_ok = (h > 0 ? 1 : 0) | 2 | (h < H - 1 ? 4 : 0);
+            float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = v * 8 + j;
-            float val = 0.f;
-            if (k < K) {
-                const int tap = k / CIN, c = k - tap * CIN;
-                const int dh = tap / 3;
-                const int hh = h + dh - 1, ww = w + (tap - dh * 3) - 1;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(xn + (static_cast<size_t>(c) * H + hh) * W + ww);
-            }
-            f[j] = val;
+            for (int j = 0; j < 8; ++j) f[j] = (rmask[j] & rows_ok) ? __ldg(xn + base + off[j]) : 0.f;
+            uint4 o;
+            o.x = pack_h2(f[0], f[1], y_f16); o.y = pack_h2(f[2], f[3], y_f16);
+            o.z = pack_h2(f[4], f[5], y_f16); o.w = pack_h2(f[6], f[7], y_f16);
+            *reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * H + h) * W + w) * KPAD + v * 8) = o;
         }
-        uint4 o;
-        o.x = pack_h2(f[0], f[1], y_f16); o.y = pack_h2(f[2], f[3], y_f16);
-        o.z = pack_h2(f[4], f[5], y_f16); o.w = pack_h2(f[6], f[7], y_f16);
-        *reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * H + h) * W + w) * KPAD + v * 8) = o;
     }
 }
 
@@ -382,7 +389,7 @@ int dfw_im2col3x3_small(const float* x, void* y, int y_f16, int N, int H, int W,
     const long long total = static_cast<long long>(N) * H * W * (Kpad / 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     uint16_t* y16 = reinterpret_cast<uint16_t*>(y);
-    const bool grid_ok = H <= 65535 && N <= 65535;
+    const bool grid_ok = H <= 65535 && N <= 65535 && static_cast<long long>(Cin) * H * W < (1LL << 31);
     if (grid_ok && Cin == 3 && Kpad == 64) launch_im2col_t<3, 64>(x, y16, N, H, W, y_f16, st);
     else if (grid_ok && Cin == 4 && Kpad == 64) launch_im2col_t<4, 64>(x, y16, N, H, W, y_f16, st);
     else if (grid_ok && Cin == 8 && Kpad == 128) launch_im2col_t<8, 128>(x, y16, N, H, W, y_f16, st);

@@ -95,6 +95,11 @@ def main():
         g = torch.ones(128, device="cuda"); b = torch.zeros(128, device="cuda")
         nbytes = x.numel() * (2 + 2)          # algorithmic: read fp16 once, write fp16 once
         return (lambda: ops.groupnorm(x, g, b, eps=1e-6, silu=True, out_dtype=torch.float16)), None, nbytes
+    def im2col():
+        x = torch.randn(16, 3, 512, 512, device="cuda")
+        nbytes = x.numel() * 4 + 16 * 512 * 512 * 64 * 2
+        return (lambda: ops.im2col3x3_small(x, 64, torch.float16)), None, nbytes
+    cases.update(im2col=im2col)
     cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, gn=gn, gn16=gn16)
     which = list(cases) if args.which == ["all"] else args.which
     for name in which:
