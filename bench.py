@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true")
     ap.add_argument("--vae-stream", default="half", choices=["half", "f32"], help="VAE residual-stream storage")
-    ap.add_argument("--unet-stream", default="f32", choices=["half", "f32"], help="UNet residual-stream storage")
+    ap.add_argument("--unet-stream", default="half", choices=["half", "f32"], help="UNet residual-stream storage")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
     args = ap.parse_args()

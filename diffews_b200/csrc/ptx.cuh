@@ -245,6 +245,18 @@ __device__ __forceinline__ void tmem_regs_ready(uint32_t (&v)[32]) {
           "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
         :: "memory");
 }
+__device__ __forceinline__ void tmem_regs_ready16(uint32_t (&v)[16]) {
+    asm volatile(""
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+          "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+        :: "memory");
+}
+// 2^x on a packed pair of fp16 values: ONE MUFU op for two elements (the fp32 ex2 does one)
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
 // registers -> TMEM, 32 lanes x 32 columns
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(

@@ -102,7 +102,9 @@ class MyUNet2DConditionModel:
                  cross_attention_dim=1024, precision: Optional[Precision] = None):
         sd = state_dict
         self.device = torch.device(device)
-        self.prec = precision or Precision()
+        # default = every activation tensor 16-bit (the reference's --half_precision layout: main_oss.py:332-336);
+        # Precision() (fp32 residual stream and conv1 -> norm2 intermediates) stays selectable
+        self.prec = precision or Precision(stream_f32=False, mid_f32=False)
         prec, dev = self.prec, self.device
         c = tuple(block_out_channels)
         self.config = SimpleNamespace(in_channels=4, in_channels_ref=8, out_channels=4, block_out_channels=c,

@@ -191,11 +191,11 @@ def test_pipeline_full_size_512(full_models):
     assert min(agree) >= 0.995 and max(unet_err) <= UNET_RTOL and max(e2e_err) <= 2e-2
 
 
-def test_pipeline_full_width_half_stream_128(full_models):
-    """Optional policy: UNet residual stream and conv->norm intermediates in fp16 as well (everything 16-bit)."""
+def test_pipeline_full_width_f32_stream_128(full_models):
+    """Optional policy: UNet residual stream and conv->norm intermediates kept in fp32 (default: everything 16-bit)."""
     from diffews_b200.layers import Precision
-    agree, e2e_err, unet_err = _pipeline_parity(full_models, 128, 2, 1, unet_precision=Precision(stream_f32=False, mid_f32=False))
-    print("full pipeline 128 (fp16 UNet stream): mask agreement", agree, "e2e latent", e2e_err, "unet-only latent", unet_err)
+    agree, e2e_err, unet_err = _pipeline_parity(full_models, 128, 2, 1, unet_precision=Precision(stream_f32=True, mid_f32=True))
+    print("full pipeline 128 (fp32 UNet stream): mask agreement", agree, "e2e latent", e2e_err, "unet-only latent", unet_err)
     assert min(agree) >= 0.995 and max(unet_err) <= UNET_RTOL and max(e2e_err) <= 2e-2
 
 
