@@ -157,6 +157,18 @@ def run_reference(args):
     return 0
 
 
+def _igemm_traffic():
+    """DRAM bytes of one launch of the dominant igemm shape, from the committed ncu --set full capture (GB), else None."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_igemm_traffic.json")) as f:
+            t = json.load(f)
+        return {"unit": "GB", "dram_per_launch": round(t["dram_bytes_per_launch"] / 1e9, 3),
+                "algorithmic_per_launch": round(t["algorithmic_bytes_per_launch"] / 1e9, 3), "layer": t["layer"],
+                "source": "profiles/r01_ncu_full_kernels.tsv"}
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,7 +344,7 @@ def main():
             achieved = ig["flops"] / (ig["ms"] * 1e9)
             roofline = {"bound": "tensor", "kernel": "igemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear)",
                         "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": f"{peak_kind} sustained bf16",
+                        "frac": round(achieved / peak_tf, 4), "traffic": _igemm_traffic(), "peak_source": f"{peak_kind} sustained bf16",
                         "launches": ig["launches"], "share_of_step": round(ig["ms"] / ms_total_instr, 3),
                         "timed_in": "instrumented eager pass of the same steps (events around every launch)"}
 
