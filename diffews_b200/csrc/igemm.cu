@@ -98,7 +98,23 @@ struct IgemmCfg {
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-GELU x * Phi(x) with erfc from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf, far below the 16-bit output
+// rounding): q = erfc(|x|/sqrt 2) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-x^2/2), t = 1 / (1 + p |x|/sqrt 2);
+// Phi(x) = 1 - q/2 for x >= 0, q/2 otherwise.  ~17 instructions (2 MUFU) instead of erff()'s ~30: the GEGLU projections
+// (K = 320 / 640) are bound by this epilogue, not by their MMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    const float hq = 0.5f * poly * t * e;                 // q / 2
+    return x * (x >= 0.f ? 1.0f - hq : hq);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // Butterfly reduce-scatter over the warp: on return v[0] of lane l holds the sum over all 32 lanes of element
@@ -872,6 +888,277 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// "T128": channel-major accumulator variant for the Cout = 128, 3x3, stride-1 convolutions (the 512^2 layers of the
+// VAE, 1/7 of the whole step).  With pixels as M and 128 channels as N every tcgen05.mma (128x128x16) has to read
+// 4 KiB of A and 4 KiB of B from smem in its 64 cycles -- the 128 B/clk of the smem port, so the tensor pipe stalls
+// on operands (73 % active in ncu).  Here the roles are swapped: A = the weight tile [128 ch x 64], B = a 16 x 16-pixel
+// patch [256 px x 64]: one 128x256x16 MMA reads 4 + 8 KiB in 128 cycles (96 B/clk, like the N = 256 layers, 91 %).
+// The accumulator is then D^T: TMEM lane = output channel, column = pixel of the tile.  Epilogue: a thread owns one
+// channel, so bias is a scalar, the GroupNorm statistics are two running registers (no shuffles until the image
+// changes), and each warp writes its own [64 px x 32 ch] staging block with 2-byte stores (a warp store = one 64 B
+// pixel row, conflict-free) and TMA-stores it -- no CTA-level barrier anywhere in the epilogue.
+//   warp 0  patch producer: (16+2) x 16 px x 64 ch per (channel block, horizontal tap), the 3 vertical taps are the
+//           same patch at +0 / +2048 / +4096 B
+//   warp 1  MMA issuer      warp 2  TMEM allocator + weight-tile producer      warp 3  residual loader (TMA)
+//   warps 4-11  epilogue: channel quarter q = warp % 4, pixel half eg = (warp - 4) / 4 (tile rows 8 eg .. 8 eg + 7)
+// ---------------------------------------------------------------------------------------------------------
+struct T128Cfg {
+    static constexpr int PATCH_BYTES = 18 * 16 * 128;       // 36 KiB
+    static constexpr int A_SLOTS = 3;
+    static constexpr int W_TILE_BYTES = 128 * 128;          // 16 KiB
+    static constexpr int W_SLOTS = 3;
+    static constexpr int STG_BYTES = 64 * 64;               // 64 pixels x 32 channels x 2 B
+    static constexpr int NBAR = 2 * A_SLOTS + 2 * W_SLOTS + 4 + 32;
+    static constexpr int SMEM_USED = A_SLOTS * PATCH_BYTES + W_SLOTS * W_TILE_BYTES + 16 * STG_BYTES + 8 * NBAR + 16;
+    static constexpr int SMEM_BYTES = SMEM_USED + 512;      // smem is declared __align__(1024); the kernel traps otherwise
+    static_assert(SMEM_BYTES <= 232448, "smem budget");
+};
+struct T128Maps {
+    CUtensorMap patch, w, out, res;
+};
+struct T128Params {
+    int N, H, W;
+    int kb_per_tap;
+    int tiles_w, tiles_h, total_units;
+    const float* bias;
+    int f16, has_res;
+    float out_scale;
+    float* gn_partial;
+    long long gn_img_stride;
+};
+
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__ T128Params p) {
+    using Cfg = T128Cfg;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    if (base - raw > static_cast<uint32_t>(Cfg::SMEM_BYTES - Cfg::SMEM_USED)) __trap();
+    auto sP = [&](int s) { return base + s * Cfg::PATCH_BYTES; };
+    auto sW = [&](int s) { return base + Cfg::A_SLOTS * Cfg::PATCH_BYTES + s * Cfg::W_TILE_BYTES; };
+    const uint32_t stg_base = base + Cfg::A_SLOTS * Cfg::PATCH_BYTES + Cfg::W_SLOTS * Cfg::W_TILE_BYTES;
+    auto sS = [&](int w8, int b) { return stg_base + (w8 * 2 + b) * Cfg::STG_BYTES; };
+    const uint32_t bar = stg_base + 16 * Cfg::STG_BYTES;
+    auto pa_full = [&](int i) { return bar + 8u * i; };
+    auto pa_empty = [&](int i) { return bar + 8u * (Cfg::A_SLOTS + i); };
+    auto w_full = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + i); };
+    auto w_empty = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + Cfg::W_SLOTS + i); };
+    const uint32_t b2 = bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS);
+    auto tfull = [&](int a) { return b2 + 8u * a; };
+    auto tempty = [&](int a) { return b2 + 8u * (2 + a); };
+    auto res_full = [&](int i) { return b2 + 8u * (4 + i); };        // i = warp8 * 2 + buffer
+    auto buf_free = [&](int i) { return b2 + 8u * (20 + i); };
+    const uint32_t tmem_slot = b2 + 8u * 36;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.patch); tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.out);
+        if (p.has_res) tma_prefetch_desc(&maps.res);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(pa_full(i), 1); mbar_init(pa_empty(i), 1); }
+        for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+        for (int i = 0; i < 16; ++i) { mbar_init(res_full(i), 1); mbar_init(buf_free(i), 1); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    auto decode = [&](int u, int& n, int& h0, int& w0) {
+        n = u / tiles_per_img;
+        const int r = u - n * tiles_per_img;
+        h0 = (r / p.tiles_w) * 16;
+        w0 = (r % p.tiles_w) * 16;
+    };
+
+    if (warp == 0) {
+        int as = 0;
+        uint32_t aph = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            int n, h0, w0;
+            decode(u, n, h0, w0);
+            for (int kb = 0; kb < p.kb_per_tap; ++kb)
+                for (int dw = -1; dw <= 1; ++dw) {
+                    mbar_wait(pa_empty(as), aph ^ 1u, 21);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(pa_full(as), Cfg::PATCH_BYTES);
+                        tma_load_4d(sP(as), &maps.patch, pa_full(as), kb * BLOCK_K, w0 + dw, h0 - 1, n);
+                    }
+                    __syncwarp();
+                    if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
+                }
+        }
+    } else if (warp == 2) {
+        int ws = 0;
+        uint32_t wph = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
+            for (int kb = 0; kb < p.kb_per_tap; ++kb)
+                for (int dw = 0; dw < 3; ++dw)
+                    for (int dh = 0; dh < 3; ++dh) {
+                        mbar_wait(w_empty(ws), wph ^ 1u, 22);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(w_full(ws), Cfg::W_TILE_BYTES);
+                            tma_load_3d(sW(ws), &maps.w, w_full(ws), ((dh * 3 + dw) * p.kb_per_tap + kb) * BLOCK_K, 0, 0);
+                        }
+                        __syncwarp();
+                        if (++ws == Cfg::W_SLOTS) { ws = 0; wph ^= 1u; }
+                    }
+    } else if (warp == 1) {
+        const uint32_t fmt = p.f16 ? 0u : 1u;
+        const uint32_t idesc = umma_idesc(128, 256, fmt, fmt, 0);
+        int as = 0, ws = 0, acc = 0;
+        uint32_t aph = 0, wph = 0, acc_phase = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            mbar_wait(tempty(acc), acc_phase ^ 1u, 23);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            bool first = true;
+            for (int kb = 0; kb < p.kb_per_tap; ++kb)
+                for (int dw = 0; dw < 3; ++dw) {
+                    mbar_wait(pa_full(as), aph, 24);
+                    for (int dh = 0; dh < 3; ++dh) {
+                        mbar_wait(w_full(ws), wph, 25);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t adesc = umma_desc_sw128(sW(ws));
+                            const uint64_t bdesc = umma_desc_sw128(sP(as) + dh * 16 * 128);   // tile row r = patch row r + dh
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (!first || k > 0) ? 1u : 0u);
+                            tc_commit(w_empty(ws));
+                            if (dh == 2) tc_commit(pa_empty(as));
+                            if (dh == 2 && dw == 2 && kb == p.kb_per_tap - 1) tc_commit(tfull(acc));
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++ws == Cfg::W_SLOTS) { ws = 0; wph ^= 1u; }
+                    }
+                    if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
+                }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (warp == 3) {
+        if (p.has_res) {
+            uint32_t k = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++k) {
+                int n, h0, w0;
+                decode(u, n, h0, w0);
+                for (int sb = 0; sb < 2; ++sb)
+                    for (int w8 = 0; w8 < 8; ++w8) {
+                        const int i = w8 * 2 + sb;
+                        mbar_wait(buf_free(i), (k & 1u) ^ 1u, 26);        // the store that last used this block has drained
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(res_full(i), Cfg::STG_BYTES);
+                            tma_load_4d(sS(w8, sb), &maps.res, res_full(i), 32 * (w8 & 3), w0, h0 + 8 * (w8 >> 2) + 4 * sb, n);
+                        }
+                        __syncwarp();
+                    }
+            }
+        }
+    } else {
+        const int w8 = warp - 4;
+        const int q = w8 & 3, eg = w8 >> 2;
+        const int ch = 32 * q + lane;
+        const float bias_v = p.bias ? __ldg(p.bias + ch) : 0.f;
+        const float out_scale = p.out_scale;
+        const bool has_res = p.has_res != 0, has_gn = p.gn_partial != nullptr;
+        const int f16 = p.f16;
+        uint8_t* stg_generic = smem_raw + (stg_base - raw);
+        float gs = 0.f, gss = 0.f;
+        int gn_img = -1;
+        auto gn_flush = [&](int img) {
+            float s = gs, ss = gss;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            if ((lane & 3) == 0) {                    // 4 channels per group (128 / 32)
+                float* dst = p.gn_partial + static_cast<size_t>(img) * p.gn_img_stride +
+                             (blockIdx.x * GN_SLOTS_PER_CTA + eg) * 64 + (ch >> 2) * 2;
+                dst[0] = s; dst[1] = ss;
+            }
+            gs = 0.f; gss = 0.f;
+        };
+        int acc = 0, free_i = -1;       // free_i: staging block whose store is still draining (handed back to the loader
+        uint32_t acc_phase = 0, k = 0;  // half a sub-block later, so its refill runs a whole sub-block ahead of its reuse)
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++k) {
+            int n, h0, w0;
+            decode(u, n, h0, w0);
+            if (has_gn && n != gn_img) {
+                if (gn_img >= 0) gn_flush(gn_img);
+                gn_img = n;
+            }
+            mbar_wait(tfull(acc), acc_phase, 27);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256 + eg * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int sb = 0; sb < 2; ++sb) {
+                uint16_t* stage = reinterpret_cast<uint16_t*>(stg_generic + (w8 * 2 + sb) * Cfg::STG_BYTES);
+                if (has_res) {
+                    mbar_wait(res_full(w8 * 2 + sb), k & 1u, 28);
+                } else {
+                    if (lane == 0) tma_store_wait_read<1>();          // this block's previous store (two stores ago) has drained
+                    __syncwarp();
+                }
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + sb * 64 + half * 32, v);
+                    tmem_ld_wait();
+                    uint16_t* sp = stage + (half * 32) * 32 + lane;          // [pixel][32 channels]
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float f = (__uint_as_float(v[i]) + bias_v) * out_scale;
+                        if (has_res) {
+                            const uint32_t r = sp[i * 32];
+                            f += f16 ? __half2float(__ushort_as_half(static_cast<unsigned short>(r)))
+                                     : __uint_as_float(r << 16);
+                        }
+                        gs += f; gss = fmaf(f, f, gss);
+                        sp[i * 32] = static_cast<uint16_t>(pack_h2(f, 0.f, f16) & 0xffffu);
+                    }
+                    if (has_res && half == 0 && free_i >= 0) {
+                        if (lane == 0) {
+                            tma_store_wait_read<0>();                   // the previous sub-block's store has drained
+                            mbar_arrive(buf_free(free_i));
+                        }
+                        free_i = -1;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&maps.out, sS(w8, sb), 32 * q, w0, h0 + 8 * eg + 4 * sb, n);
+                    tma_store_commit();
+                }
+                free_i = w8 * 2 + sb;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (has_gn && gn_img >= 0) gn_flush(gn_img);
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // Pick the output tile (TW x TH x TN = 128 pixels) that wastes the fewest out-of-range pixels.
 void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
     auto pick = [](int extent, int cap) {
@@ -887,6 +1174,78 @@ void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
     TH = pick(H, 128 / TW);
     TN = 128 / (TW * TH);
     (void)N;
+}
+
+// Host side of the T128 variant (see igemm_t128_kernel).  Returns DFW_OK after launching, or 1 when the layer is not
+// eligible (the caller falls through to the generic kernel).
+int try_launch_t128(const void* x, const void* w, const float* bias, const void* residual, void* y, int N, int Hin, int Win,
+                    int Cin, int Cout, int ksize, int stride, int pad_mode, int flags, float out_scale, int bias_sample_stride,
+                    long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
+                    long long gn_img_stride, cudaStream_t stream) {
+    static const bool enabled = [] { const char* e = getenv("DFW_T128"); return !(e && e[0] == '0'); }();
+    if (!enabled || ksize != 3 || stride != 1 || pad_mode != 0 || up_phase >= 0 || w_batch_stride != 0 || w_row_stride != 0 ||
+        Cout != 128 || Cin % BLOCK_K != 0 || Win % 16 != 0 || Hin % 16 != 0 || bias_sample_stride != 0 ||
+        (flags & (DFW_EPI_OUT_F32 | DFW_EPI_RES_F32 | DFW_EPI_GEGLU | DFW_EPI_SILU)) != 0 ||
+        (gn_partial != nullptr && gn_groups != 32) ||
+        ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) != 0)
+        return 1;
+    const long long units = static_cast<long long>(N) * (Hin / 16) * (Win / 16);
+    if (units < 4LL * sm_count() || units >= (1LL << 31)) return 1;
+    T128Maps maps;
+    T128Params p{};
+    p.N = N; p.H = Hin; p.W = Win;
+    p.kb_per_tap = Cin / BLOCK_K;
+    p.tiles_w = Win / 16; p.tiles_h = Hin / 16;
+    p.total_units = static_cast<int>(units);
+    p.bias = bias;
+    p.f16 = (flags & DFW_EPI_F16) ? 1 : 0;
+    p.has_res = residual != nullptr ? 1 : 0;
+    p.out_scale = out_scale;
+    p.gn_partial = gn_partial;
+    p.gn_img_stride = gn_img_stride > 0 ? gn_img_stride : static_cast<long long>(sm_count()) * GN_SLOTS_PER_CTA * 64;
+    const uint64_t esz = 2;
+    int rc;
+    {
+        const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                                  static_cast<uint64_t>(N)};
+        const uint64_t strides[3] = {Cin * esz, static_cast<uint64_t>(Win) * Cin * esz,
+                                     static_cast<uint64_t>(Hin) * Win * Cin * esz};
+        const uint32_t box[4] = {BLOCK_K, 16, 18, 1};
+        rc = encode_tmap_bf16_sw128(&maps.patch, x, 4, dims, strides, box);
+        if (rc != DFW_OK) return rc;
+    }
+    {
+        const uint64_t Kt = 9ull * Cin;
+        const uint64_t dims[3] = {Kt, 128, 1};
+        const uint64_t strides[2] = {Kt * esz, Kt * 128 * esz};
+        const uint32_t box[3] = {BLOCK_K, 128, 1};
+        rc = encode_tmap_bf16_sw128(&maps.w, w, 3, dims, strides, box);
+        if (rc != DFW_OK) return rc;
+    }
+    {
+        const uint64_t dims[4] = {128, static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin), static_cast<uint64_t>(N)};
+        const uint64_t strides[3] = {128 * esz, static_cast<uint64_t>(Win) * 128 * esz,
+                                     static_cast<uint64_t>(Hin) * Win * 128 * esz};
+        const uint32_t box[4] = {32, 16, 4, 1};
+        rc = encode_tmap(&maps.out, y, 2, 0, 4, dims, strides, box);
+        if (rc != DFW_OK) return rc;
+        if (residual != nullptr) {
+            rc = encode_tmap(&maps.res, residual, 2, 0, 4, dims, strides, box);
+            if (rc != DFW_OK) return rc;
+        } else {
+            maps.res = maps.out;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T128Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
+    igemm_t128_kernel<<<grid, IGEMM_THREADS, T128Cfg::SMEM_BYTES, stream>>>(maps, p);
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
 }
 
 template <int BLOCK_N, int TPU = 1>
@@ -928,6 +1287,12 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     if (stride == 2) DFW_REQUIRE(ksize == 3 && Hin % 2 == 0 && Win % 2 == 0);
     const bool geglu = (flags & DFW_EPI_GEGLU) != 0;
     if (geglu) DFW_REQUIRE(Cout % 256 == 0 && residual == nullptr && !(flags & DFW_EPI_OUT_F32));
+
+    // Cout = 128 3x3 stride-1 layers on large images: channel-major accumulator kernel
+    rc = try_launch_t128(x, w, bias, residual, y, N, Hin, Win, Cin, Cout, ksize, stride, pad_mode, flags, out_scale,
+                         bias_sample_stride, w_row_stride, w_batch_stride, up_phase, gn_partial, gn_groups, gn_img_stride,
+                         stream);
+    if (rc != 1) return rc;
 
     IgemmMaps maps;
     IgemmParams p{};

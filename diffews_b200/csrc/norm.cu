@@ -118,9 +118,13 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restr
         for (int idx = threadIdx.x; idx < 8 * groups; idx += nthr) {
             const int g = idx % groups, sl = idx / groups;
             float s = 0.f, ss = 0.f;
+            // independent 8-byte loads, 8 in flight per thread: the fold is a chain of L2 latencies otherwise
+            // (nchunks is 2-8 x #SMs when the statistics come from a conv epilogue)
+            const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * nchunks * groups + g;
+#pragma unroll 8
             for (int c = sl; c < nchunks; c += 8) {
-                const float* pp = partial + ((static_cast<size_t>(n) * nchunks + c) * groups + g) * 2;
-                s += __ldg(pp); ss += __ldg(pp + 1);
+                const float2 v = __ldg(pp + static_cast<size_t>(c) * groups);
+                s += v.x; ss += v.y;
             }
             s_red[sl][g][0] = s; s_red[sl][g][1] = ss;
         }
