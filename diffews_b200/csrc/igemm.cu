@@ -919,6 +919,7 @@ struct T128Maps {
 };
 struct T128Params {
     int N, H, W;
+    int ktaps;            // 3: 3x3 / pad 1;  1: 1x1 (the patch is the bare 16 x 16 tile)
     int kb_per_tap;
     int tiles_w, tiles_h, total_units;
     const float* bias;
@@ -987,12 +988,14 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             int n, h0, w0;
             decode(u, n, h0, w0);
+            const int pad = p.ktaps >> 1;
+            const uint32_t patch_bytes = (16 + 2 * pad) * 16 * 128;
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
-                for (int dw = -1; dw <= 1; ++dw) {
+                for (int dw = 0; dw < p.ktaps; ++dw) {
                     mbar_wait(pa_empty(as), aph ^ 1u, 21);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(pa_full(as), Cfg::PATCH_BYTES);
-                        tma_load_4d(sP(as), &maps.patch, pa_full(as), kb * BLOCK_K, w0 + dw, h0 - 1, n);
+                        mbar_arrive_expect_tx(pa_full(as), patch_bytes);
+                        tma_load_4d(sP(as), &maps.patch, pa_full(as), kb * BLOCK_K, w0 + dw - pad, h0 - pad, n);
                     }
                     __syncwarp();
                     if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
@@ -1003,12 +1006,12 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         uint32_t wph = 0;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
-                for (int dw = 0; dw < 3; ++dw)
-                    for (int dh = 0; dh < 3; ++dh) {
+                for (int dw = 0; dw < p.ktaps; ++dw)
+                    for (int dh = 0; dh < p.ktaps; ++dh) {
                         mbar_wait(w_empty(ws), wph ^ 1u, 22);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(w_full(ws), Cfg::W_TILE_BYTES);
-                            tma_load_3d(sW(ws), &maps.w, w_full(ws), ((dh * 3 + dw) * p.kb_per_tap + kb) * BLOCK_K, 0, 0);
+                            tma_load_3d(sW(ws), &maps.w, w_full(ws), ((dh * p.ktaps + dw) * p.kb_per_tap + kb) * BLOCK_K, 0, 0);
                         }
                         __syncwarp();
                         if (++ws == Cfg::W_SLOTS) { ws = 0; wph ^= 1u; }
@@ -1023,10 +1026,11 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
             bool first = true;
+            const int last = p.ktaps - 1;
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
-                for (int dw = 0; dw < 3; ++dw) {
+                for (int dw = 0; dw < p.ktaps; ++dw) {
                     mbar_wait(pa_full(as), aph, 24);
-                    for (int dh = 0; dh < 3; ++dh) {
+                    for (int dh = 0; dh < p.ktaps; ++dh) {
                         mbar_wait(w_full(ws), wph, 25);
                         tc_fence_after();
                         if (elect_one()) {
@@ -1036,8 +1040,8 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                             for (int k = 0; k < BLOCK_K / 16; ++k)
                                 umma_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (!first || k > 0) ? 1u : 0u);
                             tc_commit(w_empty(ws));
-                            if (dh == 2) tc_commit(pa_empty(as));
-                            if (dh == 2 && dw == 2 && kb == p.kb_per_tap - 1) tc_commit(tfull(acc));
+                            if (dh == last) tc_commit(pa_empty(as));
+                            if (dh == last && dw == last && kb == p.kb_per_tap - 1) tc_commit(tfull(acc));
                         }
                         __syncwarp();
                         first = false;
@@ -1183,7 +1187,7 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
                     long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
                     long long gn_img_stride, cudaStream_t stream) {
     static const bool enabled = [] { const char* e = getenv("DFW_T128"); return !(e && e[0] == '0'); }();
-    if (!enabled || ksize != 3 || stride != 1 || pad_mode != 0 || up_phase >= 0 || w_batch_stride != 0 || w_row_stride != 0 ||
+    if (!enabled || (ksize != 3 && ksize != 1) || stride != 1 || pad_mode != 0 || up_phase >= 0 || w_batch_stride != 0 || w_row_stride != 0 ||
         Cout != 128 || Cin % BLOCK_K != 0 || Win % 16 != 0 || Hin % 16 != 0 || bias_sample_stride != 0 ||
         (flags & (DFW_EPI_OUT_F32 | DFW_EPI_RES_F32 | DFW_EPI_GEGLU | DFW_EPI_SILU)) != 0 ||
         (gn_partial != nullptr && gn_groups != 32) ||
@@ -1194,6 +1198,7 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     T128Maps maps;
     T128Params p{};
     p.N = N; p.H = Hin; p.W = Win;
+    p.ktaps = ksize;
     p.kb_per_tap = Cin / BLOCK_K;
     p.tiles_w = Win / 16; p.tiles_h = Hin / 16;
     p.total_units = static_cast<int>(units);
@@ -1210,12 +1215,12 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
                                   static_cast<uint64_t>(N)};
         const uint64_t strides[3] = {Cin * esz, static_cast<uint64_t>(Win) * Cin * esz,
                                      static_cast<uint64_t>(Hin) * Win * Cin * esz};
-        const uint32_t box[4] = {BLOCK_K, 16, 18, 1};
+        const uint32_t box[4] = {BLOCK_K, 16, static_cast<uint32_t>(16 + ksize - 1), 1};
         rc = encode_tmap_bf16_sw128(&maps.patch, x, 4, dims, strides, box);
         if (rc != DFW_OK) return rc;
     }
     {
-        const uint64_t Kt = 9ull * Cin;
+        const uint64_t Kt = static_cast<uint64_t>(ksize) * ksize * Cin;
         const uint64_t dims[3] = {Kt, 128, 1};
         const uint64_t strides[2] = {Kt * esz, Kt * 128 * esz};
         const uint32_t box[3] = {BLOCK_K, 128, 1};

@@ -383,22 +383,23 @@ def conv_t128():
     import torch.nn.functional as F
     from diffews_b200 import ops
     from diffews_b200.weights import conv_weight_to_gemm
-    for (N, H, W, Ci, res, dt) in [(3, 256, 256, 128, True, torch.float16), (4, 128, 256, 256, False, torch.float16),
-                                   (5, 272, 144, 64, True, torch.bfloat16), (16, 112, 96, 128, False, torch.float16)]:
+    for (N, H, W, Ci, res, dt, ks) in [(3, 256, 256, 128, True, torch.float16, 3), (4, 128, 256, 256, False, torch.float16, 3),
+                                       (5, 272, 144, 64, True, torch.bfloat16, 3), (16, 112, 96, 128, False, torch.float16, 3),
+                                       (4, 256, 256, 64, False, torch.float16, 1), (3, 144, 272, 256, True, torch.float16, 1)]:
         Co = 128
-        x = _mk((N, H, W, Ci), 1, 1).to(dt); w = _mk((Co, Ci, 3, 3), (Ci * 9) ** -0.5, 2).to(dt); b = _mk((Co,), 1, 3)
+        x = _mk((N, H, W, Ci), 1, 1).to(dt); w = _mk((Co, Ci, ks, ks), (Ci * ks * ks) ** -0.5, 2).to(dt); b = _mk((Co,), 1, 3)
         r = _mk((N, H, W, Co), 1, 4).to(dt) if res else None
         g = _mk((Co,), 1, 5); be = _mk((Co,), 1, 6)
-        y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=3, residual=r, gn_stats=True)
+        y = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=ks, residual=r, gn_stats=True)
         assert hasattr(y, "_gn_partial")
-        ref = _conv_ref(x, w, b) + (r.float() if res else 0)
+        ref = _conv_ref(x, w, b, 1, (ks - 1) // 2) + (r.float() if res else 0)
         e = rel(y, ref)
         yn = ops.groupnorm(y, g, be, eps=1e-6, silu=True, out_dtype=dt)
         refn = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, g, be, 1e-6)).permute(0, 2, 3, 1)
         e2 = rel(yn, refn)
-        y2 = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=3, residual=r)            # without statistics
+        y2 = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=ks, residual=r)           # without statistics
         same = torch.equal(y, y2)
-        print(f"t128 N{N} {H}x{W} {Ci}->128 res={res} {dt}: conv rel {e:.2e}  gn(fused stats) rel {e2:.2e}  equal w/o stats {same}")
+        print(f"t128 N{N} {H}x{W} {Ci}->128 k{ks} res={res} {dt}: conv rel {e:.2e}  gn(fused stats) rel {e2:.2e}  equal w/o stats {same}")
         assert e < (6e-3 if dt == torch.bfloat16 else 1e-3) and e2 < (8e-3 if dt == torch.bfloat16 else 1e-3) and same
 
 
