@@ -922,6 +922,8 @@ struct T128Params {
     int ktaps;            // 3: 3x3 / pad 1;  1: 1x1 (the patch is the bare 16 x 16 tile)
     int kb_per_tap;
     int tiles_w, tiles_h, total_units;
+    int n_slabs;          // Cout / 128: a unit = (image, 128-channel slab, 16 x 16 tile), tiles fastest
+    int gn_cpg;           // channels per GroupNorm group (4 / 8 / 16)
     const float* bias;
     int f16, has_res;
     float out_scale;
@@ -975,9 +977,11 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
-    auto decode = [&](int u, int& n, int& h0, int& w0) {
-        n = u / tiles_per_img;
-        const int r = u - n * tiles_per_img;
+    auto decode = [&](int u, int& n, int& slab, int& h0, int& w0) {
+        const int ns = u / tiles_per_img;              // image * n_slabs + slab
+        const int r = u - ns * tiles_per_img;
+        n = ns / p.n_slabs;
+        slab = ns - n * p.n_slabs;
         h0 = (r / p.tiles_w) * 16;
         w0 = (r % p.tiles_w) * 16;
     };
@@ -986,8 +990,8 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         int as = 0;
         uint32_t aph = 0;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-            int n, h0, w0;
-            decode(u, n, h0, w0);
+            int n, slab, h0, w0;
+            decode(u, n, slab, h0, w0);
             const int pad = p.ktaps >> 1;
             const uint32_t patch_bytes = (16 + 2 * pad) * 16 * 128;
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
@@ -1004,18 +1008,21 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     } else if (warp == 2) {
         int ws = 0;
         uint32_t wph = 0;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            const int slab = (u / tiles_per_img) % p.n_slabs;
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
                 for (int dw = 0; dw < p.ktaps; ++dw)
                     for (int dh = 0; dh < p.ktaps; ++dh) {
                         mbar_wait(w_empty(ws), wph ^ 1u, 22);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(w_full(ws), Cfg::W_TILE_BYTES);
-                            tma_load_3d(sW(ws), &maps.w, w_full(ws), ((dh * p.ktaps + dw) * p.kb_per_tap + kb) * BLOCK_K, 0, 0);
+                            tma_load_3d(sW(ws), &maps.w, w_full(ws), ((dh * p.ktaps + dw) * p.kb_per_tap + kb) * BLOCK_K,
+                                        slab * 128, 0);
                         }
                         __syncwarp();
                         if (++ws == Cfg::W_SLOTS) { ws = 0; wph ^= 1u; }
                     }
+        }
     } else if (warp == 1) {
         const uint32_t fmt = p.f16 ? 0u : 1u;
         const uint32_t idesc = umma_idesc(128, 256, fmt, fmt, 0);
@@ -1056,15 +1063,16 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         if (p.has_res) {
             uint32_t k = 0;
             for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++k) {
-                int n, h0, w0;
-                decode(u, n, h0, w0);
+                int n, slab, h0, w0;
+                decode(u, n, slab, h0, w0);
                 for (int sb = 0; sb < 2; ++sb)
                     for (int w8 = 0; w8 < 8; ++w8) {
                         const int i = w8 * 2 + sb;
                         mbar_wait(buf_free(i), (k & 1u) ^ 1u, 26);        // the store that last used this block has drained
                         if (elect_one()) {
                             mbar_arrive_expect_tx(res_full(i), Cfg::STG_BYTES);
-                            tma_load_4d(sS(w8, sb), &maps.res, res_full(i), 32 * (w8 & 3), w0, h0 + 8 * (w8 >> 2) + 4 * sb, n);
+                            tma_load_4d(sS(w8, sb), &maps.res, res_full(i), slab * 128 + 32 * (w8 & 3), w0,
+                                        h0 + 8 * (w8 >> 2) + 4 * sb, n);
                         }
                         __syncwarp();
                     }
@@ -1073,21 +1081,23 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     } else {
         const int w8 = warp - 4;
         const int q = w8 & 3, eg = w8 >> 2;
-        const int ch = 32 * q + lane;
-        const float bias_v = p.bias ? __ldg(p.bias + ch) : 0.f;
+        const int ch = 32 * q + lane;                    // channel inside the 128-channel slab
         const float out_scale = p.out_scale;
         const bool has_res = p.has_res != 0, has_gn = p.gn_partial != nullptr;
         const int f16 = p.f16;
         uint8_t* stg_generic = smem_raw + (stg_base - raw);
-        float gs = 0.f, gss = 0.f;
-        int gn_img = -1;
-        auto gn_flush = [&](int img) {
+        float gs = 0.f, gss = 0.f, bias_v = 0.f;
+        int gn_key = -1;                                  // image * n_slabs + slab the running sums belong to
+        const int cpg = p.gn_cpg;
+        auto gn_flush = [&](int key) {                    // a CTA meets every (image, slab) in one contiguous run of units
             float s = gs, ss = gss;
-            s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            if ((lane & 3) == 0) {                    // 4 channels per group (128 / 32)
+            for (int o = 1; o < cpg; o <<= 1) {           // cpg (4 / 8 / 16) consecutive lanes = one group
+                s += __shfl_xor_sync(0xffffffffu, s, o);  ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            }
+            if ((lane & (cpg - 1)) == 0) {
+                const int img = key / p.n_slabs, slab = key - img * p.n_slabs;
                 float* dst = p.gn_partial + static_cast<size_t>(img) * p.gn_img_stride +
-                             (blockIdx.x * GN_SLOTS_PER_CTA + eg) * 64 + (ch >> 2) * 2;
+                             (blockIdx.x * GN_SLOTS_PER_CTA + eg) * 64 + ((slab * 128 + ch) / cpg) * 2;
                 dst[0] = s; dst[1] = ss;
             }
             gs = 0.f; gss = 0.f;
@@ -1095,11 +1105,13 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         int acc = 0, free_i = -1;       // free_i: staging block whose store is still draining (handed back to the loader
         uint32_t acc_phase = 0, k = 0;  // half a sub-block later, so its refill runs a whole sub-block ahead of its reuse)
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++k) {
-            int n, h0, w0;
-            decode(u, n, h0, w0);
-            if (has_gn && n != gn_img) {
-                if (gn_img >= 0) gn_flush(gn_img);
-                gn_img = n;
+            int n, slab, h0, w0;
+            decode(u, n, slab, h0, w0);
+            const int key = n * p.n_slabs + slab;
+            if (key != gn_key) {
+                if (has_gn && gn_key >= 0) gn_flush(gn_key);
+                gn_key = key;
+                bias_v = p.bias ? __ldg(p.bias + slab * 128 + ch) : 0.f;
             }
             mbar_wait(tfull(acc), acc_phase, 27);
             tc_fence_after();
@@ -1141,7 +1153,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&maps.out, sS(w8, sb), 32 * q, w0, h0 + 8 * eg + 4 * sb, n);
+                    tma_store_4d(&maps.out, sS(w8, sb), slab * 128 + 32 * q, w0, h0 + 8 * eg + 4 * sb, n);
                     tma_store_commit();
                 }
                 free_i = w8 * 2 + sb;
@@ -1152,7 +1164,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (has_gn && gn_img >= 0) gn_flush(gn_img);
+        if (has_gn && gn_key >= 0) gn_flush(gn_key);
         if (lane == 0) tma_store_wait_all<0>();
     }
     tc_fence_before();
@@ -1187,13 +1199,14 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
                     long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
                     long long gn_img_stride, cudaStream_t stream) {
     static const bool enabled = [] { const char* e = getenv("DFW_T128"); return !(e && e[0] == '0'); }();
+    static const int max_cout = [] { const char* e = getenv("DFW_T128_MAXC"); return e ? atoi(e) : 512; }();
     if (!enabled || (ksize != 3 && ksize != 1) || stride != 1 || pad_mode != 0 || up_phase >= 0 || w_batch_stride != 0 || w_row_stride != 0 ||
-        Cout != 128 || Cin % BLOCK_K != 0 || Win % 16 != 0 || Hin % 16 != 0 || bias_sample_stride != 0 ||
+        Cout % 128 != 0 || Cout > max_cout || Cout > 512 || Cin % BLOCK_K != 0 || Win % 16 != 0 || Hin % 16 != 0 || bias_sample_stride != 0 ||
         (flags & (DFW_EPI_OUT_F32 | DFW_EPI_RES_F32 | DFW_EPI_GEGLU | DFW_EPI_SILU)) != 0 ||
         (gn_partial != nullptr && gn_groups != 32) ||
         ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) != 0)
         return 1;
-    const long long units = static_cast<long long>(N) * (Hin / 16) * (Win / 16);
+    const long long units = static_cast<long long>(N) * (Cout / 128) * (Hin / 16) * (Win / 16);
     if (units < 4LL * sm_count() || units >= (1LL << 31)) return 1;
     T128Maps maps;
     T128Params p{};
@@ -1202,6 +1215,8 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     p.kb_per_tap = Cin / BLOCK_K;
     p.tiles_w = Win / 16; p.tiles_h = Hin / 16;
     p.total_units = static_cast<int>(units);
+    p.n_slabs = Cout / 128;
+    p.gn_cpg = Cout / 32;
     p.bias = bias;
     p.f16 = (flags & DFW_EPI_F16) ? 1 : 0;
     p.has_res = residual != nullptr ? 1 : 0;
@@ -1221,16 +1236,17 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     }
     {
         const uint64_t Kt = static_cast<uint64_t>(ksize) * ksize * Cin;
-        const uint64_t dims[3] = {Kt, 128, 1};
-        const uint64_t strides[2] = {Kt * esz, Kt * 128 * esz};
+        const uint64_t dims[3] = {Kt, static_cast<uint64_t>(Cout), 1};
+        const uint64_t strides[2] = {Kt * esz, Kt * Cout * esz};
         const uint32_t box[3] = {BLOCK_K, 128, 1};
         rc = encode_tmap_bf16_sw128(&maps.w, w, 3, dims, strides, box);
         if (rc != DFW_OK) return rc;
     }
     {
-        const uint64_t dims[4] = {128, static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin), static_cast<uint64_t>(N)};
-        const uint64_t strides[3] = {128 * esz, static_cast<uint64_t>(Win) * 128 * esz,
-                                     static_cast<uint64_t>(Hin) * Win * 128 * esz};
+        const uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                                  static_cast<uint64_t>(N)};
+        const uint64_t strides[3] = {Cout * esz, static_cast<uint64_t>(Win) * Cout * esz,
+                                     static_cast<uint64_t>(Hin) * Win * Cout * esz};
         const uint32_t box[4] = {32, 16, 4, 1};
         rc = encode_tmap(&maps.out, y, 2, 0, 4, dims, strides, box);
         if (rc != DFW_OK) return rc;

@@ -383,10 +383,12 @@ def conv_t128():
     import torch.nn.functional as F
     from diffews_b200 import ops
     from diffews_b200.weights import conv_weight_to_gemm
-    for (N, H, W, Ci, res, dt, ks) in [(3, 256, 256, 128, True, torch.float16, 3), (4, 128, 256, 256, False, torch.float16, 3),
-                                       (5, 272, 144, 64, True, torch.bfloat16, 3), (16, 112, 96, 128, False, torch.float16, 3),
-                                       (4, 256, 256, 64, False, torch.float16, 1), (3, 144, 272, 256, True, torch.float16, 1)]:
-        Co = 128
+    for (N, H, W, Ci, res, dt, ks, Co) in [
+            (3, 256, 256, 128, True, torch.float16, 3, 128), (4, 128, 256, 256, False, torch.float16, 3, 128),
+            (5, 272, 144, 64, True, torch.bfloat16, 3, 128), (16, 112, 96, 128, False, torch.float16, 3, 128),
+            (4, 256, 256, 64, False, torch.float16, 1, 128), (3, 144, 272, 256, True, torch.float16, 1, 128),
+            (3, 128, 128, 128, True, torch.float16, 3, 256), (2, 144, 112, 256, False, torch.float16, 3, 512),
+            (5, 96, 80, 128, True, torch.float16, 1, 256), (16, 64, 64, 512, True, torch.float16, 3, 512)]:
         x = _mk((N, H, W, Ci), 1, 1).to(dt); w = _mk((Co, Ci, ks, ks), (Ci * ks * ks) ** -0.5, 2).to(dt); b = _mk((Co,), 1, 3)
         r = _mk((N, H, W, Co), 1, 4).to(dt) if res else None
         g = _mk((Co,), 1, 5); be = _mk((Co,), 1, 6)
@@ -399,7 +401,7 @@ def conv_t128():
         e2 = rel(yn, refn)
         y2 = ops.conv2d(x, conv_weight_to_gemm(w), b, ksize=ks, residual=r)           # without statistics
         same = torch.equal(y, y2)
-        print(f"t128 N{N} {H}x{W} {Ci}->128 k{ks} res={res} {dt}: conv rel {e:.2e}  gn(fused stats) rel {e2:.2e}  equal w/o stats {same}")
+        print(f"t128 N{N} {H}x{W} {Ci}->{Co} k{ks} res={res} {dt}: conv rel {e:.2e}  gn(fused stats) rel {e2:.2e}  equal w/o stats {same}")
         assert e < (6e-3 if dt == torch.bfloat16 else 1e-3) and e2 < (8e-3 if dt == torch.bfloat16 else 1e-3) and same
 
 
