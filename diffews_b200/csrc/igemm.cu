@@ -922,7 +922,8 @@ struct T128Params {
     int ktaps;            // 3: 3x3 / pad 1;  1: 1x1 (the patch is the bare 16 x 16 tile)
     int kb_per_tap;
     int tiles_w, tiles_h, total_units;
-    int n_slabs;          // Cout / 128: a unit = (image, 128-channel slab, 16 x 16 tile), tiles fastest
+    int n_slabs;          // ceil(Cout / 128): a unit = (image, 128-channel slab, 16 x 16 tile), tiles fastest
+    int Cout;             // may end inside the last slab (1x1 only): TMA zero-fills / clips the channels beyond it
     int gn_cpg;           // channels per GroupNorm group (4 / 8 / 16)
     const float* bias;
     int f16, has_res;
@@ -1111,7 +1112,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
             if (key != gn_key) {
                 if (has_gn && gn_key >= 0) gn_flush(gn_key);
                 gn_key = key;
-                bias_v = p.bias ? __ldg(p.bias + slab * 128 + ch) : 0.f;
+                bias_v = (p.bias && slab * 128 + ch < p.Cout) ? __ldg(p.bias + slab * 128 + ch) : 0.f;
             }
             mbar_wait(tfull(acc), acc_phase, 27);
             tc_fence_after();
@@ -1199,14 +1200,21 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
                     long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
                     long long gn_img_stride, cudaStream_t stream) {
     static const bool enabled = [] { const char* e = getenv("DFW_T128"); return !(e && e[0] == '0'); }();
-    static const int max_cout = [] { const char* e = getenv("DFW_T128_MAXC"); return e ? atoi(e) : 512; }();
+    static const int max_cout = [] { const char* e = getenv("DFW_T128_MAXC"); return e ? atoi(e) : 1 << 20; }();
+    // a token matrix [M, K] (linear layers arrive as a 1 x M image) is the image [M / 16, 16]: a 16 x 16 tile is then 256
+    // consecutive rows
+    // (measured: a gain only for the projections with a residual; the others stay on the generic kernel)
+    if (ksize == 1 && N == 1 && Hin == 1 && Win % 256 == 0 && residual != nullptr) { Hin = Win / 16; Win = 16; }
+    const bool ragged = Cout % 128 != 0;                 // 1x1 only: the last slab is partly outside the tensor
     if (!enabled || (ksize != 3 && ksize != 1) || stride != 1 || pad_mode != 0 || up_phase >= 0 || w_batch_stride != 0 || w_row_stride != 0 ||
-        Cout % 128 != 0 || Cout > max_cout || Cout > 512 || Cin % BLOCK_K != 0 || Win % 16 != 0 || Hin % 16 != 0 || bias_sample_stride != 0 ||
+        Cout % 32 != 0 || Cout < 128 || Cout > max_cout || (ragged && (ksize != 1 || gn_partial != nullptr)) ||
+        (gn_partial != nullptr && Cout > 512) || Cin % BLOCK_K != 0 || Win % 16 != 0 || Hin % 16 != 0 || bias_sample_stride != 0 ||
         (flags & (DFW_EPI_OUT_F32 | DFW_EPI_RES_F32 | DFW_EPI_GEGLU | DFW_EPI_SILU)) != 0 ||
         (gn_partial != nullptr && gn_groups != 32) ||
         ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) != 0)
         return 1;
-    const long long units = static_cast<long long>(N) * (Cout / 128) * (Hin / 16) * (Win / 16);
+    const int n_slabs = (Cout + 127) / 128;
+    const long long units = static_cast<long long>(N) * n_slabs * (Hin / 16) * (Win / 16);
     if (units < 4LL * sm_count() || units >= (1LL << 31)) return 1;
     T128Maps maps;
     T128Params p{};
@@ -1215,7 +1223,8 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     p.kb_per_tap = Cin / BLOCK_K;
     p.tiles_w = Win / 16; p.tiles_h = Hin / 16;
     p.total_units = static_cast<int>(units);
-    p.n_slabs = Cout / 128;
+    p.n_slabs = n_slabs;
+    p.Cout = Cout;
     p.gn_cpg = Cout / 32;
     p.bias = bias;
     p.f16 = (flags & DFW_EPI_F16) ? 1 : 0;
