@@ -28,6 +28,9 @@ SIGNATURES = {
     "dfw_conv_gnstats_supported": (_i, [_i, _i, _i, _i]),
     "dfw_conv2d_igemm_gnstats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "dfw_groupnorm_from_partial": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "dfw_gn_scale_shift": (_i, [_vp, _i, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _vp]),
+    "dfw_conv_gnin_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "dfw_conv2d_igemm_gnin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dfw_bmm_nt": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
                                   _i, _f, _i, _vp]),

@@ -909,7 +909,9 @@ struct T128Cfg {
     static constexpr int W_TILE_BYTES = 128 * 128;          // 16 KiB
     static constexpr int W_SLOTS = 3;
     static constexpr int STG_BYTES = 64 * 64;               // 64 pixels x 32 channels x 2 B
-    static constexpr int NBAR = 2 * A_SLOTS + 2 * W_SLOTS + 4 + 32;
+    static constexpr int NBAR = 3 * A_SLOTS + 2 * W_SLOTS + 4 + 32;
+    static constexpr int THREADS = IGEMM_THREADS;              // 12 warps
+    static constexpr int THREADS_GN = IGEMM_THREADS + 256;     // + 8 operand-transform warps (GroupNorm + SiLU on the fly)
     static constexpr int SMEM_USED = A_SLOTS * PATCH_BYTES + W_SLOTS * W_TILE_BYTES + 16 * STG_BYTES + 8 * NBAR + 16;
     static constexpr int SMEM_BYTES = SMEM_USED + 512;      // smem is declared __align__(1024); the kernel traps otherwise
     static_assert(SMEM_BYTES <= 232448, "smem budget");
@@ -930,9 +932,17 @@ struct T128Params {
     float out_scale;
     float* gn_partial;
     long long gn_img_stride;
+    const float* gn_in;   // GN_IN: [N][2][Cin] fp32 scale / shift of the GroupNorm (+ SiLU) applied to x on the fly
+    int Cin;
 };
 
-__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+// GN_IN: the convolution consumes silu(groupnorm(x)) without that tensor ever existing: eight extra warps rewrite every
+// patch in place (fp32: x * scale[n, c] + shift[n, c], SiLU through one tanh.approx; pixels outside the image stay 0 =
+// the zero padding of the normalised tensor) between its TMA arrival and its MMAs.  Saves the GroupNorm-apply pass
+// (one HBM read + write of the activation) at the price of transforming each element three times (one per horizontal
+// tap) on otherwise idle FMA / MUFU pipes.
+template <bool GN_IN>
+__global__ void __launch_bounds__(GN_IN ? T128Cfg::THREADS_GN : T128Cfg::THREADS, 1)
 igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__ T128Params p) {
     using Cfg = T128Cfg;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -948,7 +958,8 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     auto pa_empty = [&](int i) { return bar + 8u * (Cfg::A_SLOTS + i); };
     auto w_full = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + i); };
     auto w_empty = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + Cfg::W_SLOTS + i); };
-    const uint32_t b2 = bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS);
+    auto pa_ready = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + i); };     // GN_IN: transformed
+    const uint32_t b2 = bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS);
     auto tfull = [&](int a) { return b2 + 8u * a; };
     auto tempty = [&](int a) { return b2 + 8u * (2 + a); };
     auto res_full = [&](int i) { return b2 + 8u * (4 + i); };        // i = warp8 * 2 + buffer
@@ -963,7 +974,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         if (p.has_res) tma_prefetch_desc(&maps.res);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(pa_full(i), 1); mbar_init(pa_empty(i), 1); }
+        for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(pa_full(i), 1); mbar_init(pa_empty(i), 1); mbar_init(pa_ready(i), 8); }
         for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
         for (int i = 0; i < 16; ++i) { mbar_init(res_full(i), 1); mbar_init(buf_free(i), 1); }
@@ -1037,7 +1048,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
             const int last = p.ktaps - 1;
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
                 for (int dw = 0; dw < p.ktaps; ++dw) {
-                    mbar_wait(pa_full(as), aph, 24);
+                    mbar_wait(GN_IN ? pa_ready(as) : pa_full(as), aph, 24);
                     for (int dh = 0; dh < p.ktaps; ++dh) {
                         mbar_wait(w_full(ws), wph, 25);
                         tc_fence_after();
@@ -1077,6 +1088,61 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                         }
                         __syncwarp();
                     }
+            }
+        }
+    } else if (warp >= 12) {
+        if constexpr (GN_IN) {
+            // operand transform: 256 threads, thread = (16-byte unit u of a 128-byte row, row r0 + 32 i)
+            const int t = threadIdx.x - 12 * 32;
+            const int un = t & 7, r0 = t >> 3;
+            const int pad = p.ktaps >> 1;
+            const int prow_n = (16 + 2 * pad) * 16;
+            uint8_t* patch0 = smem_raw + (base - raw);
+            int as = 0;
+            uint32_t aph = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                int n, slab, h0, w0;
+                decode(u, n, slab, h0, w0);
+                const float* ssp = p.gn_in + static_cast<size_t>(n) * 2 * p.Cin + un * 8;
+                for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                    float sc[8], sh[8];
+                    {
+                        const float4* a4 = reinterpret_cast<const float4*>(ssp + kb * BLOCK_K);
+                        const float4* b4 = reinterpret_cast<const float4*>(ssp + p.Cin + kb * BLOCK_K);
+                        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+                        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+                        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+                    }
+                    for (int dw = 0; dw < p.ktaps; ++dw) {
+                        mbar_wait(pa_full(as), aph, 29);
+                        uint8_t* pb = patch0 + as * Cfg::PATCH_BYTES;
+#pragma unroll 3
+                        for (int r = r0; r < prow_n; r += 32) {
+                            const int hh = h0 - pad + (r >> 4), ww = w0 + dw - pad + (r & 15);
+                            if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {           // outside: stays 0 (padding)
+                                uint4* ptr = reinterpret_cast<uint4*>(pb + r * 128 + ((un ^ (r & 7)) << 4));
+                                uint4 v = *ptr;
+                                uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 xx = unpack_h2(vw[j], p.f16);
+                                    const float y0 = fmaf(xx.x, sc[2 * j], sh[2 * j]);
+                                    const float y1 = fmaf(xx.y, sc[2 * j + 1], sh[2 * j + 1]);
+                                    float t0, t1;
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0));
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1));
+                                    const float h0f = 0.5f * y0, h1f = 0.5f * y1;
+                                    vw[j] = pack_h2(fmaf(h0f, t0, h0f), fmaf(h1f, t1, h1f), p.f16);
+                                }
+                                *ptr = v;
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(pa_ready(as));
+                        if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
+                    }
+                }
             }
         }
     } else {
@@ -1198,7 +1264,7 @@ void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
 int try_launch_t128(const void* x, const void* w, const float* bias, const void* residual, void* y, int N, int Hin, int Win,
                     int Cin, int Cout, int ksize, int stride, int pad_mode, int flags, float out_scale, int bias_sample_stride,
                     long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
-                    long long gn_img_stride, cudaStream_t stream) {
+                    long long gn_img_stride, cudaStream_t stream, const float* gn_in = nullptr, bool dry_run = false) {
     static const bool enabled = [] { const char* e = getenv("DFW_T128"); return !(e && e[0] == '0'); }();
     static const int max_cout = [] { const char* e = getenv("DFW_T128_MAXC"); return e ? atoi(e) : 1 << 20; }();
     // a token matrix [M, K] (linear layers arrive as a 1 x M image) is the image [M / 16, 16]: a 16 x 16 tile is then 256
@@ -1216,6 +1282,7 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     const int n_slabs = (Cout + 127) / 128;
     const long long units = static_cast<long long>(N) * n_slabs * (Hin / 16) * (Win / 16);
     if (units < 4LL * sm_count() || units >= (1LL << 31)) return 1;
+    if (dry_run) return DFW_OK;
     T128Maps maps;
     T128Params p{};
     p.N = N; p.H = Hin; p.W = Win;
@@ -1232,6 +1299,8 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     p.out_scale = out_scale;
     p.gn_partial = gn_partial;
     p.gn_img_stride = gn_img_stride > 0 ? gn_img_stride : static_cast<long long>(sm_count()) * GN_SLOTS_PER_CTA * 64;
+    p.gn_in = gn_in;
+    p.Cin = Cin;
     const uint64_t esz = 2;
     int rc;
     {
@@ -1268,11 +1337,15 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T128Cfg::SMEM_BYTES));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T128Cfg::SMEM_BYTES));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T128Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
-    igemm_t128_kernel<<<grid, IGEMM_THREADS, T128Cfg::SMEM_BYTES, stream>>>(maps, p);
+    if (gn_in != nullptr)
+        igemm_t128_kernel<true><<<grid, T128Cfg::THREADS_GN, T128Cfg::SMEM_BYTES, stream>>>(maps, p);
+    else
+        igemm_t128_kernel<false><<<grid, T128Cfg::THREADS, T128Cfg::SMEM_BYTES, stream>>>(maps, p);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
@@ -1561,6 +1634,27 @@ int dfw_conv2d_igemm_gnstats(const void* x, const void* w, const float* bias, co
                         static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
     return dfw::igemm_dispatch(x, w, bias, 0, residual, y, N, Hin, Win, Cin, Cout, ksize, stride, pad_mode, flags,
                                out_scale, static_cast<cudaStream_t>(stream), 0, 0, -1, gn_partial, 32);
+}
+
+int dfw_conv_gnin_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
+    if (dfw::require_sm100() != DFW_OK) return 0;
+    static unsigned char dummy[16] __attribute__((aligned(16)));
+    return dfw::try_launch_t128(dummy, dummy, nullptr, nullptr, dummy, N, H, W, Cin, Cout, ksize, 1, 0, DFW_EPI_F16, 1.0f, 0,
+                                0, 0, -1, nullptr, 32, 0, nullptr, nullptr, true) == DFW_OK ? 1 : 0;
+}
+
+int dfw_conv2d_igemm_gnin(const void* x, const float* gn_scale_shift, const void* w, const float* bias,
+                          const void* residual, void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int flags,
+                          float* gn_partial_out, void* stream) {
+    int rc = dfw::require_sm100();
+    if (rc != DFW_OK) return rc;
+    if (!x || !gn_scale_shift || !w || !y) return DFW_ERR_INVALID;
+    if (gn_partial_out != nullptr &&
+        cudaMemsetAsync(gn_partial_out, 0, static_cast<size_t>(dfw_gn_partial_floats(N)) * sizeof(float),
+                        static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
+    rc = dfw::try_launch_t128(x, w, bias, residual, y, N, Hin, Win, Cin, Cout, ksize, 1, 0, flags, 1.0f, 0, 0, 0, -1,
+                              gn_partial_out, 32, 0, static_cast<cudaStream_t>(stream), gn_scale_shift);
+    return rc == 1 ? DFW_ERR_INVALID : rc;        // 1 = shape not eligible (ask dfw_conv_gnin_supported first)
 }
 
 int dfw_bmm_nt(const void* x, const void* w, long long w_row_stride, long long w_batch_stride, const float* bias,

@@ -179,6 +179,47 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restr
     }
 }
 
+// Per-(image, channel) scale / shift of a GroupNorm whose statistics came from a conv epilogue: out[n][0][c] = rstd *
+// gamma, out[n][1][c] = beta - mean * rstd * gamma.  Same fixed-order fold (8 slices, then fp64) as gn_apply_kernel, so
+// a convolution that applies them on the fly (dfw_conv2d_igemm_gnin) sees exactly the numbers gn_apply would use.
+__global__ void gn_scale_shift_kernel(const float* __restrict__ partial, int nchunks, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* __restrict__ out, double HW, int C,
+                                      int groups, float eps) {
+    __shared__ float s_red[8][64][2];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.x, cpg = C / groups;
+    for (int idx = threadIdx.x; idx < 8 * groups; idx += blockDim.x) {
+        const int g = idx % groups, sl = idx / groups;
+        float s = 0.f, ss = 0.f;
+        const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * nchunks * groups + g;
+#pragma unroll 8
+        for (int c = sl; c < nchunks; c += 8) {
+            const float2 v = __ldg(pp + static_cast<size_t>(c) * groups);
+            s += v.x; ss += v.y;
+        }
+        s_red[sl][g][0] = s; s_red[sl][g][1] = ss;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, ss = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) { s += s_red[sl][g][0]; ss += s_red[sl][g][1]; }
+        const double cnt = HW * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = s_rstd[g] * __ldg(gamma + c);
+        out[(static_cast<size_t>(n) * 2) * C + c] = sc;
+        out[(static_cast<size_t>(n) * 2 + 1) * C + c] = __ldg(beta + c) - s_mean[g] * sc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 2048), exact two-pass statistics.
 // ---------------------------------------------------------------------------------------------------------
@@ -430,6 +471,20 @@ int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial,
                                                           pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
     if (x_dtype == 1) { DFW_GN_APPLY(1) } else if (x_dtype == 2) { DFW_GN_APPLY(2) } else { DFW_GN_APPLY(0) }
 #undef DFW_GN_APPLY
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_gn_scale_shift(const float* partial, int nchunks, const float* gamma, const float* beta, float* scale_shift,
+                       int N, long long HW, int C, int groups, float eps, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(partial && gamma && beta && scale_shift && nchunks > 0);
+    DFW_REQUIRE(N > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64 && C % groups == 0);
+    gn_scale_shift_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream_)>>>(partial, nchunks, gamma, beta, scale_shift,
+                                                                            static_cast<double>(HW), C, groups, eps);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

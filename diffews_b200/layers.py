@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import torch
 
 from . import ops
@@ -36,6 +38,13 @@ class Precision:
 
 
 PURE_BF16 = Precision(half=torch.bfloat16)
+
+# Fold GroupNorm + SiLU into the consuming convolution (ops.conv2d_gn_in, bit-identical to norm kernel + conv).  OFF by
+# default: measured on B200 it loses -- the patch transform has to run once per horizontal tap (3x the elements, one MUFU
+# tanh each: 6.9k MUFU cycles per 9.2k MMA cycles of a tile), the VAE convolutions drop from 1.27-1.42 to 0.79-0.90
+# PFLOP/s, which costs more than the 16 ms / step of GroupNorm-apply passes it removes (111 vs 123 episodes/s).
+# DFW_FUSE_GN=1 enables it.
+FUSE_GN_INTO_CONV = os.environ.get("DFW_FUSE_GN", "0") == "1"
 
 
 def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
@@ -161,8 +170,19 @@ class Resnet:
         conv1's output always feeds norm2, so conv1 always tries to (ops.conv2d falls back silently when the shape
         is not supported, e.g. the UNet's 10/20/40-channel groups)."""
         p = self.prec
-        a = self.norm1(h, silu=True)
-        t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32, gn_stats=True)
-        c = self.norm2(t, silu=True)
+        # GroupNorm + SiLU folded into the conv operand (no normalised tensor in HBM) where the kernel supports the
+        # shape and the statistics of the input already exist; otherwise norm kernel + conv
+        if FUSE_GN_INTO_CONV and conv1_bias is None and not p.mid_f32 and self.norm1.groups == 32 \
+                and ops.conv_gn_in_supported(h, self.conv1.cout, self.conv1.ksize):
+            t = ops.conv2d_gn_in(h, self.norm1.g, self.norm1.b, self.norm1.eps, self.conv1.w, self.conv1.b,
+                                 ksize=self.conv1.ksize, gn_stats=True)
+        else:
+            a = self.norm1(h, silu=True)
+            t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32, gn_stats=True)
         s = h if self.shortcut is None else self.shortcut(ops.cast16(h, p.half), out_f32=p.stream_f32)
+        if FUSE_GN_INTO_CONV and not p.stream_f32 and self.norm2.groups == 32 \
+                and ops.conv_gn_in_supported(t, self.conv2.cout, self.conv2.ksize):
+            return ops.conv2d_gn_in(t, self.norm2.g, self.norm2.b, self.norm2.eps, self.conv2.w, self.conv2.b,
+                                    ksize=self.conv2.ksize, residual=s, gn_stats=gn_stats_out)
+        c = self.norm2(t, silu=True)
         return self.conv2(c, residual=s, out_f32=p.stream_f32, gn_stats=gn_stats_out)

@@ -165,6 +165,42 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
     return y
 
 
+def conv_gn_in_supported(x, cout, ksize) -> bool:
+    """Can conv2d_gn_in consume x (which must carry the statistics its producing conv emitted)?"""
+    if getattr(x, "_gn_partial", None) is None or x.dtype not in OPERAND_DTYPES or x.dim() != 4:
+        return False
+    N, H, W, Cin = x.shape
+    return bool(lib.dfw_conv_gnin_supported(N, H, W, Cin, cout, ksize))
+
+
+def conv2d_gn_in(x, gamma, beta, eps, w, bias=None, *, ksize, residual=None, gn_stats=False, groups=32):
+    """conv(silu(groupnorm(x))) + bias (+ residual) with the normalisation applied to the conv operand on the fly:
+    x 16-bit [N,H,W,Cin] with x._gn_partial (its statistics, from the conv that produced it); returns 16-bit [N,H,W,Cout]."""
+    assert x.dtype in OPERAND_DTYPES and w.dtype == x.dtype and x.is_contiguous()
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    partial, nchunks = x._gn_partial
+    ss = torch.empty((N, 2, Cin), device=x.device, dtype=torch.float32)
+    check(lib.dfw_gn_scale_shift(partial.data_ptr(), nchunks, gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), N, H * W, Cin,
+                                 groups, float(eps), _stream()), "dfw_gn_scale_shift")
+    y = torch.empty((N, H, W, Cout), device=x.device, dtype=x.dtype)
+    flags = EPI_F16 if x.dtype == f16 else 0
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous() and residual.dtype == x.dtype
+    if bias is not None: _req(bias, torch.float32, "bias")
+    part_out = None
+    if gn_stats and gn_stats_supported(N, H, W, Cout, False, residual, False):
+        part_out = torch.empty(int(lib.dfw_gn_partial_floats(N)), device=x.device, dtype=torch.float32)
+    with _Timed("igemm", 2.0 * N * H * W * Cout * ksize * ksize * Cin,
+                f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s1 gn-in" + (" +gn" if part_out is not None else "")):
+        check(lib.dfw_conv2d_igemm_gnin(x.data_ptr(), ss.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(),
+                                        N, H, W, Cin, Cout, ksize, flags, _ptr(part_out), _stream()),
+              "dfw_conv2d_igemm_gnin")
+    if part_out is not None:
+        y._gn_partial = (part_out, part_out.numel() // (N * 64))
+    return y
+
+
 def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu=False, geglu=False, out=None):
     """x bf16 [..., K]; w bf16 [Nout, K]; returns [..., Nout_eff] (written into `out` if given)."""
     assert x.dtype in OPERAND_DTYPES and w.dtype == x.dtype, (x.dtype, w.dtype)

@@ -406,6 +406,34 @@ def conv_t128():
 
 
 @case
+def conv_gn_in():
+    """GroupNorm + SiLU applied to the conv operand on the fly == groupnorm kernel followed by the conv (same fp32
+    formula, same fp16 rounding of the normalised value, same MMA order -> expected bit-identical)."""
+    import torch
+    from diffews_b200 import ops
+    from diffews_b200.weights import conv_weight_to_gemm
+    for (N, H, W, Ci, Co, ks, res, dt) in [(3, 256, 256, 128, 128, 3, True, torch.float16), (16, 64, 64, 512, 512, 3, True, torch.float16),
+                                           (4, 144, 176, 128, 256, 3, False, torch.float16), (4, 128, 128, 256, 128, 1, False, torch.float16),
+                                           (3, 160, 128, 256, 256, 3, True, torch.bfloat16)]:
+        x0 = _mk((N, H, W, 128), 1, 1).to(dt); w0 = _mk((Ci, 128, 3, 3), (128 * 9) ** -0.5, 7).to(dt); b0 = _mk((Ci,), 1, 8)
+        x = ops.conv2d(x0, conv_weight_to_gemm(w0), b0, ksize=3, gn_stats=True)         # producer: emits the statistics
+        assert hasattr(x, "_gn_partial")
+        w = _mk((Co, Ci, ks, ks), (Ci * ks * ks) ** -0.5, 2).to(dt); b = _mk((Co,), 1, 3)
+        g = _mk((Ci,), 1, 5) + 1.0; be = _mk((Ci,), 1, 6)
+        r = _mk((N, H, W, Co), 1, 4).to(dt) if res else None
+        assert ops.conv_gn_in_supported(x, Co, ks)
+        y = ops.conv2d_gn_in(x, g, be, 1e-6, conv_weight_to_gemm(w), b, ksize=ks, residual=r, gn_stats=True)
+        xn = ops.groupnorm(x, g, be, eps=1e-6, silu=True, out_dtype=dt)
+        y_ref = ops.conv2d(xn, conv_weight_to_gemm(w), b, ksize=ks, residual=r, gn_stats=True)
+        e = rel(y, y_ref)
+        same = torch.equal(y, y_ref)
+        p1, p2 = y._gn_partial[0], y_ref._gn_partial[0]
+        pe = float((p1 - p2).abs().max() / p2.abs().max())
+        print(f"gn-in N{N} {H}x{W} {Ci}->{Co} k{ks} res={res} {dt}: rel {e:.2e} identical {same}  stats diff {pe:.1e}")
+        assert e < 1e-5 and pe < 1e-5
+
+
+@case
 def rthres():
     import torch
     from diffews_b200 import ops
