@@ -153,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -169,7 +169,28 @@ def _igemm_traffic():
         return None
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly one JSON line: everything libraries print there meanwhile (NCCL's version banner, ...) goes
+    to stderr; _emit() restores the real stdout for the line itself."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -377,7 +398,7 @@ def main():
             "frac_of_tensor_roofline_whole_path": round(value / world * FLOPS_PER_EPISODE_1SHOT_512 / (peak_tf * 1e12), 4)
             if (args.size == 512 and args.nshot == 1) else None,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
