@@ -118,6 +118,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
     auto tS = [&](int buf) { return tmem_base + buf * 128; };
     auto tO = [&](int x) { return tmem_base + ATT_SBUF * 128 + x * 64; };
 
@@ -375,6 +376,7 @@ __global__ void cross_attn_kernel(const uint16_t* __restrict__ q, const uint16_t
                                   const uint16_t* __restrict__ v, long long kv_batch_stride,
                                   uint16_t* __restrict__ o, long long total_groups, int L, int heads, int Lctx,
                                   float scale_log2, int f16) {
+    pdl_wait();
     const long long gid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
     const bool active = gid < total_groups;
@@ -476,8 +478,8 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
         attr_set = true;
     }
     dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
-    if (f16) attn_kvfused_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_)>>>(maps, p);
-    else attn_kvfused_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_)>>>(maps, p);
+    if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true>, grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_), maps, p));
+    else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false>, grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_), maps, p));
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
@@ -494,10 +496,10 @@ int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv
     const long long threads = groups * 8;
     const long long blocks = (threads + 255) / 256;
     DFW_REQUIRE(blocks < (1LL << 31));
-    cross_attn_kernel<<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(k),
-        reinterpret_cast<const uint16_t*>(v), kv_batch_stride, reinterpret_cast<uint16_t*>(o), groups, L,
-        heads, Lctx, scale * 1.4426950408889634f, f16);
+    DFW_CHECK_CUDA(launch_k(cross_attn_kernel, static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_),
+                            reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(k),
+                            reinterpret_cast<const uint16_t*>(v), kv_batch_stride, reinterpret_cast<uint16_t*>(o), groups, L,
+                            heads, Lctx, scale * 1.4426950408889634f, f16));
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -1,11 +1,19 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace dfw {
 
 std::atomic<long long> g_launches{0};
+
+bool pdl_enabled() {
+    // off by default: correct (bring-up + parity suites pass under it, CUDA-graph capture keeps the edges) but neutral on
+    // B200 -- the step is power-capped, so hiding the ~2 us launch gaps buys no time (121.1 / 119.5 vs 120.7 / 121.4 eps/s)
+    static const bool on = [] { const char* e = getenv("DFW_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
 
 int require_sm100() {
     static int cached = 1;  // 1 = unknown

@@ -40,6 +40,21 @@ int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const u
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box);
 
+// Kernel launch with the programmatic-dependent-launch attribute when DFW_PDL=1 (default: plain launch).  Only for kernels that call
+// pdl_wait() before their first global access.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

@@ -391,6 +391,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();                      // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int kblocks = p.ntaps * p.kb_per_tap;
 
@@ -988,6 +990,8 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
     const int tiles_per_img = p.tiles_w * p.tiles_h;
     auto decode = [&](int u, int& n, int& slab, int& h0, int& w0) {
         const int ns = u / tiles_per_img;              // image * n_slabs + slab
@@ -1343,9 +1347,9 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     }
     const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
     if (gn_in != nullptr)
-        igemm_t128_kernel<true><<<grid, T128Cfg::THREADS_GN, T128Cfg::SMEM_BYTES, stream>>>(maps, p);
+        DFW_CHECK_CUDA(launch_k(igemm_t128_kernel<true>, grid, T128Cfg::THREADS_GN, T128Cfg::SMEM_BYTES, stream, maps, p));
     else
-        igemm_t128_kernel<false><<<grid, T128Cfg::THREADS, T128Cfg::SMEM_BYTES, stream>>>(maps, p);
+        DFW_CHECK_CUDA(launch_k(igemm_t128_kernel<false>, grid, T128Cfg::THREADS, T128Cfg::SMEM_BYTES, stream, maps, p));
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
@@ -1364,7 +1368,7 @@ int launch_igemm(const IgemmMaps& maps, IgemmParams& p, cudaStream_t stream) {
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_nimg * p.n_tiles;
     const int units = (p.total_tiles + TPU - 1) / TPU;
     const int grid = units < sm_count() ? units : sm_count();
-    igemm_kernel<BLOCK_N, TPU><<<grid, IGEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    DFW_CHECK_CUDA(launch_k(igemm_kernel<BLOCK_N, TPU>, grid, IGEMM_THREADS, Cfg::SMEM_BYTES, stream, maps, p));
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -55,6 +55,7 @@ template <int XD>
 __global__ void gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial, int HW, int C, int groups,
                                 int rows_per_chunk, int RPI) {
     extern __shared__ float sm[];  // [RPI][C][2]
+    pdl_wait();
     const int V = C / 8;
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int vc = threadIdx.x % V, r = threadIdx.x / V;
@@ -107,6 +108,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restr
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 void* __restrict__ y, int HW, int C, int groups, int nchunks, float eps,
                                 int rows_per_chunk, int RPI, int apply_silu, int y_f16) {
+    pdl_wait();
     __shared__ float s_red[8][64][2];
     __shared__ float s_mean[64], s_rstd[64];
     const int V = C / 8;
@@ -292,6 +294,7 @@ template <int XD, int NV>
 __global__ void __launch_bounds__(256) layernorm_v4_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, void* __restrict__ y, int M,
                                                            int C, float eps, int y_f16) {
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
@@ -338,10 +341,10 @@ static bool launch_layernorm_v4(const void* x, const float* gamma, const float* 
                                 int y_f16, cudaStream_t stream) {
     const int nv = (C / 4 + 31) / 32;
     const int blocks = (M + 7) / 8;
-    if (nv <= 3) layernorm_v4_kernel<XD, 3><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
-    else if (nv <= 5) layernorm_v4_kernel<XD, 5><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
-    else if (nv <= 10) layernorm_v4_kernel<XD, 10><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
-    else if (nv <= 16) layernorm_v4_kernel<XD, 16><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
+    if (nv <= 3) launch_k(layernorm_v4_kernel<XD, 3>, blocks, 256, 0, stream, x, gamma, beta, y, M, C, eps, y_f16);
+    else if (nv <= 5) launch_k(layernorm_v4_kernel<XD, 5>, blocks, 256, 0, stream, x, gamma, beta, y, M, C, eps, y_f16);
+    else if (nv <= 10) launch_k(layernorm_v4_kernel<XD, 10>, blocks, 256, 0, stream, x, gamma, beta, y, M, C, eps, y_f16);
+    else if (nv <= 16) launch_k(layernorm_v4_kernel<XD, 16>, blocks, 256, 0, stream, x, gamma, beta, y, M, C, eps, y_f16);
     else return false;
     return true;
 }
@@ -351,6 +354,7 @@ static bool launch_layernorm_v4(const void* x, const float* gamma, const float* 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ s, uint16_t* __restrict__ p, int L, float scale,
                                     int y_f16) {
+    pdl_wait();
     __shared__ float red[32];
     const float* row = s + static_cast<long long>(blockIdx.x) * L;
     uint16_t* out = p + static_cast<long long>(blockIdx.x) * L;
@@ -444,9 +448,9 @@ int dfw_groupnorm_silu(const void* x, int x_dtype, const float* gamma, const flo
     dim3 grid(pl.nchunks, N);
     DFW_REQUIRE(pl.smem <= 48 * 1024);
 #define DFW_GN_LAUNCH(XD)                                                                                          \
-    gn_stats_kernel<XD><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI); \
-    gn_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, partial, gamma, beta, y, HW, C, groups, pl.nchunks, eps,  \
-                                                          pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
+    launch_k(gn_stats_kernel<XD>, grid, pl.threads, pl.smem, stream, x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI); \
+    launch_k(gn_apply_kernel<XD>, grid, pl.threads, 0, stream, x, partial, gamma, beta, y, HW, C, groups, pl.nchunks, eps,  \
+             pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
     if (x_dtype == 1) { DFW_GN_LAUNCH(1) } else if (x_dtype == 2) { DFW_GN_LAUNCH(2) } else { DFW_GN_LAUNCH(0) }
 #undef DFW_GN_LAUNCH
     g_launches.fetch_add(2);
@@ -467,8 +471,8 @@ int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial,
     GnPlan pl = gn_plan(N, HW, C);
     dim3 grid(pl.nchunks, N);
 #define DFW_GN_APPLY(XD)                                                                                            \
-    gn_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, partial, gamma, beta, y, HW, C, groups, nchunks, eps,      \
-                                                          pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
+    launch_k(gn_apply_kernel<XD>, grid, pl.threads, 0, stream, x, partial, gamma, beta, y, HW, C, groups, nchunks, eps,      \
+             pl.rows_per_chunk, pl.RPI, apply_silu, y_f16);
     if (x_dtype == 1) { DFW_GN_APPLY(1) } else if (x_dtype == 2) { DFW_GN_APPLY(2) } else { DFW_GN_APPLY(0) }
 #undef DFW_GN_APPLY
     g_launches.fetch_add(1);
@@ -521,7 +525,7 @@ int dfw_softmax_rows(const float* s, void* p, int y_f16, int M, int L, float sca
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(s && p && M > 0 && L > 0 && L % 4 == 0);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    softmax_rows_kernel<<<M, 256, 0, stream>>>(s, reinterpret_cast<uint16_t*>(p), L, scale, y_f16);
+    launch_k(softmax_rows_kernel, M, 256, 0, stream, s, reinterpret_cast<uint16_t*>(p), L, scale, y_f16);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -43,6 +43,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return y;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialisation attribute may start (run its
+// prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still draining;
+// pdl_wait() blocks until the predecessor has completed and its writes are visible, so it must precede every global
+// access.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as SM resources free up: only the
+// persistent one-CTA-per-SM kernels call it (at their start); a multi-wave kernel that triggered early would see the
+// successor's idle CTAs take SM slots ahead of its own remaining CTAs (measured: -1.2 % when every kernel triggered).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
