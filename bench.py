@@ -363,7 +363,7 @@ def main():
         ig = summ.get("igemm")
         if ig and ig["ms"] > 0:
             achieved = ig["flops"] / (ig["ms"] * 1e9)
-            roofline = {"bound": "tensor", "kernel": "igemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear)",
+            roofline = {"bound": "tensor", "kernel": "igemm_t128_kernel / igemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear, all launches)",
                         "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": round(achieved / peak_tf, 4), "traffic": _igemm_traffic(), "peak_source": f"{peak_kind} sustained bf16",
                         "launches": ig["launches"], "share_of_step": round(ig["ms"] / ms_total_instr, 3),

@@ -248,3 +248,61 @@ def test_evaluator_dropin_matches_oracle():
     assert torch.equal(m.intersection_buf.cpu(), mo.intersection_buf) and torch.equal(m.union_buf.cpu(), mo.union_buf)
     a, b = m.compute_iou()[:2], mo.compute_iou()[:2]
     assert abs(float(a[0]) - float(b[0])) < 1e-4 and abs(float(a[1]) - float(b[1])) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Kernel-level parity of the convolution paths the pipeline tests reach only at full size: the channel-major (T128)
+# kernel and the GroupNorm+SiLU-into-conv variant, against the oracle's own operators (torch fp32 on the CPU).
+# ---------------------------------------------------------------------------------------------------------------------
+def _conv_case(N, H, W, Ci, Co, ks, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, H, W, Ci, generator=g).half()
+    w = (torch.randn(Co, Ci, ks, ks, generator=g) * (Ci * ks * ks) ** -0.5).half()
+    b = torch.randn(Co, generator=g)
+    r = torch.randn(N, H, W, Co, generator=g).half()
+    return x, w, b, r
+
+
+@pytest.mark.parametrize("N,H,W,Ci,Co,ks,res", [(5, 144, 112, 128, 128, 3, True), (3, 128, 128, 64, 256, 3, False),
+                                                (16, 64, 64, 128, 512, 1, True), (1, 16, 16, 128, 128, 3, True)])
+def test_conv_paths_match_oracle_conv(N, H, W, Ci, Co, ks, res):
+    """3x3 / 1x1 convolution + bias (+ residual) and the fused GroupNorm statistics of its output, vs F.conv2d /
+    F.group_norm in fp32 on the CPU (the last shape is too small for the channel-major kernel: generic path)."""
+    import torch.nn.functional as F
+    from diffews_b200 import ops
+    from diffews_b200.weights import conv_weight_to_gemm
+    x, w, b, r = _conv_case(N, H, W, Ci, Co, ks)
+    y = ops.conv2d(x.cuda(), conv_weight_to_gemm(w).cuda().half(), b.cuda(), ksize=ks, residual=r.cuda() if res else None,
+                   gn_stats=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=(ks - 1) // 2).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    e = rel_l2(y, ref)
+    assert e <= 1e-3, e                                     # fp16 output rounding: ~2e-4
+    gam = torch.randn(Co, generator=torch.Generator().manual_seed(5)); bet = torch.randn(Co, generator=torch.Generator().manual_seed(6))
+    yn = ops.groupnorm(y, gam.cuda(), bet.cuda(), eps=1e-6, silu=True, out_dtype=torch.float16)
+    refn = F.silu(F.group_norm(y.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, 1e-6)).permute(0, 2, 3, 1)
+    assert rel_l2(yn, refn) <= 1e-3
+
+
+def test_conv_gn_in_equals_norm_then_conv():
+    """dfw_conv2d_igemm_gnin (GroupNorm + SiLU applied to the conv operand in shared memory) is bit-identical to the
+    norm kernel followed by the convolution, and both match the fp32 CPU operators."""
+    import torch.nn.functional as F
+    from diffews_b200 import ops
+    from diffews_b200.weights import conv_weight_to_gemm
+    N, H, W, C = 3, 256, 256, 128
+    x0, w0, b0, _ = _conv_case(N, H, W, 64, C, 3, seed=1)
+    x = ops.conv2d(x0.cuda(), conv_weight_to_gemm(w0).cuda().half(), b0.cuda(), ksize=3, gn_stats=True)
+    assert ops.conv_gn_in_supported(x, C, 3)
+    _, w, b, r = _conv_case(N, H, W, C, C, 3, seed=2)
+    gam = torch.randn(C, generator=torch.Generator().manual_seed(5)) + 1.0
+    bet = torch.randn(C, generator=torch.Generator().manual_seed(6))
+    wg = conv_weight_to_gemm(w).cuda().half()
+    y = ops.conv2d_gn_in(x, gam.cuda(), bet.cuda(), 1e-6, wg, b.cuda(), ksize=3, residual=r.cuda())
+    xn = ops.groupnorm(x, gam.cuda(), bet.cuda(), eps=1e-6, silu=True, out_dtype=torch.float16)
+    y2 = ops.conv2d(xn, wg, b.cuda(), ksize=3, residual=r.cuda())
+    assert torch.equal(y, y2)
+    xr = F.silu(F.group_norm(x.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, 1e-6))
+    ref = F.conv2d(xr, w.float(), b, padding=1).permute(0, 2, 3, 1) + r.float()
+    assert rel_l2(y, ref) <= 2e-3
