@@ -1,4 +1,5 @@
 """CPU tests of the host-side logic: weight re-layouts, synthetic episodes, scheduler, sharding, gloo all-reduce."""
+import json
 import os
 
 import pytest
@@ -107,3 +108,28 @@ def test_data_parallel_counts_equal_single_process():
     for rank, i_buf, u_buf, miou, fb in res:
         assert i_buf == ib.tolist() and u_buf == ub.tolist()
     assert res[0][3] == res[1][3] and res[0][4] == res[1][4]
+
+
+def test_checkpoint_layout_roundtrip(tmp_path):
+    """diffusers directory layout (main_oss.py:338-369): safetensors + config.json per sub-model are read back verbatim;
+    a plain SD-2.1 UNet gets the 8-channel support stem the reference's conversion script builds."""
+    from safetensors.torch import save_file
+    from diffews_b200 import checkpoint as ck
+    g = torch.Generator().manual_seed(0)
+    sd = {"conv_in.weight": torch.randn(8, 4, 3, 3, generator=g), "conv_in.bias": torch.randn(8, generator=g),
+          "mid_block.resnets.0.norm1.weight": torch.randn(8, generator=g)}
+    (tmp_path / "unet").mkdir()
+    save_file(sd, str(tmp_path / "unet" / "diffusion_pytorch_model.safetensors"))
+    (tmp_path / "unet" / "config.json").write_text(json.dumps({"block_out_channels": [8, 16], "attention_head_dim": [5, 10]}))
+    back = ck.load_state_dict(str(tmp_path / "unet"))
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    cfg = ck.load_config(str(tmp_path / "unet"))
+    assert ck._heads_from_config(cfg, cfg["block_out_channels"]) == (5, 10)
+    assert ck._heads_from_config({}, (320, 640)) == (5, 10) and ck._heads_from_config({"attention_head_dim": 8}, (64, 64)) == (8, 8)
+    full = ck.with_support_stem(back)
+    assert full["conv_in_ref.weight"].shape == (8, 8, 3, 3)
+    assert torch.equal(full["conv_in_ref.weight"][:, :4], sd["conv_in.weight"] / 2)
+    assert torch.equal(full["conv_in_ref.weight"][:, 4:], sd["conv_in.weight"] / 2)
+    assert ck.with_support_stem(full) is full
+    torch.save(sd, str(tmp_path / "unet" / "w.bin"))
+    assert torch.equal(ck.load_state_dict(str(tmp_path / "unet" / "w.bin"))["conv_in.bias"], sd["conv_in.bias"])

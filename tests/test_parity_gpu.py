@@ -306,3 +306,37 @@ def test_conv_gn_in_equals_norm_then_conv():
     xr = F.silu(F.group_norm(x.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, 1e-6))
     ref = F.conv2d(xr, w.float(), b, padding=1).permute(0, 2, 3, 1) + r.float()
     assert rel_l2(y, ref) <= 2e-3
+
+
+def test_checkpoint_loader_equals_from_module(small_models, tmp_path):
+    """A diffusers-layout checkpoint directory (safetensors + config.json, what main_oss.py:338-369 reads) loaded through
+    diffews_b200.checkpoint gives bit-identical UNet / VAE engines to building them from the live modules."""
+    import json
+    from safetensors.torch import save_file
+    from diffews_b200 import checkpoint as ck
+    from diffews_b200.synthetic import prompt_embedding
+    from diffews_b200.unet import MyUNet2DConditionModel
+    from diffews_b200.vae import AutoencoderKL
+    unet_o, vae_o = small_models[0], small_models[1]
+    for name, mod, cfg in (("unet", unet_o, {"block_out_channels": list(unet_o.block_out_channels),
+                                             "attention_head_dim": list(unet_o.heads), "cross_attention_dim": 1024}),
+                           ("vae", vae_o, {"block_out_channels": [b.resnets[0].conv1.out_channels
+                                                                   for b in vae_o.encoder.down_blocks]})):
+        (tmp_path / name).mkdir()
+        save_file({k: v.contiguous() for k, v in mod.state_dict().items()},
+                  str(tmp_path / name / "diffusion_pytorch_model.safetensors"))
+        (tmp_path / name / "config.json").write_text(json.dumps(cfg))
+    u1, u2 = ck.load_unet(str(tmp_path)), MyUNet2DConditionModel.from_module(unet_o)
+    v1, v2 = ck.load_vae(str(tmp_path)), AutoencoderKL.from_module(vae_o)
+    g = torch.Generator().manual_seed(3)
+    sup = (torch.randn(2, 8, 16, 16, generator=g) * 0.8).cuda(); qry = (torch.randn(2, 4, 16, 16, generator=g) * 0.8).cuda()
+    ehs = prompt_embedding().repeat(2, 1, 1).cuda()
+    outs = []
+    for u in (u1, u2):
+        u.clear_attn_bank()
+        u(sup, torch.tensor(1), ehs, is_target=False)
+        outs.append(u(qry, torch.tensor(1), ehs).sample)
+        u.clear_attn_bank()
+    assert torch.equal(outs[0], outs[1])
+    img = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).cuda()
+    assert torch.equal(v1.encode_mean(img), v2.encode_mean(img))
