@@ -29,9 +29,14 @@ SIGNATURES = {
     "dfw_conv2d_igemm_gnstats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "dfw_groupnorm_from_partial": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "dfw_gn_scale_shift": (_i, [_vp, _i, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _vp]),
+    "dfw_groupnorm_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i]),
+    "dfw_groupnorm_silu_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "dfw_conv_gnin_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "dfw_conv2d_igemm_gnin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dfw_bmm_nt": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "dfw_attn_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
+    "dfw_attn_kvfused_bwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp,
+                                  _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
                                   _i, _f, _i, _vp]),
     "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _i, _vp]),

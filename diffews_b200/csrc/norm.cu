@@ -181,6 +181,175 @@ __global__ void gn_apply_kernel(const void* __restrict__ x, const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) backward (BASELINE config 4: training-shape forward + backward of the GroupNorm kernels;
+// ref: the nn.GroupNorm + SiLU autograd of every diffusers ResnetBlock2D under train_tools/...v3.py:1320-1396).
+//   z = xh * gamma + beta, xh = (x - mean) * rstd, y = silu(z) or z;   dz = dy * act'(z)
+//   dgamma_c = sum dz xh, dbeta_c = sum dz;  dx = rstd (dz gamma - S1/M - xh S2/M),
+//   S1 = sum_{group} dz gamma, S2 = sum_{group} dz gamma xh, M = HW * cpg.
+// Same (row-chunk, image) decomposition and fixed-order (deterministic) folds as the forward.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_grad(float z, int silu) {
+    if (!silu) return 1.0f;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    const float sg = fmaf(0.5f, t, 0.5f);                     // sigmoid(z)
+    return sg * fmaf(z, 1.0f - sg, 1.0f);
+}
+template <int XD>
+__device__ __forceinline__ void store8(void* base, long long off, const float (&v)[8]) {
+    if constexpr (XD == 1) {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+        p[0] = make_float4(v[0], v[1], v[2], v[3]);
+        p[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        store8_16(base, off, v, XD == 2);
+    }
+}
+// fold the forward statistics partials of image n into s_mean / s_rstd (identical to gn_apply_kernel's prologue)
+__device__ __forceinline__ void gn_fold_stats(const float* __restrict__ partial, int n, int nchunks, int groups, int HW,
+                                              int cpg, float eps, float (*s_red)[64][2], float* s_mean, float* s_rstd) {
+    for (int idx = threadIdx.x; idx < 8 * groups; idx += blockDim.x) {
+        const int g = idx % groups, sl = idx / groups;
+        float s = 0.f, ss = 0.f;
+        const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * nchunks * groups + g;
+#pragma unroll 8
+        for (int c = sl; c < nchunks; c += 8) {
+            const float2 v = __ldg(pp + static_cast<size_t>(c) * groups);
+            s += v.x; ss += v.y;
+        }
+        s_red[sl][g][0] = s; s_red[sl][g][1] = ss;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, ss = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) { s += s_red[sl][g][0]; ss += s_red[sl][g][1]; }
+        const double cnt = static_cast<double>(HW) * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+}
+// pass 1: per (image, row chunk, channel) a = sum dz, b = sum dz * xh   ->  ab_partial [N][nchunks][C][2]
+template <int XD>
+__global__ void gn_bwd_reduce_kernel(const void* __restrict__ x, const void* __restrict__ dy,
+                                     const float* __restrict__ partial, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ ab_partial, int HW, int C,
+                                     int groups, float eps, int rows_per_chunk, int RPI, int silu) {
+    extern __shared__ float sm[];                                 // [RPI][C][2]
+    __shared__ float s_red[8][64][2];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int V = C / 8, cpg = C / groups;
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    gn_fold_stats(partial, n, nchunks, groups, HW, cpg, eps, s_red, s_mean, s_rstd);
+    const int vc = threadIdx.x % V, r = threadIdx.x / V;
+    const int row0 = chunk * rows_per_chunk, row1 = min(HW, row0 + rows_per_chunk);
+    float mu[8], rs[8], ga[8], be[8], a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = vc * 8 + j, g = c / cpg;
+        mu[j] = s_mean[g]; rs[j] = s_rstd[g]; ga[j] = __ldg(gamma + c); be[j] = __ldg(beta + c);
+        a[j] = 0.f; b[j] = 0.f;
+    }
+    const long long img_off = static_cast<long long>(n) * HW * C + vc * 8;
+    for (int row = row0 + r; row < row1; row += RPI) {
+        float xv[8], gv[8];
+        const long long o = img_off + static_cast<long long>(row) * C;
+        load8<XD>(x, o, xv); load8<XD>(dy, o, gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - mu[j]) * rs[j];
+            const float dz = gv[j] * act_grad(fmaf(xh, ga[j], be[j]), silu);
+            a[j] += dz; b[j] = fmaf(dz, xh, b[j]);
+        }
+    }
+    float* my = sm + (static_cast<size_t>(r) * C + vc * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[2 * j] = a[j]; my[2 * j + 1] = b[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sa = 0.f, sb = 0.f;
+        for (int rr = 0; rr < RPI; ++rr) { sa += sm[(static_cast<size_t>(rr) * C + c) * 2]; sb += sm[(static_cast<size_t>(rr) * C + c) * 2 + 1]; }
+        float* out = ab_partial + ((static_cast<size_t>(n) * nchunks + chunk) * C + c) * 2;
+        out[0] = sa; out[1] = sb;
+    }
+}
+// pass 2 (one CTA per image): ab[n][c] = sum over chunks; gs[n][g] = (S1, S2) / M; ms[n][g] = (mean, rstd)
+__global__ void gn_bwd_fold_kernel(const float* __restrict__ partial, const float* __restrict__ ab_partial,
+                                   const float* __restrict__ gamma, float* __restrict__ ab, float* __restrict__ gs,
+                                   float* __restrict__ ms, int nchunks, int HW, int C, int groups, float eps) {
+    __shared__ float s_red[8][64][2];
+    __shared__ float s_mean[64], s_rstd[64];
+    extern __shared__ float s_ab[];                               // [C][2]
+    const int n = blockIdx.x, cpg = C / groups;
+    gn_fold_stats(partial, n, nchunks, groups, HW, cpg, eps, s_red, s_mean, s_rstd);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sa = 0.f, sb = 0.f;
+        for (int k = 0; k < nchunks; ++k) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(ab_partial) + (static_cast<size_t>(n) * nchunks + k) * C + c);
+            sa += v.x; sb += v.y;
+        }
+        s_ab[2 * c] = sa; s_ab[2 * c + 1] = sb;
+        ab[(static_cast<size_t>(n) * C + c) * 2] = sa; ab[(static_cast<size_t>(n) * C + c) * 2 + 1] = sb;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float ga = __ldg(gamma + c);
+            s1 = fmaf(ga, s_ab[2 * c], s1); s2 = fmaf(ga, s_ab[2 * c + 1], s2);
+        }
+        const float inv = 1.0f / (static_cast<float>(HW) * cpg);
+        gs[(static_cast<size_t>(n) * groups + g) * 2] = s1 * inv; gs[(static_cast<size_t>(n) * groups + g) * 2 + 1] = s2 * inv;
+        ms[(static_cast<size_t>(n) * groups + g) * 2] = s_mean[g]; ms[(static_cast<size_t>(n) * groups + g) * 2 + 1] = s_rstd[g];
+    }
+}
+// pass 3: dgamma_c = sum_n b, dbeta_c = sum_n a (fixed order over images)
+__global__ void gn_bwd_param_kernel(const float* __restrict__ ab, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    int N, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sa = 0.f, sb = 0.f;
+    for (int n = 0; n < N; ++n) { sa += ab[(static_cast<size_t>(n) * C + c) * 2]; sb += ab[(static_cast<size_t>(n) * C + c) * 2 + 1]; }
+    dbeta[c] = sa; dgamma[c] = sb;
+}
+// pass 4: dx
+template <int XD>
+__global__ void gn_bwd_apply_kernel(const void* __restrict__ x, const void* __restrict__ dy, const float* __restrict__ gs,
+                                    const float* __restrict__ ms, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, void* __restrict__ dx, int HW, int C, int groups,
+                                    int rows_per_chunk, int RPI, int silu) {
+    const int V = C / 8, cpg = C / groups;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int vc = threadIdx.x % V, r = threadIdx.x / V;
+    const int row0 = chunk * rows_per_chunk, row1 = min(HW, row0 + rows_per_chunk);
+    float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = vc * 8 + j, g = c / cpg;
+        const size_t o = (static_cast<size_t>(n) * groups + g) * 2;
+        mu[j] = __ldg(ms + o); rs[j] = __ldg(ms + o + 1); m1[j] = __ldg(gs + o); m2[j] = __ldg(gs + o + 1);
+        ga[j] = __ldg(gamma + c); be[j] = __ldg(beta + c);
+    }
+    const long long img_off = static_cast<long long>(n) * HW * C + vc * 8;
+    for (int row = row0 + r; row < row1; row += RPI) {
+        float xv[8], gv[8], o8[8];
+        const long long o = img_off + static_cast<long long>(row) * C;
+        load8<XD>(x, o, xv); load8<XD>(dy, o, gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - mu[j]) * rs[j];
+            const float dz = gv[j] * act_grad(fmaf(xh, ga[j], be[j]), silu);
+            o8[j] = rs[j] * (fmaf(dz, ga[j], -m1[j]) - xh * m2[j]);
+        }
+        store8<XD>(dx, o, o8);
+    }
+}
+
 // Per-(image, channel) scale / shift of a GroupNorm whose statistics came from a conv epilogue: out[n][0][c] = rstd *
 // gamma, out[n][1][c] = beta - mean * rstd * gamma.  Same fixed-order fold (8 slices, then fp64) as gn_apply_kernel, so
 // a convolution that applies them on the fly (dfw_conv2d_igemm_gnin) sees exactly the numbers gn_apply would use.
@@ -476,6 +645,48 @@ int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial,
     if (x_dtype == 1) { DFW_GN_APPLY(1) } else if (x_dtype == 2) { DFW_GN_APPLY(2) } else { DFW_GN_APPLY(0) }
 #undef DFW_GN_APPLY
     g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+long long dfw_groupnorm_bwd_workspace_bytes(int N, int HW, int C, int groups) {
+    if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % 8 != 0) return -1;
+    const dfw::GnPlan pl = dfw::gn_plan(N, HW, C);
+    const size_t fl = static_cast<size_t>(N) * pl.nchunks * groups * 2 + static_cast<size_t>(N) * pl.nchunks * C * 2 +
+                      static_cast<size_t>(N) * C * 2 + static_cast<size_t>(N) * groups * 4;
+    return static_cast<long long>(fl * sizeof(float) + 256);
+}
+
+int dfw_groupnorm_silu_bwd(const void* x, const void* dy, int dtype, const float* gamma, const float* beta, void* dx,
+                           float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int apply_silu,
+                           void* workspace, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(x && dy && gamma && beta && dx && dgamma && dbeta && workspace);
+    DFW_REQUIRE(dtype >= 0 && dtype <= 2);
+    DFW_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0 && C / 8 <= 1024);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    GnPlan pl = gn_plan(N, HW, C);
+    DFW_REQUIRE(pl.smem <= 48 * 1024 && static_cast<size_t>(C) * 2 * sizeof(float) <= 40 * 1024);
+    float* partial = reinterpret_cast<float*>(workspace);
+    float* ab_partial = partial + static_cast<size_t>(N) * pl.nchunks * groups * 2;
+    float* ab = ab_partial + static_cast<size_t>(N) * pl.nchunks * C * 2;
+    float* gs = ab + static_cast<size_t>(N) * C * 2;
+    float* ms = gs + static_cast<size_t>(N) * groups * 2;
+    dim3 grid(pl.nchunks, N);
+#define DFW_GN_BWD(XD)                                                                                                  \
+    gn_stats_kernel<XD><<<grid, pl.threads, pl.smem, stream>>>(x, partial, HW, C, groups, pl.rows_per_chunk, pl.RPI);   \
+    gn_bwd_reduce_kernel<XD><<<grid, pl.threads, pl.smem, stream>>>(x, dy, partial, gamma, beta, ab_partial, HW, C,     \
+                                                                    groups, eps, pl.rows_per_chunk, pl.RPI, apply_silu); \
+    gn_bwd_fold_kernel<<<N, 256, static_cast<size_t>(C) * 2 * sizeof(float), stream>>>(partial, ab_partial, gamma, ab, gs, \
+                                                                                       ms, pl.nchunks, HW, C, groups, eps); \
+    gn_bwd_param_kernel<<<(C + 255) / 256, 256, 0, stream>>>(ab, dgamma, dbeta, N, C);                                  \
+    gn_bwd_apply_kernel<XD><<<grid, pl.threads, 0, stream>>>(x, dy, gs, ms, gamma, beta, dx, HW, C, groups,             \
+                                                             pl.rows_per_chunk, pl.RPI, apply_silu);
+    if (dtype == 1) { DFW_GN_BWD(1) } else if (dtype == 2) { DFW_GN_BWD(2) } else { DFW_GN_BWD(0) }
+#undef DFW_GN_BWD
+    g_launches.fetch_add(5);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }

@@ -296,6 +296,32 @@ def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
     return o
 
 
+def attn_kvfused_backward(q, k_self, v_self, k_bank, v_bank, o, d_o, heads, scale):
+    """Backward of attn_kvfused: contiguous [B, L, heads*64] tensors of one 16-bit dtype (o = forward output, d_o its
+    gradient).  Returns (dq, dk_self, dv_self, dk_bank, dv_bank); the bank gradients are None without a bank."""
+    B, Lq, C = q.shape
+    assert C == heads * 64 and q.dtype in OPERAND_DTYPES
+    h16 = q.dtype
+    Ls = k_self.shape[1]
+    Lb = 0 if k_bank is None else k_bank.shape[1]
+    ts = [q, k_self, v_self, o, d_o] + ([k_bank, v_bank] if Lb else [])
+    for t in ts:
+        assert t.dtype == h16 and t.is_cuda and t.is_contiguous()
+    assert o.shape == q.shape and d_o.shape == q.shape and v_self.shape == k_self.shape
+    dq = torch.empty_like(q); dks = torch.empty_like(k_self); dvs = torch.empty_like(v_self)
+    dkb = torch.empty_like(k_bank) if Lb else None
+    dvb = torch.empty_like(v_bank) if Lb else None
+    ws = torch.empty(int(lib.dfw_attn_bwd_workspace_bytes(B, heads, Lq, Ls, Lb)), device=q.device, dtype=torch.uint8)
+    kb = (k_bank.data_ptr(), v_bank.data_ptr(), k_bank.stride(0), k_bank.stride(1)) if Lb else (0, 0, 0, 0)
+    with _Timed("attn", 2.5 * 4.0 * B * heads * Lq * (Ls + Lb) * 64, f"attn-bwd B{B} h{heads} Lq{Lq} Lk{Ls + Lb}"):
+        check(lib.dfw_attn_kvfused_bwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
+                                       k_self.stride(0), k_self.stride(1), kb[0], kb[1], kb[2], kb[3], o.data_ptr(),
+                                       d_o.data_ptr(), o.stride(0), o.stride(1), dq.data_ptr(), dks.data_ptr(), dvs.data_ptr(),
+                                       _ptr(dkb), _ptr(dvb), B, heads, Lq, Ls, Lb, float(scale), int(h16 == f16), ws.data_ptr(),
+                                       _stream()), "dfw_attn_kvfused_bwd")
+    return dq, dks, dvs, dkb, dvb
+
+
 def cross_attn(q, k, v, heads, scale):
     """q [B,L,C] bf16; k,v [Bk,Lctx,C] with Bk in {1,B}."""
     h16 = q.dtype
@@ -342,6 +368,23 @@ def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=bf16
                                      ws.data_ptr(), _stream()),
               "dfw_groupnorm_silu")
     return y
+
+
+def groupnorm_backward(x, dy, gamma, beta, *, groups=32, eps=1e-5, silu=False):
+    """Backward of y = [silu](group_norm(x)): x, dy [N, ..., C] channels-last of one dtype (bf16 | fp16 | fp32);
+    returns (dx like x, dgamma fp32 [C], dbeta fp32 [C])."""
+    assert x.is_cuda and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype
+    assert x.dtype in (bf16, f16, torch.float32)
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    ws = torch.empty(int(lib.dfw_groupnorm_bwd_workspace_bytes(N, HW, C, groups)), device=x.device, dtype=torch.uint8)
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32); db = torch.empty(C, device=x.device, dtype=torch.float32)
+    with _Timed("groupnorm", 2 * _nb(x, dy) + _nb(dx), f"gn-bwd N{N} HW{HW} C{C} {x.dtype}".replace("torch.", "")):
+        check(lib.dfw_groupnorm_silu_bwd(x.data_ptr(), dy.data_ptr(), _xd(x), gamma.data_ptr(), beta.data_ptr(),
+                                         dx.data_ptr(), dg.data_ptr(), db.data_ptr(), N, HW, C, groups, float(eps), int(silu),
+                                         ws.data_ptr(), _stream()), "dfw_groupnorm_silu_bwd")
+    return dx, dg, db
 
 
 def layernorm(x, gamma, beta, eps=1e-5, out_dtype=bf16):

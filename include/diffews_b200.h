@@ -115,6 +115,21 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
                          int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
                          int heads, int Lq, int Ls, int Lb, float scale, int f16, void* stream);
 
+/* K1b  BACKWARD of K1 (BASELINE config 4: training-shape forward + backward of the KV-fused attention; ref: autograd of
+ *      xformers.ops.memory_efficient_attention on cat([key, folded bank]) -- attention_processor.py:251-271 under
+ *      train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1320-1396).  Same tensor conventions as the forward;
+ *      o = the forward output, d_o its gradient (same strides as o); dq like q, dk/dv_self like k/v_self, dk/dv_bank like
+ *      the bank.  Lq, Ls, Lb multiples of 64.  First correct CUDA path: all contractions on the tcgen05 batched GEMM with
+ *      the L_q x L_k logits materialised per (episode, head) in `workspace` (dfw_attn_bwd_workspace_bytes, 256-B aligned);
+ *      deterministic. */
+long long dfw_attn_bwd_workspace_bytes(int B, int heads, int Lq, int Ls, int Lb);
+int dfw_attn_kvfused_bwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+                         const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
+                         const void* k_bank, const void* v_bank, long long kv_bank_batch_stride, int kv_bank_row_stride,
+                         const void* o, const void* d_o, long long o_batch_stride, int o_row_stride, void* dq, void* dk_self,
+                         void* dv_self, void* dk_bank, void* dv_bank, int B, int heads, int Lq, int Ls, int Lb, float scale,
+                         int f16, void* workspace, void* stream);
+
 /* K2  cross-attention to a short prompt embedding (Lctx <= 128 keys, head_dim 64), CUDA cores.
  * ref: BasicTransformerBlock.attn2 (upstream) reached from unet_2d_condition.py:1161; Lctx = 2 at eval
  *      (marigold_pipeline_rgb_latent_noise.py:591-601).
@@ -148,6 +163,14 @@ int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial,
  * tensor (x, w, y, residual 16-bit of one format, flags = DFW_EPI_F16 or 0; stride 1, pad (ksize-1)/2; optional statistics
  * of ITS output in gn_partial_out).  Only for the shapes dfw_conv_gnin_supported accepts (Cout % 128 == 0, H, W % 16 == 0,
  * enough tiles to fill the GPU); otherwise use dfw_groupnorm_from_partial + dfw_conv2d_igemm. */
+/* GroupNorm (+SiLU) BACKWARD (BASELINE config 4; the nn.GroupNorm -> SiLU autograd of every diffusers ResnetBlock2D in the
+ * training step train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1320-1396).  x, dy, dx [N, HW, C] of one dtype
+ * (0 bf16, 1 fp32, 2 fp16); dgamma, dbeta fp32 [C]; statistics are recomputed from x; deterministic (fixed-order folds). */
+long long dfw_groupnorm_bwd_workspace_bytes(int N, int HW, int C, int groups);
+int dfw_groupnorm_silu_bwd(const void* x, const void* dy, int dtype, const float* gamma, const float* beta, void* dx,
+                           float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int apply_silu,
+                           void* workspace, void* stream);
+
 int dfw_gn_scale_shift(const float* partial, int nchunks, const float* gamma, const float* beta, float* scale_shift,
                        int N, long long HW, int C, int groups, float eps, void* stream);
 int dfw_conv_gnin_supported(int N, int H, int W, int Cin, int Cout, int ksize);

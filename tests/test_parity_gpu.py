@@ -340,3 +340,62 @@ def test_checkpoint_loader_equals_from_module(small_models, tmp_path):
     assert torch.equal(outs[0], outs[1])
     img = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).cuda()
     assert torch.equal(v1.encode_mean(img), v2.encode_mean(img))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4 (training shapes): backward of the GroupNorm(+SiLU) kernel against torch autograd in fp32 on the CPU
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,H,C,silu,dt", [(7, 64, 320, True, torch.float16), (1, 32, 640, True, torch.float32),
+                                            (7, 16, 1280, False, torch.float16), (2, 24, 128, True, torch.bfloat16),
+                                            (1, 8, 2560, True, torch.float16)])
+def test_groupnorm_silu_backward_matches_autograd(N, H, C, silu, dt):
+    import torch.nn.functional as F
+    from diffews_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(N, H, H, C, generator=g) * 1.5 + 0.3).to(dt)
+    dy = torch.randn(N, H, H, C, generator=g).to(dt)
+    gam = torch.randn(C, generator=g) * 0.5 + 1.0; bet = torch.randn(C, generator=g) * 0.2
+    dx, dg, db = ops.groupnorm_backward(x.cuda(), dy.cuda(), gam.cuda(), bet.cuda(), groups=32, eps=1e-5, silu=silu)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    y = F.group_norm(xr, 32, gr, br, 1e-5)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    tol = 2e-2 if dt == torch.bfloat16 else 3e-3
+    assert rel_l2(dx, xr.grad.permute(0, 2, 3, 1)) <= tol
+    assert rel_l2(dg, gr.grad) <= 2e-3 and rel_l2(db, br.grad) <= 2e-3
+
+
+@pytest.mark.parametrize("B,h,Lq,Ls,Lb,dt", [(1, 5, 256, 256, 1792, torch.float16),      # 7-shot shape at 16x16 (config 4)
+                                             (2, 2, 128, 128, 128, torch.float16), (1, 3, 192, 192, 0, torch.float16),
+                                             (1, 5, 64, 64, 448, torch.bfloat16)])
+def test_attention_backward_matches_autograd(B, h, Lq, Ls, Lb, dt):
+    """BASELINE config 4: forward + backward of the KV-fused attention vs torch autograd (fp32, CPU) of
+    softmax(q [k_self; k_bank]^T / 8) [v_self; v_bank] -- the reference's cat([key, folded bank]) attention."""
+    from diffews_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    C = h * 64
+    mk = lambda L: torch.randn(B, L, C, generator=g).to(dt)
+    q, ks, vs, d_o = mk(Lq), mk(Ls), mk(Ls), mk(Lq)
+    kb, vb = (mk(Lb), mk(Lb)) if Lb else (None, None)
+    cu = lambda t: None if t is None else t.cuda()
+    o = ops.attn_kvfused(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), h, 0.125)
+    dq, dks, dvs, dkb, dvb = ops.attn_kvfused_backward(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), o, cu(d_o), h, 0.125)
+    leaves = [t.float().clone().requires_grad_(True) if t is not None else None for t in (q, ks, vs, kb, vb)]
+    qf, ksf, vsf, kbf, vbf = leaves
+    K = ksf if kbf is None else torch.cat([ksf, kbf], 1)
+    V = vsf if vbf is None else torch.cat([vsf, vbf], 1)
+    hd = lambda t: t.view(B, -1, h, 64).transpose(1, 2)
+    ref = torch.softmax(hd(qf) @ hd(K).transpose(-1, -2) * 0.125, -1) @ hd(V)
+    ref = ref.transpose(1, 2).reshape(B, Lq, C)
+    ref.backward(d_o.float())
+    tol = 2.5e-2 if dt == torch.bfloat16 else 4e-3
+    assert rel_l2(o, ref) <= tol
+    for name, got, leaf in (("dq", dq, qf), ("dk_self", dks, ksf), ("dv_self", dvs, vsf), ("dk_bank", dkb, kbf), ("dv_bank", dvb, vbf)):
+        if leaf is None:
+            assert got is None
+            continue
+        e = rel_l2(got, leaf.grad)
+        print(name, e)
+        assert e <= tol, (name, e)
