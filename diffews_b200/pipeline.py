@@ -11,7 +11,7 @@ reference; inputs and outputs keep the reference's NCHW fp32 tensor layouts.  Wh
   * `output_type="pt"` returns the uint8 segmentation as a CUDA tensor [B,3,H,W] (batched evaluation, which the
     reference cannot do: its eval loop only works for bsz=1).  Default "pil" matches the reference.
   * only `mode='seg'` (any non-'depth' mode is treated as seg by the reference, :280, :532) and
-    `denoising_steps == 1` ("nosample") are on the hot path; others raise NotImplementedError.
+    `denoising_steps == 1` ("nosample") is the hot path; more steps run the same two UNet passes per step (:706-767).
 """
 from __future__ import annotations
 
@@ -108,11 +108,9 @@ class MarigoldPipelineRGBLatentNoise:
         seg [B,3,H,W] float in [0,255]."""
         if mode == "depth":
             raise NotImplementedError("mode='depth' is not on the DiffewS hot path")
-        if num_inference_steps != 1:
-            raise NotImplementedError("multi-step sampling is not on the 'nosample' hot path (SURVEY §8f rank 4)")
         device = self.device
         self.scheduler.set_timesteps(num_inference_steps, device="cpu")          # :644
-        t = int(self.scheduler.timesteps[0])
+        timesteps = [int(x) for x in self.scheduler.timesteps]
         B, Bk = rgb_in_tag.shape[0], rgb_in_ref.shape[0]
         # :649-651, :674  — three VAE encodes; the support image / mask latents land in the two channel halves
         rgb_latent_ref = self.encode_rgb(rgb_in_ref.to(device))
@@ -122,21 +120,27 @@ class MarigoldPipelineRGBLatentNoise:
         depth_latent = rgb_latent_tag
         batch_embed = self._batch_embed(B)                                       # :680-692
         batch_embed_ref = self._batch_embed(Bk)
-        self.unet.clear_attn_bank()                                              # :715
-        self.unet(latents_rgb_cond_ref, t * self.test_timestep, encoder_hidden_states=batch_embed_ref,
-                  is_target=False)                                               # :719-720 support pass (fills banks)
-        noise_pred = self.unet(depth_latent, t * self.test_timestep, encoder_hidden_states=batch_embed).sample
-        self.unet.clear_attn_bank()                                              # :725
-        # :764-769 scheduler.step(...).pred_original_sample ; :787-795 decode, clip, *0.5+0.5, *255
-        if self.scheduler.is_pure_negation(t):
-            rows = self.vae.decode_rows(noise_pred, in_scale=-1.0 / self.seg_latent_scale_factor)   # z0 = -v, fused
-        else:
-            z0 = self.scheduler.step(noise_pred, t, depth_latent).pred_original_sample
-            rows = self.vae.decode_rows(z0, in_scale=1.0 / self.seg_latent_scale_factor)
+        unet_in = depth_latent
+        for i, t in enumerate(timesteps):                                        # :706-767 (one iteration on the hot path)
+            self.unet.clear_attn_bank()                                          # :715
+            self.unet(latents_rgb_cond_ref, t * self.test_timestep, encoder_hidden_states=batch_embed_ref,
+                      is_target=False)                                           # :719-720 support pass (fills banks)
+            noise_pred = self.unet(depth_latent, t * self.test_timestep, encoder_hidden_states=batch_embed).sample
+            self.unet.clear_attn_bank()                                          # :725
+            last = i == len(timesteps) - 1
+            if last and self.scheduler.is_pure_negation(t):
+                rows = self.vae.decode_rows(noise_pred, in_scale=-1.0 / self.seg_latent_scale_factor)   # z0 = -v, fused
+                break
+            # :764-769 scheduler.step(...): x_{t-1} for the next iteration, pred_original_sample after the last
+            step_out = self.scheduler.step(noise_pred, t, depth_latent)
+            if last:
+                rows = self.vae.decode_rows(step_out.pred_original_sample, in_scale=1.0 / self.seg_latent_scale_factor)
+            else:
+                unet_in = depth_latent = step_out.prev_sample.contiguous()
         H, W = rgb_in_tag.shape[-2:]
         seg_f32, seg_u8 = ops.seg_post(rows, H, W, want_f32=True, want_u8=_want_u8)
         self._last_noise_pred = noise_pred
-        self._last_unet_inputs = (latents_rgb_cond_ref, depth_latent)
+        self._last_unet_inputs = (latents_rgb_cond_ref, unet_in)
         return (seg_f32, seg_u8) if _want_u8 else seg_f32
 
     # ------------------------------------------------------------------------------------------------------------

@@ -31,6 +31,24 @@ def ddim_step_pred_original(model_output, timestep: int, sample, alphas_cumprod=
     return (a_t ** 0.5) * sample - ((1 - a_t) ** 0.5) * model_output
 
 
+def ddim_timesteps(num_inference_steps: int, n_train=1000, steps_offset=1):
+    """DDIMScheduler.set_timesteps, timestep_spacing='leading' (scheduler_1.0_1.0/scheduler_config.json), pipeline:644."""
+    ratio = n_train // num_inference_steps
+    return [int(i * ratio) + steps_offset for i in reversed(range(num_inference_steps))]
+
+
+def ddim_step_prev_sample(model_output, timestep: int, sample, num_inference_steps: int, alphas_cumprod=None,
+                          set_alpha_to_one=False):
+    """diffusers DDIMScheduler.step (eta = 0, v_prediction): x_{t-1} = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps."""
+    ac = ddim_alphas_cumprod() if alphas_cumprod is None else alphas_cumprod
+    a_t = ac[timestep]
+    prev_t = timestep - 1000 // num_inference_steps
+    a_prev = ac[prev_t] if prev_t >= 0 else (torch.tensor(1.0) if set_alpha_to_one else ac[0])
+    x0 = (a_t ** 0.5) * sample - ((1 - a_t) ** 0.5) * model_output
+    eps = (a_t ** 0.5) * model_output + ((1 - a_t) ** 0.5) * sample
+    return (a_prev ** 0.5) * x0 + ((1 - a_prev) ** 0.5) * eps
+
+
 def encode_rgb(vae, rgb_in):                                   # pipeline:839-862
     moments = vae.quant_conv(vae.encoder(rgb_in))
     mean, _logvar = torch.chunk(moments, 2, dim=1)
@@ -43,8 +61,9 @@ def decode_seg(vae, seg_latent):                               # pipeline:887-90
 
 
 @torch.no_grad()
-def single_infer(unet, vae, text_embed, rgb_in_ref, rgb_in_tag, gt_in_ref, test_timestep=1, return_latent=False):
-    timesteps = [1]                                            # set_timesteps(1): leading spacing, offset 1 (:644)
+def single_infer(unet, vae, text_embed, rgb_in_ref, rgb_in_tag, gt_in_ref, test_timestep=1, return_latent=False,
+                 num_inference_steps=1):
+    timesteps = ddim_timesteps(num_inference_steps)            # 1 step: [1] (leading spacing, offset 1, :644)
     rgb_latent_ref = encode_rgb(vae, rgb_in_ref)
     rgb_latent_tag = encode_rgb(vae, rgb_in_tag)
     gt_latent_ref = encode_rgb(vae, gt_in_ref)
@@ -57,7 +76,8 @@ def single_infer(unet, vae, text_embed, rgb_in_ref, rgb_in_tag, gt_in_ref, test_
         unet(latents_rgb_cond_ref, t * test_timestep, batch_embed_ref, is_target=False)
         noise_pred = unet(depth_latent, t * test_timestep, batch_embed)
         unet.clear_attn_bank()
-        z0 = ddim_step_pred_original(noise_pred, t, depth_latent)
+        z0 = ddim_step_pred_original(noise_pred, t, depth_latent)                     # :764-769
+        depth_latent = ddim_step_prev_sample(noise_pred, t, depth_latent, num_inference_steps)
     seg = decode_seg(vae, z0)
     seg = torch.clip(seg, -1.0, 1.0)
     seg = (seg * 0.5) + 0.5

@@ -399,3 +399,25 @@ def test_attention_backward_matches_autograd(B, h, Lq, Ls, Lb, dt):
         e = rel_l2(got, leaf.grad)
         print(name, e)
         assert e <= tol, (name, e)
+
+
+def test_pipeline_multi_step_matches_oracle(small_models):
+    """denoising_steps > 1 (pipeline:706-767; unused by the DiffewS scripts but part of the __call__ surface): the same two
+    UNet passes per DDIM step, engine vs oracle."""
+    from diffews_b200.pipeline import MarigoldPipelineRGBLatentNoise
+    from diffews_b200.synthetic import make_batch, pipeline_inputs, prompt_embedding
+    from diffews_b200.unet import MyUNet2DConditionModel
+    from diffews_b200.vae import AutoencoderKL
+    from oracle import pipeline as opipe
+    unet_o, vae_o = small_models[0], small_models[1]
+    batch = make_batch(5, 2, 64, 1)
+    ref, tag, gt = pipeline_inputs(batch)
+    emb = prompt_embedding()
+    want = opipe.single_infer(unet_o, vae_o, emb, ref, tag, gt, num_inference_steps=3)
+    pipe = MarigoldPipelineRGBLatentNoise(MyUNet2DConditionModel.from_module(unet_o), AutoencoderKL.from_module(vae_o),
+                                          text_embeds=emb)
+    pipe.test_timestep = 1
+    got = pipe.single_infer(ref.cuda(), tag.cuda(), gt.cuda(), None, 3, False, "seg", 0)
+    agree = ((got.cpu() > 127.5) == (want > 127.5)).float().mean().item()
+    print("3-step pipeline: channel-threshold agreement", agree, "rel-L2", rel_l2(got, want))
+    assert rel_l2(got, want) <= 3e-2 and agree >= 0.99
