@@ -79,6 +79,39 @@ class EpisodeRunner:
         return self._eager_step({k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v)
                                  for k, v in batch.items()})
 
+    # ---- input prefetch: the H2D copy of batch i+1 overlaps the kernels of batch i ------------------------------------
+    @torch.no_grad()
+    def prefetch(self, batch: dict):
+        """Start copying a (pinned host) batch of the captured shapes into a staging buffer on a copy stream.  The next
+        `step_prefetched()` consumes it.  Call it right after launching a step: the copy then runs under that step."""
+        assert getattr(self, "_graph", None) is not None, "enable_cuda_graph first"
+        dev = self.pipe.device
+        if not hasattr(self, "_stage"):
+            self._stage = {k: torch.empty_like(v) for k, v in self._static.items()}
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_free = None
+        cs = self._copy_stream
+        if self._stage_free is not None:
+            cs.wait_event(self._stage_free)          # the previous step has moved the staging buffer into the graph's inputs
+        with torch.cuda.stream(cs):
+            for k, dst in self._stage.items():
+                dst.copy_(batch[k], non_blocking=True)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_ready.record(cs)
+
+    @torch.no_grad()
+    def step_prefetched(self):
+        """Run one step on the batch handed to the last `prefetch()` (device-to-device move into the captured input
+        buffers, then the graph).  Same return value as `step()`."""
+        cur = torch.cuda.current_stream(self.pipe.device)
+        cur.wait_event(self._stage_ready)
+        for k, dst in self._static.items():
+            dst.copy_(self._stage[k], non_blocking=True)
+        self._stage_free = torch.cuda.Event()
+        self._stage_free.record(cur)
+        self._graph.replay()
+        return self._static_out
+
     @torch.no_grad()
     def _eager_step(self, batch: dict):
         query_img, query_mask = batch["query_img"], batch["query_mask"]

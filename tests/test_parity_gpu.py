@@ -219,6 +219,16 @@ def test_runner_cuda_graph_equals_eager(small_models):
     assert torch.equal(eager.meter.intersection_buf, graphed.meter.intersection_buf)
     assert torch.equal(eager.meter.union_buf, graphed.meter.union_buf)
     assert int(graphed.meter.union_buf.sum()) > 0
+    # pinned-host batches through the prefetch path (H2D of the next batch under the current step) give the same counts
+    h0 = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in make_batch(0, 2, 64, 1).items()}
+    h1 = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in make_batch(2, 2, 64, 1).items()}
+    graphed.prefetch(h0)
+    p0 = [t.clone() for t in graphed.step_prefetched()]
+    graphed.prefetch(h1)
+    p1 = [t.clone() for t in graphed.step_prefetched()]
+    torch.cuda.synchronize()
+    for a, b in zip(e0 + e1, p0 + p1):
+        assert torch.equal(a, b)
     miou, fb, _ = graphed.finish()
     assert 0.0 <= float(miou) <= 100.0 and 0.0 <= float(fb) <= 100.0
 
