@@ -40,6 +40,7 @@ SIGNATURES = {
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
                                   _i, _f, _i, _vp]),
     "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "dfw_cross_attn_collapsed": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp]),
     "dfw_groupnorm_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "dfw_groupnorm_silu": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "dfw_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

@@ -425,6 +425,78 @@ __global__ void cross_attn_kernel(const uint16_t* __restrict__ q, const uint16_t
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K2b: cross attention to a FIXED short prompt, collapsed algebraically.  With the prompt's K / V constant (same
+// empty-prompt embedding for every sample, Lctx = 2 at eval: pipeline:591-601, :690-692) the whole attn2 block
+//     to_out(softmax(to_q(x) K^T * scale) V) + bias
+// is  logits = x @ Wlog^T  with  Wlog[(h, j)] = scale * K[j, h] @ Wq[h]   (a [heads * Lctx, C] matrix, one small GEMM)
+// and out    = bias + sum_{h, j} softmax_j(logits[h, :])[j] * U[(h, j)]   with  U[(h, j)] = Wo[:, h] @ V[j, h]  ([.., C]),
+// i.e. two C x C GEMMs and the attention kernel become one skinny GEMM plus this bandwidth kernel (+ residual).
+// CTA = 16 tokens: phase 1 one thread per (token, logit) -> probabilities in smem; phase 2 one thread per
+// (token, 8 channels): acc = bias + sum p * U (U read through L1), + residual, 16-byte store.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int XC_TOK = 16;      // tokens per CTA
+constexpr int XC_OCT = 16;      // 8-channel octets per CTA: the CTA's slice of U (heads*Lctx x 128 floats) stays in L1
+template <int RD>    // residual / output dtype: 0 bf16, 1 fp32, 2 fp16
+__global__ void __launch_bounds__(256) cross_attn_collapsed_kernel(const float* __restrict__ logits, int ld_logits,
+                                                                   const float* __restrict__ U, const float* __restrict__ bias,
+                                                                   const void* __restrict__ residual, void* __restrict__ out,
+                                                                   long long M, int C, int heads, int Lctx) {
+    // thread = (token, 8 channels); no shared memory, no barrier: the per-head softmax over the Lctx (2 at eval) logits
+    // is recomputed by the 16 threads of a token (a handful of MUFU ops) and every load is independent of the others
+    const int ol = threadIdx.x % XC_OCT, tl = threadIdx.x / XC_OCT;
+    const long long m = static_cast<long long>(blockIdx.y) * XC_TOK + tl;
+    const int oc = blockIdx.x * XC_OCT + ol;
+    if (m >= M || oc * 8 >= C) return;
+    const long long off = m * C + oc * 8;
+    float acc[8];
+    if (residual != nullptr) {
+        if constexpr (RD == 1) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + off);
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            acc[0] = r0.x; acc[1] = r0.y; acc[2] = r0.z; acc[3] = r0.w; acc[4] = r1.x; acc[5] = r1.y; acc[6] = r1.z; acc[7] = r1.w;
+        } else {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(residual) + off));
+            unpack8(r, RD == 2, acc);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    }
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + oc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + oc * 8) + 1);
+        acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w; acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+    }
+    const float* lg = logits + m * ld_logits;
+    const float* up = U + oc * 8;
+    for (int h = 0; h < heads; ++h) {
+        float l[8];
+        float mx = -INFINITY;
+        for (int j = 0; j < Lctx; ++j) { l[j] = __ldg(lg + h * Lctx + j); mx = fmaxf(mx, l[j]); }
+        float sum = 0.f;
+        for (int j = 0; j < Lctx; ++j) { l[j] = __expf(l[j] - mx); sum += l[j]; }
+        const float inv = __fdividef(1.0f, sum);
+        for (int j = 0; j < Lctx; ++j) {
+            const float pj = l[j] * inv;
+            const float4* u4 = reinterpret_cast<const float4*>(up + static_cast<size_t>(h * Lctx + j) * C);
+            const float4 u0 = __ldg(u4), u1 = __ldg(u4 + 1);
+            acc[0] = fmaf(pj, u0.x, acc[0]); acc[1] = fmaf(pj, u0.y, acc[1]); acc[2] = fmaf(pj, u0.z, acc[2]); acc[3] = fmaf(pj, u0.w, acc[3]);
+            acc[4] = fmaf(pj, u1.x, acc[4]); acc[5] = fmaf(pj, u1.y, acc[5]); acc[6] = fmaf(pj, u1.z, acc[6]); acc[7] = fmaf(pj, u1.w, acc[7]);
+        }
+    }
+    if constexpr (RD == 1) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off);
+        op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+        constexpr int f16 = (RD == 2);
+        uint4 o;
+        o.x = pack_h2(acc[0], acc[1], f16); o.y = pack_h2(acc[2], acc[3], f16);
+        o.z = pack_h2(acc[4], acc[5], f16); o.w = pack_h2(acc[6], acc[7], f16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + off) = o;
+    }
+}
+
 }  // namespace
 }  // namespace dfw
 
@@ -500,6 +572,24 @@ int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv
                             reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(k),
                             reinterpret_cast<const uint16_t*>(v), kv_batch_stride, reinterpret_cast<uint16_t*>(o), groups, L,
                             heads, Lctx, scale * 1.4426950408889634f, f16));
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_cross_attn_collapsed(const float* logits, int ld_logits, const float* U, const float* bias, const void* residual,
+                             void* out, int dtype, long long M, int C, int heads, int Lctx, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(logits && U && bias && out && M > 0 && C > 0 && C % 8 == 0 && heads > 0 && Lctx > 0);
+    DFW_REQUIRE(heads * Lctx <= 96 && Lctx <= 8 && ld_logits >= heads * Lctx && dtype >= 0 && dtype <= 2);
+    DFW_REQUIRE((M + XC_TOK - 1) / XC_TOK <= 65535);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const dim3 grid((C / 8 + XC_OCT - 1) / XC_OCT, static_cast<unsigned>((M + XC_TOK - 1) / XC_TOK));
+    if (dtype == 1) cross_attn_collapsed_kernel<1><<<grid, 256, 0, st>>>(logits, ld_logits, U, bias, residual, out, M, C, heads, Lctx);
+    else if (dtype == 2) cross_attn_collapsed_kernel<2><<<grid, 256, 0, st>>>(logits, ld_logits, U, bias, residual, out, M, C, heads, Lctx);
+    else cross_attn_collapsed_kernel<0><<<grid, 256, 0, st>>>(logits, ld_logits, U, bias, residual, out, M, C, heads, Lctx);
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

@@ -370,6 +370,21 @@ def groupnorm(x, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=bf16
     return y
 
 
+def cross_attn_collapsed(logits, U, bias, residual, heads, lctx, out_dtype):
+    """logits fp32 [B, L, >= heads*lctx]; U fp32 [heads*lctx, C]; bias fp32 [C]; residual [B, L, C] or None -> [B, L, C]."""
+    _req(logits, torch.float32, "logits"); _req(U, torch.float32, "U"); _req(bias, torch.float32, "bias")
+    B, L, ld = logits.shape
+    C = U.shape[1]
+    out = torch.empty((B, L, C), device=logits.device, dtype=out_dtype)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == out_dtype and residual.is_contiguous()
+    with _Timed("cross_attn", _nb(logits, out, residual), f"cross_attn_collapsed B{B} L{L} h{heads} ctx{lctx}"):
+        check(lib.dfw_cross_attn_collapsed(logits.data_ptr(), ld, U.data_ptr(), bias.data_ptr(), _ptr(residual),
+                                           out.data_ptr(), _xd(out), B * L, C, heads, lctx, _stream()),
+              "dfw_cross_attn_collapsed")
+    return out
+
+
 def groupnorm_backward(x, dy, gamma, beta, *, groups=32, eps=1e-5, silu=False):
     """Backward of y = [silu](group_norm(x)): x, dy [N, ..., C] channels-last of one dtype (bf16 | fp16 | fp32);
     returns (dx like x, dgamma fp32 [C], dbeta fp32 [C])."""

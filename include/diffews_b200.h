@@ -138,6 +138,15 @@ int dfw_attn_kvfused_bwd(const void* q, long long q_batch_stride, int q_row_stri
 int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv_batch_stride, void* o, int B,
                        int L, int heads, int Lctx, float scale, int f16, void* stream);
 
+/* K2b  the same attn2 block for a FIXED short prompt (one empty-prompt embedding shared by every sample, Lctx = 2 at
+ * eval: marigold_pipeline_rgb_latent_noise.py:591-601, :690-692), collapsed: with K, V constant,
+ *   to_out(softmax(to_q(x) K^T scale) V) + b  ==  b + sum_{h,j} softmax_j(x @ Wlog^T)[h,j] * U[(h,j)],
+ *   Wlog[(h,j)] = scale K[j,h] @ Wq[h]  ([heads*Lctx, C], applied with dfw_linear -> `logits`),  U[(h,j)] = Wo[:,h] @ V[j,h].
+ * logits fp32 [M, ld_logits] (first heads*Lctx columns used, <= 96); U fp32 [heads*Lctx, C]; bias fp32 [C];
+ * residual (nullable) / out [M, C] of `dtype` (0 bf16, 1 fp32, 2 fp16). */
+int dfw_cross_attn_collapsed(const float* logits, int ld_logits, const float* U, const float* bias, const void* residual,
+                             void* out, int dtype, long long M, int C, int heads, int Lctx, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K4  GroupNorm(32 groups) (+SiLU), NHWC, fp32 statistics, deterministic two-stage reduction.
  * ref: nn.GroupNorm(+SiLU) in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out

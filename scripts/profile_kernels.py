@@ -100,6 +100,14 @@ def main():
         nbytes = x.numel() * 4 + 16 * 512 * 512 * 64 * 2
         return (lambda: ops.im2col3x3_small(x, 64, torch.float16)), None, nbytes
     cases.update(im2col=im2col)
+
+    def xattn(M=65536, C=320, h=5):
+        lg = torch.randn(16, M // 16, 16 * ((2 * h + 15) // 16), device="cuda")
+        U = torch.randn(2 * h, C, device="cuda"); b = torch.randn(C, device="cuda")
+        r = torch.randn(16, M // 16, C, device="cuda").half()
+        nbytes = lg.numel() * 4 + 2 * r.numel() * 2
+        return (lambda: ops.cross_attn_collapsed(lg, U, b, r, h, 2, torch.float16)), None, nbytes
+    cases.update(xattn=xattn, xattn1280=lambda: xattn(4096, 1280, 20))
     cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, gn=gn, gn16=gn16)
     which = list(cases) if args.which == ["all"] else args.which
     for name in which:

@@ -431,3 +431,30 @@ def test_pipeline_multi_step_matches_oracle(small_models):
     agree = ((got.cpu() > 127.5) == (want > 127.5)).float().mean().item()
     print("3-step pipeline: channel-threshold agreement", agree, "rel-L2", rel_l2(got, want))
     assert rel_l2(got, want) <= 3e-2 and agree >= 0.99
+
+
+def test_cross_attention_collapsed_matches_attention_kernel():
+    """dfw_cross_attn_collapsed (attn2 against a fixed 2-token prompt folded to a skinny GEMM + a bandwidth kernel) gives
+    the same block output as to_q -> dfw_cross_attn_fwd -> to_out (+ residual)."""
+    import diffews_b200.unet as U
+    from diffews_b200.unet import CrossAttention
+    g = torch.Generator().manual_seed(9)
+    C, h, L, B = 320, 5, 1024, 3
+    sd = {f"a.{n}.weight": torch.randn(C, C if n != "to_k" and n != "to_v" else 1024, generator=g) * (C ** -0.5 if n in ("to_q", "to_out.0") else 1024 ** -0.5)
+          for n in ("to_q", "to_k", "to_v", "to_out.0")}
+    sd["a.to_out.0.bias"] = torch.randn(C, generator=g) * 0.1
+    att = CrossAttention(sd, "a", "cuda", h, wdtype=torch.float16)
+    ehs = (torch.randn(1, 2, 1024, generator=g)).cuda().half()
+    x = torch.randn(B, L, C, generator=g).cuda().half()
+    res = torch.randn(B, L, C, generator=g).cuda().half()
+    old = U.COLLAPSE_CROSS_ATTN
+    try:
+        U.COLLAPSE_CROSS_ATTN = False
+        want = att(x, att.kv(ehs), res, False)
+        U.COLLAPSE_CROSS_ATTN = True
+        kv = att.kv(ehs)
+        assert isinstance(kv[0], str)
+        got = att(x, kv, res, False)
+    finally:
+        U.COLLAPSE_CROSS_ATTN = old
+    assert rel_l2(got, want) <= 2e-3
