@@ -344,15 +344,25 @@ def main():
         runner.step(dev_batches[0])
         barrier()
         ops.set_timer(timer)
+        # Eager launches are issued by Python at ~30-60 us per op: for kernels shorter than that the GPU would drain its
+        # queue and the event pair would time the host, not the kernel.  A 25 ms device-side sleep at the head of every
+        # step lets the host run ahead (the launch queue holds the backlog), so the events bracket back-to-back GPU
+        # work; the sleeps are timed and subtracted.
+        sleep_cycles = int(25e-3 * torch.cuda.get_device_properties(dev).clock_rate * 1e3) if hasattr(
+            torch.cuda.get_device_properties(dev), "clock_rate") else int(25e-3 * 1.9e9)
+        sleeps = []
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         for i in range(args.steps):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(); torch.cuda._sleep(sleep_cycles); s1.record()
+            sleeps.append((s0, s1))
             runner.step(dev_batches[i % pool])
         t1e.record()
         barrier()
         ops.set_timer(None)
         runner._graph = runner_graph
-        ms_total_instr = t0e.elapsed_time(t1e)
+        ms_total_instr = t0e.elapsed_time(t1e) - sum(a.elapsed_time(b) for a, b in sleeps)
     if timer is not None:
         summ = timer.summary()
         kernels = {}
