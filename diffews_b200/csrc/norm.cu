@@ -3,6 +3,7 @@
 // ref: nn.GroupNorm + SiLU inside diffusers ResnetBlock2D / Transformer2DModel.norm / conv_norm_out
 //      (diffews/models/unet_2d_condition.py:1246-1248), BasicTransformerBlock.norm1/2/3 (upstream).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -575,7 +576,11 @@ GnPlan gn_plan(int N, int HW, int C) {
     pl.RPI = pl.V >= 256 ? 1 : 256 / pl.V;
     if (pl.RPI > HW) pl.RPI = HW;
     pl.threads = pl.V * pl.RPI;
-    int want = (8 * 148 + N - 1) / N;                 // ~8 CTAs per SM over the whole batch
+    // exactly one wave: the kernels run 3 CTAs of <= 320 threads per SM (register-limited, ncu), and a second partial
+    // wave plus the per-CTA statistics fold cost 30 % on the L2-sized tensors
+    static const int per_sm = [] { const char* e = getenv("DFW_GN_CTAS_PER_SM"); return e ? atoi(e) : 3; }();
+    int want = (per_sm * sm_count() + (per_sm > 3 ? N - 1 : 0)) / N;
+    if (want < 1) want = 1;
     int max_chunks = (HW + pl.RPI * 16 - 1) / (pl.RPI * 16);  // at least 16 rows per thread
     if (max_chunks < 1) max_chunks = 1;
     pl.nchunks = want < max_chunks ? want : max_chunks;

@@ -101,6 +101,15 @@ def main():
         return (lambda: ops.im2col3x3_small(x, 64, torch.float16)), None, nbytes
     cases.update(im2col=im2col)
 
+    def gnapply_small():
+        x0 = torch.randn(16, 64, 64, 512, device="cuda").half()
+        w = conv_weight_to_gemm(torch.randn(512, 512, 3, 3, device="cuda") * 0.01).half()
+        y = ops.conv2d(x0, w, torch.zeros(512, device="cuda"), ksize=3, gn_stats=True)
+        g = torch.ones(512, device="cuda"); b = torch.zeros(512, device="cuda")
+        nbytes = y.numel() * 4
+        return (lambda: ops.groupnorm(y, g, b, eps=1e-6, silu=True, out_dtype=torch.float16)), None, nbytes
+    cases.update(gnapply_small=gnapply_small)
+
     def xattn(M=65536, C=320, h=5):
         lg = torch.randn(16, M // 16, 16 * ((2 * h + 15) // 16), device="cuda")
         U = torch.randn(2 * h, C, device="cuda"); b = torch.randn(C, device="cuda")
