@@ -173,3 +173,24 @@ def test_oracle_pipeline_golden_fixture():
     # counts depend on threshold ties; allow a handful of pixels of slack across BLAS builds
     for a, b in zip(inter[:, 0].tolist() + union[:, 0].tolist(), gold["inter"] + gold["union"]):
         assert abs(a - b) <= 8
+
+
+def test_ddim_multi_step_schedule_and_identity():
+    """set_timesteps (leading spacing, offset 1) and the full DDIM step under the DiffewS scheduler (beta == 1 =>
+    alpha_cumprod == 0): x0 = -v at every step and x_{t-1} == x_t, i.e. extra steps re-run the same prediction at other
+    timesteps (pipeline:706-767 with scheduler_1.0_1.0/scheduler_config.json)."""
+    import torch
+    from oracle import pipeline as op
+    from diffews_b200.scheduler import DDIMSchedulerCustomized
+    assert op.ddim_timesteps(1) == [1]
+    assert op.ddim_timesteps(4) == [751, 501, 251, 1]
+    sch = DDIMSchedulerCustomized()
+    sch.set_timesteps(4)
+    assert [int(t) for t in sch.timesteps] == op.ddim_timesteps(4)
+    g = torch.Generator().manual_seed(0)
+    v, x = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    for t in op.ddim_timesteps(4):
+        assert torch.equal(op.ddim_step_pred_original(v, t, x), -v)
+        assert torch.allclose(op.ddim_step_prev_sample(v, t, x, 4), x)
+        out = sch.step(v, t, x)
+        assert torch.allclose(out.pred_original_sample, -v) and torch.allclose(out.prev_sample, x)
