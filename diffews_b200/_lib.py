@@ -56,6 +56,9 @@ SIGNATURES = {
     "dfw_rthres_workspace_bytes": (_ll, [_i]),
     "dfw_rthres_iou_hist": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dfw_iou_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "dfw_preproc_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
+    "dfw_resize_normalize_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _ll, _vp]),
+    "dfw_mask_nearest": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
 }
 
 

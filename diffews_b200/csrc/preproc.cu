@@ -1,0 +1,258 @@
+// K9 — episode preprocessing on the GPU: the data format either side of the hot path.
+//
+// ref: evaluation_util/data/dataset.py:36-40   transforms.Resize((S,S)) -> ToTensor() -> Normalize([0.5],[0.5])
+//      evaluation_util/data/coco.py:38-47      transform(query / supports); F.interpolate(mask, (S,S), mode='nearest')
+//      evaluation_util/data/coco.py:92-93      mask = (label == class + 1)
+//      evaluation_util/data/pascal.py:78-83    boundary = floor(mask / 255) (ignore index), mask = (label == class + 1)
+//      evaluation_util/data/fss.py:80-84       mask = (L >= 128)
+//
+// `Resize` on a PIL image is Pillow's ImagingResample (third-party, src/libImaging/Resample.c): a separable two-pass
+// convolution — horizontal first, uint8 intermediate, then vertical — with per-output-pixel coefficient windows computed
+// in double precision and quantised to 22-bit fixed point.  This file restates that algorithm so the result is the same
+// BYTES as the reference's CPU path: the coefficient arithmetic uses explicit round-to-nearest double intrinsics in the
+// reference's operation order (no FMA contraction), the accumulation is the same int32 sum with the same rounding
+// constant, and ToTensor / Normalize are the same three fp32 operations (true division by 255, subtract, divide).
+//
+// All images of a batch (different sizes) are processed by ONE launch per pass: the caller packs the decoded images
+// into one device buffer and passes a descriptor table (offset, h, w, row stride) that lives in the same buffer.
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dfw {
+extern std::atomic<long long> g_launches;
+namespace {
+
+constexpr int PRECISION_BITS = 32 - 8 - 2;      // Resample.c
+
+struct ImageDesc {                               // mirrors DfwImageDesc (include/diffews_b200.h)
+    long long offset;
+    int h, w, row_stride, param;
+};
+
+struct CoefLayout {                              // workspace: [bounds int2][kk int32][tmp u8]
+    int out_max, ks;
+    long long kk_off, tmp_off;                   // byte offsets
+    long long tmp_per_image;
+};
+
+__host__ __device__ inline int ksize_for(int in_size, int out_size) {
+    const double scale = static_cast<double>(in_size) / out_size;
+    const double fs = scale < 1.0 ? 1.0 : scale;
+    return static_cast<int>(ceil(fs)) * 2 + 1;
+}
+
+// One thread per (output index, axis, image): Resample.c precompute_coeffs + normalize_coeffs_8bpc, bilinear filter.
+__global__ void preproc_coeffs_kernel(const ImageDesc* __restrict__ descs, int2* __restrict__ bounds,
+                                      int* __restrict__ kk, int out_w, int out_h, int out_max, int ks) {
+    const int img = blockIdx.z, axis = blockIdx.y;
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int out_size = axis == 0 ? out_w : out_h;
+    if (xx >= out_size) return;
+    const ImageDesc d = descs[img];
+    const int in_size = axis == 0 ? d.w : d.h;
+    const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = filterscale;                       // bilinear support 1.0 * filterscale
+    const double ss = __ddiv_rn(1.0, filterscale);
+    const double center = __dmul_rn(static_cast<double>(xx) + 0.5, scale);   // in0 == 0
+    int xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+    if (xmax > in_size) xmax = in_size;
+    int n = xmax - xmin;
+    if (n > ks) n = ks;                                       // cannot happen (ks is sized from the largest image)
+    const long long slot = (static_cast<long long>(img) * 2 + axis) * out_max + xx;
+    int* k = kk + slot * ks;
+    double ww = 0.0;
+    for (int x = 0; x < n; ++x) {
+        double t = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+        if (t < 0.0) t = -t;
+        ww = __dadd_rn(ww, t < 1.0 ? __dsub_rn(1.0, t) : 0.0);
+    }
+    for (int x = 0; x < ks; ++x) {
+        int q = 0;
+        if (x < n) {
+            double t = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+            if (t < 0.0) t = -t;
+            double w = t < 1.0 ? __dsub_rn(1.0, t) : 0.0;
+            if (ww != 0.0) w = __ddiv_rn(w, ww);
+            const double v = __dmul_rn(w, static_cast<double>(1 << PRECISION_BITS));
+            q = w < 0.0 ? static_cast<int>(__dadd_rn(-0.5, v)) : static_cast<int>(__dadd_rn(0.5, v));
+        }
+        k[x] = q;
+    }
+    bounds[slot] = make_int2(xmin, n);
+}
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+    v >>= PRECISION_BITS;
+    return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// Horizontal pass: src [h, w, 3] u8 -> tmp [h, out_w, 3] u8.  Thread = one output pixel (3 channels).
+__global__ void preproc_horizontal_kernel(const uint8_t* __restrict__ base, const ImageDesc* __restrict__ descs,
+                                          const int2* __restrict__ bounds, const int* __restrict__ kk,
+                                          uint8_t* __restrict__ tmp, long long tmp_per_image, int out_w, int out_max,
+                                          int ks) {
+    const int img = blockIdx.z;
+    const ImageDesc d = descs[img];
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xx >= out_w || y >= d.h) return;
+    const long long slot = (static_cast<long long>(img) * 2 + 0) * out_max + xx;
+    const int2 b = bounds[slot];
+    const int* k = kk + slot * ks;
+    const uint8_t* row = base + d.offset + static_cast<long long>(y) * d.row_stride + b.x * 3;
+    int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+    for (int x = 0; x < b.y; ++x) {
+        const int c = __ldg(k + x);
+        s0 += static_cast<int>(__ldg(row + 3 * x + 0)) * c;
+        s1 += static_cast<int>(__ldg(row + 3 * x + 1)) * c;
+        s2 += static_cast<int>(__ldg(row + 3 * x + 2)) * c;
+    }
+    uint8_t* o = tmp + static_cast<long long>(img) * tmp_per_image + (static_cast<long long>(y) * out_w + xx) * 3;
+    o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
+}
+
+// Vertical pass + ToTensor + Normalize: tmp [h, out_w, 3] u8 -> dst [3, out_h, out_w] fp32 (and / or u8 HWC).
+__global__ void preproc_vertical_kernel(const ImageDesc* __restrict__ descs, const int2* __restrict__ bounds,
+                                        const int* __restrict__ kk, const uint8_t* __restrict__ tmp,
+                                        long long tmp_per_image, float* __restrict__ dst_f32,
+                                        uint8_t* __restrict__ dst_u8, int out_w, int out_h, int out_max, int ks,
+                                        float mean, float stdv) {
+    __shared__ float lut[256];
+    // ToTensor: fp32(v) / 255 (true division); Normalize: (x - mean) / std — the reference's three fp32 roundings
+    for (int v = threadIdx.y * blockDim.x + threadIdx.x; v < 256; v += blockDim.x * blockDim.y)
+        lut[v] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), mean), stdv);
+    __syncthreads();
+    const int img = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_w || yy >= out_h) return;
+    const long long slot = (static_cast<long long>(img) * 2 + 1) * out_max + yy;
+    const int2 b = bounds[slot];
+    const int* k = kk + slot * ks;
+    const uint8_t* col = tmp + static_cast<long long>(img) * tmp_per_image +
+                         (static_cast<long long>(b.x) * out_w + x) * 3;
+    int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+    for (int j = 0; j < b.y; ++j) {
+        const int c = __ldg(k + j);
+        const uint8_t* p = col + static_cast<long long>(j) * out_w * 3;
+        s0 += static_cast<int>(p[0]) * c;
+        s1 += static_cast<int>(p[1]) * c;
+        s2 += static_cast<int>(p[2]) * c;
+    }
+    const uint8_t r = clip8(s0), g = clip8(s1), bl = clip8(s2);
+    const long long plane = static_cast<long long>(out_h) * out_w;
+    const long long pix = static_cast<long long>(yy) * out_w + x;
+    if (dst_f32) {
+        float* o = dst_f32 + static_cast<long long>(img) * 3 * plane + pix;
+        o[0] = lut[r]; o[plane] = lut[g]; o[2 * plane] = lut[bl];
+    }
+    if (dst_u8) {
+        uint8_t* o = dst_u8 + (static_cast<long long>(img) * plane + pix) * 3;
+        o[0] = r; o[1] = g; o[2] = bl;
+    }
+}
+
+// F.interpolate(mode='nearest') source index (ATen UpSampleKernel.cpp nearest_idx): fp32 product, floor, clamp.
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+    if (out_size == in_size) return dst;
+    if (out_size == 2 * in_size) return dst >> 1;
+    const float scale = __fdiv_rn(static_cast<float>(in_size), static_cast<float>(out_size));
+    const int s = static_cast<int>(floorf(__fmul_rn(static_cast<float>(dst), scale)));
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+// Label mask [h, w] u8 -> binary mask [out_h, out_w] fp32 (+ optional ignore boundary).  mode 0: label == param
+// (COCO / PASCAL: param = class + 1); mode 1: label >= 128 (FSS-1000).  boundary = floor(label / 255) = (label == 255).
+__global__ void preproc_mask_kernel(const uint8_t* __restrict__ base, const ImageDesc* __restrict__ descs,
+                                    float* __restrict__ mask_out, float* __restrict__ boundary_out, int out_h,
+                                    int out_w, int mode) {
+    const int img = blockIdx.z;
+    const ImageDesc d = descs[img];
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xx >= out_w || yy >= out_h) return;
+    const int sy = nearest_src(yy, d.h, out_h), sx = nearest_src(xx, d.w, out_w);
+    const int v = __ldg(base + d.offset + static_cast<long long>(sy) * d.row_stride + sx);
+    const bool on = mode == 0 ? (v == d.param) : (v >= 128);
+    const long long o = (static_cast<long long>(img) * out_h + yy) * out_w + xx;
+    mask_out[o] = on ? 1.0f : 0.0f;
+    if (boundary_out) boundary_out[o] = v == 255 ? 1.0f : 0.0f;
+}
+
+CoefLayout coef_layout(int n, int max_h, int max_w, int out_h, int out_w) {
+    CoefLayout L;
+    L.out_max = out_h > out_w ? out_h : out_w;
+    const int kh = ksize_for(max_h, out_h), kw = ksize_for(max_w, out_w);
+    L.ks = kh > kw ? kh : kw;
+    const long long slots = static_cast<long long>(n) * 2 * L.out_max;
+    L.kk_off = slots * static_cast<long long>(sizeof(int2));
+    L.tmp_off = L.kk_off + slots * L.ks * static_cast<long long>(sizeof(int));
+    L.tmp_off = (L.tmp_off + 255) & ~255LL;
+    L.tmp_per_image = (static_cast<long long>(max_h) * out_w * 3 + 255) & ~255LL;
+    return L;
+}
+
+}  // namespace
+}  // namespace dfw
+
+extern "C" {
+
+long long dfw_preproc_workspace_bytes(int n, int max_h, int max_w, int out_h, int out_w) {
+    if (n <= 0 || max_h <= 0 || max_w <= 0 || out_h <= 0 || out_w <= 0) return -1;
+    const dfw::CoefLayout L = dfw::coef_layout(n, max_h, max_w, out_h, out_w);
+    return L.tmp_off + static_cast<long long>(n) * L.tmp_per_image;
+}
+
+int dfw_resize_normalize_u8(const void* base, const void* descs, int n, int max_h, int max_w, float* dst_f32,
+                            uint8_t* dst_u8, int out_h, int out_w, float mean, float stdv, void* workspace,
+                            long long workspace_bytes, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(base && descs && workspace && (dst_f32 || dst_u8));
+    DFW_REQUIRE(n > 0 && n <= 65535 && max_h > 0 && max_w > 0 && out_h > 0 && out_w > 0);
+    DFW_REQUIRE(max_h < (1 << 15) && max_w < (1 << 15) && out_h < (1 << 15) && out_w < (1 << 15));
+    DFW_REQUIRE(stdv != 0.0f);
+    DFW_REQUIRE((reinterpret_cast<uintptr_t>(descs) & 7) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+    DFW_REQUIRE(workspace_bytes >= dfw_preproc_workspace_bytes(n, max_h, max_w, out_h, out_w));
+    const CoefLayout L = coef_layout(n, max_h, max_w, out_h, out_w);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    int2* bounds = reinterpret_cast<int2*>(ws);
+    int* kk = reinterpret_cast<int*>(ws + L.kk_off);
+    uint8_t* tmp = ws + L.tmp_off;
+    const ImageDesc* d = reinterpret_cast<const ImageDesc*>(descs);
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(base);
+    preproc_coeffs_kernel<<<dim3((L.out_max + 127) / 128, 2, n), 128, 0, st>>>(d, bounds, kk, out_w, out_h, L.out_max, L.ks);
+    const dim3 blk(64, 4);
+    preproc_horizontal_kernel<<<dim3((out_w + 63) / 64, (max_h + 3) / 4, n), blk, 0, st>>>(b, d, bounds, kk, tmp, L.tmp_per_image,
+                                                                                            out_w, L.out_max, L.ks);
+    preproc_vertical_kernel<<<dim3((out_w + 63) / 64, (out_h + 3) / 4, n), blk, 0, st>>>(d, bounds, kk, tmp, L.tmp_per_image,
+                                                                                          dst_f32, dst_u8, out_w, out_h,
+                                                                                          L.out_max, L.ks, mean, stdv);
+    g_launches.fetch_add(3);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_mask_nearest(const void* base, const void* descs, int n, float* mask_out, float* boundary_out, int out_h,
+                     int out_w, int mode, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(base && descs && mask_out && n > 0 && n <= 65535 && out_h > 0 && out_w > 0 && (mode == 0 || mode == 1));
+    DFW_REQUIRE((out_h + 3) / 4 <= 65535);
+    DFW_REQUIRE((reinterpret_cast<uintptr_t>(descs) & 7) == 0);
+    preproc_mask_kernel<<<dim3((out_w + 63) / 64, (out_h + 3) / 4, n), dim3(64, 4), 0, static_cast<cudaStream_t>(stream_)>>>(
+        reinterpret_cast<const uint8_t*>(base), reinterpret_cast<const ImageDesc*>(descs), mask_out, boundary_out, out_h,
+        out_w, mode);
+    g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+}  // extern "C"

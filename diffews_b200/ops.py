@@ -553,3 +553,40 @@ def iou_accumulate(inter, union, class_id, inter_buf, union_buf):
     nclass = inter_buf.shape[1]
     check(lib.dfw_iou_accumulate(inter.data_ptr(), union.data_ptr(), class_id.data_ptr(), inter_buf.data_ptr(),
                                  union_buf.data_ptr(), B, nclass, _stream()), "dfw_iou_accumulate")
+
+
+# ---- K9: episode preprocessing (dataset.py:36-40, coco.py:38-47) --------------------------------------------------
+IMAGE_DESC_BYTES = 24      # sizeof(DfwImageDesc): int64 offset, int32 h, w, row_stride, param
+
+
+def resize_normalize_u8(buf, desc_offset, n, max_h, max_w, out_h, out_w, mean=0.5, std=0.5, want_f32=True,
+                        want_u8=False):
+    """`buf`: uint8 device buffer holding n DfwImageDesc records at byte `desc_offset` and the decoded RGB (HWC uint8)
+    images they point to.  Returns (fp32 [n,3,out_h,out_w] normalised, uint8 [n,out_h,out_w,3] resized) — the same
+    bytes as torchvision's Resize -> ToTensor -> Normalize on the CPU."""
+    _req(buf, torch.uint8, "buf")
+    assert desc_offset % 8 == 0 and buf.data_ptr() % 8 == 0
+    dev = buf.device
+    dst = torch.empty((n, 3, out_h, out_w), device=dev, dtype=torch.float32) if want_f32 else None
+    dst8 = torch.empty((n, out_h, out_w, 3), device=dev, dtype=torch.uint8) if want_u8 else None
+    nbytes = int(lib.dfw_preproc_workspace_bytes(n, max_h, max_w, out_h, out_w))
+    if nbytes < 0:
+        raise ValueError("resize_normalize_u8: bad sizes")
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    check(lib.dfw_resize_normalize_u8(buf.data_ptr(), buf.data_ptr() + desc_offset, n, max_h, max_w, _ptr(dst), _ptr(dst8),
+                                      out_h, out_w, float(mean), float(std), ws.data_ptr(), nbytes, _stream()),
+          "dfw_resize_normalize_u8")
+    return dst, dst8
+
+
+def mask_nearest(buf, desc_offset, n, out_h, out_w, mode=0, want_boundary=False):
+    """Label masks (uint8 [h,w], described like images) -> fp32 {0,1} [n,out_h,out_w] at torch 'nearest' positions
+    (+ the PASCAL ignore boundary floor(label / 255) when asked)."""
+    _req(buf, torch.uint8, "buf")
+    assert desc_offset % 8 == 0 and buf.data_ptr() % 8 == 0
+    dev = buf.device
+    m = torch.empty((n, out_h, out_w), device=dev, dtype=torch.float32)
+    bd = torch.empty((n, out_h, out_w), device=dev, dtype=torch.float32) if want_boundary else None
+    check(lib.dfw_mask_nearest(buf.data_ptr(), buf.data_ptr() + desc_offset, n, m.data_ptr(), _ptr(bd), out_h, out_w, int(mode),
+                               _stream()), "dfw_mask_nearest")
+    return m, bd

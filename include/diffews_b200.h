@@ -261,6 +261,34 @@ int dfw_rthres_iou_hist(const uint8_t* pred_u8, int pred_is_mask, const uint8_t*
 int dfw_iou_accumulate(const long long* area_inter, const long long* area_union, const long long* class_id,
                        long long* inter_buf, long long* union_buf, int B, int nclass, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K9  Episode preprocessing (the data format in front of the hot path).
+ * ref: evaluation_util/data/dataset.py:36-40 (Resize((S,S)) -> ToTensor -> Normalize([0.5],[0.5])),
+ *      evaluation_util/data/coco.py:38-47, :92-93, pascal.py:42-55, :78-83, fss.py:38-47, :80-84.
+ * All decoded images of a batch sit in ONE device buffer `base`; `descs` (device, n entries, 8-byte aligned, may live
+ * inside the same buffer) says where.  Results are byte-identical to the reference's CPU path: Pillow's two-pass
+ * fixed-point bilinear resample (ImagingResample, uint8 intermediate) and torch's nearest index rule.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct DfwImageDesc {
+    long long offset; /* byte offset of pixel (0,0) from `base`                                        */
+    int h, w;         /* source height / width                                                         */
+    int row_stride;   /* bytes per source row (>= 3*w for RGB images, >= w for label masks)            */
+    int param;        /* dfw_mask_nearest mode 0: the label value that maps to 1 (class + 1)           */
+} DfwImageDesc;
+
+/* bytes of scratch dfw_resize_normalize_u8 needs for n images no larger than max_h x max_w (-1 on bad arguments) */
+long long dfw_preproc_workspace_bytes(int n, int max_h, int max_w, int out_h, int out_w);
+/* RGB uint8 HWC images -> dst_f32 [n,3,out_h,out_w] = ((resized / 255) - mean) / std  (fp32, the reference's op order)
+ * and / or dst_u8 [n,out_h,out_w,3] = the resized bytes (== PIL.Image.resize((out_w,out_h), BILINEAR)); either may be
+ * NULL.  3 launches for the whole batch (coefficients, horizontal pass, vertical pass + normalise). */
+int dfw_resize_normalize_u8(const void* base, const void* descs, int n, int max_h, int max_w, float* dst_f32,
+                            uint8_t* dst_u8, int out_h, int out_w, float mean, float std, void* workspace,
+                            long long workspace_bytes, void* stream);
+/* uint8 label masks [h,w] -> mask_out fp32 [n,out_h,out_w] in {0,1} at F.interpolate(mode="nearest") positions;
+ * mode 0: label == desc.param; mode 1: label >= 128.  boundary_out (NULL ok) = floor(label / 255) (PASCAL ignore). */
+int dfw_mask_nearest(const void* base, const void* descs, int n, float* mask_out, float* boundary_out, int out_h,
+                     int out_w, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

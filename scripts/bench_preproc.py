@@ -1,0 +1,115 @@
+"""Measurement of the episode-preprocessing kernels at the BASELINE config-2 batch shape.
+
+One batch = 16 one-shot episodes = 32 decoded 480x640 RGB images + 32 class masks -> 32 x [3,512,512] fp32 + 32 x
+[512,512] fp32.  Reports, as one JSON line: device-resident time per batch (CUDA events), the same with the pinned-host
+-> device copy of the raw bytes inside the timed region, achieved GB/s against the algorithmic bytes (source bytes read
+once + output bytes written once) and the measured HBM peak, and the reference's CPU path (torchvision Resize ->
+ToTensor -> Normalize + F.interpolate nearest, what evaluation_util/data/coco.py:38-47 runs per image) timed beside it.
+
+    python scripts/bench_preproc.py [--reps 50]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--episodes", type=int, default=16)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--src", type=int, nargs=2, default=[480, 640])
+    a = ap.parse_args()
+    from diffews_b200 import ops
+    from diffews_b200.data import EpisodeCollator
+    S, (h, w) = a.size, a.src
+    n = 2 * a.episodes
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(n)]
+    labs = [rng.integers(0, 81, (h, w), dtype=np.uint8) for _ in range(n)]
+    total, offs, desc = EpisodeCollator.pack(imgs + labs, [0] * n + [5] * n)
+    pinned = torch.empty(total, dtype=torch.uint8).pin_memory()
+    host = pinned.numpy()
+    host[:desc.nbytes] = desc.view(np.uint8)
+    for arr, o in zip(imgs + labs, offs):
+        host[o:o + arr.size] = arr.reshape(-1)
+    dev = pinned.cuda()
+    label_desc = n * ops.IMAGE_DESC_BYTES
+
+    def kernels(buf):
+        x, _ = ops.resize_normalize_u8(buf, 0, n, h, w, S, S)
+        m, _ = ops.mask_nearest(buf, label_desc, n, S, S, 0)
+        return x, m
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n0 = ops.launch_count()
+    ms_dev = timed(lambda: kernels(dev), a.reps)
+    launches = (ops.launch_count() - n0) // (a.reps + 3)
+    stage = torch.empty(total, dtype=torch.uint8, device="cuda")
+
+    def e2e():
+        stage.copy_(pinned, non_blocking=True)
+        kernels(stage)
+    ms_e2e = timed(e2e, a.reps)
+    alg_bytes = n * (h * w * 3 + 3 * S * S * 4) + n * (S * S + S * S * 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = None
+    for k in ("hbm_gbs", "hbm_gbps"):
+        if isinstance(peaks.get(k), (int, float)):
+            peak = float(peaks[k])
+            break
+    # CPU: the reference's per-image path, one core (PIL's resample is single-threaded)
+    from PIL import Image
+    from torchvision import transforms
+    tf = transforms.Compose([transforms.Resize(size=(S, S)), transforms.ToTensor(), transforms.Normalize([0.5], [0.5])])
+    torch.set_num_threads(1)
+    t0 = time.perf_counter()
+    k = 8
+    for i in range(k):
+        tf(Image.fromarray(imgs[i]))
+        lab = torch.from_numpy(labs[i].copy())
+        lab[lab != 5] = 0
+        lab[lab == 5] = 1
+        torch.nn.functional.interpolate(lab[None, None].float(), (S, S), mode="nearest").squeeze()
+    cpu_ms_per_image = (time.perf_counter() - t0) / k * 1e3
+    out = {"what": "episode preprocessing (Pillow-exact bilinear resize + ToTensor + Normalize, class mask + nearest)",
+           "batch": f"{a.episodes} 1-shot episodes: {n} RGB {h}x{w} + {n} masks -> {S}x{S}",
+           "launches_per_batch": int(launches),
+           "ms_per_batch_device": round(ms_dev, 4), "ms_per_batch_with_h2d": round(ms_e2e, 4),
+           "episodes_per_s_device": round(a.episodes / ms_dev * 1e3, 1),
+           "episodes_per_s_with_h2d": round(a.episodes / ms_e2e * 1e3, 1),
+           "h2d_bytes_per_batch": int(total), "reference_h2d_bytes_per_batch": int(n * (3 * S * S * 4 + S * S * 4)),
+           "roofline": {"bound": "hbm", "achieved": round(alg_bytes / ms_dev / 1e6, 1), "peak": peak, "unit": "GB/s",
+                        "frac": (round(alg_bytes / ms_dev / 1e6 / peak, 4) if peak else None),
+                        "algorithmic_bytes_per_batch": int(alg_bytes)},
+           "cpu_baseline": {"ms_per_image_and_mask": round(cpu_ms_per_image, 3), "cores": 1, "kind": "reference",
+                            "episodes_per_s": round(1e3 / (2 * cpu_ms_per_image), 1),
+                            "sample": f"{k} images through torchvision Resize/ToTensor/Normalize + F.interpolate nearest"}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+"""Golden vectors for the episode data layer, produced by the UNMODIFIED reference datasets.
+
+Runs in the build container only (it imports /root/reference/evaluation_util/data/{coco,pascal,fss}.py by file path —
+they need torch, PIL, numpy only — and torchvision's Resize/ToTensor/Normalize exactly as dataset.py:36-40 builds them)
+on the synthetic trees of tests/data_tree.py, and writes tests/golden/data_layer.json: per episode the sampled names,
+class id, and SHA-256 of every tensor's bytes (fp32, C order), plus a few raw values.  The tests rebuild the same trees
+and compare the oracle (CPU) and the CUDA data layer (GPU) against these.
+
+    python scripts/make_golden_data.py
+"""
+import hashlib
+import importlib.util
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+from torchvision import transforms
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import data_tree  # noqa: E402
+
+REF = "/root/reference/evaluation_util/data"
+IMG_SIZE = 48
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.contiguous().to(torch.float32).numpy().tobytes()).hexdigest()
+
+
+def episodes(ds, n, root):
+    out = []
+    for idx in range(n):
+        b = ds[idx]
+        e = {"query_name": os.path.relpath(b["query_name"], root) if os.path.isabs(str(b["query_name"])) else b["query_name"],
+             "support_names": [os.path.relpath(s, root) if os.path.isabs(str(s)) else s for s in b["support_names"]],
+             "class_id": int(b["class_id"]),
+             "query_img": sha(b["query_img"]), "query_mask": sha(b["query_mask"]),
+             "support_imgs": sha(b["support_imgs"]), "support_masks": sha(b["support_masks"]),
+             "query_img_shape": list(b["query_img"].shape), "support_imgs_shape": list(b["support_imgs"].shape),
+             "query_mask_sum": float(b["query_mask"].sum()), "query_img_first": b["query_img"].flatten()[:4].tolist()}
+        if "query_ignore_idx" in b:
+            e["query_ignore_idx"] = sha(b["query_ignore_idx"])
+            e["support_ignore_idxs"] = sha(b["support_ignore_idxs"])
+        if "org_query_imsize" in b:
+            e["org_query_imsize"] = list(b["org_query_imsize"])
+        out.append(e)
+    return out
+
+
+def main():
+    tf = transforms.Compose([transforms.Resize(size=(IMG_SIZE, IMG_SIZE)), transforms.ToTensor(),
+                             transforms.Normalize([0.5], [0.5])])                      # dataset.py:36-40
+    gold = {"img_size": IMG_SIZE, "made_by": "scripts/make_golden_data.py (reference datasets, unmodified)",
+            "versions": {"torch": torch.__version__, "numpy": np.__version__}}
+    with tempfile.TemporaryDirectory() as root:
+        data_tree.build_coco_tree(root)
+        data_tree.build_pascal_tree(root)
+        data_tree.build_fss_tree(root)
+        coco, pascal, fss = _load("coco"), _load("pascal"), _load("fss")
+        for shot in (1, 2):
+            np.random.seed(0)
+            ds = coco.DatasetCOCO(root, fold=0, transform=tf, split="val", shot=shot, use_original_imgsize=False)
+            gold[f"coco_shot{shot}"] = episodes(ds, 6, root)
+        np.random.seed(0)
+        ds = pascal.DatasetPASCAL(root, fold=0, transform=tf, split="val", shot=1, use_original_imgsize=False)
+        gold["pascal_shot1"] = episodes(ds, 6, root)
+        np.random.seed(0)
+        ds = fss.DatasetFSS(root, fold=0, transform=tf, split="test", shot=2, use_original_imgsize=False)
+        gold["fss_shot2"] = episodes(ds, 5, root)
+    path = os.path.join(ROOT, "tests", "golden", "data_layer.json")
+    with open(path, "w") as f:
+        json.dump(gold, f, indent=1)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
