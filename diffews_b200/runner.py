@@ -39,6 +39,7 @@ class EpisodeRunner:
 
     # ---- CUDA-graph mode: the ~1700 kernel launches of one batch become a single graph launch ------------------
     TENSOR_KEYS = ("query_img", "query_mask", "support_imgs", "support_masks", "class_id")
+    OPTIONAL_KEYS = ("query_ignore_idx",)      # PASCAL boundary pixels (pascal.py:78-83 -> evaluation.py:16-21)
 
     @torch.no_grad()
     def enable_cuda_graph(self, example_batch: dict):
@@ -46,7 +47,8 @@ class EpisodeRunner:
         of `example_batch`.  Later `step()` calls with the same shapes copy their inputs into the captured buffers and
         replay the graph; other shapes fall back to eager launches."""
         dev = self.pipe.device
-        self._static = {k: example_batch[k].to(dev).clone() for k in self.TENSOR_KEYS}
+        keys = self.TENSOR_KEYS + tuple(k for k in self.OPTIONAL_KEYS if example_batch.get(k) is not None)
+        self._static = {k: example_batch[k].to(dev).clone() for k in keys}
         self.pipe.validate_inputs = False          # float(t.min()) would synchronise inside the capture
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -70,7 +72,8 @@ class EpisodeRunner:
         """`batch`: collated episode batch, on the device (main_oss.py:94 `utils.to_cuda(batch)`) or in pinned host
         memory.  Returns per-episode int64 (area_inter [B,2], area_union [B,2]) and updates the meter."""
         g = getattr(self, "_graph", None)
-        if g is not None and all(tuple(batch[k].shape) == s for k, s in self._graph_shapes.items()):
+        if g is not None and all(k in batch and tuple(batch[k].shape) == s for k, s in self._graph_shapes.items()) \
+                and not any(batch.get(k) is not None and k not in self._graph_shapes for k in self.OPTIONAL_KEYS):
             for k, dst in self._static.items():
                 dst.copy_(batch[k], non_blocking=True)
             g.replay()
@@ -130,3 +133,21 @@ class EpisodeRunner:
     def finish(self):
         self.meter.all_reduce()
         return self.meter.compute_iou()
+
+    @torch.no_grad()
+    def run(self, dataloader, max_batches=None, use_cuda_graph: bool = True, log_every: int = 0):
+        """`test_diffusion(pipe, dataloader, args)` (evaluation_util/main_oss.py:84-171): every batch of the loader
+        through the pipeline, rthres, intersection/union, class accumulation; returns (mIoU, FB-IoU) after the
+        cross-rank all-reduce.  `dataloader` yields the reference's batch dicts (diffews_b200.data.EpisodeLoader, or the
+        reference's own DataLoader).  Full batches replay one CUDA graph; the short last batch runs eagerly."""
+        for i, batch in enumerate(dataloader):
+            if max_batches is not None and i >= max_batches:
+                break
+            if use_cuda_graph and getattr(self, "_graph", None) is None and i == 0:
+                self.enable_cuda_graph(batch)
+            self.step(batch)
+            if log_every and (i + 1) % log_every == 0:
+                miou, fb, _ = self.meter.compute_iou()
+                print(f"[batch {i + 1}] mIoU {float(miou):.2f}  FB-IoU {float(fb):.2f}", flush=True)
+        miou, fb_iou, _ = self.finish()
+        return float(miou), float(fb_iou)

@@ -61,14 +61,39 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # Device-resident leg: the two launches are captured in CUDA graphs (the Python / ctypes call costs more than the
+    # kernels), three graphs over three distinct input copies replayed round-robin so that neither the 39 MB of source
+    # bytes nor the 168 MB of outputs of a batch are still in the 126 MB L2 when they are touched again.
+    bufs = [dev, dev.clone(), dev.clone()]
     n0 = ops.launch_count()
-    ms_dev = timed(lambda: kernels(dev), a.reps)
-    launches = (ops.launch_count() - n0) // (a.reps + 3)
+    kernels(dev)
+    launches = ops.launch_count() - n0
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for bf in bufs:
+            kernels(bf)
+    torch.cuda.current_stream().wait_stream(side)
+    graphs, keep = [], []
+    for bf in bufs:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep.append(kernels(bf))
+        graphs.append(g)
+    it = [0]
+
+    def replay():
+        graphs[it[0] % 3].replay()
+        it[0] += 1
+    ms_dev = timed(replay, a.reps)
     stage = torch.empty(total, dtype=torch.uint8, device="cuda")
+    gs = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gs):
+        keep.append(kernels(stage))
 
     def e2e():
         stage.copy_(pinned, non_blocking=True)
-        kernels(stage)
+        gs.replay()
     ms_e2e = timed(e2e, a.reps)
     alg_bytes = n * (h * w * 3 + 3 * S * S * 4) + n * (S * S + S * S * 4)
     peaks = {}
@@ -97,7 +122,8 @@ def main():
     cpu_ms_per_image = (time.perf_counter() - t0) / k * 1e3
     out = {"what": "episode preprocessing (Pillow-exact bilinear resize + ToTensor + Normalize, class mask + nearest)",
            "batch": f"{a.episodes} 1-shot episodes: {n} RGB {h}x{w} + {n} masks -> {S}x{S}",
-           "launches_per_batch": int(launches),
+           "launches_per_batch": int(launches), "timing": "CUDA events around graph replays, 3 alternating input copies "
+           "(working set > L2)",
            "ms_per_batch_device": round(ms_dev, 4), "ms_per_batch_with_h2d": round(ms_e2e, 4),
            "episodes_per_s_device": round(a.episodes / ms_dev * 1e3, 1),
            "episodes_per_s_with_h2d": round(a.episodes / ms_e2e * 1e3, 1),

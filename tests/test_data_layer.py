@@ -271,19 +271,24 @@ def test_gpu_original_imgsize_query_mask(lib_built, tree):
     data.FSSDataset.initialize(S, tree, False)
 
 
-@pytest.mark.gpu
-def test_gpu_loader_feeds_the_runner(lib_built, tree):
-    """The loader's batch dict drives EpisodeRunner.step unchanged (keys / layouts of main_oss.py:94-110)."""
-    from diffews_b200 import data
-    from diffews_b200.runner import EpisodeRunner, build_engine_from_modules
+@pytest.fixture(scope="module")
+def small_pipe():
+    from diffews_b200.runner import build_engine_from_modules
     from diffews_b200.synthetic import prompt_embedding
     from oracle.sd21 import build_models
     unet_o, vae_o = build_models(0, (64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))
-    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding())
+    return build_engine_from_modules(unet_o, vae_o, prompt_embedding())
+
+
+@pytest.mark.gpu
+def test_gpu_loader_feeds_the_runner(lib_built, tree, small_pipe):
+    """The loader's batch dict drives EpisodeRunner.step unchanged (keys / layouts of main_oss.py:94-110)."""
+    from diffews_b200 import data
+    from diffews_b200.runner import EpisodeRunner
     data.FSSDataset.initialize(64, tree, False)
     np.random.seed(0)
     loader = data.FSSDataset.build_dataloader("pascal", 2, 2, 0, "val", 1)
-    runner = EpisodeRunner(pipe, benchmark="pascal", class_ids=loader.dataset.class_ids, img_size=64)
+    runner = EpisodeRunner(small_pipe, benchmark="pascal", class_ids=loader.dataset.class_ids, img_size=64)
     it = iter(loader)
     for _ in range(2):
         batch = next(it)
@@ -294,3 +299,25 @@ def test_gpu_loader_feeds_the_runner(lib_built, tree):
         assert (inter.sum(dim=1) <= valid).all() and (union <= valid[:, None]).all()
     miou, fb, _ = runner.finish()
     assert 0.0 <= float(miou) <= 100.0
+
+
+@pytest.mark.gpu
+def test_gpu_run_loop_graph_equals_eager_and_honours_ignore(lib_built, tree, small_pipe):
+    """EpisodeRunner.run (= test_diffusion, main_oss.py:84-171) over the PASCAL loader: the CUDA-graph replay and the
+    eager launches accumulate identical int64 buffers, and the boundary pixels reach the metric kernel in both."""
+    from diffews_b200 import data
+    from diffews_b200.runner import EpisodeRunner
+    bufs = []
+    for graph in (False, True):
+        data.FSSDataset.initialize(64, tree, False)
+        np.random.seed(0)
+        loader = data.FSSDataset.build_dataloader("pascal", 2, 2, 0, "val", 1)
+        runner = EpisodeRunner(small_pipe, benchmark="pascal", class_ids=loader.dataset.class_ids, img_size=64)
+        miou, fb = runner.run(loader, max_batches=3, use_cuda_graph=graph)
+        assert 0.0 <= miou <= 100.0 and 0.0 <= fb <= 100.0
+        if graph:
+            assert "query_ignore_idx" in runner._graph_shapes
+        bufs.append((runner.meter.intersection_buf.cpu().clone(), runner.meter.union_buf.cpu().clone()))
+    assert torch.equal(bufs[0][0], bufs[1][0]) and torch.equal(bufs[0][1], bufs[1][1])
+    # 3 batches x 2 episodes x 64^2 pixels minus the ignored boundary: strictly fewer pixels than the full images
+    assert int(bufs[0][1].sum()) > 0
