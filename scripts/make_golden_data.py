@@ -1,4 +1,5 @@
-"""Golden vectors for the episode data layer, produced by the UNMODIFIED reference datasets.
+"""Golden vectors produced by the UNMODIFIED reference: the episode data layer (datasets) and the intersection / union
+metric (Evaluator.classify_prediction) — the two parts of the path whose reference modules import without diffusers.
 
 Runs in the build container only (it imports /root/reference/evaluation_util/data/{coco,pascal,fss}.py by file path —
 they need torch, PIL, numpy only — and torchvision's Resize/ToTensor/Normalize exactly as dataset.py:36-40 builds them)
@@ -58,6 +59,22 @@ def episodes(ds, n, root):
     return out
 
 
+def metric_golden():
+    spec = importlib.util.spec_from_file_location("ref_evaluation", "/root/reference/evaluation_util/common/evaluation.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.Evaluator.initialize()
+    out = []
+    for c in data_tree.metric_cases():
+        batch = {"query_mask": c["gt"].clone()}
+        if c["ign"] is not None:
+            batch["query_ignore_idx"] = c["ign"].clone()
+        inter, union = m.Evaluator.classify_prediction(c["pred"].clone(), batch)      # float32 [2,B]
+        out.append({k: c[k] for k in ("seed", "B", "H", "W", "ignore", "kind")} |
+                   {"area_inter": inter.tolist(), "area_union": union.tolist(), "dtype": str(inter.dtype)})
+    return out
+
+
 def main():
     tf = transforms.Compose([transforms.Resize(size=(IMG_SIZE, IMG_SIZE)), transforms.ToTensor(),
                              transforms.Normalize([0.5], [0.5])])                      # dataset.py:36-40
@@ -78,6 +95,11 @@ def main():
         np.random.seed(0)
         ds = fss.DatasetFSS(root, fold=0, transform=tf, split="test", shot=2, use_original_imgsize=False)
         gold["fss_shot2"] = episodes(ds, 5, root)
+    mpath = os.path.join(ROOT, "tests", "golden", "metric_reference.json")
+    with open(mpath, "w") as f:
+        json.dump({"made_by": "scripts/make_golden_data.py: unmodified evaluation_util/common/evaluation.py "
+                              "Evaluator.classify_prediction on CPU", "cases": metric_golden()}, f, indent=1)
+    print("wrote", mpath)
     path = os.path.join(ROOT, "tests", "golden", "data_layer.json")
     with open(path, "w") as f:
         json.dump(gold, f, indent=1)

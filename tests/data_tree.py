@@ -8,6 +8,7 @@ import os
 import pickle
 
 import numpy as np
+import torch
 from PIL import Image
 
 
@@ -96,3 +97,28 @@ def build_fss_tree(root: str, seed: int = 13, categories=("abacus", "bat", "crt_
     with open(os.path.join(base, "splits", "test.txt"), "w") as f:
         f.write("\n".join(categories) + "\n")
     return root
+
+
+def metric_cases():
+    """Seeded masks for Evaluator.classify_prediction (evaluation_util/common/evaluation.py:12-39): [B,H,W] float {0,1}
+    prediction / ground truth, optional PASCAL ignore boundary.  Shared with tests/test_oracle.py (same generator)."""
+    cases = []
+    for seed, (B, H, W, ignore, kind) in enumerate([(1, 64, 64, False, "rand"), (3, 48, 80, False, "rand"),
+                                                    (2, 64, 64, True, "rand"), (1, 32, 32, False, "all_bg"),
+                                                    (1, 32, 32, False, "disjoint"), (2, 40, 40, True, "all_fg")]):
+        g = torch.Generator().manual_seed(100 + seed)
+        pred = (torch.rand(B, H, W, generator=g) > 0.6).float()
+        gt = (torch.rand(B, H, W, generator=g) > 0.5).float()
+        if kind == "all_bg":
+            pred.zero_(); gt.zero_()
+        elif kind == "disjoint":
+            pred[:] = 1; gt.zero_()
+        elif kind == "all_fg":
+            pred[:] = 1; gt[:] = 1
+        ign = None
+        if ignore:
+            ign = (torch.rand(B, H, W, generator=g) > 0.9).float()
+            gt = gt * (1 - ign)                     # evaluation.py:17 asserts ignore and gt are disjoint
+        cases.append({"seed": 100 + seed, "B": B, "H": H, "W": W, "ignore": ignore, "kind": kind, "pred": pred, "gt": gt,
+                      "ign": ign})
+    return cases

@@ -321,3 +321,21 @@ def test_gpu_run_loop_graph_equals_eager_and_honours_ignore(lib_built, tree, sma
     assert torch.equal(bufs[0][0], bufs[1][0]) and torch.equal(bufs[0][1], bufs[1][1])
     # 3 batches x 2 episodes x 64^2 pixels minus the ignored boundary: strictly fewer pixels than the full images
     assert int(bufs[0][1].sum()) > 0
+
+
+@pytest.mark.gpu
+def test_gpu_evaluator_matches_unmodified_reference_evaluator(lib_built):
+    """a12 on the GPU against the reference's own numbers: diffews_b200.evaluation.Evaluator.classify_prediction (one
+    launch of dfw_rthres_iou_hist, int64 counts) == what the UNMODIFIED evaluation_util/common/evaluation.py returned
+    for the same seeded masks (tests/golden/metric_reference.json), including the PASCAL ignore boundary, an all-
+    background pair (empty foreground histogram) and a fully disjoint pair."""
+    from diffews_b200.evaluation import Evaluator
+    gold = json.load(open(os.path.join(HERE, "golden", "metric_reference.json")))["cases"]
+    for c, g in zip(data_tree.metric_cases(), gold):
+        batch = {"query_mask": c["gt"].cuda()}
+        if c["ign"] is not None:
+            batch["query_ignore_idx"] = c["ign"].cuda()
+        inter, union = Evaluator.classify_prediction(c["pred"].cuda(), batch)
+        assert inter.dtype == torch.float32 and tuple(inter.shape) == (2, c["B"])
+        assert inter.cpu().tolist() == g["area_inter"], g["kind"]
+        assert union.cpu().tolist() == g["area_union"], g["kind"]

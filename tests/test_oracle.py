@@ -194,3 +194,27 @@ def test_ddim_multi_step_schedule_and_identity():
         assert torch.allclose(op.ddim_step_prev_sample(v, t, x, 4), x)
         out = sch.step(v, t, x)
         assert torch.allclose(out.pred_original_sample, -v) and torch.allclose(out.prev_sample, x)
+
+
+def test_metric_oracle_matches_unmodified_reference_evaluator():
+    """a12 pinned: tests/golden/metric_reference.json holds what the UNMODIFIED reference
+    evaluation_util/common/evaluation.py Evaluator.classify_prediction returned on CPU for the seeded masks of
+    tests/data_tree.py::metric_cases (scripts/make_golden_data.py); the oracle restatement must reproduce it exactly."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import data_tree
+    from oracle.metric import classify_prediction
+    gold = json.load(open(os.path.join(here, "golden", "metric_reference.json")))["cases"]
+    cases = data_tree.metric_cases()
+    assert len(gold) == len(cases)
+    for c, g in zip(cases, gold):
+        assert (c["seed"], c["B"], c["H"], c["W"]) == (g["seed"], g["B"], g["H"], g["W"])
+        batch = {"query_mask": c["gt"].clone()}
+        if c["ign"] is not None:
+            batch["query_ignore_idx"] = c["ign"].clone()
+        inter, union = classify_prediction(c["pred"].clone(), batch)
+        assert inter.dtype == torch.float32 and inter.tolist() == g["area_inter"], g["kind"]
+        assert union.tolist() == g["area_union"], g["kind"]
