@@ -15,6 +15,7 @@
 //   warps 4-7  softmax: one thread per query row (= TMEM lane): running max / sum in the log2 domain, P_j -> bf16 ->
 //              swizzled smem, O accumulated in registers with the per-tile rescale (no TMEM read-modify-write).
 #include <atomic>
+#include <cstdlib>
 
 #include <type_traits>
 
@@ -357,6 +358,309 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Split-row variant (DFW_ATTN_SPLIT=1): same CTA tile, TMEM plan, producer and MMA warps as above, but every query
+// tile gets EIGHT softmax warps instead of four: warp (q, h) owns TMEM lane quadrant q (rows 32q..32q+31) and key
+// columns 64h..64h+63 of each S tile.  Why: scripts/microbench/mufu_issue.cu shows that a MUFU does NOT hold the
+// issue port while the quarter-rate XU datapath works (5 FMA-pipe instructions per ex2 still run at 8.4 cycles per
+// MUFU), so the 12.3 issue cycles per logit of the 4-warp version are an overlap problem, not a floor: with two
+// softmax warps per sub-partition the XU idles whenever both are in a non-MUFU phase (max pass, TMEM wait, packing,
+// barrier).  Four warps per sub-partition make that rare.  Each thread now holds its 64 logits in registers across
+// both passes (no second TMEM read).  The two halves of a row exchange their partial row max (and, once, their
+// partial row sum) through smem with a 64-thread named barrier; both then derive bit-identical m / alpha, so the
+// warp-uniform lazy-rescale decision agrees without further communication.  Half 0 performs the (rare) O rescale;
+// the epilogue splits O's 64 columns between the halves.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS_SPLIT = 128 + ATT_QT * 8 * 32;          // 4 control warps + 2 x 8 softmax warps
+constexpr int ATT_XCH_BYTES = 2 * ATT_QT * 2 * ATT_M * 4 /*max, 2 parities*/ + ATT_QT * 2 * ATT_M * 4 /*sum*/;
+constexpr int ATT_SMEM_SPLIT = ATT_SMEM + ATT_XCH_BYTES;
+
+template <bool F16>
+__global__ void __launch_bounds__(ATT_THREADS_SPLIT, 1)
+attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    auto sQ = [&](int x) { return base + x * TILE_BYTES; };
+    const uint32_t kv_base = base + ATT_QT * TILE_BYTES;
+    auto sK = [&](int s) { return kv_base + s * 2 * TILE_BYTES; };
+    auto sV = [&](int s) { return kv_base + s * 2 * TILE_BYTES + TILE_BYTES; };
+    const uint32_t p_base = kv_base + KV_STAGES * 2 * TILE_BYTES;
+    auto sP = [&](int x) { return p_base + x * 2 * TILE_BYTES; };
+    const uint32_t bar_base = p_base + ATT_QT * 2 * TILE_BYTES;
+    const uint32_t q_full = bar_base;
+    auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KV_STAGES + s); };
+    auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * KV_STAGES + buf); };
+    auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KV_STAGES + x); };
+    auto pv_done = [&](int x) { return bar_base + 8u * (6 + 2 * KV_STAGES + x); };
+    const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * KV_STAGES);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+    uint8_t* sP_generic = smem_raw + (p_base - raw_u32);
+    float* xch_max = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_u32));       // [parity][x][h][128]
+    float* xch_sum = xch_max + 2 * ATT_QT * 2 * ATT_M;                                       // [x][h][128]
+
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_M * ATT_QT;
+    const int head = blockIdx.y;
+    const int b = blockIdx.z;
+    const int ntiles = p.n_self + p.n_bank;
+    const bool has_b = (q0 + ATT_M) < p.Lq;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.q);
+        tma_prefetch_desc(&maps.k_self);
+        tma_prefetch_desc(&maps.v_self);
+        if (p.n_bank) { tma_prefetch_desc(&maps.k_bank); tma_prefetch_desc(&maps.v_bank); }
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+        for (int x = 0; x < ATT_SBUF; ++x) mbar_init(s_full(x), 1);
+        for (int x = 0; x < ATT_QT; ++x) { mbar_init(p_full(x), 256); mbar_init(pv_done(x), 1); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+    auto tS = [&](int buf) { return tmem_base + buf * 128; };
+    auto tO = [&](int x) { return tmem_base + ATT_SBUF * 128 + x * 64; };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+            tma_load_3d(sQ(0), &maps.q, q_full, head * ATT_D, q0, b);
+            if (has_b) tma_load_3d(sQ(1), &maps.q, q_full, head * ATT_D, q0 + ATT_M, b);
+        }
+        __syncwarp();
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % KV_STAGES;
+            const uint32_t ph = (j / KV_STAGES) & 1;
+            mbar_wait(kv_empty(s), ph ^ 1u, 10);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(kv_full(s), 2 * TILE_BYTES);
+                if (j < p.n_self) {
+                    tma_load_3d(sK(s), &maps.k_self, kv_full(s), head * ATT_D, j * ATT_N, b);
+                    tma_load_3d(sV(s), &maps.v_self, kv_full(s), head * ATT_D, j * ATT_N, b);
+                } else {
+                    const int jb = j - p.n_self;
+                    tma_load_3d(sK(s), &maps.k_bank, kv_full(s), head * ATT_D, jb * ATT_N, b);
+                    tma_load_3d(sV(s), &maps.v_bank, kv_full(s), head * ATT_D, jb * ATT_N, b);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const uint32_t fmt = F16 ? 0u : 1u;
+        const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);
+        const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);
+        const int nq = has_b ? 2 : 1;
+        auto issue_s = [&](int x, int j) {
+            const int s = j % KV_STAGES;
+            const int buf = (nq * j + x) % ATT_SBUF;
+            const uint64_t adesc = umma_desc_sw128(sQ(x));
+            const uint64_t bdesc = umma_desc_sw128(sK(s));
+#pragma unroll
+            for (int k = 0; k < ATT_D / 16; ++k)
+                umma_ss(tS(buf), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+            tc_commit(s_full(buf));
+        };
+        mbar_wait(q_full, 0, 12);
+        mbar_wait(kv_full(0), 0, 11);
+        tc_fence_after();
+        if (elect_one()) {
+            for (int x = 0; x < nq; ++x) issue_s(x, 0);
+        }
+        __syncwarp();
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % KV_STAGES;
+            if (j + 1 < ntiles) {
+                mbar_wait(kv_full((j + 1) % KV_STAGES), ((j + 1) / KV_STAGES) & 1, 11);
+                tc_fence_after();
+            }
+            for (int x = 0; x < nq; ++x) {
+                if (j + 1 < ntiles) {
+                    if (elect_one()) issue_s(x, j + 1);
+                    __syncwarp();
+                }
+                mbar_wait(p_full(x), j & 1, 13);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < ATT_N / 16; ++ks) {
+                        const uint64_t adesc = umma_desc_sw128(sP(x) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
+                        const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
+                        umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(pv_done(x));
+                    if (x == nq - 1) tc_commit(kv_empty(s));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        const int sw = warp - 4;
+        const int x = sw >> 3;                        // query tile of this softmax warp
+        const int qd = sw & 3;                        // TMEM lane quadrant (== warp % 4, the only lanes this warp may touch)
+        const int hf = (sw >> 2) & 1;                 // key-column half
+        const int row = qd * 32 + lane;
+        const int qrow0 = q0 + x * ATT_M;
+        if (x == 0 || has_b) {
+            const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+            const int nq = has_b ? 2 : 1;
+            const uint32_t to = tO(x) + lane_off;
+            const int pair_bar = 1 + x * 4 + qd;      // named barrier of the two warps that share these 32 rows
+            float m_used = -INFINITY, l_run = 0.f;
+            uint8_t* prow = sP_generic + x * 2 * TILE_BYTES + hf * TILE_BYTES + row * 128;
+            for (int j = 0; j < ntiles; ++j) {
+                int valid;
+                if (j < p.n_self) valid = min(ATT_N, p.Ls - j * ATT_N);
+                else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
+                const int vloc = max(0, min(64, valid - hf * 64));            // valid columns of this half
+                const int seq = nq * j + x, sbuf = seq % ATT_SBUF;
+                const uint32_t ts = tS(sbuf) + lane_off + hf * 64;
+                mbar_wait(s_full(sbuf), (seq / ATT_SBUF) & 1, 15);
+                tc_fence_after();
+                // 16-column chunks, software-pipelined like the 4-warp kernel (load of chunk c+1 in flight while chunk c
+                // is processed); 640 threads leave 96 registers per thread, which rules out holding all 64 logits
+                float psum = 0.f;
+                auto run_tile = [&](auto full_tag) {
+                constexpr bool full = decltype(full_tag)::value;
+                uint32_t va[16], vb[16];
+                auto chunk_max = [&](const uint32_t (&v)[16], int c, float& mx) {
+                    if constexpr (full) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c * 16 + i < vloc) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    }
+                };
+                // pass 1: partial row max over this half's 64 logits, exchanged with the other half
+                float mx = -INFINITY;
+                tmem_ld_32x16(ts, va);
+                tmem_ld_wait(); tmem_regs_ready16(va);
+                tmem_ld_32x16(ts + 16, vb);
+                chunk_max(va, 0, mx);
+                tmem_ld_wait(); tmem_regs_ready16(vb);
+                tmem_ld_32x16(ts + 32, va);
+                chunk_max(vb, 1, mx);
+                tmem_ld_wait(); tmem_regs_ready16(va);
+                tmem_ld_32x16(ts + 48, vb);
+                chunk_max(va, 2, mx);
+                tmem_ld_wait(); tmem_regs_ready16(vb);
+                tmem_ld_32x16(ts, va);                               // chunk 0 again, for pass 2
+                chunk_max(vb, 3, mx);
+                float* xm = xch_max + ((j & 1) * ATT_QT + x) * 2 * ATT_M;
+                xm[hf * ATT_M + row] = mx;
+                named_bar_sync(pair_bar, 64);
+                mx = fmaxf(mx, xm[(hf ^ 1) * ATT_M + row]);
+                tmem_ld_wait(); tmem_regs_ready16(va);
+                const float m_new = fmaxf(m_used, mx * p.scale_log2);
+                if (__any_sync(0xffffffffu, m_new > m_used + ATT_RESCALE_TAU)) {
+                    const float alpha = ex2_approx(m_used - m_new);   // 0 on the first tile
+                    if (j > 0 && hf == 0) {
+                        mbar_wait(pv_done(x), (j - 1) & 1, 14);       // O_X holds tiles < j
+                        tc_fence_after();
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(to + c * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            tmem_st_32x32(to + c * 32, v);
+                        }
+                        tmem_st_wait();
+                    }
+                    l_run *= alpha;
+                    m_used = m_new;
+                }
+                // pass 2: p = exp2(s*c - m) -> 16-bit -> this thread's 128-byte row of P sub-tile hf
+                if (j > 0) mbar_wait(pv_done(x), (j - 1) & 1, 17);    // PV(j-1) has finished reading the P buffer
+                const float sc = p.scale_log2, mu = m_used;
+                auto chunk_p = [&](const uint32_t (&v)[16], int c) {
+                    float pf[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float e = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mu));
+                        if constexpr (!full) { if (c * 16 + i >= vloc) e = 0.f; }
+                        pf[i] = e;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) psum += (pf[i] + pf[i + 1]) + (pf[i + 2] + pf[i + 3]);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        uint4 w;
+                        w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], F16);
+                        w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], F16);
+                        w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], F16);
+                        w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], F16);
+                        const int unit = (c * 2 + u) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(prow + unit * 16) = w;
+                    }
+                };
+                tmem_ld_32x16(ts + 16, vb);
+                chunk_p(va, 0);
+                tmem_ld_wait(); tmem_regs_ready16(vb);
+                tmem_ld_32x16(ts + 32, va);
+                chunk_p(vb, 1);
+                tmem_ld_wait(); tmem_regs_ready16(va);
+                tmem_ld_32x16(ts + 48, vb);
+                chunk_p(va, 2);
+                tmem_ld_wait(); tmem_regs_ready16(vb);
+                chunk_p(vb, 3);
+                };
+                if (vloc == 64) run_tile(std::true_type{});
+                else run_tile(std::false_type{});
+                l_run += psum;
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(p_full(x));
+            }
+            // epilogue: O_X / l, 32 of the 64 channels per half
+            mbar_wait(pv_done(x), (ntiles - 1) & 1, 16);
+            tc_fence_after();
+            float* xs = xch_sum + x * 2 * ATT_M;
+            xs[hf * ATT_M + row] = l_run;
+            named_bar_sync(pair_bar, 64);
+            const float inv = 1.0f / (l_run + xs[(hf ^ 1) * ATT_M + row]);
+            const bool row_ok = (qrow0 + row) < p.Lq;
+            uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
+                           static_cast<long long>(qrow0 + row) * p.o_row_stride + head * ATT_D + hf * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(to + hf * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 w;
+                    w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, F16);
+                    w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, F16);
+                    w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, F16);
+                    w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, F16);
+                    *reinterpret_cast<uint4*>(op + i) = w;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    }
+}
+
 int make_seq_map(CUtensorMap* m, const void* base, int C, int L, int B, int row_stride, long long batch_stride) {
     const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(row_stride) * 2, static_cast<uint64_t>(batch_stride) * 2};
@@ -547,9 +851,19 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     if (!attr_set) {
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_SPLIT));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_SPLIT));
         attr_set = true;
     }
     dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
+    static const bool split_rows = [] { const char* e = getenv("DFW_ATTN_SPLIT"); return e && e[0] == '1'; }();
+    if (split_rows) {
+        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_split_kernel<true>, grid, ATT_THREADS_SPLIT, ATT_SMEM_SPLIT, static_cast<cudaStream_t>(stream_), maps, p));
+        else DFW_CHECK_CUDA(launch_k(attn_kvfused_split_kernel<false>, grid, ATT_THREADS_SPLIT, ATT_SMEM_SPLIT, static_cast<cudaStream_t>(stream_), maps, p));
+        g_launches.fetch_add(1);
+        DFW_CHECK_CUDA(cudaGetLastError());
+        return DFW_OK;
+    }
     if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true>, grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_), maps, p));
     else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false>, grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_), maps, p));
     g_launches.fetch_add(1);

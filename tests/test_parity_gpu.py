@@ -467,3 +467,17 @@ def test_pipeline_small_width_other_sizes(small_models, size):
     agree, e2e_err, unet_err = _pipeline_parity(small_models, size, 1, 1, start=7)
     print(f"small pipeline {size}: mask agreement", agree, "e2e latent", e2e_err, "unet-only latent", unet_err)
     assert min(agree) >= 0.98 and max(unet_err) <= UNET_RTOL and max(e2e_err) <= 3e-2
+
+
+def test_attention_split_rows_variant_in_subprocess():
+    """The kept-but-off split-row attention kernel (DFW_ATTN_SPLIT=1) against the torch fp32
+    reference on the bring-up shapes (ragged query / key tiles, bank of 0 / 1 / 2 supports, strided fused-QKV input).
+    The switch is read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DFW_ATTN_SPLIT="1", DFW_BRINGUP_CHILD="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_bringup.py"), "attn"], env=env,
+                       capture_output=True, text=True, timeout=170)
+    assert r.returncode == 0 and "CASE_OK attn" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
