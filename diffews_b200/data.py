@@ -351,17 +351,33 @@ class EpisodeCollator:
 class EpisodeLoader:
     """`DataLoader(dataset, batch_size=bsz, shuffle=split=='trn', num_workers=0)` (dataset.py:44-50) with the collation
     on the GPU.  Sampling order == the reference's single-process loader: indices 0..len-1 in order at test time, a
-    torch.randperm drawn like RandomSampler at training time; the last batch may be short."""
+    torch.randperm drawn like RandomSampler at training time; the last batch may be short.
 
-    def __init__(self, dataset: _EpisodeDataset, bsz: int, shuffle: bool = False, device="cuda", decode_threads: int = 8):
+    Data-parallel evaluation: with `world` > 1 every rank draws EVERY episode from the numpy RNG (names
+    only — cheap), so all ranks walk the reference's single-process episode sequence, and rank r decodes / collates
+    batches r, r + world, ...  The all-reduced int64 counts are then bit-identical to a one-GPU run of the same seed."""
+
+    def __init__(self, dataset: _EpisodeDataset, bsz: int, shuffle: bool = False, device="cuda", decode_threads: int = 8,
+                 rank: Optional[int] = None, world: Optional[int] = None):
         self.dataset = dataset
         self.batch_size = bsz
         self.shuffle = shuffle
         self.collate = EpisodeCollator(dataset, device)
         self.pool = ThreadPoolExecutor(decode_threads) if decode_threads > 1 else None
+        if rank is None or world is None:
+            import torch.distributed as dist
+            on = dist.is_available() and dist.is_initialized()
+            rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+        if not 0 <= rank < world:
+            raise ValueError(f"rank {rank} outside world {world}")
+        self.rank, self.world = rank, world
+
+    def _num_batches(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
     def __len__(self):
-        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+        n = self._num_batches()
+        return (n - self.rank + self.world - 1) // self.world
 
     def _indices(self):
         n = len(self.dataset)
@@ -374,8 +390,10 @@ class EpisodeLoader:
 
     def raw_batches(self):
         idx = self._indices()
-        for s in range(0, len(idx), self.batch_size):
+        for bi, s in enumerate(range(0, len(idx), self.batch_size)):
             sampled = [self.dataset.sample_names(i) for i in idx[s:s + self.batch_size]]     # RNG order = reference
+            if bi % self.world != self.rank:
+                continue
             yield [self.dataset.decode(sm, self.pool) for sm in sampled]
 
     def __iter__(self):
@@ -394,11 +412,12 @@ class FSSDataset:
         cls.transform = EpisodeTransform(img_size)
 
     @classmethod
-    def build_dataloader(cls, benchmark, bsz, nworker, fold, split, shot=1, device="cuda"):
+    def build_dataloader(cls, benchmark, bsz, nworker, fold, split, shot=1, device="cuda", rank=None, world=None):
         if benchmark not in cls.datasets:
             raise NotImplementedError(f"benchmark {benchmark!r}: only {sorted(cls.datasets)} are built "
                                       "(lvis / paco_part / pascal_part need detectron2 / pycocotools metadata)")
         shuffle = split == "trn"
         dataset = cls.datasets[benchmark](cls.datapath, fold=fold, transform=cls.transform, split=split, shot=shot,
                                           use_original_imgsize=cls.use_original_imgsize)
-        return EpisodeLoader(dataset, bsz, shuffle=shuffle, device=device, decode_threads=max(1, nworker))
+        return EpisodeLoader(dataset, bsz, shuffle=shuffle, device=device, decode_threads=max(1, nworker), rank=rank,
+                             world=world)

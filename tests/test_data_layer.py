@@ -159,6 +159,28 @@ def test_loader_visits_reference_order_and_keeps_short_batch(tree):
     assert names[:5] == [g["query_name"] for g in GOLD["fss_shot2"]]
 
 
+def test_loader_shards_batches_over_ranks_without_changing_the_episode_sequence(tree):
+    """world = 2: every rank consumes the numpy RNG for every episode, rank r keeps batches r, r+2, ...; the union is
+    the single-process sequence (so all-reduced counts equal a one-GPU run of the same seed)."""
+    from diffews_b200.data import EpisodeLoader
+    ds = _dataset(tree, "coco_shot2")
+    def names(rank, world):
+        np.random.seed(0)
+        loader = EpisodeLoader(ds, bsz=2, device="cpu", decode_threads=1, rank=rank, world=world)
+        out = []
+        for i, raws in enumerate(loader.raw_batches()):
+            out.append([(r["query_name"], tuple(r["support_names"]), r["class_sample"]) for r in raws])
+            if i == 2:
+                break
+        return out
+    single = names(0, 1)
+    r0, r1 = names(0, 2), names(1, 2)
+    assert r0[0] == single[0] and r1[0] == single[1] and r0[1] == single[2]
+    assert [e[0] for b in single[:1] for e in b] == [g["query_name"] for g in GOLD["coco_shot2"][:2]]
+    lens = [len(EpisodeLoader(ds, bsz=16, device="cpu", decode_threads=1, rank=r, world=8)) for r in range(8)]
+    assert lens == [8, 8, 8, 8, 8, 8, 8, 7] and sum(lens) == 63                 # 1000 episodes / 16 -> 63 batches
+
+
 def test_collate_without_gpu_fails_loudly(tree):
     from diffews_b200.data import EpisodeLoader
     if torch.cuda.is_available():
