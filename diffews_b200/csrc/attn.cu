@@ -24,6 +24,9 @@
 
 namespace dfw {
 extern std::atomic<long long> g_launches;
+#ifdef DFW_ATTN_TRACE
+extern long long* g_attn_trace;
+#endif
 namespace {
 
 constexpr int ATT_M = 128;       // query rows per tile (one tcgen05 M)
@@ -35,6 +38,8 @@ constexpr int TILE_BYTES = 128 * 128;             // 128 rows x 128 B
 constexpr int ATT_THREADS = 384;                  // 4 control warps + 2 x 4 softmax warps
 constexpr int ATT_SMEM = ATT_QT * TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ +
                          ATT_QT * 2 * TILE_BYTES /*P*/ + 1024 + 256;
+constexpr int ATT_SMEM_MI = ATT_QT * TILE_BYTES + 2 * 2 * TILE_BYTES + ATT_QT * 2 * 2 * TILE_BYTES + 1024 + 256;   // 2 K/V stages, 2 P buffers per tile
+static_assert(ATT_SMEM_MI <= 227 * 1024, "dynamic smem limit of sm_100");
 constexpr int ATT_SBUF = 3;                       // S accumulators rotate over 3 TMEM buffers: the MMA warp computes
                                                   // S_X(j+1) while the softmax group of X still reads S_X(j)
 constexpr int ATT_TMEM_COLS = 512;                // S buffers [0,128) [128,256) [256,384); O_A [384,448) O_B [448,512)
@@ -53,7 +58,16 @@ struct AttnParams {
     long long o_batch_stride;
     int o_row_stride;
     int f16;              // 16-bit tensors are fp16 (else bf16)
+#ifdef DFW_ATTN_TRACE
+    long long* trace;     // debug build only (scripts/attn_trace.py): clock64 stamps of CTA (0,0,0), [warp][tile][8]
+#endif
 };
+#ifdef DFW_ATTN_TRACE
+#define ATT_STAMP(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 64) \
+        p.trace[(warp * 64 + j) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define ATT_STAMP(slot) do { } while (0)
+#endif
 
 // CTA = 256 query rows (two 128-row tiles A, B) of one (episode, head).
 //   warp 0      TMA producer: Q_A, Q_B once; (K_j, V_j) 128-key tiles through a 3-stage ring, from two tensor maps
@@ -65,26 +79,32 @@ struct AttnParams {
 //               and sum in the log2 domain; O is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row of
 //               the warp raises its max by more than 2^TAU, so the common case never touches O; P -> 16-bit ->
 //               128B-swizzled smem (the K-major A operand of the PV MMA)
-template <bool F16>
+template <bool F16, bool MI>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    // MI: 2 K/V stages and TWO P buffers per query tile (the softmax of tile j+1 never waits for PV(j));
+    // single issuer: 3 K/V stages, one P buffer.  Both fit the same ATT_SMEM.
+    constexpr int KVS = MI ? 2 : KV_STAGES;
+    constexpr int NPB = MI ? 2 : 1;
+    static_assert(ATT_QT * TILE_BYTES + KVS * 2 * TILE_BYTES + ATT_QT * NPB * 2 * TILE_BYTES + 1024 + 256 <= (MI ? ATT_SMEM_MI : ATT_SMEM), "smem");
     auto sQ = [&](int x) { return base + x * TILE_BYTES; };
     const uint32_t kv_base = base + ATT_QT * TILE_BYTES;
     auto sK = [&](int s) { return kv_base + s * 2 * TILE_BYTES; };
     auto sV = [&](int s) { return kv_base + s * 2 * TILE_BYTES + TILE_BYTES; };
-    const uint32_t p_base = kv_base + KV_STAGES * 2 * TILE_BYTES;
-    auto sP = [&](int x) { return p_base + x * 2 * TILE_BYTES; };
-    const uint32_t bar_base = p_base + ATT_QT * 2 * TILE_BYTES;
+    const uint32_t p_base = kv_base + KVS * 2 * TILE_BYTES;
+    auto sP = [&](int x, int pb) { return p_base + (x * NPB + pb) * 2 * TILE_BYTES; };
+    const uint32_t bar_base = p_base + ATT_QT * NPB * 2 * TILE_BYTES;
     const uint32_t q_full = bar_base;
     auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KV_STAGES + s); };
-    auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * KV_STAGES + buf); };      // one per S buffer
-    auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KV_STAGES + x); };
-    auto pv_done = [&](int x) { return bar_base + 8u * (6 + 2 * KV_STAGES + x); };
-    const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * KV_STAGES);
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KVS + s); };
+    auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * KVS + buf); };      // one per S buffer
+    auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KVS + x); };
+    auto pv_done = [&](int x, int pb) { return bar_base + 8u * (6 + 2 * KVS + x * 2 + pb); };   // one per P buffer
+    const uint32_t tmem_slot = bar_base + 8u * (10 + 2 * KVS);
+    auto s_free = [&](int buf) { return bar_base + 8u * (11 + 2 * KVS + buf); };     // MI only: S buffer read out
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
     uint8_t* sP_generic = smem_raw + (p_base - raw_u32);
 
@@ -106,9 +126,12 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-        for (int x = 0; x < ATT_SBUF; ++x) mbar_init(s_full(x), 1);
-        for (int x = 0; x < ATT_QT; ++x) { mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1); }
+        for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), (MI && has_b) ? 2 : 1); }
+        for (int x = 0; x < ATT_SBUF; ++x) { mbar_init(s_full(x), 1); mbar_init(s_free(x), 128); }
+        for (int x = 0; x < ATT_QT; ++x) {
+            mbar_init(p_full(x), 128);
+            for (int pb = 0; pb < NPB; ++pb) mbar_init(pv_done(x, pb), 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -132,8 +155,8 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             }
             __syncwarp();
             for (int j = 0; j < ntiles; ++j) {
-                const int s = j % KV_STAGES;
-                const uint32_t ph = (j / KV_STAGES) & 1;
+                const int s = j % KVS;
+                const uint32_t ph = (j / KVS) & 1;
                 mbar_wait(kv_empty(s), ph ^ 1u, 10);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(kv_full(s), 2 * TILE_BYTES);
@@ -149,7 +172,59 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {
+    } else if (MI && warp >= 1 && warp <= 3) {
+        // Three MMA issuers instead of one.  A single thread cannot issue tcgen05.mma faster than one per ~82 cycles
+        // (scripts/microbench/umma_rate.cu: 82 cycles per M128 N128 K16 and 84 per M128 N64 K16 from one warp, 64.5 / 48.4
+        // from two), so one issuer needs 2000 cycles per key-tile pair for the 8 S and 16 PV instructions and the
+        // softmax warps spend ~600 cycles per tile waiting for PV-done / S-ready behind it (scripts/attn_trace.py).
+        //   warp 1: every S = Q K^T, in sequence order, as soon as its TMEM buffer has been read out (s_free)
+        //   warp 2: O_A += P_A V   warp 3: O_B += P_B V, each as soon as its own P tile is ready
+        const uint32_t fmt = F16 ? 0u : 1u;
+        const int nq = has_b ? 2 : 1;
+        if (warp == 1) {
+            const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);
+            mbar_wait(q_full, 0, 12);
+            const int total = nq * ntiles;
+            for (int seq = 0; seq < total; ++seq) {
+                const int j = nq == 2 ? (seq >> 1) : seq, x = nq == 2 ? (seq & 1) : 0;
+                const int buf = seq % ATT_SBUF;
+                if (x == 0) mbar_wait(kv_full(j % KVS), (j / KVS) & 1, 11);            // K_j landed
+                if (seq >= ATT_SBUF) mbar_wait(s_free(buf), ((seq / ATT_SBUF) - 1) & 1, 18);       // S(seq-3) read out
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(sQ(x));
+                    const uint64_t bdesc = umma_desc_sw128(sK(j % KVS));
+#pragma unroll
+                    for (int k = 0; k < ATT_D / 16; ++k)
+                        umma_ss(tS(buf), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                    tc_commit(s_full(buf));
+                }
+                __syncwarp();
+            }
+        } else {
+            const int x = warp - 2;
+            if (x == 0 || has_b) {
+                const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);
+                for (int j = 0; j < ntiles; ++j) {
+                    const int s = j % KVS;
+                    mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, O_X rescaled
+                    mbar_wait(kv_full(s), (j / KVS) & 1, 19);           // V_j (landed long ago; orders the TMA writes for this thread)
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < ATT_N / 16; ++ks) {
+                            const uint64_t adesc = umma_desc_sw128(sP(x, j % NPB) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
+                            const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
+                            umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        tc_commit(pv_done(x, j % NPB));
+                        tc_commit(kv_empty(s));                               // count = number of query tiles
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (!MI && warp == 1) {
         {
             const uint32_t fmt = F16 ? 0u : 1u;
             const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (=K) is K-major
@@ -158,7 +233,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             // S tiles are numbered in issue order, seq = nq * j + x, and live in TMEM buffer seq % 3.  S(seq) may be
             // issued once K_j has landed and the softmax of S(seq - 3) has finished (its p_full was waited two PVs ago).
             auto issue_s = [&](int x, int j) {          // called by the elected lane
-                const int s = j % KV_STAGES;
+                const int s = j % KVS;
                 const int buf = (nq * j + x) % ATT_SBUF;
                 const uint64_t adesc = umma_desc_sw128(sQ(x));
                 const uint64_t bdesc = umma_desc_sw128(sK(s));
@@ -175,9 +250,9 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             }
             __syncwarp();
             for (int j = 0; j < ntiles; ++j) {
-                const int s = j % KV_STAGES;
+                const int s = j % KVS;
                 if (j + 1 < ntiles) {
-                    mbar_wait(kv_full((j + 1) % KV_STAGES), ((j + 1) / KV_STAGES) & 1, 11);
+                    mbar_wait(kv_full((j + 1) % KVS), ((j + 1) / KVS) & 1, 11);
                     tc_fence_after();
                 }
                 for (int x = 0; x < nq; ++x) {
@@ -187,16 +262,18 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                         if (elect_one()) issue_s(x, j + 1);
                         __syncwarp();
                     }
+                    ATT_STAMP(x * 2);
                     mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, S_X(j) consumed, O_X rescaled
                     tc_fence_after();
+                    ATT_STAMP(x * 2 + 1);
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < ATT_N / 16; ++ks) {
-                            const uint64_t adesc = umma_desc_sw128(sP(x) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
+                            const uint64_t adesc = umma_desc_sw128(sP(x, 0) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
                             const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
                             umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
                         }
-                        tc_commit(pv_done(x));
+                        tc_commit(pv_done(x, 0));
                         if (x == nq - 1) tc_commit(kv_empty(s));              // K_j / V_j fully consumed by both tiles
                     }
                     __syncwarp();
@@ -213,15 +290,17 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             const int nq = has_b ? 2 : 1;
             const uint32_t to = tO(x) + lane_off;
             float m_used = -INFINITY, l_run = 0.f;
-            uint8_t* pbuf = sP_generic + x * 2 * TILE_BYTES;
             for (int j = 0; j < ntiles; ++j) {
+                uint8_t* pbuf = sP_generic + (x * NPB + j % NPB) * 2 * TILE_BYTES;
                 int valid;
                 if (j < p.n_self) valid = min(ATT_N, p.Ls - j * ATT_N);
                 else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
                 const int seq = nq * j + x, sbuf = seq % ATT_SBUF;
                 const uint32_t ts = tS(sbuf) + lane_off;
+                ATT_STAMP(0);
                 mbar_wait(s_full(sbuf), (seq / ATT_SBUF) & 1, 15);
                 tc_fence_after();
+                ATT_STAMP(1);
                 // The TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is
                 // processed (tcgen05.wait::ld waits for everything outstanding, so it is placed after the compute).
                 // The whole tile body is instantiated twice (full tile / ragged last tile) so the common full-tile path
@@ -258,12 +337,13 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                     chunk_max(vb, 3, mx);
                     tmem_ld_wait(); tmem_regs_ready(va);
                     const float m_new = fmaxf(m_used, mx * p.scale_log2);
+                    ATT_STAMP(2);
                     // lazy rescale: only when some row of the warp moved its max by more than 2^TAU (warp-uniform
                     // branch, tcgen05.ld/st are warp-collective)
                     if (__any_sync(0xffffffffu, m_new > m_used + ATT_RESCALE_TAU)) {
                         const float alpha = ex2_approx(m_used - m_new);   // 0 on the first tile
                         if (j > 0) {
-                            mbar_wait(pv_done(x), (j - 1) & 1, 14);       // O_X holds tiles < j
+                            mbar_wait(pv_done(x, (j - 1) % NPB), ((j - 1) / NPB) & 1, 14);       // O_X holds tiles < j
                             tc_fence_after();
 #pragma unroll
                             for (int c = 0; c < 2; ++c) {
@@ -281,7 +361,9 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                     }
                     // pass 2: p = exp2(s*c - m_used) -> 16-bit -> swizzled K-major P tile.  The P buffer is still being
                     // read by the PV MMA of tile j-1 until pv_done (S no longer orders this: it is computed ahead).
-                    if (j > 0) mbar_wait(pv_done(x), (j - 1) & 1, 17);
+                    ATT_STAMP(3);
+                    if (j >= NPB) mbar_wait(pv_done(x, j % NPB), (j / NPB - 1) & 1, 17);   // PV(j - NPB) has read this P buffer
+                    ATT_STAMP(4);
                     const float sc = p.scale_log2, mu = m_used;
                     auto chunk_p = [&](const uint32_t (&v)[32], int c) {
                         float pf[32];
@@ -314,17 +396,22 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                     tmem_ld_32x32(ts + 96, vb);
                     chunk_p(va, 2);
                     tmem_ld_wait(); tmem_regs_ready(vb);
+                    if constexpr (MI) {                  // S_X(j) is now entirely in registers: hand the buffer back
+                        tc_fence_before();
+                        mbar_arrive(s_free(sbuf));
+                    }
                     chunk_p(vb, 3);
                 };
                 if (valid == ATT_N) run_tile(std::true_type{});
                 else run_tile(std::false_type{});
                 l_run += psum;
+                ATT_STAMP(5);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(p_full(x));
             }
             // epilogue: O_X / l
-            mbar_wait(pv_done(x), (ntiles - 1) & 1, 16);
+            mbar_wait(pv_done(x, (ntiles - 1) % NPB), ((ntiles - 1) / NPB) & 1, 16);
             tc_fence_after();
             const float inv = 1.0f / l_run;
             const bool row_ok = (qrow0 + row) < p.Lq;
@@ -804,6 +891,11 @@ __global__ void __launch_bounds__(256) cross_attn_collapsed_kernel(const float* 
 }  // namespace
 }  // namespace dfw
 
+#ifdef DFW_ATTN_TRACE
+namespace dfw { long long* g_attn_trace = nullptr; }
+extern "C" void dfw_attn_trace_buffer(void* p) { dfw::g_attn_trace = reinterpret_cast<long long*>(p); }
+#endif
+
 extern "C" {
 
 int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
@@ -847,10 +939,15 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     p.f16 = f16;
     p.o_batch_stride = o_batch_stride;
     p.o_row_stride = o_row_stride;
+#ifdef DFW_ATTN_TRACE
+    p.trace = g_attn_trace;
+#endif
     static bool attr_set = false;
     if (!attr_set) {
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MI));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MI));
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_SPLIT));
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_SPLIT));
         attr_set = true;
@@ -864,8 +961,17 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
         DFW_CHECK_CUDA(cudaGetLastError());
         return DFW_OK;
     }
-    if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true>, grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_), maps, p));
-    else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false>, grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream_), maps, p));
+    // single MMA-issuing warp (default) or the three-issuer / double-buffered-P schedule (DFW_ATTN_MI=1: correct, measured
+    // 7 % slower, see the kernel and DESIGN.md section 4)
+    static const bool multi_issue = [] { const char* e = getenv("DFW_ATTN_MI"); return e && e[0] == '1'; }();
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (multi_issue) {
+        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true, true>, grid, ATT_THREADS, ATT_SMEM_MI, st, maps, p));
+        else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false, true>, grid, ATT_THREADS, ATT_SMEM_MI, st, maps, p));
+    } else {
+        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true, false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
+        else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false, false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
+    }
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;

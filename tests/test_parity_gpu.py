@@ -469,15 +469,18 @@ def test_pipeline_small_width_other_sizes(small_models, size):
     assert min(agree) >= 0.98 and max(unet_err) <= UNET_RTOL and max(e2e_err) <= 3e-2
 
 
-def test_attention_split_rows_variant_in_subprocess():
-    """The kept-but-off split-row attention kernel (DFW_ATTN_SPLIT=1) against the torch fp32
-    reference on the bring-up shapes (ragged query / key tiles, bank of 0 / 1 / 2 supports, strided fused-QKV input).
-    The switch is read once per process, hence the child process."""
+@pytest.mark.parametrize("switch", ["DFW_ATTN_SPLIT", "DFW_ATTN_MI"])
+def test_attention_variants_in_subprocess(switch):
+    """The kept-but-off attention schedules (DESIGN.md section 4) — DFW_ATTN_SPLIT=1: eight softmax warps per query tile;
+    DFW_ATTN_MI=1: three MMA-issuing warps, two P buffers per tile, two K/V stages — against the torch fp32 reference on
+    the bring-up shapes (ragged query / key tiles, bank of 0 / 1 / 2 supports, strided fused-QKV input).  The switches
+    are read once per process, hence the child process."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DFW_ATTN_SPLIT="1", DFW_BRINGUP_CHILD="1")
+    env = dict(os.environ, DFW_BRINGUP_CHILD="1")
+    env[switch] = "1"
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_bringup.py"), "attn"], env=env,
                        capture_output=True, text=True, timeout=170)
     assert r.returncode == 0 and "CASE_OK attn" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
