@@ -381,6 +381,10 @@ class EpisodeLoader:
 
     def _indices(self):
         n = len(self.dataset)
+        # torch's DataLoader iterator first draws its `_base_seed` from the global torch RNG (both modes), then — on the
+        # first batch — RandomSampler draws the permutation seed: same consumption here, so a `torch.manual_seed(s)` run
+        # visits the reference's indices
+        torch.empty((), dtype=torch.int64).random_()
         if not self.shuffle:
             return list(range(n))
         seed = int(torch.empty((), dtype=torch.int64).random_().item())         # torch RandomSampler.__iter__

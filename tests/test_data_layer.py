@@ -361,3 +361,26 @@ def test_gpu_evaluator_matches_unmodified_reference_evaluator(lib_built):
         assert inter.dtype == torch.float32 and tuple(inter.shape) == (2, c["B"])
         assert inter.cpu().tolist() == g["area_inter"], g["kind"]
         assert union.cpu().tolist() == g["area_union"], g["kind"]
+
+
+def test_training_shuffle_draws_like_torch_random_sampler(tree):
+    """split == 'trn' -> DataLoader(shuffle=True) (dataset.py:46-48).  torch's RandomSampler draws a seed from the global
+    torch RNG and permutes with a private generator; EpisodeLoader._indices must consume the global RNG identically so a
+    seeded training run visits the same indices as the reference's loader."""
+    from torch.utils.data import DataLoader, Dataset
+    from diffews_b200.data import EpisodeLoader
+
+    class Idx(Dataset):
+        def __len__(self):
+            return 30
+
+        def __getitem__(self, i):
+            return i
+
+    ds = _dataset(tree, "fss_shot2")                      # 30 items
+    for seed in (0, 7):
+        torch.manual_seed(seed)
+        ref = [int(b) for b in DataLoader(Idx(), batch_size=1, shuffle=True, num_workers=0)]
+        torch.manual_seed(seed)
+        got = EpisodeLoader(ds, bsz=4, shuffle=True, device="cpu", decode_threads=1)._indices()
+        assert got == ref and sorted(got) == list(range(30))
