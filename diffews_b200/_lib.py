@@ -59,6 +59,10 @@ SIGNATURES = {
     "dfw_preproc_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "dfw_resize_normalize_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _ll, _vp]),
     "dfw_mask_nearest": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "dfw_grad_norm_clip_coef": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "dfw_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _f, _i, _vp, _i, _vp]),
+    "dfw_mse_workspace_floats": (_ll, []),
+    "dfw_mse_loss": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
 }
 
 

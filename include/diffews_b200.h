@@ -289,6 +289,40 @@ int dfw_resize_normalize_u8(const void* base, const void* descs, int n, int max_
 int dfw_mask_nearest(const void* base, const void* descs, int n, float* mask_out, float* boundary_out, int out_h,
                      int out_w, int mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K10  Training-step tail (first pieces): MSE loss, global gradient-norm clipping, fused AdamW.
+ * ref: train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1384 (F.mse_loss(pred.float(), target.float())),
+ *      :1393 (clip_grad_norm_), :1186-1194 + :1394 (torch.optim.AdamW(...).step()).
+ * One launch covers every parameter tensor: `tensors` is a DEVICE array of DfwAdamTensor; the work is cut into chunks of
+ * `chunk_elems` (% 4 == 0) elements, chunk c = elements [chunk_offset[c], +chunk_elems) of tensor chunk_tensor[c]
+ * (both DEVICE arrays of n_chunks entries).  fp32 parameters / gradients / moments.  Deterministic (no fp atomics).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct DfwAdamTensor {
+    void* param;        /* fp32 [numel], updated in place                                    */
+    const void* grad;   /* fp32 [numel]                                                      */
+    void* exp_avg;      /* fp32 [numel]                                                      */
+    void* exp_avg_sq;   /* fp32 [numel]                                                      */
+    void* param16;      /* NULL or 16-bit [numel]: receives the rounded updated parameter    */
+    long long numel;
+} DfwAdamTensor;
+
+/* norm_out[0] = sqrt(sum of all grad^2); coef_out[0] = min(1, max_norm / (norm + 1e-6)) (torch clip_grad_norm_, L2);
+ * partial: n_chunks floats of scratch.  The gradients are NOT modified: pass coef_out as dfw_adamw_step's grad_scale. */
+int dfw_grad_norm_clip_coef(const void* tensors, const int* chunk_tensor, const long long* chunk_offset, int n_chunks,
+                            int chunk_elems, float max_norm, float* partial, float* norm_out, float* coef_out,
+                            void* stream);
+/* torch.optim.AdamW single-tensor arithmetic: p *= 1 - lr*wd; m += (1-b1)(g-m); v = v*b2 + (1-b2) g*g;
+ * p += -(lr/(1-b1^step)) * m / (sqrt(v)/sqrt(1-b2^step) + eps), with g = grad * grad_scale[0] (device scalar, NULL = 1).
+ * p16_format 0: no 16-bit copy; 1: bf16; 2: fp16 into DfwAdamTensor.param16.  step counts from 1. */
+int dfw_adamw_step(const void* tensors, const int* chunk_tensor, const long long* chunk_offset, int n_chunks,
+                   int chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   const float* grad_scale, int p16_format, void* stream);
+/* loss_out[0] = mean((pred - target)^2); dpred (NULL ok) = upstream * 2 (pred - target) / n.
+ * workspace: dfw_mse_workspace_floats() floats. */
+long long dfw_mse_workspace_floats(void);
+int dfw_mse_loss(const float* pred, const float* target, long long n, float upstream, float* loss_out, float* dpred,
+                 float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

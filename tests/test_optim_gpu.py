@@ -1,0 +1,85 @@
+"""GPU parity of the training-step tail (first pieces) against torch's own CPU implementation of the
+calls the reference makes (train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1384, :1393, :1186-1194 + :1394):
+F.mse_loss, torch.nn.utils.clip_grad_norm_, torch.optim.AdamW.  Floating point: the tolerance is 2e-6 relative on the
+parameters after several steps (same formula, fp32, different summation / FMA contraction)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(320, 320, 3, 3), (1280,), (5, 7), (1,), (640, 2560), (65536 * 2 + 3,)]
+
+
+def _params(seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(s, generator=g) * 0.05 for s in SHAPES]
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("max_norm", [None, 0.5, 1e6])
+def test_adamw_and_clip_match_torch(lib_built, max_norm):
+    from diffews_b200.optim import AdamW
+    ref_p = [torch.nn.Parameter(p.clone()) for p in _params(0)]
+    dev_p = [p.detach().clone().cuda() for p in ref_p]
+    half = [torch.empty(p.numel(), dtype=torch.float16, device="cuda") for p in dev_p]
+    kw = dict(lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    ref_opt = torch.optim.AdamW(ref_p, foreach=False, **kw)
+    opt = AdamW(dev_p, half_copies=half, **kw)
+    for it in range(4):
+        grads = [g * (3.0 if it == 1 else 1.0) for g in _params(100 + it)]
+        for p, g in zip(ref_p, grads):
+            p.grad = g.clone()
+        for p, g in zip(dev_p, grads):
+            p.grad = g.clone().cuda()
+        if max_norm is not None:
+            n_ref = torch.nn.utils.clip_grad_norm_(ref_p, max_norm)
+            n_dev = opt.clip_grad_norm_(max_norm)
+            assert rel(n_dev.cpu(), n_ref.reshape(1)) < 1e-6
+        ref_opt.step()
+        opt.step()
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(dev_p, ref_p)):
+        assert rel(a.cpu(), b.detach()) < 2e-6, (i, rel(a.cpu(), b.detach()))
+        st = ref_opt.state[b]
+        assert rel(opt.state[i]["exp_avg"].cpu(), st["exp_avg"]) < 2e-6
+        assert rel(opt.state[i]["exp_avg_sq"].cpu(), st["exp_avg_sq"]) < 2e-6
+        assert torch.equal(half[i].cpu(), a.cpu().reshape(-1).half())          # the fused 16-bit copy is exactly the rounding
+    # the gradients were not modified by the clip (the coefficient is applied inside the step)
+    assert torch.equal(dev_p[0].grad.cpu(), _params(103)[0])
+
+
+def test_adamw_is_deterministic(lib_built):
+    from diffews_b200.optim import AdamW
+    outs = []
+    for _ in range(2):
+        ps = [p.cuda() for p in _params(1)]
+        opt = AdamW(ps, lr=1e-3)
+        for it in range(2):
+            for p, g in zip(ps, _params(50 + it)):
+                p.grad = g.cuda()
+            n = opt.clip_grad_norm_(1.0)
+            opt.step()
+        outs.append([p.cpu().clone() for p in ps] + [n.cpu().clone()])
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 64, 64), (7, 4, 96, 96), (3,), (2, 4, 17, 5)])
+def test_mse_loss_matches_torch(lib_built, shape):
+    from diffews_b200.optim import mse_loss
+    g = torch.Generator().manual_seed(3)
+    pred = torch.randn(shape, generator=g).requires_grad_(True)
+    target = torch.randn(shape, generator=g)
+    ref = torch.nn.functional.mse_loss(pred.float(), target.float(), reduction="mean")
+    ref.backward()
+    loss, dpred = mse_loss(pred.detach().cuda(), target.cuda())
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert rel(dpred.cpu(), pred.grad) < 1e-6
+
+
+def test_optimizer_refuses_cpu_parameters():
+    from diffews_b200.optim import AdamW
+    with pytest.raises(TypeError):
+        AdamW([torch.zeros(4)])
