@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libdiffews_b200.so")
 DFW_OK, DFW_ERR_INVALID, DFW_ERR_CUDA, DFW_ERR_ARCH = 0, -1, -2, -3
 EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU, EPI_F16 = 1, 2, 4, 8, 16
 
-_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_vp, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> (restype, argtypes): mirrors include/diffews_b200.h one to one (tests/test_abi.py checks the header).
 SIGNATURES = {
@@ -60,7 +60,7 @@ SIGNATURES = {
     "dfw_resize_normalize_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _ll, _vp]),
     "dfw_mask_nearest": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "dfw_grad_norm_clip_coef": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
-    "dfw_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _f, _i, _vp, _i, _vp]),
+    "dfw_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _d, _i, _vp, _i, _vp]),
     "dfw_mse_workspace_floats": (_ll, []),
     "dfw_mse_loss": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
 }

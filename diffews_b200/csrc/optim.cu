@@ -209,25 +209,26 @@ int dfw_grad_norm_clip_coef(const void* tensors, const int* chunk_tensor, const 
 }
 
 int dfw_adamw_step(const void* tensors, const int* chunk_tensor, const long long* chunk_offset, int n_chunks,
-                   int chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   int chunk_elems, double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                    const float* grad_scale, int p16_format, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(tensors && chunk_tensor && chunk_offset && n_chunks > 0 && chunk_elems > 0 && chunk_elems % 4 == 0);
-    DFW_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f);
+    DFW_REQUIRE(step >= 1 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0);
     DFW_REQUIRE(p16_format >= 0 && p16_format <= 2);
     // the scalars torch computes in Python doubles (torch/optim/adamw.py _single_tensor_adamw), then rounds to fp32
     AdamScalars sc;
-    sc.decay = static_cast<float>(1.0 - static_cast<double>(lr) * static_cast<double>(weight_decay));
-    sc.w1 = static_cast<float>(1.0 - static_cast<double>(beta1));
-    sc.beta2 = beta2;
-    sc.w2 = static_cast<float>(1.0 - static_cast<double>(beta2));
-    const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
-    const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
+    // (hyper-parameters arrive as doubles: torch keeps them as Python floats, and 1 - float(0.999) is 1.3e-5 off 0.001)
+    sc.decay = static_cast<float>(1.0 - lr * weight_decay);
+    sc.w1 = static_cast<float>(1.0 - beta1);
+    sc.beta2 = static_cast<float>(beta2);
+    sc.w2 = static_cast<float>(1.0 - beta2);
+    const double bc1 = 1.0 - std::pow(beta1, step);
+    const double bc2 = 1.0 - std::pow(beta2, step);
     sc.bc2_sqrt = static_cast<float>(std::sqrt(bc2));
-    sc.neg_step = static_cast<float>(-(static_cast<double>(lr) / bc1));
-    sc.eps = eps;
+    sc.neg_step = static_cast<float>(-(lr / bc1));
+    sc.eps = static_cast<float>(eps);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const AdamTensor* ts = reinterpret_cast<const AdamTensor*>(tensors);
     if (p16_format == 0) adamw_chunks_kernel<0><<<n_chunks, OPT_THREADS, 0, st>>>(ts, chunk_tensor, chunk_offset, chunk_elems, sc, grad_scale);

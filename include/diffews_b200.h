@@ -313,9 +313,10 @@ int dfw_grad_norm_clip_coef(const void* tensors, const int* chunk_tensor, const 
                             void* stream);
 /* torch.optim.AdamW single-tensor arithmetic: p *= 1 - lr*wd; m += (1-b1)(g-m); v = v*b2 + (1-b2) g*g;
  * p += -(lr/(1-b1^step)) * m / (sqrt(v)/sqrt(1-b2^step) + eps), with g = grad * grad_scale[0] (device scalar, NULL = 1).
- * p16_format 0: no 16-bit copy; 1: bf16; 2: fp16 into DfwAdamTensor.param16.  step counts from 1. */
+ * p16_format 0: no 16-bit copy; 1: bf16; 2: fp16 into DfwAdamTensor.param16.  step counts from 1.  The hyper-parameters
+ * are doubles because torch derives 1-beta, 1-lr*wd and the bias corrections from Python floats before rounding to fp32. */
 int dfw_adamw_step(const void* tensors, const int* chunk_tensor, const long long* chunk_offset, int n_chunks,
-                   int chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   int chunk_elems, double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                    const float* grad_scale, int p16_format, void* stream);
 /* loss_out[0] = mean((pred - target)^2); dpred (NULL ok) = upstream * 2 (pred - target) / n.
  * workspace: dfw_mse_workspace_floats() floats. */
