@@ -44,6 +44,8 @@ SIGNATURES = {
     "dfw_groupnorm_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "dfw_groupnorm_silu": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "dfw_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "dfw_layernorm_bwd_workspace_bytes": (_ll, [_i, _i]),
+    "dfw_layernorm_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "dfw_softmax_rows": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
     "dfw_upsample2x_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),

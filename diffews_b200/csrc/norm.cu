@@ -520,6 +520,125 @@ static bool launch_layernorm_v4(const void* x, const float* gamma, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// LayerNorm backward (training shapes).  Statistics are recomputed from x (nothing is saved by the
+// forward).  Warp per row, the row's x and dy held in registers:
+//     xh = (x - mean) * rstd ;  a = mean_c(dy * gamma) ;  b = mean_c(dy * gamma * xh)
+//     dx = rstd * (dy * gamma - a - xh * b)
+// dgamma = sum_rows dy * xh and dbeta = sum_rows dy: every warp accumulates its rows into its own [2, C] slice of
+// shared memory (owner-only read-modify-write, no atomics), the CTA folds its 8 slices in warp order into
+// partial[cta][2][C], and a second kernel folds the CTAs in index order -- deterministic.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LNB_WARPS = 8;
+template <int XD>
+__device__ __forceinline__ void ln_store4(void* y, long long off, float4 v) {
+    if constexpr (XD == 1) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + off) = v;
+    } else {
+        uint2 o;
+        o.x = pack_h2(v.x, v.y, XD == 2);
+        o.y = pack_h2(v.z, v.w, XD == 2);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + off) = o;
+    }
+}
+template <int XD, int NV>
+__global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy,
+                                                                       const float* __restrict__ gamma, void* __restrict__ dx,
+                                                                       float* __restrict__ partial, int M, int C, float eps) {
+    extern __shared__ float lnb_sm[];                       // [LNB_WARPS][2][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int V = C / 4;
+    float* my = lnb_sm + static_cast<size_t>(warp) * 2 * C;
+    for (int c = lane; c < 2 * C; c += 32) my[c] = 0.f;
+    __syncwarp();
+    float4 g[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int vc = lane + 32 * k;
+        g[k] = vc < V ? __ldg(reinterpret_cast<const float4*>(gamma) + vc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float invC = 1.0f / C;
+    for (int row = blockIdx.x * LNB_WARPS + warp; row < M; row += gridDim.x * LNB_WARPS) {
+        const long long row_off = static_cast<long long>(row) * C;
+        float4 v[NV], d[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int vc = lane + 32 * k;
+            const bool ok = vc < V;
+            v[k] = ok ? ln_load4<XD>(x, row_off + vc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d[k] = ok ? ln_load4<XD>(dy, row_off + vc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * invC;
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (lane + 32 * k < V) {
+                v[k].x -= mean; v[k].y -= mean; v[k].z -= mean; v[k].w -= mean;
+                ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss);
+                ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rstd = rsqrtf(ss * invC + eps);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int vc = lane + 32 * k;
+            if (vc < V) {
+                v[k].x *= rstd; v[k].y *= rstd; v[k].z *= rstd; v[k].w *= rstd;          // xh
+                float* dg = my + vc * 4;
+                float* db = my + C + vc * 4;
+                dg[0] += d[k].x * v[k].x; dg[1] += d[k].y * v[k].y; dg[2] += d[k].z * v[k].z; dg[3] += d[k].w * v[k].w;
+                db[0] += d[k].x; db[1] += d[k].y; db[2] += d[k].z; db[3] += d[k].w;
+                d[k].x *= g[k].x; d[k].y *= g[k].y; d[k].z *= g[k].z; d[k].w *= g[k].w;  // dy * gamma
+                a += (d[k].x + d[k].y) + (d[k].z + d[k].w);
+                b += (d[k].x * v[k].x + d[k].y * v[k].y) + (d[k].z * v[k].z + d[k].w * v[k].w);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        a *= invC; b *= invC;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int vc = lane + 32 * k;
+            if (vc < V) {
+                float4 o4;
+                o4.x = rstd * (d[k].x - a - v[k].x * b); o4.y = rstd * (d[k].y - a - v[k].y * b);
+                o4.z = rstd * (d[k].z - a - v[k].z * b); o4.w = rstd * (d[k].w - a - v[k].w * b);
+                ln_store4<XD>(dx, row_off + vc * 4, o4);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += LNB_WARPS * 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < LNB_WARPS; ++w) acc += lnb_sm[static_cast<size_t>(w) * 2 * C + c];
+        partial[static_cast<size_t>(blockIdx.x) * 2 * C + c] = acc;
+    }
+}
+__global__ void layernorm_bwd_fold_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 2 * C) return;
+    float acc = 0.f;
+    for (int b = 0; b < nblocks; ++b) acc += partial[static_cast<size_t>(b) * 2 * C + c];
+    if (c < C) dgamma[c] = acc;
+    else dbeta[c - C] = acc;
+}
+inline int lnb_blocks(int M) {
+    const int want = (M + LNB_WARPS - 1) / LNB_WARPS, cap = 2 * sm_count();
+    return want < cap ? want : cap;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Row softmax (fp32 logits -> bf16 probabilities), one CTA per row.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ s, uint16_t* __restrict__ p, int L, float scale,
@@ -731,6 +850,47 @@ int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* b
     else
         layernorm_kernel<0><<<blocks, warps_per_block * 32, 0, stream>>>(x, gamma, beta, y, M, C, eps, y_f16);
     g_launches.fetch_add(1);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+long long dfw_layernorm_bwd_workspace_bytes(int M, int C) {
+    if (M <= 0 || C <= 0) return -1;
+    return static_cast<long long>(dfw::lnb_blocks(M)) * 2 * C * sizeof(float);
+}
+
+int dfw_layernorm_bwd(const void* x, const void* dy, int dtype, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                      int M, int C, float eps, void* workspace, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && workspace && M > 0 && C > 0 && C % 8 == 0 && C <= 1280);
+    DFW_REQUIRE(dtype >= 0 && dtype <= 2);
+    DFW_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const int blocks = lnb_blocks(M);
+    const size_t smem = static_cast<size_t>(LNB_WARPS) * 2 * C * sizeof(float);
+    float* partial = reinterpret_cast<float*>(workspace);
+    const int nv = (C / 4 + 31) / 32;
+#define DFW_LNB_LAUNCH(XD, NV)                                                                                      \
+    do {                                                                                                            \
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<XD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            static_cast<int>(smem)));                                              \
+        layernorm_bwd_kernel<XD, NV><<<blocks, LNB_WARPS * 32, smem, st>>>(x, dy, gamma, dx, partial, M, C, eps);      \
+    } while (0)
+#define DFW_LNB_DTYPE(NV)                                  \
+    do {                                                   \
+        if (dtype == 1) DFW_LNB_LAUNCH(1, NV);             \
+        else if (dtype == 2) DFW_LNB_LAUNCH(2, NV);        \
+        else DFW_LNB_LAUNCH(0, NV);                        \
+    } while (0)
+    if (nv <= 3) DFW_LNB_DTYPE(3);
+    else if (nv <= 5) DFW_LNB_DTYPE(5);
+    else DFW_LNB_DTYPE(10);
+#undef DFW_LNB_DTYPE
+#undef DFW_LNB_LAUNCH
+    layernorm_bwd_fold_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partial, blocks, C, dgamma, dbeta);
+    g_launches.fetch_add(2);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }

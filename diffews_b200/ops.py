@@ -413,6 +413,21 @@ def layernorm(x, gamma, beta, eps=1e-5, out_dtype=bf16):
     return y
 
 
+def layernorm_backward(x, dy, gamma, eps=1e-5):
+    """Backward of `layernorm` (statistics recomputed from x).  x, dy [.., C] of one dtype (bf16 / fp16 / fp32);
+    returns (dx like x, dgamma fp32 [C], dbeta fp32 [C])."""
+    assert x.is_cuda and x.is_contiguous() and dy.is_contiguous() and x.dtype == dy.dtype and x.shape == dy.shape
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32)
+    db = torch.empty(C, device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(lib.dfw_layernorm_bwd_workspace_bytes(M, C)), device=x.device, dtype=torch.uint8)
+    check(lib.dfw_layernorm_bwd(x.data_ptr(), dy.data_ptr(), _xd(x), gamma.data_ptr(), dx.data_ptr(), dg.data_ptr(),
+                                db.data_ptr(), M, C, float(eps), ws.data_ptr(), _stream()), "dfw_layernorm_bwd")
+    return dx, dg, db
+
+
 def softmax_rows(s, scale, out_dtype=bf16):
     _req(s, torch.float32, "s")
     L = s.shape[-1]

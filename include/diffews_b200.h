@@ -190,6 +190,12 @@ int dfw_conv2d_igemm_gnin(const void* x, const float* gn_scale_shift, const void
 /* K7  LayerNorm over the last dim. x [M, C] (x_dtype 0 bf16 / 1 fp32 / 2 fp16) -> y bf16 (fp16 if y_f16) [M, C].
  * C % 8 == 0, C <= 2048.
  * ref: BasicTransformerBlock.norm1/2/3 (upstream). */
+/* LayerNorm backward (statistics recomputed from x): x, dy, dx [M, C] of one dtype (0 bf16 / 1 fp32 / 2 fp16);
+ * dgamma, dbeta fp32 [C]; C % 8 == 0, C <= 1280; workspace: dfw_layernorm_bwd_workspace_bytes(M, C).  Deterministic.
+ * ref: autograd of BasicTransformerBlock.norm1/2/3 in the training step (train...v3.py:1386 accelerator.backward). */
+long long dfw_layernorm_bwd_workspace_bytes(int M, int C);
+int dfw_layernorm_bwd(const void* x, const void* dy, int dtype, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                      int M, int C, float eps, void* workspace, void* stream);
 int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_f16, int M, int C,
                   float eps, void* stream);
 

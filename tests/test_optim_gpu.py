@@ -95,3 +95,26 @@ def test_optimizer_refuses_cpu_parameters():
     from diffews_b200.optim import AdamW
     with pytest.raises(TypeError):
         AdamW([torch.zeros(4)])
+
+
+@pytest.mark.parametrize("M,C,dt", [(4096, 320, torch.float16), (1024, 640, torch.float32), (77, 1280, torch.float16),
+                                    (3, 320, torch.bfloat16), (5000, 1280, torch.float32)])
+def test_layernorm_backward_matches_autograd(lib_built, M, C, dt):
+    """Backward of BasicTransformerBlock's LayerNorms (eps 1e-5) against torch autograd in fp32 on the same (rounded)
+    inputs; run twice: bit-identical (fixed reduction order)."""
+    from diffews_b200 import ops
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 1.7 + 0.3).to(dt)
+    dy = torch.randn(M, C, generator=g).to(dt)
+    gamma = torch.randn(C, generator=g) * 0.5 + 1.0
+    beta = torch.randn(C, generator=g) * 0.1
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5).backward(dy.float())
+    outs = [ops.layernorm_backward(x.cuda(), dy.cuda(), gamma.cuda(), 1e-5) for _ in range(2)]
+    torch.cuda.synchronize()
+    dx, dg, db = outs[0]
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+    tol = 1e-5 if dt == torch.float32 else (6e-3 if dt == torch.bfloat16 else 8e-4)
+    assert dx.dtype == dt and rel(dx.cpu(), xr.grad) < tol, rel(dx.cpu(), xr.grad)
+    assert rel(dg.cpu(), gr.grad) < 2e-5 and rel(db.cpu(), br.grad) < 2e-5
