@@ -51,7 +51,16 @@ def main():
     # torch's own fused optimizer beside it (library baseline, same tensors)
     ref = torch.optim.AdamW(ps, lr=1e-5, fused=True)
     ms_torch = timed(ref.step)
-    print(json.dumps({"what": "fused multi-tensor AdamW (+fp16 operand copy) and gradient-norm clip", "tensors": len(ps),
+    # LayerNorm backward at the config-2/4 token counts (16 x 4096 tokens of 320 channels; 16 x 256 of 1280), fp16
+    from diffews_b200 import ops
+    ln = {}
+    for M, C in ((65536, 320), (16384, 640), (4096, 1280)):
+        x = torch.randn(M, C, device="cuda").half(); dy = torch.randn(M, C, device="cuda").half()
+        gam = torch.ones(C, device="cuda")
+        ms = timed(lambda: ops.layernorm_backward(x, dy, gam, 1e-5), reps=20)
+        ln[f"M{M}_C{C}"] = {"ms": round(ms, 4), "gb_per_s": round(M * C * 6 / ms / 1e6, 1)}
+    print(json.dumps({"layernorm_bwd_fp16 (6 B / element: x, dy read, dx written)": ln,
+                      "what": "fused multi-tensor AdamW (+fp16 operand copy) and gradient-norm clip", "tensors": len(ps),
                       "parameters": n, "working_set_gb": round(n * 18 / 1e9, 2), "launches": {"clip": 2, "step": 1},
                       "ms_clip": round(ms_clip, 3), "ms_step": round(ms_step, 3),
                       "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "clip_achieved": round(gbs_clip, 1),
