@@ -63,6 +63,7 @@ SIGNATURES = {
     "dfw_mask_nearest": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "dfw_grad_norm_clip_coef": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "dfw_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _d, _i, _vp, _i, _vp]),
+    "dfw_geglu_bwd": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),
     "dfw_mse_workspace_floats": (_ll, []),
     "dfw_mse_loss": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
 }

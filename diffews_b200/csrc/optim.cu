@@ -186,6 +186,63 @@ __global__ void __launch_bounds__(OPT_THREADS) mse_final_kernel(const float* __r
 
 constexpr int MSE_BLOCKS = 592;     // 4 x 148 SMs
 
+// GEGLU backward (diffusers GEGLU: v, g = proj(x).chunk(2, -1); y = v * gelu_erf(g)):
+//   dv = dy * gelu(g) ;  dg = dy * v * (Phi(g) + g * phi(g)),  Phi = 0.5 (1 + erf(g / sqrt 2)), phi = exp(-g^2 / 2) / sqrt(2 pi)
+// h [M, 2F] (value | gate), dy [M, F], dh [M, 2F], one dtype (0 bf16 / 1 fp32 / 2 fp16).  Thread = 4 consecutive columns.
+template <int XD>
+__device__ __forceinline__ float4 load4(const void* x, long long off) {
+    if constexpr (XD == 1) {
+        return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + off));
+    } else {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + off));
+        if constexpr (XD == 2) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+            return make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+            return make_float4(a.x, a.y, b.x, b.y);
+        }
+    }
+}
+template <int XD>
+__device__ __forceinline__ void store4(void* y, long long off, float4 v) {
+    if constexpr (XD == 1) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + off) = v;
+    } else if constexpr (XD == 2) {
+        uint2 o;
+        *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(v.x, v.y);
+        *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + off) = o;
+    } else {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + off) = o;
+    }
+}
+template <int XD>
+__global__ void __launch_bounds__(OPT_THREADS) geglu_bwd_kernel(const void* __restrict__ h, const void* __restrict__ dy,
+                                                                void* __restrict__ dh, long long M, int F) {
+    const int F4 = F / 4;
+    const long long total = M * F4;
+    for (long long i = static_cast<long long>(blockIdx.x) * OPT_THREADS + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * OPT_THREADS) {
+        const long long row = i / F4;
+        const int c = static_cast<int>(i - row * F4) * 4;
+        const float4 v = load4<XD>(h, row * 2 * F + c), g = load4<XD>(h, row * 2 * F + F + c), d = load4<XD>(dy, row * F + c);
+        auto one = [](float vv, float gg, float dd, float& dv, float& dg) {
+            const float cdf = 0.5f * (1.0f + erff(gg * 0.70710678118654752f));
+            const float pdf = 0.39894228040143268f * expf(-0.5f * gg * gg);
+            dv = dd * (gg * cdf);
+            dg = dd * vv * (cdf + gg * pdf);
+        };
+        float4 dv, dg;
+        one(v.x, g.x, d.x, dv.x, dg.x); one(v.y, g.y, d.y, dv.y, dg.y); one(v.z, g.z, d.z, dv.z, dg.z); one(v.w, g.w, d.w, dv.w, dg.w);
+        store4<XD>(dh, row * 2 * F + c, dv);
+        store4<XD>(dh, row * 2 * F + F + c, dg);
+    }
+}
+
 }  // namespace
 }  // namespace dfw
 
@@ -254,6 +311,25 @@ int dfw_mse_loss(const float* pred, const float* target, long long n, float upst
     mse_partial_kernel<<<blocks, OPT_THREADS, 0, st>>>(pred, target, n, upstream * 2.0f * inv_n, dpred, workspace);
     mse_final_kernel<<<1, OPT_THREADS, 0, st>>>(workspace, blocks, inv_n, loss_out);
     g_launches.fetch_add(2);
+    DFW_CHECK_CUDA(cudaGetLastError());
+    return DFW_OK;
+}
+
+int dfw_geglu_bwd(const void* h, const void* dy, void* dh, int dtype, long long M, int F, void* stream_) {
+    using namespace dfw;
+    int rc = require_sm100();
+    if (rc != DFW_OK) return rc;
+    DFW_REQUIRE(h && dy && dh && M > 0 && F > 0 && F % 8 == 0 && dtype >= 0 && dtype <= 2);
+    DFW_REQUIRE(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const long long total = M * (F / 4);
+    long long want = (total + OPT_THREADS - 1) / OPT_THREADS;
+    const long long cap = 16LL * sm_count();
+    const int blocks = static_cast<int>(want < cap ? want : cap);
+    if (dtype == 1) geglu_bwd_kernel<1><<<blocks, OPT_THREADS, 0, st>>>(h, dy, dh, M, F);
+    else if (dtype == 2) geglu_bwd_kernel<2><<<blocks, OPT_THREADS, 0, st>>>(h, dy, dh, M, F);
+    else geglu_bwd_kernel<0><<<blocks, OPT_THREADS, 0, st>>>(h, dy, dh, M, F);
+    g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
 }

@@ -428,6 +428,17 @@ def layernorm_backward(x, dy, gamma, eps=1e-5):
     return dx, dg, db
 
 
+def geglu_backward(h, dy):
+    """Backward of diffusers GEGLU's activation: h [.., 2F] = (value | gate) pre-activations, dy [.., F] -> dh like h."""
+    assert h.is_cuda and h.is_contiguous() and dy.is_contiguous() and h.dtype == dy.dtype
+    F = dy.shape[-1]
+    assert h.shape[-1] == 2 * F and h.shape[:-1] == dy.shape[:-1]
+    dh = torch.empty_like(h)
+    check(lib.dfw_geglu_bwd(h.data_ptr(), dy.data_ptr(), dh.data_ptr(), _xd(h), dy.numel() // F, F, _stream()),
+          "dfw_geglu_bwd")
+    return dh
+
+
 def softmax_rows(s, scale, out_dtype=bf16):
     _req(s, torch.float32, "s")
     L = s.shape[-1]

@@ -326,6 +326,10 @@ int dfw_adamw_step(const void* tensors, const int* chunk_tensor, const long long
                    const float* grad_scale, int p16_format, void* stream);
 /* loss_out[0] = mean((pred - target)^2); dpred (NULL ok) = upstream * 2 (pred - target) / n.
  * workspace: dfw_mse_workspace_floats() floats. */
+/* GEGLU backward (diffusers GEGLU: v, g = proj(x).chunk(2, -1); y = v * gelu_erf(g); FeedForward of BasicTransformerBlock,
+ * upstream): h [M, 2F] = (value | gate) pre-activations, dy [M, F] -> dh [M, 2F]; one dtype (0 bf16 / 1 fp32 / 2 fp16),
+ * F % 8 == 0. */
+int dfw_geglu_bwd(const void* h, const void* dy, void* dh, int dtype, long long M, int F, void* stream);
 long long dfw_mse_workspace_floats(void);
 int dfw_mse_loss(const float* pred, const float* target, long long n, float upstream, float* loss_out, float* dpred,
                  float* workspace, void* stream);

@@ -118,3 +118,18 @@ def test_layernorm_backward_matches_autograd(lib_built, M, C, dt):
     tol = 1e-5 if dt == torch.float32 else (6e-3 if dt == torch.bfloat16 else 8e-4)
     assert dx.dtype == dt and rel(dx.cpu(), xr.grad) < tol, rel(dx.cpu(), xr.grad)
     assert rel(dg.cpu(), gr.grad) < 2e-5 and rel(db.cpu(), br.grad) < 2e-5
+
+
+@pytest.mark.parametrize("M,F,dt", [(4096, 1280, torch.float16), (257, 2560, torch.float32), (64, 5120, torch.bfloat16)])
+def test_geglu_backward_matches_autograd(lib_built, M, F, dt):
+    """diffusers GEGLU (FeedForward of BasicTransformerBlock): y = v * gelu_erf(g) with (v | g) = h.chunk(2, -1)."""
+    from diffews_b200 import ops
+    g = torch.Generator().manual_seed(F)
+    h = (torch.randn(M, 2 * F, generator=g) * 1.5).to(dt)
+    dy = torch.randn(M, F, generator=g).to(dt)
+    hr = h.float().requires_grad_(True)
+    v, gate = hr.chunk(2, dim=-1)
+    (v * torch.nn.functional.gelu(gate)).backward(dy.float())
+    dh = ops.geglu_backward(h.cuda(), dy.cuda())
+    tol = 1e-5 if dt == torch.float32 else (6e-3 if dt == torch.bfloat16 else 8e-4)
+    assert dh.dtype == dt and rel(dh.cpu(), hr.grad) < tol, rel(dh.cpu(), hr.grad)
