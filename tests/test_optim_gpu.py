@@ -133,3 +133,36 @@ def test_geglu_backward_matches_autograd(lib_built, M, F, dt):
     dh = ops.geglu_backward(h.cuda(), dy.cuda())
     tol = 1e-5 if dt == torch.float32 else (6e-3 if dt == torch.bfloat16 else 8e-4)
     assert dh.dtype == dt and rel(dh.cpu(), hr.grad) < tol, rel(dh.cpu(), hr.grad)
+
+
+def test_linear_backward_matches_autograd(lib_built):
+    """dx / dW / dbias of an nn.Linear on the tcgen05 GEMM (first correct path, diffews_b200/backward.py)."""
+    from diffews_b200.backward import linear_backward
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 200, 320, 640                                  # M not a multiple of 64: rows are zero-padded
+    x = torch.randn(M, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).half()
+    dy = torch.randn(M, N, generator=g).half()
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    b = torch.zeros(N, requires_grad=True)
+    torch.nn.functional.linear(xr, wr, b).backward(dy.float())
+    dx, dw, db = linear_backward(x.cuda(), w.cuda(), dy.cuda())
+    assert rel(dx.cpu(), xr.grad) < 2e-3 and rel(dw.cpu(), wr.grad) < 1e-4 and rel(db.cpu(), b.grad) < 1e-5
+
+
+def test_conv3x3_backward_matches_autograd(lib_built):
+    from diffews_b200.backward import conv3x3_backward
+    from diffews_b200.weights import conv_weight_to_gemm
+    g = torch.Generator().manual_seed(12)
+    N, H, Ci, Co = 2, 16, 64, 128
+    x = torch.randn(N, Ci, H, H, generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * (9 * Ci) ** -0.5).half()
+    dy = torch.randn(N, Co, H, H, generator=g).half()
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    b = torch.zeros(Co, requires_grad=True)
+    torch.nn.functional.conv2d(xr, wr, b, padding=1).backward(dy.float())
+    dx, dw, db = conv3x3_backward(x.permute(0, 2, 3, 1).contiguous().cuda(), conv_weight_to_gemm(w).cuda().half(),
+                                  dy.permute(0, 2, 3, 1).contiguous().cuda())
+    assert rel(dx.cpu().permute(0, 3, 1, 2), xr.grad) < 2e-3
+    assert rel(dw.cpu(), conv_weight_to_gemm(wr.grad)) < 1e-4
+    assert rel(db.cpu(), b.grad) < 1e-5
