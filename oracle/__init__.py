@@ -4,8 +4,9 @@ A CPU restatement (plain PyTorch fp32 / numpy) of the reference's algorithm for 
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import it, and only as the
 checker.  The product package `diffews_b200` never imports `oracle`.
 
-PARITY UNPINNED (UNet / VAE / metric part; the data layer in oracle/data.py IS pinned against the unmodified
-reference datasets, see its header): the reference (ga1i13o/DiffewS) ships no tests, golden vectors or fixtures for this path, and it
+PARITY UNPINNED for the UNet / VAE / scheduler part; PINNED for oracle/data.py (unmodified reference datasets) and for
+oracle/metric.py classify_prediction + AverageMeter (unmodified reference Evaluator / AverageMeter): tests/golden/,
+scripts/make_golden_data.py: the reference (ga1i13o/DiffewS) ships no tests, golden vectors or fixtures for this path, and it
 cannot be imported here (it needs diffusers==0.25.0, xformers, accelerate, matplotlib, detectron2 — none installed, no
 network).  The arithmetic lives in the third-party dependency diffusers==0.25.0 (requirements.txt:2), restated from
 its published architecture; the restatement is anchored on (i) the reference's own call sites cited per function,

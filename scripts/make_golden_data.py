@@ -75,6 +75,39 @@ def metric_golden():
     return out
 
 
+def meter_golden(metric):
+    """The UNMODIFIED evaluation_util/common/logger.py AverageMeter (update / compute_iou, logger.py:10-51) fed with the
+    reference Evaluator's own outputs.  The class hard-codes `.cuda()` (logger.py:15, :30-31); there is no GPU in the
+    build container, so `torch.Tensor.cuda` is patched to the identity for the duration of the run — the module's
+    source is not touched."""
+    spec = importlib.util.spec_from_file_location("ref_logger", "/root/reference/evaluation_util/common/logger.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+
+    class DS:
+        benchmark = "coco"
+        class_ids = [4 * v for v in range(20)]                # COCO-20i fold 0 (coco.py:60-66)
+
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        meter = m.AverageMeter(DS())
+        g = torch.Generator().manual_seed(5)
+        class_ids = []
+        for rep in range(3):                                   # the same episodes land in different classes
+            for c in metric:
+                cid = torch.tensor(DS.class_ids)[torch.randint(0, 20, (c["B"],), generator=g)]
+                class_ids.append(cid.tolist())
+                meter.update(torch.tensor(c["area_inter"]), torch.tensor(c["area_union"]), cid, None)
+        miou, fb_iou, head = meter.compute_iou()
+    finally:
+        torch.Tensor.cuda = orig
+    return {"benchmark": "coco", "class_ids_interest": DS.class_ids, "update_class_ids": class_ids,
+            "miou": float(miou), "fb_iou": float(fb_iou), "iou_head": head.tolist(),
+            "intersection_buf": meter.intersection_buf.tolist(), "union_buf": meter.union_buf.tolist(),
+            "buf_dtype": str(meter.intersection_buf.dtype)}
+
+
 def main():
     tf = transforms.Compose([transforms.Resize(size=(IMG_SIZE, IMG_SIZE)), transforms.ToTensor(),
                              transforms.Normalize([0.5], [0.5])])                      # dataset.py:36-40
@@ -97,8 +130,11 @@ def main():
         gold["fss_shot2"] = episodes(ds, 5, root)
     mpath = os.path.join(ROOT, "tests", "golden", "metric_reference.json")
     with open(mpath, "w") as f:
+        cases = metric_golden()
         json.dump({"made_by": "scripts/make_golden_data.py: unmodified evaluation_util/common/evaluation.py "
-                              "Evaluator.classify_prediction on CPU", "cases": metric_golden()}, f, indent=1)
+                              "Evaluator.classify_prediction and evaluation_util/common/logger.py AverageMeter on CPU "
+                              "(Tensor.cuda patched to the identity: no GPU in the build container)",
+                   "cases": cases, "meter": meter_golden(cases)}, f, indent=1)
     print("wrote", mpath)
     path = os.path.join(ROOT, "tests", "golden", "data_layer.json")
     with open(path, "w") as f:

@@ -218,3 +218,27 @@ def test_metric_oracle_matches_unmodified_reference_evaluator():
         inter, union = classify_prediction(c["pred"].clone(), batch)
         assert inter.dtype == torch.float32 and inter.tolist() == g["area_inter"], g["kind"]
         assert union.tolist() == g["area_union"], g["kind"]
+
+
+def test_meter_oracle_matches_unmodified_reference_average_meter():
+    """a13 pinned: the `meter` block of tests/golden/metric_reference.json is what the UNMODIFIED
+    evaluation_util/common/logger.py AverageMeter (update + compute_iou) produced when fed the reference Evaluator's own
+    per-episode outputs (scripts/make_golden_data.py; Tensor.cuda patched to the identity, the source untouched).  The
+    oracle meter must reproduce it in its float32-faithful mode exactly, and in the int64 mode the B200 path uses to
+    float32 rounding (the counts here are far below 2^24, so the buffers are equal too)."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "metric_reference.json")))
+    cases, mg = gold["cases"], gold["meter"]
+    for exact in (False, True):
+        meter = om.AverageMeter(mg["benchmark"], mg["class_ids_interest"], exact=exact)
+        it = iter(mg["update_class_ids"])
+        for rep in range(3):
+            for c in cases:
+                meter.update(torch.tensor(c["area_inter"]), torch.tensor(c["area_union"]), torch.tensor(next(it)))
+        miou, fb_iou, head = meter.compute_iou()
+        assert meter.intersection_buf.float().tolist() == mg["intersection_buf"]
+        assert meter.union_buf.float().tolist() == mg["union_buf"]
+        assert float(miou) == mg["miou"] and float(fb_iou) == mg["fb_iou"]
+        assert head.tolist() == mg["iou_head"]
