@@ -122,3 +122,18 @@ def metric_cases():
         cases.append({"seed": 100 + seed, "B": B, "H": H, "W": W, "ignore": ignore, "kind": kind, "pred": pred, "gt": gt,
                       "ign": ign})
     return cases
+
+
+def attn_cases():
+    """Seeded weights / inputs for one KV-bank self-attention layer (C = 128 = 2 heads x 64, 12 tokens): the reference
+    protocol is clear bank -> support call on [B*k, S, C] (stores K, V) -> query call on [B, S, C] (attends to
+    [self ; folded bank]).  Shared by scripts/make_golden_attn.py and tests/test_oracle.py."""
+    cases = []
+    for B, k in ((2, 1), (2, 3), (1, 5)):
+        g = torch.Generator().manual_seed(1000 + 10 * B + k)
+        C, S = 128, 12
+        w = {n: torch.randn(C, C, generator=g) * C ** -0.5 for n in ("to_q", "to_k", "to_v", "to_out")}
+        w["to_out_bias"] = torch.randn(C, generator=g) * 0.1
+        cases.append({"B": B, "k": k, "C": C, "S": S, "heads": 2, "w": w,
+                      "x_support": torch.randn(B * k, S, C, generator=g), "x_query": torch.randn(B, S, C, generator=g)})
+    return cases

@@ -242,3 +242,39 @@ def test_meter_oracle_matches_unmodified_reference_average_meter():
         assert meter.union_buf.float().tolist() == mg["union_buf"]
         assert float(miou) == mg["miou"] and float(fb_iou) == mg["fb_iou"]
         assert head.tolist() == mg["iou_head"]
+
+
+def test_attention_oracle_matches_unmodified_reference_processor():
+    """a5 pinned: tests/golden/attn_reference.json holds the query-pass outputs of the reference's OWN
+    diffews/models/attention_processor.py (MyAttention + MyXFormersAttnProcessor for k = 1, 3, 5; MyAttnProcessor2_0 for
+    k = 1), executed unmodified over stand-ins for the diffusers / xformers names it imports
+    (scripts/make_golden_attn.py).  The oracle's KV-bank attention — the k-shot fold restated as a shot-major
+    concatenation — must reproduce them (fp32, different but equivalent op order: 2e-6)."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import data_tree
+    gold = json.load(open(os.path.join(here, "golden", "attn_reference.json")))["cases"]
+    cases = data_tree.attn_cases()
+    assert len(gold) == len(cases)
+    for c, g in zip(cases, gold):
+        assert (c["B"], c["k"]) == (g["B"], g["k"])
+        attn = sd21.Attention(c["C"], heads=c["heads"], dim_head=c["C"] // c["heads"], bank=True)
+        with torch.no_grad():
+            attn.to_q.weight.copy_(c["w"]["to_q"]); attn.to_k.weight.copy_(c["w"]["to_k"])
+            attn.to_v.weight.copy_(c["w"]["to_v"]); attn.to_out[0].weight.copy_(c["w"]["to_out"])
+            attn.to_out[0].bias.copy_(c["w"]["to_out_bias"])
+            attn.clear_bank()
+            sup = attn(c["x_support"])
+            qry = attn(c["x_query"])
+        for name in ("xformers", "sdpa"):
+            if name not in g:
+                continue
+            ref = torch.tensor(g[name]["query_out"]).view_as(qry)
+            assert (qry - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 2e-6, (c["B"], c["k"], name)
+            assert abs(float(sup.double().sum()) - g[name]["support_out_sum"]) <= 1e-4 * abs(g[name]["support_out_sum"]) + 1e-3
+        if "sdpa" in g:     # the reference's two processors agree with each other at k = 1
+            a, b = torch.tensor(g["xformers"]["query_out"]), torch.tensor(g["sdpa"]["query_out"])
+            assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item() + 2e-6
