@@ -92,7 +92,45 @@ def install_stubs():
     mod("xformers", ops=ops)
 
 
+def scheduler_golden():
+    """marigold/util/scheduler_customized.py executed UNMODIFIED over stand-ins for its diffusers imports (the base
+    classes as empty classes, `register_to_config` as the identity): DDIMSchedulerCustomized only overrides __init__
+    and _get_variance (:107-180), so what this pins is the beta / alpha tables the reference builds from
+    scheduler_1.0_1.0/scheduler_config.json — the premise (every alpha_cumprod == 0) of the z0 = -v collapse.
+    set_timesteps / step are stock diffusers code (restated in diffews_b200/scheduler.py and the oracle)."""
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    base = type("DDIMScheduler", (), {})
+    mod("diffusers", DDIMScheduler=base, DDPMScheduler=type("DDPMScheduler", (), {}))
+    mod("diffusers.configuration_utils", ConfigMixin=object, register_to_config=lambda f: f)
+    mod("diffusers.schedulers")
+    mod("diffusers.schedulers.scheduling_ddim", DDIMSchedulerOutput=dict)
+    mod("diffusers.utils")
+    mod("diffusers.utils.torch_utils", randn_tensor=torch.randn)
+    spec = importlib.util.spec_from_file_location("ref_scheduler", "/root/reference/marigold/util/scheduler_customized.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cfg = json.load(open("/root/reference/scheduler_1.0_1.0/scheduler_config.json"))
+    import inspect
+    allowed = set(inspect.signature(ref.DDIMSchedulerCustomized.__init__).parameters) - {"self"}
+    kw = {k: v for k, v in cfg.items() if k in allowed}            # what ConfigMixin.from_config passes on
+    sch = ref.DDIMSchedulerCustomized(**kw)
+    return {"config_used": kw, "betas_head": sch.betas[:3].tolist(), "betas_min": float(sch.betas.min()),
+            "betas_max": float(sch.betas.max()), "alphas_cumprod_abs_max": float(sch.alphas_cumprod.abs().max()),
+            "alphas_cumprod_len": int(sch.alphas_cumprod.numel()), "final_alpha_cumprod": float(sch.final_alpha_cumprod),
+            "init_noise_sigma": float(sch.init_noise_sigma), "timesteps_head": sch.timesteps[:3].tolist(),
+            "variance_t1_prev0": float(sch._get_variance(1, 0)), "variance_t1_prevneg": float(sch._get_variance(1, -999))}
+
+
 def main():
+    sg = scheduler_golden()
+    with open(os.path.join(ROOT, "tests", "golden", "scheduler_reference.json"), "w") as f:
+        json.dump({"made_by": "scripts/make_golden_attn.py: unmodified marigold/util/scheduler_customized.py "
+                              "DDIMSchedulerCustomized.__init__ / _get_variance over import stand-ins", **sg}, f, indent=1)
+    print("scheduler:", sg["alphas_cumprod_abs_max"], sg["final_alpha_cumprod"], sg["variance_t1_prev0"])
     install_stubs()
     spec = importlib.util.spec_from_file_location("ref_attention_processor",
                                                   "/root/reference/diffews/models/attention_processor.py")

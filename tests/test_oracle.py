@@ -278,3 +278,27 @@ def test_attention_oracle_matches_unmodified_reference_processor():
         if "sdpa" in g:     # the reference's two processors agree with each other at k = 1
             a, b = torch.tensor(g["xformers"]["query_out"]), torch.tensor(g["sdpa"]["query_out"])
             assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item() + 2e-6
+
+
+def test_scheduler_tables_match_unmodified_reference_scheduler():
+    """a10 premise pinned: tests/golden/scheduler_reference.json = the beta / alpha tables that the UNMODIFIED
+    marigold/util/scheduler_customized.py DDIMSchedulerCustomized.__init__ builds from scheduler_1.0_1.0/
+    scheduler_config.json (scripts/make_golden_attn.py).  Every alpha_cumprod is exactly 0 there, which is what makes the
+    v-prediction DDIM step collapse to z0 = -v; the product scheduler must build the same tables and detect the collapse."""
+    import json
+    import os
+    from diffews_b200.scheduler import DDIMSchedulerCustomized
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = json.load(open(os.path.join(here, "golden", "scheduler_reference.json")))
+    sch = DDIMSchedulerCustomized(**g["config_used"])
+    assert sch.betas[:3].tolist() == g["betas_head"]
+    assert float(sch.betas.min()) == g["betas_min"] and float(sch.betas.max()) == g["betas_max"]
+    assert float(sch.alphas_cumprod.abs().max()) == g["alphas_cumprod_abs_max"] == 0.0
+    assert sch.alphas_cumprod.numel() == g["alphas_cumprod_len"]
+    assert float(sch.final_alpha_cumprod) == g["final_alpha_cumprod"] == 0.0
+    assert sch.timesteps[:3].tolist() == g["timesteps_head"]
+    sch.set_timesteps(1)
+    t = int(sch.timesteps[0])
+    assert sch.is_pure_negation(t)
+    v, x = torch.randn(2, 4, 8, 8), torch.randn(2, 4, 8, 8)
+    assert torch.equal(sch.step(v, t, x).pred_original_sample, -v)
