@@ -4,15 +4,15 @@ A CPU restatement (plain PyTorch fp32 / numpy) of the reference's algorithm for 
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import it, and only as the
 checker.  The product package `diffews_b200` never imports `oracle`.
 
-PARITY: PINNED for oracle/data.py (golden vectors produced by the unmodified reference datasets) and for oracle/metric.py
-classify_prediction + AverageMeter (unmodified reference Evaluator / AverageMeter) and for the KV-bank attention of
-oracle/sd21.py (unmodified reference attention_processor.py over stand-ins for its diffusers / xformers imports) —
-tests/golden/, generated by scripts/make_golden_data.py and scripts/make_golden_attn.py.  UNPINNED for the UNet / VAE layer wiring and the scheduler (oracle/sd21.py, oracle/pipeline.py): the
-reference (ga1i13o/DiffewS) ships no tests, golden vectors or fixtures for it, and those modules cannot be imported here
-(they need diffusers==0.25.0, xformers, accelerate, matplotlib, detectron2 — none installed, no network).
-The arithmetic lives in the third-party dependency diffusers==0.25.0 (requirements.txt:2), restated from
-its published architecture; the restatement is anchored on (i) the reference's own call sites cited per function,
-(ii) exact agreement of the parameter counts and state-dict keys with SD-2.1 (UNet 865 910 724 + 23 360 conv_in_ref,
-VAE 83 653 863), (iii) structural self-checks (k-shot fold == shot-major concat; scheduler step == negation; rthres
-fp32 tie semantics; histc drops 255), all in tests/test_oracle.py.
+PARITY — pinned against outputs of the reference itself, run in the build container: scripts/make_golden_*.py execute the
+reference's own files UNMODIFIED (only the names they import from packages that are not installed — diffusers, xformers,
+accelerate, matplotlib, detectron2 ... — are replaced by stand-ins that carry no arithmetic of the path) and commit what
+they return under tests/golden/: the whole `test_diffusion` loop (eval_loop_reference.json), the pipeline's __call__ /
+single_infer (pipeline_reference.json), the KV-bank attention processors (attn_reference.json), the scheduler tables
+(scheduler_reference.json), Evaluator / AverageMeter (metric_reference.json) and the datasets (data_layer.json).
+tests/test_oracle.py and tests/test_data_layer.py hold this oracle to them.  NOT backed by a reference run: the insides of the
+diffusers modules the reference instantiates (UNet blocks, VAE encoder / decoder, DDIMScheduler.step) — diffusers==0.25.0
+(requirements.txt:2) is absent, so oracle/sd21.py restates its published architecture, anchored on (i) the reference's call
+sites cited per function, (ii) exact agreement of the parameter counts and state-dict keys with SD-2.1 (UNet 865 910 724 +
+23 360 conv_in_ref, VAE 83 653 863), (iii) structural self-checks in tests/test_oracle.py.
 """

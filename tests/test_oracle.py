@@ -302,3 +302,99 @@ def test_scheduler_tables_match_unmodified_reference_scheduler():
     assert sch.is_pure_negation(t)
     v, x = torch.randn(2, 4, 8, 8), torch.randn(2, 4, 8, 8)
     assert torch.equal(sch.step(v, t, x).pred_original_sample, -v)
+
+
+def test_pipeline_oracle_matches_unmodified_reference_single_infer():
+    """a2 / a3 / a9 / a10 wiring pinned: tests/golden/pipeline_reference.json = the output of the reference's OWN
+    MarigoldPipelineRGBLatentNoise.single_infer (diffews/marigold_pipeline_rgb_latent_noise.py executed unmodified over
+    import stand-ins, scripts/make_golden_pipeline.py) when it drives the oracle UNet / VAE and the restated scheduler.
+    The oracle's restatement of single_infer on the same sub-modules and inputs must give the same image (same fp32 ops in
+    the same order; 2e-3 on the 0..255 scale leaves room for another CPU's conv kernels)."""
+    import base64
+    import json
+    import os
+    import numpy as np
+    from diffews_b200.synthetic import make_batch, pipeline_inputs, prompt_embedding
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "pipeline_reference.json")))["cases"]
+    unet, vae = sd21.build_models(0, (64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))
+    for g in gold:
+        ref_imgs, tag, gt = pipeline_inputs(make_batch(0, g["B"], g["size"], g["k"]))
+        seg = op.single_infer(unet, vae, prompt_embedding(), ref_imgs, tag, gt)
+        lat = op.encode_rgb(vae, tag)
+        want = torch.from_numpy(np.frombuffer(base64.b64decode(g["seg"]["sub_f32_b64"]), dtype=np.float32).copy())
+        want = want.view(g["seg"]["sub_shape"])
+        assert list(seg.shape) == g["seg"]["shape"]
+        assert (seg[:, :, ::4, ::4] - want).abs().max().item() <= 2e-3, (g["B"], g["k"])
+        assert abs(float(seg.double().mean()) - g["seg"]["mean"]) <= 1e-3
+        assert float(seg.min()) == g["seg"]["min"] and float(seg.max()) == g["seg"]["max"]
+        assert abs(float(lat.double().abs().mean()) - g["encode_rgb_tag_abs_mean"]) <= 1e-6
+
+
+def test_pipeline_oracle_matches_unmodified_reference_call():
+    """a1 pinned: the `call` block of tests/golden/pipeline_reference.json is what the reference's OWN
+    MarigoldPipelineRGBLatentNoise.__call__ returned (unmodified file; tensor inputs, a real file in rgb_paths, bsz 1 —
+    exactly how test_diffusion calls it, main_oss.py:113-123): a PIL RGB image, `uncertainty=None`.  The oracle's
+    single_infer + the uint8 truncation of pipeline:534 must give the same bytes (<= 1 LSB on <= 0.1 % of the pixels is
+    tolerated for another CPU's conv kernels)."""
+    import base64
+    import json
+    import os
+    import numpy as np
+    from diffews_b200.synthetic import make_batch, pipeline_inputs, prompt_embedding
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = json.load(open(os.path.join(here, "golden", "pipeline_reference.json")))["call"]
+    assert g["type"] == "Image" and g["dtype"] == "uint8" and g["uncertainty_is_none"]
+    unet, vae = sd21.build_models(0, (64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))
+    ref_imgs, tag, gt = pipeline_inputs(make_batch(0, g["B"], g["size"], g["k"]))
+    seg_u8 = op.to_uint8(op.single_infer(unet, vae, prompt_embedding(), ref_imgs, tag, gt))     # [1,3,H,W]
+    img = seg_u8[0].permute(1, 2, 0).numpy()                                                      # chw2hwc
+    assert list(img.shape) == g["shape"]
+    want = np.frombuffer(base64.b64decode(g["u8_b64"]), dtype=np.uint8).reshape(g["size"] // 2, g["size"] // 2, 3)
+    diff = np.abs(img[::2, ::2].astype(np.int32) - want.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+    assert abs(int(img.astype(np.int64).sum()) - g["sum"]) <= 16
+
+
+def test_oracle_eval_loop_matches_unmodified_reference_test_diffusion(tmp_path):
+    """The whole path pinned at loop level: tests/golden/eval_loop_reference.json = per-episode intersection / union and
+    the final mIoU / FB-IoU of the reference's OWN `test_diffusion` (evaluation_util/main_oss.py:84-171, unmodified, with
+    its own dataset, transform, pipeline __call__, inline rthres, Evaluator and AverageMeter; the oracle UNet / VAE and the
+    restated scheduler plugged in — scripts/make_golden_eval_loop.py).  The oracle's restatement of the same loop (data
+    layer, input folding, single_infer, uint8 truncation, rthres, counts, meter) must reproduce it: identical episodes, counts
+    within 2 pixels (exactly equal on the build machine; the slack is for another CPU's conv kernels), mIoU within 0.05."""
+    import json
+    import os
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import data_tree
+    from diffews_b200 import data as pdata
+    from diffews_b200.synthetic import prompt_embedding
+    from oracle import data as od
+    gold = json.load(open(os.path.join(here, "golden", "eval_loop_reference.json")))
+    S = gold["img_size"]
+    tree = str(tmp_path)
+    data_tree.build_coco_tree(tree)
+    ds = pdata.DatasetCOCO(tree, fold=0, transform=pdata.EpisodeTransform(S), split="test", shot=1,
+                           use_original_imgsize=False)
+    unet, vae = sd21.build_models(0, (64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))
+    meter = om.AverageMeter("coco", ds.class_ids, exact=False)
+    np.random.seed(0)
+    for idx, g in enumerate(gold["episodes"]):
+        raw = ds.raw_episode(idx)
+        assert raw["query_name"] == g["query_name"] and raw["support_names"] == g["support_names"]
+        assert raw["class_sample"] == g["class_id"]
+        batch = {"query_img": od.transform_image(raw["query_img"], S)[None],
+                 "query_mask": od.coco_mask(raw["query_label"], raw["class_sample"], S)[None],
+                 "support_imgs": torch.stack([od.transform_image(a, S) for a in raw["support_imgs"]])[None],
+                 "support_masks": torch.stack([od.coco_mask(l, raw["class_sample"], S) for l in raw["support_labels"]])[None],
+                 "class_id": torch.tensor([raw["class_sample"]])}
+        inter, union, pred_mask, _, _ = op.evaluate_episode(unet, vae, prompt_embedding(), batch)
+        assert abs(int(pred_mask.sum()) - g["pred_fg"]) <= 2
+        assert (inter - torch.tensor(g["area_inter"])).abs().max().item() <= 2, (idx, inter.tolist(), g["area_inter"])
+        assert (union - torch.tensor(g["area_union"])).abs().max().item() <= 2
+        meter.update(inter, union, batch["class_id"])
+    miou, fb_iou, _ = meter.compute_iou()
+    assert abs(float(miou) - gold["miou"]) <= 0.05 and abs(float(fb_iou) - gold["fb_iou"]) <= 0.05
