@@ -1,7 +1,11 @@
 """CPU tests that pin the ORACLE (tests/ may import oracle/; the product never does).
 
-The reference ships no tests / golden vectors for this path ("parity unpinned", oracle/__init__.py).  These tests pin
-the restatement on what *can* be checked without the reference's un-installable dependencies:
+The reference ships no tests / golden vectors for this path, so the pins are of two kinds:
+  (1) against the reference's OWN code run in the build container (scripts/make_golden_*.py execute its files unmodified
+      over stand-ins for the un-installable imports; fixtures in tests/golden/): the whole test_diffusion loop, the
+      pipeline's __call__ / single_infer, the KV-bank attention processors, the scheduler tables, Evaluator / AverageMeter
+      (the tests named *_unmodified_reference_* at the end of this file);
+  (2) structural checks that need no reference run:
   - parameter counts of the restated SD-2.1 UNet / VAE equal the published totals (state-dict compatibility),
   - the k-shot bank fold of attention_processor.py:253-267 restated literally == the oracle's shot-major concat,
   - the DDIM step with scheduler_1.0_1.0/scheduler_config.json == exact negation,
