@@ -8,7 +8,8 @@ PARITY — pinned against outputs of the reference itself, run in the build cont
 reference's own files UNMODIFIED (only the names they import from packages that are not installed — diffusers, xformers,
 accelerate, matplotlib, detectron2 ... — are replaced by stand-ins that carry no arithmetic of the path) and commit what
 they return under tests/golden/: the whole `test_diffusion` loop (eval_loop_reference.json), the pipeline's __call__ /
-single_infer (pipeline_reference.json), the KV-bank attention processors (attn_reference.json), the scheduler tables
+single_infer (pipeline_reference.json), MyUNet2DConditionModel.forward on a hand-assembled instance
+(unet_wiring_reference.json), the KV-bank attention processors (attn_reference.json), the scheduler tables
 (scheduler_reference.json), Evaluator / AverageMeter (metric_reference.json) and the datasets (data_layer.json).
 tests/test_oracle.py and tests/test_data_layer.py hold this oracle to them.  NOT backed by a reference run: the insides of the
 diffusers modules the reference instantiates (UNet blocks, VAE encoder / decoder, DDIMScheduler.step) — diffusers==0.25.0

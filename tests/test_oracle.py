@@ -402,3 +402,33 @@ def test_oracle_eval_loop_matches_unmodified_reference_test_diffusion(tmp_path):
         meter.update(inter, union, batch["class_id"])
     miou, fb_iou, _ = meter.compute_iou()
     assert abs(float(miou) - gold["miou"]) <= 0.05 and abs(float(fb_iou) - gold["fb_iou"]) <= 0.05
+
+
+def test_unet_oracle_matches_unmodified_reference_forward_wiring():
+    """a4 wiring pinned: tests/golden/unet_wiring_reference.json = the query-pass output of the reference's OWN
+    MyUNet2DConditionModel.forward (+ clear_attn_bank), executed unmodified on an instance hand-assembled from the oracle's
+    blocks behind call-protocol adapters (scripts/make_golden_unet_wiring.py).  The oracle UNet's own forward — the
+    restatement of that wiring — must give the same tensor on the same inputs."""
+    import base64
+    import json
+    import os
+    import numpy as np
+    from diffews_b200.synthetic import prompt_embedding
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "unet_wiring_reference.json")))["cases"]
+    unet, _ = sd21.build_models(0, (64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))
+    ehs = prompt_embedding()
+    for g in gold:
+        B, k, lat = g["B"], g["k"], g["lat"]
+        gen = torch.Generator().manual_seed(300 + 10 * B + k)
+        sup = torch.randn(B * k, 8, lat, lat, generator=gen) * 0.8
+        qry = torch.randn(B, 4, lat, lat, generator=gen) * 0.8
+        with torch.no_grad():
+            unet.clear_attn_bank()
+            s = unet(sup, 1, ehs.repeat(B * k, 1, 1), is_target=False)
+            y = unet(qry, 1, ehs.repeat(B, 1, 1))
+            unet.clear_attn_bank()
+        want = torch.from_numpy(np.frombuffer(base64.b64decode(g["f32_b64"]), dtype=np.float32).copy()).view(g["shape"])
+        assert g["type"] == "UNet2DConditionOutput" and list(y.shape) == g["shape"]
+        assert (y - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item()), (B, k)
+        assert abs(float(s.double().abs().mean()) - g["support_abs_mean"]) <= 1e-6
