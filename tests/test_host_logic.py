@@ -133,3 +133,63 @@ def test_checkpoint_layout_roundtrip(tmp_path):
     assert ck.with_support_stem(full) is full
     torch.save(sd, str(tmp_path / "unet" / "w.bin"))
     assert torch.equal(ck.load_state_dict(str(tmp_path / "unet" / "w.bin"))["conv_in.bias"], sd["conv_in.bias"])
+
+
+def _gloo_loader_worker(rank, world, port, tree, q):
+    import sys
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from diffews_b200 import data
+    data.FSSDataset.initialize(48, tree, False)
+    np.random.seed(0)
+    loader = data.FSSDataset.build_dataloader("coco", 2, 1, 0, "val", 1, device="cpu")   # rank / world from the group
+    names = []
+    for i, raws in enumerate(loader.raw_batches()):
+        names.append([(r["query_name"], r["support_names"][0], r["class_sample"]) for r in raws])
+        if i == 1:
+            break
+    gathered = [None] * world
+    dist.all_gather_object(gathered, names)
+    q.put((rank, loader.rank, loader.world, len(loader), gathered))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_loader_shards_by_process_group_rank(tmp_path):
+    """world_size-2 gloo: EpisodeLoader picks rank / world up from torch.distributed, every rank walks the reference's
+    numpy episode sequence and keeps batches rank, rank + 2, ...; interleaving the ranks' batches gives exactly the
+    single-process sequence (so the all-reduced counts equal a one-GPU run of the same seed)."""
+    import socket
+    import sys
+    import numpy as np
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import data_tree
+    from diffews_b200 import data
+    tree = str(tmp_path)
+    data_tree.build_coco_tree(tree)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_gloo_loader_worker, args=(r, 2, port, tree, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    data.FSSDataset.initialize(48, tree, False)
+    np.random.seed(0)
+    single = data.FSSDataset.build_dataloader("coco", 2, 1, 0, "val", 1, device="cpu", rank=0, world=1)
+    want = []
+    for i, raws in enumerate(single.raw_batches()):
+        want.append([(r["query_name"], r["support_names"][0], r["class_sample"]) for r in raws])
+        if i == 3:
+            break
+    for rank, lr, lw, n, gathered in res:
+        assert (lr, lw) == (rank, 2) and n == 250
+        assert gathered[0] == [want[0], want[2]] and gathered[1] == [want[1], want[3]]
