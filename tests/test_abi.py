@@ -65,3 +65,22 @@ def test_ops_refuse_cpu_tensors(lib_built):
     with pytest.raises(Exception):
         ops.linear(x, x)
     from diffews_b200.unet import MyUNet2DConditionModel  # noqa: F401  (imports without a GPU)
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/diffews_b200.h must compile as C99 (no C++, no torch / CUDA types in signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "include/diffews_b200.h"\n'
+                   "int main(void) { DfwImageDesc d; DfwAdamTensor t; (void)d; (void)t; return dfw_version() < 0; }\n")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", ROOT, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "diffews_b200.h")).read(), flags=re.S)
+    for banned in ("torch", "Tensor", "at::", "cudaStream_t", "std::", "template"):
+        assert banned not in code, banned
