@@ -1,0 +1,126 @@
+// Softmax inner loop of the KV-fused attention kernel (attn.cu, v3), shared with scripts/microbench/softmax_rate.cu.
+//
+// One thread owns one query row (= one TMEM lane) and the 128 logits of a key tile, held in registers for both passes
+// (so the S accumulator in TMEM is free again right after the load).  Head dim 64 makes the exponentials the bound:
+// at full tensor rate a 128 x 128 tile takes 512 cycles, the 16 384 exponentials take 1024 on the SM's 16-lane XU.
+// So a compile-time fraction of the exponentials (NPOLY of every 8 packed pairs) is evaluated on the FMA pipe instead:
+//   2^x = 2^n * p(f),  n = round(x), f = x - n in [-0.5, 0.5],  p = degree-3 minimax (max relative error 7.5e-5, below
+//   the 4.9e-4 half-ulp of the fp16 P it is rounded to), n added into the exponent field with one integer add-shift.
+// Packed fp32x2 instructions (FFMA2 / FADD2, sm_100) carry the scale-and-subtract, the range reduction, the Horner steps
+// and the row sum: two logits per issue slot.
+#pragma once
+#include "ptx.cuh"
+
+namespace dfw {
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {      // one F2FP: {hi, lo} -> packed fp16
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+constexpr float EXP2_C0 = 0.9999280571937561f, EXP2_C1 = 0.6932609677314758f, EXP2_C2 = 0.2426111251115799f,
+                EXP2_C3 = 0.055171653628349304f;
+constexpr float EXP2_MAGIC = 12582912.0f;        // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer (|x| < 2^22)
+
+// 2^x for a packed pair on the FMA / ALU pipes (no MUFU).  x <= ~100; x < -126 is clamped (result ~1e-38, 0 in fp16).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const uint64_t xc = f2_pack(x0, x1);
+    const uint64_t t2 = f2_add(xc, f2_pack(EXP2_MAGIC, EXP2_MAGIC));
+    const uint64_t n2 = f2_add(t2, f2_pack(-EXP2_MAGIC, -EXP2_MAGIC));
+    const uint64_t f2 = f2_fma(n2, f2_pack(-1.0f, -1.0f), xc);
+    uint64_t p2 = f2_fma(f2_pack(EXP2_C3, EXP2_C3), f2, f2_pack(EXP2_C2, EXP2_C2));
+    p2 = f2_fma(p2, f2, f2_pack(EXP2_C1, EXP2_C1));
+    p2 = f2_fma(p2, f2, f2_pack(EXP2_C0, EXP2_C0));
+    float t0, t1, p0, p1;
+    f2_unpack(t2, t0, t1);
+    f2_unpack(p2, p0, p1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// Row max of 128 raw logits (3-input max, four independent chains).
+__device__ __forceinline__ float row_max128(const uint32_t (&s)[128]) {
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; i += 8) {
+        m0 = fmax3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        m2 = fmax3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        m3 = fmax3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// p = 2^(s * sc - mu) for logits s[base .. base+32) -> 16 packed 16-bit pairs in pk[], row sum accumulated in sum2
+// (two packed accumulators).  NPOLY of every 8 pairs take the polynomial path; spread evenly over the 8.
+template <bool F16, int NPOLY>
+__device__ __forceinline__ void exp_chunk32(const uint32_t* s, uint64_t sc2, uint64_t nmu2, uint64_t (&sum2)[2],
+                                            uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) {
+        const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * pi]), __uint_as_float(s[2 * pi + 1])), sc2, nmu2);
+        float e0, e1;
+        // pair (pi % 8) takes the polynomial when floor((j + 1) * NPOLY / 8) > floor(j * NPOLY / 8)
+        const int j = pi & 7;
+        const bool poly = ((j + 1) * NPOLY) / 8 > (j * NPOLY) / 8;
+        if (poly) {
+            exp2_poly2(x2, e0, e1);
+        } else {
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+        }
+        sum2[pi & 1] = f2_add(sum2[pi & 1], f2_pack(e0, e1));
+        pk[pi] = F16 ? cvt_f16x2(e0, e1) : cvt_bf16x2(e0, e1);
+    }
+}
+
+// 16 consecutive 32-bit TMEM columns <- registers (thread i of the warp writes lane base + i)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// 128 consecutive fp32 TMEM columns -> registers (four x32 loads; the caller waits)
+__device__ __forceinline__ void tmem_ld_row128(uint32_t taddr, uint32_t (&s)[128]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
+        tmem_ld_32x32(taddr + c * 32, v);
+    }
+}
+
+}  // namespace dfw

@@ -30,7 +30,8 @@ __global__ void rthres_max_kernel(const uint8_t* __restrict__ pred, EpisodeWs* _
     const int b = blockIdx.y;
     const uint8_t* p = pred + static_cast<long long>(b) * per_ep;
     unsigned int m = 0;
-    const long long nvec = per_ep / 16;
+    // 128-bit loads only when this episode's plane group starts 16-byte aligned (3*H*W % 16 != 0 shifts episodes b > 0)
+    const long long nvec = (reinterpret_cast<uintptr_t>(p) & 15) == 0 ? per_ep / 16 : 0;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
@@ -79,7 +80,10 @@ rthres_hist_kernel(const uint8_t* __restrict__ pred, int pred_is_mask, const uin
         if (gv < 2u) c[4 + gv]++;
         return static_cast<uint8_t>(pv);
     };
-    const int nvec = HW / 4;
+    // 32-bit vector path only when every plane of this episode is 4-byte aligned (odd H*W or an offset view: scalar)
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(pr) | reinterpret_cast<uintptr_t>(pg) | reinterpret_cast<uintptr_t>(pb) |
+                               reinterpret_cast<uintptr_t>(gtb) | reinterpret_cast<uintptr_t>(igb) | reinterpret_cast<uintptr_t>(mo);
+    const int nvec = (align_or & 3) == 0 ? HW / 4 : 0;
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         const unsigned int r4 = __ldg(reinterpret_cast<const unsigned int*>(pr) + i);
@@ -133,7 +137,10 @@ __global__ void iou_accumulate_kernel(const long long* __restrict__ inter, const
     if (i >= B * 2) return;
     const int b = i / 2, v = i % 2;
     const long long c = class_id[b];
-    if (c < 0 || c >= nclass) return;
+    if (c < 0 || c >= nclass) {        // the reference's index_add_ (logger.py:36-37) raises a device-side assert here
+        printf("[dfw] iou_accumulate: class_id[%d] = %lld is outside [0, %d)\n", b, c, nclass);
+        __trap();
+    }
     atomicAdd(reinterpret_cast<unsigned long long*>(inter_buf + static_cast<long long>(v) * nclass + c),
               static_cast<unsigned long long>(inter[b * 2 + v]));
     atomicAdd(reinterpret_cast<unsigned long long*>(union_buf + static_cast<long long>(v) * nclass + c),
@@ -154,9 +161,7 @@ int dfw_rthres_iou_hist(const uint8_t* pred_u8, int pred_is_mask, const uint8_t*
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(pred_u8 && gt && area_inter && area_union && workspace && B > 0 && H > 0 && W > 0);
-    const int HW = H * W;
-    DFW_REQUIRE(HW % 4 == 0);  // 32-bit vector path on the uint8 planes (all supported image sizes are multiples of 8)
-    DFW_REQUIRE((reinterpret_cast<uintptr_t>(pred_u8) & 15) == 0 && (reinterpret_cast<uintptr_t>(gt) & 3) == 0);
+    const int HW = H * W;     // any size / alignment: the kernels take the vector paths only where the planes are aligned
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     EpisodeWs* ws = reinterpret_cast<EpisodeWs*>(workspace);
     DFW_CHECK_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(B) * sizeof(EpisodeWs), stream));

@@ -81,13 +81,22 @@ class AverageMeter:
                            union_b.t().round().to(torch.int64).contiguous(), class_id)
         self.loss_buf.append(torch.tensor(0.0) if loss is None else loss)
 
+    def reset(self):
+        """Zero the counters IN PLACE (a captured CUDA graph holds the buffers' device pointers)."""
+        self.intersection_buf.zero_()
+        self.union_buf.zero_()
+        self.loss_buf = []
+
     def all_reduce(self):
-        """Data-parallel evaluation: sum the integer counts over ranks (NCCL, order-independent, bit-exact)."""
+        """Data-parallel evaluation: sum the integer counts over ranks (NCCL, order-independent, bit-exact).
+        The result is copied back INTO the existing buffers: EpisodeRunner's CUDA graph captured their device pointers
+        (dfw_iou_accumulate), so the attributes must never be rebound to new tensors."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             packed = torch.stack([self.intersection_buf, self.union_buf])
             dist.all_reduce(packed, op=dist.ReduceOp.SUM)
-            self.intersection_buf, self.union_buf = packed[0].contiguous(), packed[1].contiguous()
+            self.intersection_buf.copy_(packed[0])
+            self.union_buf.copy_(packed[1])
 
     def compute_iou(self):
         inter = self.intersection_buf.float()

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import torch
 
-from .evaluation import AverageMeter, Evaluator
+from .evaluation import NCLASS, AverageMeter, Evaluator
 
 
 def shard_episodes(n_total: int, rank: int, world: int) -> range:
@@ -30,10 +30,16 @@ def build_engine_from_modules(unet_module, vae_module, text_embeds, device="cuda
 
 class EpisodeRunner:
     def __init__(self, pipe, benchmark: str = "coco", class_ids=None, r_threshold: float = 0.25, img_size: int = 512):
+        """`class_ids`: the classes mIoU is averaged over.  The reference builds `AverageMeter(dataloader.dataset)`
+        (main_oss.py:87), i.e. the FOLD's classes (20 of 80 for COCO-20i): `run(dataloader)` does the same from
+        `dataloader.dataset.class_ids`.  Leaving it None outside `run()` averages over every class of the benchmark,
+        which is only right for synthetic episodes that draw from all of them (bench.py)."""
         self.pipe = pipe
         self.r_threshold = r_threshold
         self.img_size = img_size
-        nclass = {"coco": 80, "lvis": 1203, "pascal": 20, "fss": 1000}[benchmark]
+        self.benchmark = benchmark
+        self._class_ids_given = class_ids is not None
+        nclass = NCLASS[benchmark]
         self.meter = AverageMeter(benchmark=benchmark, class_ids=class_ids if class_ids is not None else range(nclass),
                                   device=pipe.device)
 
@@ -70,7 +76,10 @@ class EpisodeRunner:
     @torch.no_grad()
     def step(self, batch: dict):
         """`batch`: collated episode batch, on the device (main_oss.py:94 `utils.to_cuda(batch)`) or in pinned host
-        memory.  Returns per-episode int64 (area_inter [B,2], area_union [B,2]) and updates the meter."""
+        memory.  Returns per-episode int64 (area_inter [B,2], area_union [B,2]) and updates the meter.
+        In graph mode the returned tensors are the graph's static outputs: the next replay overwrites them, so clone
+        them to keep per-batch results (eager mode returns fresh tensors).  The rthres threshold uses the PER-EPISODE
+        maximum (the reference's `pred_mask.max()` is a whole-batch max, identical at its only supported bsz = 1)."""
         g = getattr(self, "_graph", None)
         if g is not None and all(k in batch and tuple(batch[k].shape) == s for k, s in self._graph_shapes.items()) \
                 and not any(batch.get(k) is not None and k not in self._graph_shapes for k in self.OPTIONAL_KEYS):
@@ -140,6 +149,15 @@ class EpisodeRunner:
         through the pipeline, rthres, intersection/union, class accumulation; returns (mIoU, FB-IoU) after the
         cross-rank all-reduce.  `dataloader` yields the reference's batch dicts (diffews_b200.data.EpisodeLoader, or the
         reference's own DataLoader).  Full batches replay one CUDA graph; the short last batch runs eagerly."""
+        ds = getattr(dataloader, "dataset", None)
+        if ds is not None and hasattr(ds, "class_ids"):
+            # main_oss.py:87 `AverageMeter(dataloader.dataset)`: mIoU averages over the fold's classes only
+            ids = torch.as_tensor(list(ds.class_ids), dtype=torch.long, device=self.meter.device)
+            if self._class_ids_given and not torch.equal(ids, self.meter.class_ids_interest):
+                raise ValueError("EpisodeRunner class_ids differ from dataloader.dataset.class_ids")
+            if getattr(ds, "benchmark", self.benchmark) != self.benchmark:
+                raise ValueError(f"dataset benchmark {ds.benchmark!r} != runner benchmark {self.benchmark!r}")
+            self.meter.class_ids_interest = ids
         for i, batch in enumerate(dataloader):
             if max_batches is not None and i >= max_batches:
                 break

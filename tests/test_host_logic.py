@@ -75,7 +75,18 @@ def _gloo_worker(rank, world, port, q):
     for i in shard_episodes(40, rank, world):      # host stand-in for the accumulation kernel (no GPU here)
         m.intersection_buf[:, cls[i]] += inter[i]
         m.union_buf[:, cls[i]] += union[i]
+    ptrs = (m.intersection_buf.data_ptr(), m.union_buf.data_ptr())
     m.all_reduce()
+    # a captured CUDA graph holds these pointers (EpisodeRunner.enable_cuda_graph): the reduction must land IN PLACE
+    assert ptrs == (m.intersection_buf.data_ptr(), m.union_buf.data_ptr())
+    first = (m.intersection_buf.clone(), m.union_buf.clone())
+    m.reset()                                       # second fold on the same meter: zero in place, accumulate, reduce again
+    assert ptrs == (m.intersection_buf.data_ptr(), m.union_buf.data_ptr()) and int(m.union_buf.sum()) == 0
+    for i in shard_episodes(40, rank, world):
+        m.intersection_buf[:, cls[i]] += inter[i]
+        m.union_buf[:, cls[i]] += union[i]
+    m.all_reduce()
+    assert torch.equal(first[0], m.intersection_buf) and torch.equal(first[1], m.union_buf)
     miou, fb, _ = m.compute_iou()
     # plain lists, not tensors: a tensor in a Queue travels as a shared-memory handle that dies with this process
     q.put((rank, m.intersection_buf.tolist(), m.union_buf.tolist(), float(miou), float(fb)))
