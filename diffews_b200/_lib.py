@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(HERE, "libdiffews_b200.so")
 DFW_OK, DFW_ERR_INVALID, DFW_ERR_CUDA, DFW_ERR_ARCH = 0, -1, -2, -3
 EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU, EPI_F16 = 1, 2, 4, 8, 16
 
+# process-wide options (include/diffews_b200.h DFW_OPT_*)
+OPT_PDL, OPT_T128, OPT_T128_MAXC, OPT_HALO, OPT_GN_CTAS_PER_SM, OPT_PREPROC_TWO_PASS, OPT_ATTN_V2, OPT_SEG_HEAD = range(8)
+
 _vp, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> (restype, argtypes): mirrors include/diffews_b200.h one to one (tests/test_abi.py checks the header).
@@ -21,6 +24,8 @@ SIGNATURES = {
     "dfw_version": (_i, []),
     "dfw_device_ok": (_i, []),
     "dfw_launch_count": (_ll, []),
+    "dfw_set_option": (_i, [_i, _i]),
+    "dfw_get_option": (_i, [_i]),
     "dfw_conv2d_igemm": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "dfw_upconv2x_igemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "attn_softmax.cuh"
 
 namespace dfw {
 extern std::atomic<long long> g_launches;
@@ -38,8 +39,6 @@ constexpr int TILE_BYTES = 128 * 128;             // 128 rows x 128 B
 constexpr int ATT_THREADS = 384;                  // 4 control warps + 2 x 4 softmax warps
 constexpr int ATT_SMEM = ATT_QT * TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ +
                          ATT_QT * 2 * TILE_BYTES /*P*/ + 1024 + 256;
-constexpr int ATT_SMEM_MI = ATT_QT * TILE_BYTES + 2 * 2 * TILE_BYTES + ATT_QT * 2 * 2 * TILE_BYTES + 1024 + 256;   // 2 K/V stages, 2 P buffers per tile
-static_assert(ATT_SMEM_MI <= 227 * 1024, "dynamic smem limit of sm_100");
 constexpr int ATT_SBUF = 3;                       // S accumulators rotate over 3 TMEM buffers: the MMA warp computes
                                                   // S_X(j+1) while the softmax group of X still reads S_X(j)
 constexpr int ATT_TMEM_COLS = 512;                // S buffers [0,128) [128,256) [256,384); O_A [384,448) O_B [448,512)
@@ -79,17 +78,15 @@ struct AttnParams {
 //               and sum in the log2 domain; O is only rescaled (tcgen05.ld -> scale -> tcgen05.st) when some row of
 //               the warp raises its max by more than 2^TAU, so the common case never touches O; P -> 16-bit ->
 //               128B-swizzled smem (the K-major A operand of the PV MMA)
-template <bool F16, bool MI>
+template <bool F16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
+attn_kvfused_v2_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
-    // MI: 2 K/V stages and TWO P buffers per query tile (the softmax of tile j+1 never waits for PV(j));
-    // single issuer: 3 K/V stages, one P buffer.  Both fit the same ATT_SMEM.
-    constexpr int KVS = MI ? 2 : KV_STAGES;
-    constexpr int NPB = MI ? 2 : 1;
-    static_assert(ATT_QT * TILE_BYTES + KVS * 2 * TILE_BYTES + ATT_QT * NPB * 2 * TILE_BYTES + 1024 + 256 <= (MI ? ATT_SMEM_MI : ATT_SMEM), "smem");
+    constexpr bool MI = false;      // (the three-issuer schedule of round 1 was slower and is gone)
+    constexpr int KVS = KV_STAGES;
+    constexpr int NPB = 1;
     auto sQ = [&](int x) { return base + x * TILE_BYTES; };
     const uint32_t kv_base = base + ATT_QT * TILE_BYTES;
     auto sK = [&](int s) { return kv_base + s * 2 * TILE_BYTES; };
@@ -172,59 +169,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (MI && warp >= 1 && warp <= 3) {
-        // Three MMA issuers instead of one.  A single thread cannot issue tcgen05.mma faster than one per ~82 cycles
-        // (scripts/microbench/umma_rate.cu: 82 cycles per M128 N128 K16 and 84 per M128 N64 K16 from one warp, 64.5 / 48.4
-        // from two), so one issuer needs 2000 cycles per key-tile pair for the 8 S and 16 PV instructions and the
-        // softmax warps spend ~600 cycles per tile waiting for PV-done / S-ready behind it (scripts/attn_trace.py).
-        //   warp 1: every S = Q K^T, in sequence order, as soon as its TMEM buffer has been read out (s_free)
-        //   warp 2: O_A += P_A V   warp 3: O_B += P_B V, each as soon as its own P tile is ready
-        const uint32_t fmt = F16 ? 0u : 1u;
-        const int nq = has_b ? 2 : 1;
-        if (warp == 1) {
-            const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);
-            mbar_wait(q_full, 0, 12);
-            const int total = nq * ntiles;
-            for (int seq = 0; seq < total; ++seq) {
-                const int j = nq == 2 ? (seq >> 1) : seq, x = nq == 2 ? (seq & 1) : 0;
-                const int buf = seq % ATT_SBUF;
-                if (x == 0) mbar_wait(kv_full(j % KVS), (j / KVS) & 1, 11);            // K_j landed
-                if (seq >= ATT_SBUF) mbar_wait(s_free(buf), ((seq / ATT_SBUF) - 1) & 1, 18);       // S(seq-3) read out
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t adesc = umma_desc_sw128(sQ(x));
-                    const uint64_t bdesc = umma_desc_sw128(sK(j % KVS));
-#pragma unroll
-                    for (int k = 0; k < ATT_D / 16; ++k)
-                        umma_ss(tS(buf), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-                    tc_commit(s_full(buf));
-                }
-                __syncwarp();
-            }
-        } else {
-            const int x = warp - 2;
-            if (x == 0 || has_b) {
-                const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);
-                for (int j = 0; j < ntiles; ++j) {
-                    const int s = j % KVS;
-                    mbar_wait(p_full(x), j & 1, 13);                          // P_X(j) in smem, O_X rescaled
-                    mbar_wait(kv_full(s), (j / KVS) & 1, 19);           // V_j (landed long ago; orders the TMA writes for this thread)
-                    tc_fence_after();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int ks = 0; ks < ATT_N / 16; ++ks) {
-                            const uint64_t adesc = umma_desc_sw128(sP(x, j % NPB) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
-                            const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
-                            umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-                        }
-                        tc_commit(pv_done(x, j % NPB));
-                        tc_commit(kv_empty(s));                               // count = number of query tiles
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else if (!MI && warp == 1) {
+    } else if (warp == 1) {
         {
             const uint32_t fmt = F16 ? 0u : 1u;
             const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (=K) is K-major
@@ -446,46 +391,62 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Split-row variant (DFW_ATTN_SPLIT=1): same CTA tile, TMEM plan, producer and MMA warps as above, but every query
-// tile gets EIGHT softmax warps instead of four: warp (q, h) owns TMEM lane quadrant q (rows 32q..32q+31) and key
-// columns 64h..64h+63 of each S tile.  Why: scripts/microbench/mufu_issue.cu shows that a MUFU does NOT hold the
-// issue port while the quarter-rate XU datapath works (5 FMA-pipe instructions per ex2 still run at 8.4 cycles per
-// MUFU), so the 12.3 issue cycles per logit of the 4-warp version are an overlap problem, not a floor: with two
-// softmax warps per sub-partition the XU idles whenever both are in a non-MUFU phase (max pass, TMEM wait, packing,
-// barrier).  Four warps per sub-partition make that rare.  Each thread now holds its 64 logits in registers across
-// both passes (no second TMEM read).  The two halves of a row exchange their partial row max (and, once, their
-// partial row sum) through smem with a 64-thread named barrier; both then derive bit-identical m / alpha, so the
-// warp-uniform lazy-rescale decision agrees without further communication.  Half 0 performs the (rare) O rescale;
-// the epilogue splits O's 64 columns between the halves.
+// v3 (round 2, default).  Same CTA tile (2 x 128 query rows of one (episode, head)), same TMA producer and K/V ring fed
+// from two tensor maps, same 3 rotating S accumulators + 2 O accumulators in TMEM.  What changed, each on evidence from
+// scripts/microbench (profiles/r02_microbench_*.log):
+//   * The "one tcgen05.mma per ~82 cycles per issuing thread" floor of round 1 was the issue loop itself (descriptor
+//     assembly, a runtime modulo): with the descriptors hoisted one thread issues M128 N128 K16 at 64.2 and M128 N64 K16
+//     at 32.1 cycles (99.6 % / 99.7 % of the tensor pipe, umma_ts.cu).  The MMA warp keeps per-stage descriptor bases in
+//     registers and adds immediates.
+//   * P never goes through shared memory.  The softmax threads write the 16-bit probabilities back into TMEM, over the
+//     first 64 columns of the very S accumulator they came from (each thread holds its whole row in registers by then),
+//     and O += P V runs with the A operand in TMEM (tcgen05.mma ".ts" form).  With P in smem the PV instruction read 6 KiB
+//     of operands per 32 cycles of math and ran at 48 cycles (the 128 B/clk smem port); from TMEM it runs at 32.  It also
+//     removes the 16 STS.128 + proxy fence per row, 64 KiB of smem (now two more K/V stages) and the wait for "PV(j-1) has
+//     read the P buffer": the buffer of S(seq) is next written by S(seq + 3), which the same thread issues after PV(seq),
+//     and MMAs of one thread execute in order.
+//   * One pass over the logits.  The row maximum is not recomputed per tile (attn_softmax.cuh): P = 2^(s c - m_used) is
+//     evaluated against the maximum in use and only when a row sum of the warp exceeds 2^10 (or on the first / a ragged
+//     tile) the warp re-reads S, takes the exact maximum, rescales O and l and redoes the tile.
+//   * NPOLY/16 of the exponentials run on the FMA pipe (degree-3 polynomial, packed fp32x2 arithmetic) next to the
+//     16-lane XU; scale-and-subtract, row sum and the fp16 pack are packed instructions too.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS_SPLIT = 128 + ATT_QT * 8 * 32;          // 4 control warps + 2 x 8 softmax warps
-constexpr int ATT_XCH_BYTES = 2 * ATT_QT * 2 * ATT_M * 4 /*max, 2 parities*/ + ATT_QT * 2 * ATT_M * 4 /*sum*/;
-constexpr int ATT_SMEM_SPLIT = ATT_SMEM + ATT_XCH_BYTES;
+constexpr int KV_STAGES3 = 5;
+constexpr int ATT_SMEM3 = ATT_QT * TILE_BYTES + KV_STAGES3 * 2 * TILE_BYTES + 1024 + 256;
+static_assert(ATT_SMEM3 <= 227 * 1024, "dynamic smem limit of sm_100");
+constexpr int ATT_NPOLY = 5;                      // of every 16 logit pairs on the polynomial path (softmax_rate.cu)
+
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
 
 template <bool F16>
-__global__ void __launch_bounds__(ATT_THREADS_SPLIT, 1)
-attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    constexpr int KVS = KV_STAGES3;
     auto sQ = [&](int x) { return base + x * TILE_BYTES; };
     const uint32_t kv_base = base + ATT_QT * TILE_BYTES;
     auto sK = [&](int s) { return kv_base + s * 2 * TILE_BYTES; };
     auto sV = [&](int s) { return kv_base + s * 2 * TILE_BYTES + TILE_BYTES; };
-    const uint32_t p_base = kv_base + KV_STAGES * 2 * TILE_BYTES;
-    auto sP = [&](int x) { return p_base + x * 2 * TILE_BYTES; };
-    const uint32_t bar_base = p_base + ATT_QT * 2 * TILE_BYTES;
+    const uint32_t bar_base = kv_base + KVS * 2 * TILE_BYTES;
     const uint32_t q_full = bar_base;
     auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KV_STAGES + s); };
-    auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * KV_STAGES + buf); };
-    auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KV_STAGES + x); };
-    auto pv_done = [&](int x) { return bar_base + 8u * (6 + 2 * KV_STAGES + x); };
-    const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * KV_STAGES);
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KVS + s); };
+    auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * KVS + buf); };      // one per S buffer
+    auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KVS + x); };
+    auto pv_done = [&](int x) { return bar_base + 8u * (6 + 2 * KVS + x); };
+    const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * KVS);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
-    uint8_t* sP_generic = smem_raw + (p_base - raw_u32);
-    float* xch_max = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_u32));       // [parity][x][h][128]
-    float* xch_sum = xch_max + 2 * ATT_QT * 2 * ATT_M;                                       // [x][h][128]
 
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -493,7 +454,8 @@ attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_co
     const int head = blockIdx.y;
     const int b = blockIdx.z;
     const int ntiles = p.n_self + p.n_bank;
-    const bool has_b = (q0 + ATT_M) < p.Lq;
+    const bool has_b = (q0 + ATT_M) < p.Lq;          // second query tile holds at least one valid row
+    const int nq = has_b ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.q);
@@ -503,9 +465,9 @@ attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+        for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
         for (int x = 0; x < ATT_SBUF; ++x) mbar_init(s_full(x), 1);
-        for (int x = 0; x < ATT_QT; ++x) { mbar_init(p_full(x), 256); mbar_init(pv_done(x), 1); }
+        for (int x = 0; x < ATT_QT; ++x) { mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -519,18 +481,20 @@ attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_co
     pdl_wait();
     auto tS = [&](int buf) { return tmem_base + buf * 128; };
     auto tO = [&](int x) { return tmem_base + ATT_SBUF * 128 + x * 64; };
-
+    // register budget (setmaxnreg inside each role branch, so ptxas allocates per role): the softmax threads hold a
+    // whole row of 128 logits in the exact path; the control warps need few
     if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+            mbar_arrive_expect_tx(q_full, nq * TILE_BYTES);
             tma_load_3d(sQ(0), &maps.q, q_full, head * ATT_D, q0, b);
             if (has_b) tma_load_3d(sQ(1), &maps.q, q_full, head * ATT_D, q0 + ATT_M, b);
         }
         __syncwarp();
+        int s = 0;
+        uint32_t ph = 1;
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j % KV_STAGES;
-            const uint32_t ph = (j / KV_STAGES) & 1;
-            mbar_wait(kv_empty(s), ph ^ 1u, 10);
+            mbar_wait(kv_empty(s), ph, 10);
             if (elect_one()) {
                 mbar_arrive_expect_tx(kv_full(s), 2 * TILE_BYTES);
                 if (j < p.n_self) {
@@ -543,119 +507,116 @@ attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_co
                 }
             }
             __syncwarp();
+            if (++s == KVS) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         const uint32_t fmt = F16 ? 0u : 1u;
-        const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);
-        const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);
-        const int nq = has_b ? 2 : 1;
-        auto issue_s = [&](int x, int j) {
-            const int s = j % KV_STAGES;
-            const int buf = (nq * j + x) % ATT_SBUF;
-            const uint64_t adesc = umma_desc_sw128(sQ(x));
-            const uint64_t bdesc = umma_desc_sw128(sK(s));
+        const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (= K) is K-major
+        const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);   // O += P V  : A (= P) in TMEM, B (= V) MN-major
+        // descriptor bases, hoisted: a stage / k-step only moves the 14-bit start-address field (address >> 4)
+        const uint64_t dq0 = umma_desc_sw128(sQ(0)), dq1 = umma_desc_sw128(sQ(1));
+        const uint64_t dk0 = umma_desc_sw128(sK(0)), dv0 = umma_desc_sw128(sV(0));
+        constexpr uint32_t STAGE_STEP = (2 * TILE_BYTES) >> 4;
+        // S tiles are numbered in issue order, seq = nq * j + x, and live in TMEM buffer seq % 3; P(seq) overwrites the
+        // first 64 columns of that buffer and is consumed by PV(seq), issued before S(seq + 3) by this same thread.
+        auto issue_s = [&](int x, int stage, int buf) {          // called by the elected lane
+            const uint64_t adesc = x ? dq1 : dq0;
+            const uint64_t bdesc = dk0 + static_cast<uint64_t>(stage * STAGE_STEP);
+            const uint32_t d = tS(buf);
 #pragma unroll
-            for (int k = 0; k < ATT_D / 16; ++k)
-                umma_ss(tS(buf), adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
             tc_commit(s_full(buf));
         };
         mbar_wait(q_full, 0, 12);
         mbar_wait(kv_full(0), 0, 11);
         tc_fence_after();
         if (elect_one()) {
-            for (int x = 0; x < nq; ++x) issue_s(x, 0);
+            for (int x = 0; x < nq; ++x) issue_s(x, 0, x);
         }
         __syncwarp();
+        int s = 0, s1 = (KVS > 1) ? 1 : 0;              // stage of tile j, of tile j + 1
+        uint32_t ph1 = (KVS > 1) ? 0u : 1u;             // kv_full parity of tile j + 1
+        int buf = 0;                                    // S buffer of (x = 0, j)
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j % KV_STAGES;
             if (j + 1 < ntiles) {
-                mbar_wait(kv_full((j + 1) % KV_STAGES), ((j + 1) / KV_STAGES) & 1, 11);
+                mbar_wait(kv_full(s1), ph1, 11);
                 tc_fence_after();
             }
+            int bx = buf;                               // buffer of (x, j)
+            int bn = buf + nq; if (bn >= ATT_SBUF) bn -= ATT_SBUF;      // buffer of (x, j + 1) = seq + nq
             for (int x = 0; x < nq; ++x) {
-                if (j + 1 < ntiles) {
-                    if (elect_one()) issue_s(x, j + 1);
+                if (j + 1 < ntiles) {                   // run ahead: S_X(j+1) goes to the tensor pipe before P_X(j) is waited for
+                    if (elect_one()) issue_s(x, s1, bn);
                     __syncwarp();
                 }
-                mbar_wait(p_full(x), j & 1, 13);
+                ATT_STAMP(x * 2);
+                mbar_wait(p_full(x), j & 1, 13);        // P_X(j) in TMEM, O_X rescaled if it had to be
                 tc_fence_after();
+                ATT_STAMP(x * 2 + 1);
                 if (elect_one()) {
+                    const uint64_t bdesc = dv0 + static_cast<uint64_t>(s * STAGE_STEP);
+                    const uint32_t d = tO(x), a = tS(bx);
 #pragma unroll
-                    for (int ks = 0; ks < ATT_N / 16; ++ks) {
-                        const uint64_t adesc = umma_desc_sw128(sP(x) + (ks >> 2) * TILE_BYTES) + 2u * (ks & 3);
-                        const uint64_t bdesc = umma_desc_sw128(sV(s) + ks * 16 * 128);
-                        umma_ss(tO(x), adesc, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-                    }
+                    for (int ks = 0; ks < ATT_N / 16; ++ks)
+                        umma_ts(d, a + ks * 8, bdesc + static_cast<uint64_t>(ks * ((16 * 128) >> 4)), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
                     tc_commit(pv_done(x));
-                    if (x == nq - 1) tc_commit(kv_empty(s));
+                    if (x == nq - 1) tc_commit(kv_empty(s));        // K_j / V_j fully consumed by both tiles
                 }
                 __syncwarp();
+                if (++bx == ATT_SBUF) bx = 0;
+                if (++bn == ATT_SBUF) bn = 0;
             }
+            buf += nq; if (buf >= ATT_SBUF) buf -= ATT_SBUF;
+            s = s1;
+            if (++s1 == KVS) { s1 = 0; ph1 ^= 1u; }
         }
-    } else if (warp >= 4) {
-        const int sw = warp - 4;
-        const int x = sw >> 3;                        // query tile of this softmax warp
-        const int qd = sw & 3;                        // TMEM lane quadrant (== warp % 4, the only lanes this warp may touch)
-        const int hf = (sw >> 2) & 1;                 // key-column half
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int x = (warp - 4) >> 2;                // query tile of this softmax group
+        const int qd = (warp - 4) & 3;                // TMEM lane quadrant
         const int row = qd * 32 + lane;
         const int qrow0 = q0 + x * ATT_M;
         if (x == 0 || has_b) {
             const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-            const int nq = has_b ? 2 : 1;
             const uint32_t to = tO(x) + lane_off;
-            const int pair_bar = 1 + x * 4 + qd;      // named barrier of the two warps that share these 32 rows
+            const float sc = p.scale_log2;
             float m_used = -INFINITY, l_run = 0.f;
-            uint8_t* prow = sP_generic + x * 2 * TILE_BYTES + hf * TILE_BYTES + row * 128;
+            int sbuf = x;                             // seq = nq * j + x -> buffer seq % 3, parity (seq / 3) & 1
+            uint32_t sph = 0;
             for (int j = 0; j < ntiles; ++j) {
                 int valid;
                 if (j < p.n_self) valid = min(ATT_N, p.Ls - j * ATT_N);
                 else valid = min(ATT_N, p.Lb - (j - p.n_self) * ATT_N);
-                const int vloc = max(0, min(64, valid - hf * 64));            // valid columns of this half
-                const int seq = nq * j + x, sbuf = seq % ATT_SBUF;
-                const uint32_t ts = tS(sbuf) + lane_off + hf * 64;
-                mbar_wait(s_full(sbuf), (seq / ATT_SBUF) & 1, 15);
+                const uint32_t ts = tS(sbuf) + lane_off;
+                ATT_STAMP(0);
+                mbar_wait(s_full(sbuf), sph, 15);
                 tc_fence_after();
-                // 16-column chunks, software-pipelined like the 4-warp kernel (load of chunk c+1 in flight while chunk c
-                // is processed); 640 threads leave 96 registers per thread, which rules out holding all 64 logits
+                ATT_STAMP(1);
+                uint32_t pk[64];
                 float psum = 0.f;
-                auto run_tile = [&](auto full_tag) {
-                constexpr bool full = decltype(full_tag)::value;
-                uint32_t va[16], vb[16];
-                auto chunk_max = [&](const uint32_t (&v)[16], int c, float& mx) {
-                    if constexpr (full) {
+                bool slow = (j == 0) || (valid != ATT_N);         // warp-uniform
+                if (!slow) {
+                    psum = exp_row128_tmem<F16, ATT_NPOLY>(ts, sc, m_used, pk);
+                    slow = __any_sync(0xffffffffu, !(psum <= SOFTMAX_TRIGGER));
+                }
+                ATT_STAMP(2);
+                if (slow) {
+                    // exact path: whole row from TMEM (still intact: P is stored below), true maximum, O / l rescale
+                    uint32_t sv[128];
+                    tmem_ld_row128(ts, sv);
+                    tmem_ld_wait();
+                    if (valid != ATT_N) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c * 16 + i < vloc) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        for (int i = 0; i < 128; ++i)
+                            if (i >= valid) sv[i] = 0xff800000u;                     // -inf: masked key
                     }
-                };
-                // pass 1: partial row max over this half's 64 logits, exchanged with the other half
-                float mx = -INFINITY;
-                tmem_ld_32x16(ts, va);
-                tmem_ld_wait(); tmem_regs_ready16(va);
-                tmem_ld_32x16(ts + 16, vb);
-                chunk_max(va, 0, mx);
-                tmem_ld_wait(); tmem_regs_ready16(vb);
-                tmem_ld_32x16(ts + 32, va);
-                chunk_max(vb, 1, mx);
-                tmem_ld_wait(); tmem_regs_ready16(va);
-                tmem_ld_32x16(ts + 48, vb);
-                chunk_max(va, 2, mx);
-                tmem_ld_wait(); tmem_regs_ready16(vb);
-                tmem_ld_32x16(ts, va);                               // chunk 0 again, for pass 2
-                chunk_max(vb, 3, mx);
-                float* xm = xch_max + ((j & 1) * ATT_QT + x) * 2 * ATT_M;
-                xm[hf * ATT_M + row] = mx;
-                named_bar_sync(pair_bar, 64);
-                mx = fmaxf(mx, xm[(hf ^ 1) * ATT_M + row]);
-                tmem_ld_wait(); tmem_regs_ready16(va);
-                const float m_new = fmaxf(m_used, mx * p.scale_log2);
-                if (__any_sync(0xffffffffu, m_new > m_used + ATT_RESCALE_TAU)) {
-                    const float alpha = ex2_approx(m_used - m_new);   // 0 on the first tile
-                    if (j > 0 && hf == 0) {
-                        mbar_wait(pv_done(x), (j - 1) & 1, 14);       // O_X holds tiles < j
+                    const float m_new = fmaxf(m_used, row_max128(sv) * sc);
+                    const float alpha = ex2_approx(m_used - m_new);                   // 0 on the first tile
+                    if (j > 0 && __any_sync(0xffffffffu, m_new != m_used)) {
+                        mbar_wait(pv_done(x), (j - 1) & 1, 14);                       // O_X holds tiles < j
                         tc_fence_after();
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
@@ -666,75 +627,48 @@ attn_kvfused_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_co
                             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
                             tmem_st_32x32(to + c * 32, v);
                         }
-                        tmem_st_wait();
                     }
                     l_run *= alpha;
                     m_used = m_new;
+                    psum = exp_row128_staged<F16, ATT_NPOLY, 2>(sv, sc, m_used, pk);
                 }
-                // pass 2: p = exp2(s*c - m) -> 16-bit -> this thread's 128-byte row of P sub-tile hf
-                if (j > 0) mbar_wait(pv_done(x), (j - 1) & 1, 17);    // PV(j-1) has finished reading the P buffer
-                const float sc = p.scale_log2, mu = m_used;
-                auto chunk_p = [&](const uint32_t (&v)[16], int c) {
-                    float pf[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float e = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mu));
-                        if constexpr (!full) { if (c * 16 + i >= vloc) e = 0.f; }
-                        pf[i] = e;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) psum += (pf[i] + pf[i + 1]) + (pf[i + 2] + pf[i + 3]);
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        uint4 w;
-                        w.x = pack_h2(pf[u * 8 + 0], pf[u * 8 + 1], F16);
-                        w.y = pack_h2(pf[u * 8 + 2], pf[u * 8 + 3], F16);
-                        w.z = pack_h2(pf[u * 8 + 4], pf[u * 8 + 5], F16);
-                        w.w = pack_h2(pf[u * 8 + 6], pf[u * 8 + 7], F16);
-                        const int unit = (c * 2 + u) ^ (row & 7);
-                        *reinterpret_cast<uint4*>(prow + unit * 16) = w;
-                    }
-                };
-                tmem_ld_32x16(ts + 16, vb);
-                chunk_p(va, 0);
-                tmem_ld_wait(); tmem_regs_ready16(vb);
-                tmem_ld_32x16(ts + 32, va);
-                chunk_p(vb, 1);
-                tmem_ld_wait(); tmem_regs_ready16(va);
-                tmem_ld_32x16(ts + 48, vb);
-                chunk_p(va, 2);
-                tmem_ld_wait(); tmem_regs_ready16(vb);
-                chunk_p(vb, 3);
-                };
-                if (vloc == 64) run_tile(std::true_type{});
-                else run_tile(std::false_type{});
                 l_run += psum;
-                fence_proxy_async_smem();
+                ATT_STAMP(3);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t (&v)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[c * 16]);
+                    tmem_st_32x16(ts + c * 16, v);
+                }
+                tmem_st_wait();
+                ATT_STAMP(4);
                 tc_fence_before();
                 mbar_arrive(p_full(x));
+                ATT_STAMP(5);
+                sbuf += nq;
+                if (sbuf >= ATT_SBUF) { sbuf -= ATT_SBUF; sph ^= 1u; }
             }
-            // epilogue: O_X / l, 32 of the 64 channels per half
+            // epilogue: O_X / l
             mbar_wait(pv_done(x), (ntiles - 1) & 1, 16);
             tc_fence_after();
-            float* xs = xch_sum + x * 2 * ATT_M;
-            xs[hf * ATT_M + row] = l_run;
-            named_bar_sync(pair_bar, 64);
-            const float inv = 1.0f / (l_run + xs[(hf ^ 1) * ATT_M + row]);
+            const float inv = 1.0f / l_run;
             const bool row_ok = (qrow0 + row) < p.Lq;
             uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
-                           static_cast<long long>(qrow0 + row) * p.o_row_stride + head * ATT_D + hf * 32;
-            uint32_t v[32];
-            tmem_ld_32x32(to + hf * 32, v);
-            tmem_ld_wait();
-            if (row_ok) {
+                           static_cast<long long>(qrow0 + row) * p.o_row_stride + head * ATT_D;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 w;
-                    w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, F16);
-                    w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, F16);
-                    w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, F16);
-                    w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, F16);
-                    *reinterpret_cast<uint4*>(op + i) = w;
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(to + c * 32, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 w;
+                        w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, F16);
+                        w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, F16);
+                        w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, F16);
+                        w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, F16);
+                        *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+                    }
                 }
             }
         }
@@ -944,33 +878,20 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
 #endif
     static bool attr_set = false;
     if (!attr_set) {
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MI));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MI));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_SPLIT));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_SPLIT));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM3));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM3));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
     dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
-    static const bool split_rows = [] { const char* e = getenv("DFW_ATTN_SPLIT"); return e && e[0] == '1'; }();
-    if (split_rows) {
-        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_split_kernel<true>, grid, ATT_THREADS_SPLIT, ATT_SMEM_SPLIT, static_cast<cudaStream_t>(stream_), maps, p));
-        else DFW_CHECK_CUDA(launch_k(attn_kvfused_split_kernel<false>, grid, ATT_THREADS_SPLIT, ATT_SMEM_SPLIT, static_cast<cudaStream_t>(stream_), maps, p));
-        g_launches.fetch_add(1);
-        DFW_CHECK_CUDA(cudaGetLastError());
-        return DFW_OK;
-    }
-    // single MMA-issuing warp (default) or the three-issuer / double-buffered-P schedule (DFW_ATTN_MI=1: correct, measured
-    // 7 % slower, see the kernel and DESIGN.md section 4)
-    static const bool multi_issue = [] { const char* e = getenv("DFW_ATTN_MI"); return e && e[0] == '1'; }();
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    if (multi_issue) {
-        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true, true>, grid, ATT_THREADS, ATT_SMEM_MI, st, maps, p));
-        else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false, true>, grid, ATT_THREADS, ATT_SMEM_MI, st, maps, p));
+    if (get_option(DFW_OPT_ATTN_V2)) {        // round-1 kernel (P through smem, two passes over S), kept for A/B measurements
+        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_v2_kernel<true>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
+        else DFW_CHECK_CUDA(launch_k(attn_kvfused_v2_kernel<false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
     } else {
-        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true, false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
-        else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false, false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
+        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true>, grid, ATT_THREADS, ATT_SMEM3, st, maps, p));
+        else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false>, grid, ATT_THREADS, ATT_SMEM3, st, maps, p));
     }
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());

@@ -79,18 +79,17 @@ __device__ __forceinline__ float row_max128(const uint32_t (&s)[128]) {
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// p = 2^(s * sc - mu) for logits s[base .. base+32) -> 16 packed 16-bit pairs in pk[], row sum accumulated in sum2
-// (two packed accumulators).  NPOLY of every 8 pairs take the polynomial path; spread evenly over the 8.
+// p = 2^(s * sc - mu) for 32 logits -> 16 packed 16-bit pairs in pk[], row sum accumulated in sum2 (two packed
+// accumulators).  NPOLY of every 16 pairs take the polynomial path, spread evenly over the 16.
 template <bool F16, int NPOLY>
 __device__ __forceinline__ void exp_chunk32(const uint32_t* s, uint64_t sc2, uint64_t nmu2, uint64_t (&sum2)[2],
-                                            uint32_t (&pk)[16]) {
+                                            uint32_t* pk) {
 #pragma unroll
     for (int pi = 0; pi < 16; ++pi) {
         const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * pi]), __uint_as_float(s[2 * pi + 1])), sc2, nmu2);
         float e0, e1;
-        // pair (pi % 8) takes the polynomial when floor((j + 1) * NPOLY / 8) > floor(j * NPOLY / 8)
-        const int j = pi & 7;
-        const bool poly = ((j + 1) * NPOLY) / 8 > (j * NPOLY) / 8;
+        // pair pi takes the polynomial when floor((pi + 1) * NPOLY / 16) > floor(pi * NPOLY / 16)
+        const bool poly = ((pi + 1) * NPOLY) / 16 > (pi * NPOLY) / 16;
         if (poly) {
             exp2_poly2(x2, e0, e1);
         } else {
@@ -104,6 +103,72 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t* s, uint64_t sc2, uin
     }
 }
 
+// Staged variant (same results): all scale-and-subtracts, then every MUFU of the chunk back to back, then the polynomial
+// pairs (FMA-pipe work that runs while the XU drains), then the sums and conversions -- the consumers of a MUFU result
+// sit as far from its issue as the chunk allows.  NACC packed sum accumulators.
+template <bool F16, int NPOLY, int NACC>
+__device__ __forceinline__ void exp_chunk32_staged(const uint32_t* s, uint64_t sc2, uint64_t nmu2, uint64_t (&sum2)[NACC],
+                                                   uint32_t* pk) {
+    uint64_t x2[16];
+    float e[32];
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi)
+        x2[pi] = f2_fma(f2_pack(__uint_as_float(s[2 * pi]), __uint_as_float(s[2 * pi + 1])), sc2, nmu2);
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) {
+        const bool poly = ((pi + 1) * NPOLY) / 16 > (pi * NPOLY) / 16;
+        if (!poly) {
+            float x0, x1;
+            f2_unpack(x2[pi], x0, x1);
+            e[2 * pi] = ex2_approx(x0);
+            e[2 * pi + 1] = ex2_approx(x1);
+        }
+    }
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) {
+        const bool poly = ((pi + 1) * NPOLY) / 16 > (pi * NPOLY) / 16;
+        if (poly) exp2_poly2(x2[pi], e[2 * pi], e[2 * pi + 1]);
+    }
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) {
+        sum2[pi % NACC] = f2_add(sum2[pi % NACC], f2_pack(e[2 * pi], e[2 * pi + 1]));
+        pk[pi] = F16 ? cvt_f16x2(e[2 * pi], e[2 * pi + 1]) : cvt_bf16x2(e[2 * pi], e[2 * pi + 1]);
+    }
+}
+
+template <bool F16, int NPOLY, int NACC>
+__device__ __forceinline__ float exp_row128_staged(const uint32_t (&s)[128], float sc, float mu, uint32_t (&pk)[64]) {
+    const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-mu, -mu);
+    uint64_t sum2[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) sum2[i] = 0ull;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) exp_chunk32_staged<F16, NPOLY, NACC>(&s[c * 32], sc2, nmu2, sum2, &pk[c * 16]);
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { float a, b; f2_unpack(sum2[i], a, b); tot += a + b; }
+    return tot;
+}
+
+// All 128 logits of a row: pk[64] packed probabilities, returns the row sum of this tile.
+template <bool F16, int NPOLY>
+__device__ __forceinline__ float exp_row128(const uint32_t (&s)[128], float sc, float mu, uint32_t (&pk)[64]) {
+    const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-mu, -mu);
+    uint64_t sum2[2] = {0ull, 0ull};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) exp_chunk32<F16, NPOLY>(&s[c * 32], sc2, nmu2, sum2, &pk[c * 16]);
+    float a, b, c, d;
+    f2_unpack(sum2[0], a, b);
+    f2_unpack(sum2[1], c, d);
+    return (a + b) + (c + d);
+}
+
+// The running row maximum is NOT recomputed per tile.  P = 2^(s*c - m_used) is evaluated against the maximum in use;
+// as long as the tile's row sum stays <= SOFTMAX_TRIGGER every p is <= SOFTMAX_TRIGGER (finite in fp16, exact scaling in
+// the fp32 accumulators), so nothing needs to change.  Only when some row of the warp exceeds it (or on the first tile,
+// m_used = -inf -> sum = +inf) the warp takes the slow path: exact row max, new m_used, O / l rescale, exponentials redone.
+constexpr float SOFTMAX_TRIGGER = 1024.0f;
+
 // 16 consecutive 32-bit TMEM columns <- registers (thread i of the warp writes lane base + i)
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
@@ -112,6 +177,32 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
+}
+
+// Fast path over one key tile with the TMEM loads software-pipelined in 32-column chunks (the load of chunk c+1 is in
+// flight while chunk c is exponentiated; tcgen05.wait::ld waits for everything outstanding, hence the placement).
+// Returns the tile's row sum; pk[64] = packed probabilities.
+template <bool F16, int NPOLY>
+__device__ __forceinline__ float exp_row128_tmem(uint32_t ts, float sc, float mu, uint32_t (&pk)[64]) {
+    const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-mu, -mu);
+    uint64_t sum2[2] = {0ull, 0ull};
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(ts, va);
+    tmem_ld_wait(); tmem_regs_ready(va);
+    tmem_ld_32x32(ts + 32, vb);
+    exp_chunk32<F16, NPOLY>(va, sc2, nmu2, sum2, &pk[0]);
+    tmem_ld_wait(); tmem_regs_ready(vb);
+    tmem_ld_32x32(ts + 64, va);
+    exp_chunk32<F16, NPOLY>(vb, sc2, nmu2, sum2, &pk[16]);
+    tmem_ld_wait(); tmem_regs_ready(va);
+    tmem_ld_32x32(ts + 96, vb);
+    exp_chunk32<F16, NPOLY>(va, sc2, nmu2, sum2, &pk[32]);
+    tmem_ld_wait(); tmem_regs_ready(vb);
+    exp_chunk32<F16, NPOLY>(vb, sc2, nmu2, sum2, &pk[48]);
+    float a, b, c, d;
+    f2_unpack(sum2[0], a, b);
+    f2_unpack(sum2[1], c, d);
+    return (a + b) + (c + d);
 }
 
 // 128 consecutive fp32 TMEM columns -> registers (four x32 loads; the caller waits)

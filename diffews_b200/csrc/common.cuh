@@ -40,7 +40,10 @@ int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const u
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box);
 
-// Kernel launch with the programmatic-dependent-launch attribute when DFW_PDL=1 (default: plain launch).  Only for kernels that call
+// Process-wide option table (include/diffews_b200.h DFW_OPT_*): explicit, no environment variables.
+int get_option(int option);
+
+// Kernel launch with the programmatic-dependent-launch attribute when DFW_OPT_PDL is set (default: plain launch).  Only for kernels that call
 // pdl_wait() before their first global access.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>

@@ -1270,8 +1270,8 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
                     int Cin, int Cout, int ksize, int stride, int pad_mode, int flags, float out_scale, int bias_sample_stride,
                     long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
                     long long gn_img_stride, cudaStream_t stream, const float* gn_in = nullptr, bool dry_run = false) {
-    static const bool enabled = [] { const char* e = getenv("DFW_T128"); return !(e && e[0] == '0'); }();
-    static const int max_cout = [] { const char* e = getenv("DFW_T128_MAXC"); return e ? atoi(e) : 1 << 20; }();
+    const bool enabled = get_option(DFW_OPT_T128) != 0;
+    const int max_cout = get_option(DFW_OPT_T128_MAXC);
     // a token matrix [M, K] (linear layers arrive as a 1 x M image) is the image [M / 16, 16]: a 16 x 16 tile is then 256
     // consecutive rows
     // (measured: a gain only for the projections with a residual; the others stay on the generic kernel)
@@ -1411,7 +1411,7 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
     if (up_phase >= 0) DFW_REQUIRE(ksize == 3 && stride == 1 && pad_mode == 0 && residual == nullptr);
     choose_tile(Wout, Hout, N, p.TW, p.TH, p.TN);
     // halo mainloop: 3x3 / stride 1 on images that tile exactly into 8 x 16 output patches
-    static const bool halo_enabled = [] { const char* e = getenv("DFW_HALO"); return !(e && e[0] == '0'); }();
+    const bool halo_enabled = get_option(DFW_OPT_HALO) != 0;
     p.halo = (halo_enabled && ksize == 3 && stride == 1 && up_phase < 0 && w_batch_stride == 0 && Wout % 16 == 0 &&
               Hout % 8 == 0) ? 1 : 0;
     if (p.halo) { p.TW = 16; p.TH = 8; p.TN = 1; }

@@ -697,7 +697,7 @@ GnPlan gn_plan(int N, int HW, int C) {
     pl.threads = pl.V * pl.RPI;
     // exactly one wave: the kernels run 3 CTAs of <= 320 threads per SM (register-limited, ncu), and a second partial
     // wave plus the per-CTA statistics fold cost 30 % on the L2-sized tensors
-    static const int per_sm = [] { const char* e = getenv("DFW_GN_CTAS_PER_SM"); return e ? atoi(e) : 3; }();
+    const int per_sm = get_option(DFW_OPT_GN_CTAS_PER_SM) > 0 ? get_option(DFW_OPT_GN_CTAS_PER_SM) : 3;
     int want = (per_sm * sm_count() + (per_sm > 3 ? N - 1 : 0)) / N;
     if (want < 1) want = 1;
     int max_chunks = (HW + pl.RPI * 16 - 1) / (pl.RPI * 16);  // at least 16 rows per thread

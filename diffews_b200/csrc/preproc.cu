@@ -392,7 +392,7 @@ int dfw_resize_normalize_u8(const void* base, const void* descs, int n, int max_
     const uint8_t* b = reinterpret_cast<const uint8_t*>(base);
     DFW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 3) == 0);
     const FusedLayout F = fused_layout(max_h, max_w, out_h, out_w);
-    static const bool two_pass_forced = [] { const char* e = getenv("DFW_PREPROC_TWO_PASS"); return e && e[0] == '1'; }();
+    const bool two_pass_forced = get_option(DFW_OPT_PREPROC_TWO_PASS) != 0;
     const CoefLayout L = coef_layout(n, max_h, max_w, out_h, out_w);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     int2* bounds = reinterpret_cast<int2*>(ws);

@@ -43,8 +43,8 @@ PURE_BF16 = Precision(half=torch.bfloat16)
 # default: measured on B200 it loses -- the patch transform has to run once per horizontal tap (3x the elements, one MUFU
 # tanh each: 6.9k MUFU cycles per 9.2k MMA cycles of a tile), the VAE convolutions drop from 1.27-1.42 to 0.79-0.90
 # PFLOP/s, which costs more than the 16 ms / step of GroupNorm-apply passes it removes (111 vs 123 episodes/s).
-# DFW_FUSE_GN=1 enables it.
-FUSE_GN_INTO_CONV = os.environ.get("DFW_FUSE_GN", "0") == "1"
+# Set layers.FUSE_GN_INTO_CONV = True before building the engines to enable it (no environment variable).
+FUSE_GN_INTO_CONV = False
 
 
 def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:

@@ -42,6 +42,13 @@ def launch_count() -> int:
     return int(lib.dfw_launch_count())
 
 
+def set_option(option: int, value: int) -> int:
+    """dfw_set_option: process-wide kernel-selection switch (_lib.OPT_*); returns the previous value."""
+    old = int(lib.dfw_get_option(option))
+    check(lib.dfw_set_option(option, int(value)), "dfw_set_option")
+    return old
+
+
 class KernelTimer:
     """CUDA-event timing of individual tensor-core launches (bench.py's roofline leg).  When installed with
     `set_timer`, conv2d / linear / attn_kvfused bracket their launch with two events on the launching stream."""

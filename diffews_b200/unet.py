@@ -30,8 +30,8 @@ bf16 = torch.bfloat16
 # attn2 against a fixed short prompt as one skinny GEMM + a bandwidth kernel (see CrossAttention.kv).  Exact algebra and
 # 31 fewer launches per step, but measured 1.4 % SLOWER on B200 (ABAB on one box: 121.5 / 122.3 vs 123.6 / 123.7 / 124.1
 # episodes/s): the N = 16-48 GEMMs and the per-token softmax recomputation cost more than the two C x C projections they
-# replace, which are cheap on tcgen05.  Off by default; DFW_XATTN_COLLAPSE=1 enables it.
-COLLAPSE_CROSS_ATTN = os.environ.get("DFW_XATTN_COLLAPSE", "0") == "1"
+# replace, which are cheap on tcgen05.  Off by default; set unet.COLLAPSE_CROSS_ATTN = True to enable it.
+COLLAPSE_CROSS_ATTN = False
 
 
 @dataclass

@@ -2,8 +2,9 @@
  * diffews_b200 — C ABI of the B200 (sm_100a) hot path of DiffewS.
  *
  * Every entry point is `extern "C"`, takes raw DEVICE pointers + sizes + a cudaStream_t (as void*), returns an int
- * status (0 = DFW_OK, negative = error), never throws, never allocates device memory, keeps no hidden global state
- * and is stream-ordered.  There is NO CPU / other-arch fallback: on a non-sm_100 device every compute entry point
+ * status (0 = DFW_OK, negative = error), never throws, never allocates device memory, reads no environment variable
+ * and is stream-ordered.  The only process-wide state is the explicit option table below (dfw_set_option): kernel-
+ * selection switches for A/B measurements, every default being what bench.py measures.  There is NO CPU / other-arch fallback: on a non-sm_100 device every compute entry point
  * returns DFW_ERR_ARCH.
  *
  * The reference (ga1i13o/DiffewS) has no native code; each entry point below replaces a *library call site* of the
@@ -26,6 +27,20 @@ extern "C" {
 #define DFW_ERR_INVALID (-1) /* bad argument (shape / alignment / unsupported combination) */
 #define DFW_ERR_CUDA (-2)    /* a CUDA runtime/driver call failed (message on stderr)        */
 #define DFW_ERR_ARCH (-3)    /* device is not sm_100 (B200) — no fallback by design           */
+
+/* Process-wide options (dfw_set_option / dfw_get_option).  Defaults in brackets; every option only selects between
+ * kernels that compute the same result. */
+#define DFW_OPT_PDL 0               /* [0] programmatic dependent launch on the hot kernels (correct, neutral on B200)   */
+#define DFW_OPT_T128 1              /* [1] channel-major conv kernel igemm_t128 (0: everything on igemm_kernel)          */
+#define DFW_OPT_T128_MAXC 2         /* [1<<20] largest Cout routed to igemm_t128                                          */
+#define DFW_OPT_HALO 3              /* [1] halo mainloop of the generic 3x3 kernel (0: one TMA box per filter tap)       */
+#define DFW_OPT_GN_CTAS_PER_SM 4    /* [3] GroupNorm grid sizing                                                          */
+#define DFW_OPT_PREPROC_TWO_PASS 5  /* [0] data layer: two-launch resample with a uint8 intermediate in HBM              */
+#define DFW_OPT_ATTN_V2 6           /* [0] round-1 attention kernel (P through smem, two passes over S)                  */
+#define DFW_OPT_SEG_HEAD 7          /* [1] fused decoder head dfw_seg_head_u8 (0: gn-apply + conv 128->3 + seg_post)     */
+#define DFW_OPT_COUNT 8
+int dfw_set_option(int option, int value); /* DFW_ERR_INVALID for an unknown option */
+int dfw_get_option(int option);            /* current value; -1 for an unknown option */
 
 /* epilogue flags for dfw_conv2d_igemm / dfw_linear */
 #define DFW_EPI_OUT_F32 1   /* y is fp32 (default: 16-bit, bf16 or fp16 per DFW_EPI_F16)              */

@@ -17,7 +17,7 @@ using namespace dfw;
 
 constexpr int THREADS = 384;
 
-template <int NPOLY, bool SETMAXNREG>
+template <int NPOLY, bool SETMAXNREG, bool PIPELINED, int OFFSET, int STAGED>
 __global__ void __launch_bounds__(THREADS, 1) softmax_kernel(const float* S_in, uint32_t* P_out, float* sum_out,
                                                                long long* cyc, int tiles, float sc) {
     __shared__ uint32_t slot;
@@ -44,31 +44,40 @@ __global__ void __launch_bounds__(THREADS, 1) softmax_kernel(const float* S_in, 
         }
         float m_used = -INFINITY, l_run = 0.f;
         long long c0 = 0;
+        if (OFFSET > 0 && x == 1) { const long long w0 = clock64(); while (clock64() - w0 < OFFSET) { } }   // tile B out of phase
+        int slow = 0;
         for (int j = 0; j < tiles + 1; ++j) {
-            if (j == 1) c0 = clock64();            // tile 0 warms up
-            uint32_t s[128];
-            tmem_ld_row128(tS, s);
-            tmem_ld_wait();
-            const float mx = row_max128(s);
-            const float m_new = fmaxf(m_used, mx * sc);
-            if (__any_sync(0xffffffffu, m_new > m_used + 8.0f)) {
+            if (j == 1) c0 = clock64();            // tile 0 warms up (and takes the slow path: m_used = -inf)
+            uint32_t pk[64];
+            float psum;
+            if (PIPELINED) {
+                psum = exp_row128_tmem<true, NPOLY>(tS, sc, m_used, pk);
+            } else {
+                uint32_t s[128];
+                tmem_ld_row128(tS, s);
+                tmem_ld_wait();
+                if (STAGED == 0) psum = exp_row128<true, NPOLY>(s, sc, m_used, pk);
+                else psum = exp_row128_staged<true, NPOLY, (STAGED > 0 ? STAGED : 2)>(s, sc, m_used, pk);
+            }
+            if (__any_sync(0xffffffffu, !(psum <= SOFTMAX_TRIGGER))) {
+                ++slow;
+                uint32_t s[128];
+                tmem_ld_row128(tS, s);
+                tmem_ld_wait();
+                const float m_new = fmaxf(m_used, row_max128(s) * sc);
                 l_run *= ex2_approx(m_used - m_new);
                 m_used = m_new;
+                psum = exp_row128<true, NPOLY>(s, sc, m_used, pk);
             }
-            const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-m_used, -m_used);
-            uint64_t sum2[2] = {0ull, 0ull};
+            l_run += psum;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t pk[16];
-                exp_chunk32<true, NPOLY>(&s[c * 32], sc2, nmu2, sum2, pk);
-                tmem_st_32x16(tP + c * 16, pk);
+                uint32_t (&v)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[c * 16]);
+                tmem_st_32x16(tP + c * 16, v);
             }
-            float a, b, c, d;
-            f2_unpack(sum2[0], a, b);
-            f2_unpack(sum2[1], c, d);
-            l_run += (a + b) + (c + d);
             tmem_st_wait();
         }
+        if (slow != 1) l_run = -1.0f;              // exactly the first tile may take the slow path here
         const long long c1 = clock64();
         if (lane == 0) cyc[blockIdx.x * 8 + (warp - 4)] = c1 - c0;
         if (blockIdx.x == 0) {
@@ -89,12 +98,12 @@ __global__ void __launch_bounds__(THREADS, 1) softmax_kernel(const float* S_in, 
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-template <int NPOLY, bool SMR>
+template <int NPOLY, bool SMR, bool PIPE = false, int OFFSET = 0, int STAGED = 0>
 void run(const float* dS, const std::vector<float>& hS, float sc) {
     const int tiles = 200, blocks = 148;
     uint32_t* dP; float* dsum; long long* dc;
     cudaMalloc(&dP, 256 * 64 * 4); cudaMalloc(&dsum, 256 * 4); cudaMalloc(&dc, blocks * 8 * 8);
-    softmax_kernel<NPOLY, SMR><<<blocks, THREADS>>>(dS, dP, dsum, dc, tiles, sc);
+    softmax_kernel<NPOLY, SMR, PIPE, OFFSET, STAGED><<<blocks, THREADS>>>(dS, dP, dsum, dc, tiles, sc);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("NPOLY %d: %s\n", NPOLY, cudaGetErrorString(e)); exit(1); }
     std::vector<long long> hc(blocks * 8);
@@ -124,13 +133,109 @@ void run(const float* dS, const std::vector<float>& hS, float sc) {
         }
         max_sum_rel = fmax(max_sum_rel, fabs(hsum[r] - sum) / sum);
     }
-    printf("NPOLY %d/8%s: %7.1f cycles per tile per warp (= per tile pair per sub-partition) -> tensor-pipe ceiling %5.1f %% ; "
-           "P max rel err %.2e, row-sum rel err %.2e %s\n", NPOLY, SMR ? " setmaxnreg" : "", per_tile, 100.0 * 1024.0 / per_tile,
+    printf("NPOLY %d/16%s%s offset %d staged/nacc %d: %7.1f cycles per tile per warp (= per tile pair per sub-partition) -> tensor-pipe ceiling %5.1f %% ; "
+           "P max rel err %.2e, row-sum rel err %.2e %s\n", NPOLY, SMR ? " setmaxnreg" : "", PIPE ? " pipelined-ld" : "", OFFSET, STAGED, per_tile, 100.0 * 1024.0 / per_tile,
            max_rel, max_sum_rel, (max_rel < 2e-3 && max_sum_rel < 1e-4) ? "NUMERICS_OK" : "NUMERICS_BAD");
     cudaFree(dP); cudaFree(dsum); cudaFree(dc);
 }
 
+// Half-row variant: 16 softmax warps (4 per sub-partition); warp (x, h, q) owns rows 32q.. of tile x and key columns 64h..64h+63.
+// One 64-thread named barrier per tile stands in for the trigger-flag exchange between the two halves of a row.
+template <int NPOLY, int STAGED>
+__global__ void __launch_bounds__(640, 1) softmax_half_kernel(const float* S_in, long long* cyc, float* sum_out, int tiles, float sc) {
+    __shared__ uint32_t slot;
+    __shared__ float flags[2][2][4][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 2) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (warp >= 4) {
+        const int sw = warp - 4, x = sw >> 3, hf = (sw >> 2) & 1, qd = sw & 3, row = qd * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t tS = tmem + lane_off + x * 256 + hf * 64, tP = tmem + lane_off + x * 256 + 128 + hf * 32;
+        {
+            uint32_t v[32];
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(S_in[(x * 128 + row) * 128 + hf * 64 + c * 32 + i]);
+                tmem_st_32x32(tS + c * 32, v);
+            }
+            tmem_st_wait();
+        }
+        float m_used = 24.0f * sc, l_run = 0.f;          // the known maximum of the test data: every tile takes the fast path
+        long long c0 = 0;
+        const int pair_bar = 1 + x * 4 + qd;
+        for (int j = 0; j < tiles + 1; ++j) {
+            if (j == 1) c0 = clock64();
+            uint32_t pk[32];
+            const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-m_used, -m_used);
+            uint64_t sum2[2] = {0ull, 0ull};
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(tS, va);
+            tmem_ld_wait(); tmem_regs_ready(va);
+            tmem_ld_32x32(tS + 32, vb);
+            if (STAGED) exp_chunk32_staged<true, NPOLY, 2>(va, sc2, nmu2, sum2, &pk[0]);
+            else exp_chunk32<true, NPOLY>(va, sc2, nmu2, sum2, &pk[0]);
+            tmem_ld_wait(); tmem_regs_ready(vb);
+            if (STAGED) exp_chunk32_staged<true, NPOLY, 2>(vb, sc2, nmu2, sum2, &pk[16]);
+            else exp_chunk32<true, NPOLY>(vb, sc2, nmu2, sum2, &pk[16]);
+            float a, b, c, d;
+            f2_unpack(sum2[0], a, b);
+            f2_unpack(sum2[1], c, d);
+            const float psum = (a + b) + (c + d);
+            const bool trig = __any_sync(0xffffffffu, !(psum <= SOFTMAX_TRIGGER));
+            if (lane == 0) flags[j & 1][x][qd][hf] = trig ? 1.f : 0.f;
+            named_bar_sync(pair_bar, 64);
+            if (flags[j & 1][x][qd][hf ^ 1] != 0.f || trig) l_run = -1e30f;      // (never taken here)
+            l_run += psum;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t (&v)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[cc * 16]);
+                tmem_st_32x16(tP + cc * 16, v);
+            }
+            tmem_st_wait();
+        }
+        const long long c1 = clock64();
+        if (lane == 0) cyc[blockIdx.x * 16 + sw] = c1 - c0;
+        if (blockIdx.x == 0) sum_out[(x * 2 + hf) * 128 + row] = l_run / (tiles + 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int NPOLY, int STAGED>
+void run_half(const float* dS, const std::vector<float>& hS, float sc) {
+    const int tiles = 200, blocks = 148;
+    float* dsum; long long* dc;
+    cudaMalloc(&dsum, 512 * 4); cudaMalloc(&dc, blocks * 16 * 8);
+    softmax_half_kernel<NPOLY, STAGED><<<blocks, 640>>>(dS, dc, dsum, tiles, sc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("half NPOLY %d: %s\n", NPOLY, cudaGetErrorString(e)); exit(1); }
+    std::vector<long long> hc(blocks * 16);
+    std::vector<float> hsum(512);
+    cudaMemcpy(hc.data(), dc, hc.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hsum.data(), dsum, hsum.size() * 4, cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (auto v : hc) avg += v;
+    avg /= hc.size();
+    double max_sum_rel = 0;
+    for (int r = 0; r < 256; ++r) {
+        double sum = 0;
+        for (int k = 0; k < 128; ++k) sum += exp2(double(hS[r * 128 + k]) * sc - 24.0 * sc);
+        const int x = r / 128, row = r % 128;
+        const double got = double(hsum[(x * 2) * 128 + row]) + double(hsum[(x * 2 + 1) * 128 + row]);
+        max_sum_rel = fmax(max_sum_rel, fabs(got - sum) / sum);
+    }
+    printf("HALF-ROW (16 softmax warps) NPOLY %d/16 staged %d: %7.1f cycles per tile pair per sub-partition -> tensor-pipe ceiling %5.1f %% ; row-sum rel err %.2e\n",
+           NPOLY, STAGED, avg / tiles, 100.0 * 1024.0 / (avg / tiles), max_sum_rel);
+    cudaFree(dsum); cudaFree(dc);
+}
+
 int main() {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     std::vector<float> hS(256 * 128);
     srand(3);
     for (auto& v : hS) v = ((rand() % 20001) - 10000) / 10000.0f * 24.0f;      // raw logits in [-24, 24]
@@ -138,15 +243,18 @@ int main() {
     cudaMalloc(&dS, hS.size() * 4);
     cudaMemcpy(dS, hS.data(), hS.size() * 4, cudaMemcpyHostToDevice);
     const float sc = 0.125f * 1.4426950408889634f;
-    run<0, false>(dS, hS, sc);
-    run<1, false>(dS, hS, sc);
-    run<2, false>(dS, hS, sc);
-    run<3, false>(dS, hS, sc);
-    run<4, false>(dS, hS, sc);
-    run<0, true>(dS, hS, sc);
-    run<2, true>(dS, hS, sc);
-    run<3, true>(dS, hS, sc);
-    run<4, true>(dS, hS, sc);
+    run<5, true, false, 0, 2>(dS, hS, sc);
+    run_half<0, 0>(dS, hS, sc);
+    run_half<4, 0>(dS, hS, sc);
+    run_half<5, 0>(dS, hS, sc);
+    run_half<6, 0>(dS, hS, sc);
+    run_half<7, 0>(dS, hS, sc);
+    run_half<8, 0>(dS, hS, sc);
+    run_half<10, 0>(dS, hS, sc);
+    run_half<5, 1>(dS, hS, sc);
+    run_half<6, 1>(dS, hS, sc);
+    run_half<7, 1>(dS, hS, sc);
+    run_half<8, 1>(dS, hS, sc);
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }

@@ -38,7 +38,8 @@ def test_ctypes_table_mirrors_header(lib_built):
 
 def test_version_and_no_gpu_behaviour(lib_built):
     import torch
-    assert lib_built.lib.dfw_version() == 1
+    assert lib_built.lib.dfw_version() == 2
+    assert lib_built.lib.dfw_get_option(6) == 0 and lib_built.lib.dfw_set_option(99, 1) == -1   # option table: explicit, no getenv
     assert lib_built.lib.dfw_launch_count() >= 0
     if not torch.cuda.is_available():
         # no device: every compute entry point must fail loudly (negative status), never fall back
