@@ -294,7 +294,7 @@ attn_kvfused_v2_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
                             for (int c = 0; c < 2; ++c) {
                                 uint32_t v[32];
                                 tmem_ld_32x32(to + c * 32, v);
-                                tmem_ld_wait();
+                                tmem_ld_wait(); tmem_regs_ready(v);
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
                                 tmem_st_32x32(to + c * 32, v);
@@ -366,7 +366,7 @@ attn_kvfused_v2_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
             for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(to + c * 32, v);
-                tmem_ld_wait();
+                tmem_ld_wait(); tmem_regs_ready(v);
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
@@ -414,7 +414,13 @@ attn_kvfused_v2_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
 constexpr int KV_STAGES3 = 5;
 constexpr int ATT_SMEM3 = ATT_QT * TILE_BYTES + KV_STAGES3 * 2 * TILE_BYTES + 1024 + 256;
 static_assert(ATT_SMEM3 <= 227 * 1024, "dynamic smem limit of sm_100");
-constexpr int ATT_NPOLY = 5;                      // of every 16 logit pairs on the polynomial path (softmax_rate.cu)
+#ifndef ATT_MMA_WARP
+#define ATT_MMA_WARP 1
+#endif
+#ifndef DFW_ATT_NPOLY
+#define DFW_ATT_NPOLY 5
+#endif
+constexpr int ATT_NPOLY = DFW_ATT_NPOLY;                      // of every 16 logit pairs on the polynomial path (softmax_rate.cu)
 
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -463,7 +469,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         tma_prefetch_desc(&maps.v_self);
         if (p.n_bank) { tma_prefetch_desc(&maps.k_bank); tma_prefetch_desc(&maps.v_bank); }
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == ATT_MMA_WARP && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
         for (int x = 0; x < ATT_SBUF; ++x) mbar_init(s_full(x), 1);
@@ -509,7 +515,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             __syncwarp();
             if (++s == KVS) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == 1) {
+    } else if (warp == ATT_MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         const uint32_t fmt = F16 ? 0u : 1u;
         const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N, fmt, fmt, 0);   // S = Q K^T : B (= K) is K-major
@@ -607,7 +613,6 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                     // exact path: whole row from TMEM (still intact: P is stored below), true maximum, O / l rescale
                     uint32_t sv[128];
                     tmem_ld_row128(ts, sv);
-                    tmem_ld_wait();
                     if (valid != ATT_N) {
 #pragma unroll
                         for (int i = 0; i < 128; ++i)
@@ -622,7 +627,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                         for (int c = 0; c < 2; ++c) {
                             uint32_t v[32];
                             tmem_ld_32x32(to + c * 32, v);
-                            tmem_ld_wait();
+                            tmem_ld_wait(); tmem_regs_ready(v);
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
                             tmem_st_32x32(to + c * 32, v);
@@ -641,13 +646,19 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
                 }
                 tmem_st_wait();
                 ATT_STAMP(4);
+                // S_X(j+1) is computed ahead, so a warp can start (and finish) tile j+1 while a sibling is still in the
+                // exact path of tile j.  Its arrival must not be counted in phase j of p_full (the MMA warp would issue
+                // PV(j) before the sibling's rows of P exist), and parity waits on pv_done are only unambiguous while a
+                // waiter is at most one phase behind.  Both follow from observing EVERY phase of pv_done in order: before
+                // arriving for tile j, wait for PV(j-1) -- issued a whole tile ago, so normally one successful try_wait.
+                if (j > 0) mbar_wait(pv_done(x), (j - 1) & 1, 18);
                 tc_fence_before();
                 mbar_arrive(p_full(x));
                 ATT_STAMP(5);
                 sbuf += nq;
                 if (sbuf >= ATT_SBUF) { sbuf -= ATT_SBUF; sph ^= 1u; }
             }
-            // epilogue: O_X / l
+            // epilogue: O_X / l  (PV(ntiles - 2) was observed before the last arrive, so this parity wait is unambiguous)
             mbar_wait(pv_done(x), (ntiles - 1) & 1, 16);
             tc_fence_after();
             const float inv = 1.0f / l_run;
@@ -658,7 +669,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(to + c * 32, v);
-                tmem_ld_wait();
+                tmem_ld_wait(); tmem_regs_ready(v);
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {

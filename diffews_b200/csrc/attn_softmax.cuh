@@ -46,12 +46,14 @@ constexpr float EXP2_C0 = 0.9999280571937561f, EXP2_C1 = 0.6932609677314758f, EX
                 EXP2_C3 = 0.055171653628349304f;
 constexpr float EXP2_MAGIC = 12582912.0f;        // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer (|x| < 2^22)
 
-// 2^x for a packed pair on the FMA / ALU pipes (no MUFU).  x <= ~100; x < -126 is clamped (result ~1e-38, 0 in fp16).
+// 2^x for a packed pair on the FMA / ALU pipes (no MUFU).  x is clamped to [-126, 126]: below, the result (~1e-38) is 0 in
+// fp16 anyway; above, 2^126 still drives the row sum over SOFTMAX_TRIGGER (an unclamped x >= 129 would wrap the exponent
+// field into the sign bit and yield a tiny NEGATIVE value that the trigger cannot see).
 __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
     float x0, x1;
     f2_unpack(x2, x0, x1);
-    x0 = fmaxf(x0, -126.0f);
-    x1 = fmaxf(x1, -126.0f);
+    x0 = fminf(fmaxf(x0, -126.0f), 126.0f);
+    x1 = fminf(fmaxf(x1, -126.0f), 126.0f);
     const uint64_t xc = f2_pack(x0, x1);
     const uint64_t t2 = f2_add(xc, f2_pack(EXP2_MAGIC, EXP2_MAGIC));
     const uint64_t n2 = f2_add(t2, f2_pack(-EXP2_MAGIC, -EXP2_MAGIC));
@@ -167,7 +169,10 @@ __device__ __forceinline__ float exp_row128(const uint32_t (&s)[128], float sc, 
 // as long as the tile's row sum stays <= SOFTMAX_TRIGGER every p is <= SOFTMAX_TRIGGER (finite in fp16, exact scaling in
 // the fp32 accumulators), so nothing needs to change.  Only when some row of the warp exceeds it (or on the first tile,
 // m_used = -inf -> sum = +inf) the warp takes the slow path: exact row max, new m_used, O / l rescale, exponentials redone.
-constexpr float SOFTMAX_TRIGGER = 1024.0f;
+#ifndef DFW_SOFTMAX_TRIGGER
+#define DFW_SOFTMAX_TRIGGER 1024.0f
+#endif
+constexpr float SOFTMAX_TRIGGER = DFW_SOFTMAX_TRIGGER;
 
 // 16 consecutive 32-bit TMEM columns <- registers (thread i of the warp writes lane base + i)
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -205,12 +210,21 @@ __device__ __forceinline__ float exp_row128_tmem(uint32_t ts, float sc, float mu
     return (a + b) + (c + d);
 }
 
-// 128 consecutive fp32 TMEM columns -> registers (four x32 loads; the caller waits)
+// 128 consecutive fp32 TMEM columns -> registers: four x32 loads, tcgen05.wait::ld, and the compiler-level fence that
+// keeps arithmetic on the destination registers below the wait (the loads are asynchronous: without the fence nvcc is
+// free to schedule a consumer between the load and the wait -- a timing-dependent read of stale registers, seen as
+// sporadic NaN rows when the exact path ran after a fast attempt).
 __device__ __forceinline__ void tmem_ld_row128(uint32_t taddr, uint32_t (&s)[128]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
         tmem_ld_32x32(taddr + c * 32, v);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
+        tmem_regs_ready(v);
     }
 }
 

@@ -638,7 +638,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                         uint32_t v[32], gt[32];
                         tmem_ld_32x32(taddr + c * 32, v);
                         tmem_ld_32x32(taddr + 128 + c * 32, gt);
-                        tmem_ld_wait();
+                        tmem_ld_wait(); tmem_regs_ready(v); tmem_regs_ready(gt);      // compiler fence: consumers of the async load stay below the wait
                         const float* bp = p.bias ? p.bias + tc.n_tile * 256 + c * 32 : nullptr;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -661,7 +661,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 #pragma unroll
                             for (int j = 0; j < 4; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0) + j);
                         }
-                        tmem_ld_wait();
+                        tmem_ld_wait(); tmem_regs_ready16(v);      // compiler fence: consumers of the async load stay below the wait
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
                         if (bias_vec) {
@@ -679,7 +679,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col_in0) + j);
                             }
-                            tmem_ld_wait();
+                            tmem_ld_wait(); tmem_regs_ready(v);      // compiler fence: consumers of the async load stay below the wait
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                             if (bias_vec) {
@@ -812,7 +812,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                         float4 val[8];
                         const int cv = tc.n_tile * 256 + c * 32 + cq;             // permuted weight row of this lane's values
                         tmem_ld_32x32(taddr + c * 32, v);
-                        tmem_ld_wait();
+                        tmem_ld_wait(); tmem_regs_ready(v);      // compiler fence: consumers of the async load stay below the wait
                         stage_rows(stg, lane, v);
                         __syncwarp();
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
@@ -824,7 +824,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                         for (int i = 0; i < 8; ++i) val[i] = *reinterpret_cast<const float4*>(stg + (4 * i + sub) * STG_LD + cq);
                         __syncwarp();
                         tmem_ld_32x32(taddr + 128 + c * 32, v);
-                        tmem_ld_wait();
+                        tmem_ld_wait(); tmem_regs_ready(v);      // compiler fence: consumers of the async load stay below the wait
                         stage_rows(stg, lane, v);
                         __syncwarp();
 #pragma unroll
@@ -851,7 +851,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     const ResChunk rc = rc_next;
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + c * 32, v);
-                    tmem_ld_wait();
+                    tmem_ld_wait(); tmem_regs_ready(v);      // compiler fence: consumers of the async load stay below the wait
                     stage_rows(stg, lane, v);
                     __syncwarp();
                     const int col0 = tc.n_tile * BLOCK_N + c * 32;
@@ -863,7 +863,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 uint32_t v[32];
                 uint32_t v16[16];
                 tmem_ld_32x16(taddr, v16);
-                tmem_ld_wait();
+                tmem_ld_wait(); tmem_regs_ready16(v16);      // compiler fence: consumers of the async load stay below the wait
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
                 stage_rows(stg, lane, v);
@@ -1201,7 +1201,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + sb * 64 + half * 32, v);
-                    tmem_ld_wait();
+                    tmem_ld_wait(); tmem_regs_ready(v);      // compiler fence: consumers of the async load stay below the wait
                     uint16_t* sp = stage + (half * 32) * 32 + lane;          // [pixel][32 channels]
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {

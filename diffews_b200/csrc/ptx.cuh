@@ -73,16 +73,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp is parked in hardware until the phase completes (event-driven wake-up) or
+// the hint expires, instead of returning after the short default time limit and re-issuing the poll.  A polling control
+// warp otherwise competes for issue slots with the two softmax / epilogue warps of its sub-partition (attention: the
+// sub-partition that hosts the MMA warp ran its exponentials 43 % slower, profiles/r02_attn_timeline_v3_a.log).
+#ifndef DFW_MBAR_SUSPEND_HINT
+#define DFW_MBAR_SUSPEND_HINT 0x989680u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(DFW_MBAR_SUSPEND_HINT)
         : "memory");
     return done != 0;
 }

@@ -5,8 +5,8 @@ Build (here, no GPU needed):
       -DDFW_BUILD -DDFW_ATTN_TRACE -shared -cudart static -o ../../scripts/microbench/libattn_trace.so common.cu attn.cu
 Run on a B200:  python scripts/attn_trace.py
 With -DDFW_ATTN_TRACE lane 0 of every warp of CTA (0,0,0) stores clock64() at the phase boundaries of each key tile:
-softmax warps  0 before / 1 after the S-ready wait, 2 after pass 1 (row max), 3 / 4 around the PV-done wait, 5 after
-pass 2 (exp, pack, store); MMA warp  0 / 1 around the P_A-ready wait, 2 / 3 around the P_B-ready wait.
+softmax warps  0 before / 1 after the S-ready wait, 2 after the fast pass (exp + vote), 3 after the (rare) exact path,
+4 after P is in TMEM, 5 after the p_full arrive; MMA warp  0 / 1 around the P_A-ready wait, 2 / 3 around the P_B-ready wait.
 """
 import ctypes as C
 import os
@@ -44,23 +44,22 @@ def main():
     run()
     torch.cuda.synchronize()
     t = trace.cpu().view(12, 64, 8)
-    print("phase durations in SM cycles, mean over key tiles 8..59 of CTA (0,0,0); one row per softmax warp")
-    print("warp tile  wait_S  pass1  rescale  wait_PV  pass2  arrive->next  period")
+    print("v3 kernel: phase durations in SM cycles, mean over key tiles 8..59 of CTA (0,0,0); one row per softmax warp")
+    print("warp tile  wait_S  exp(fast)  slow  P->TMEM  arrive  period")
     for w in range(4, 12):
         a = t[w, 8:60].double()
         nxt = t[w, 9:61, 0].double()
         d = [(a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean(), (a[:, 4] - a[:, 3]).mean(),
-             (a[:, 5] - a[:, 4]).mean(), (nxt - a[:, 5]).mean(), (nxt - a[:, 0]).mean()]
-        print(f"{w:4d} {'AB'[(w - 4) // 4]:>4} " + " ".join(f"{float(x):7.0f}" for x in d))
+             (a[:, 5] - a[:, 4]).mean(), (nxt - a[:, 0]).mean()]
+        print(f"{w:4d} {'AB'[(w - 4) // 4]:>4} " + " ".join(f"{float(x):8.0f}" for x in d))
     m = t[1, 8:60].double()
     mn = t[1, 9:61, 0].double()
     print("MMA warp: wait_P_A %.0f  issue(PV_A,S_B) %.0f  wait_P_B %.0f  issue(PV_B,S_A next) %.0f  period %.0f" % (
         float((m[:, 1] - m[:, 0]).mean()), float((m[:, 2] - m[:, 1]).mean()), float((m[:, 3] - m[:, 2]).mean()),
         float((mn - m[:, 3]).mean()), float((mn - m[:, 0]).mean())))
-    # phase offset between the two softmax groups (start of pass 2 of B minus start of pass 2 of A, same tile)
-    off = (t[8, 8:60, 4] - t[4, 8:60, 4]).double().mean()
-    print("tile-B pass 2 starts %.0f cycles after tile-A pass 2 (same key tile)" % float(off))
-    print("tensor-pipe work per key tile pair: 4 MMAs of 128x128x64 = 1024 cycles; XU work: 2 x 128 x 8 = 2048 cycles per sub-partition")
+    off = (t[8, 8:60, 1] - t[4, 8:60, 1]).double().mean()
+    print("tile-B softmax starts %.0f cycles after tile-A softmax (same key tile)" % float(off))
+    print("tensor-pipe work per key tile pair: 1024 cycles")
 
 
 if __name__ == "__main__":

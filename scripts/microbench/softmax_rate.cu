@@ -55,7 +55,6 @@ __global__ void __launch_bounds__(THREADS, 1) softmax_kernel(const float* S_in, 
             } else {
                 uint32_t s[128];
                 tmem_ld_row128(tS, s);
-                tmem_ld_wait();
                 if (STAGED == 0) psum = exp_row128<true, NPOLY>(s, sc, m_used, pk);
                 else psum = exp_row128_staged<true, NPOLY, (STAGED > 0 ? STAGED : 2)>(s, sc, m_used, pk);
             }
@@ -63,7 +62,6 @@ __global__ void __launch_bounds__(THREADS, 1) softmax_kernel(const float* S_in, 
                 ++slow;
                 uint32_t s[128];
                 tmem_ld_row128(tS, s);
-                tmem_ld_wait();
                 const float m_new = fmaxf(m_used, row_max128(s) * sc);
                 l_run *= ex2_approx(m_used - m_new);
                 m_used = m_new;
