@@ -414,6 +414,9 @@ attn_kvfused_v2_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
 constexpr int KV_STAGES3 = 5;
 constexpr int ATT_SMEM3 = ATT_QT * TILE_BYTES + KV_STAGES3 * 2 * TILE_BYTES + 1024 + 256;
 static_assert(ATT_SMEM3 <= 227 * 1024, "dynamic smem limit of sm_100");
+#ifndef ATT_PACE
+#define ATT_PACE 0
+#endif
 #ifndef ATT_MMA_WARP
 #define ATT_MMA_WARP 1
 #endif
@@ -452,6 +455,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     auto p_full = [&](int x) { return bar_base + 8u * (4 + 2 * KVS + x); };
     auto pv_done = [&](int x) { return bar_base + 8u * (6 + 2 * KVS + x); };
     const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * KVS);
+    auto pace = [&](int i) { return bar_base + 8u * (9 + 2 * KVS + i); };            // MMA issue pacing (ATT_PACE groups in flight)
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -474,6 +478,7 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
         for (int x = 0; x < ATT_SBUF; ++x) mbar_init(s_full(x), 1);
         for (int x = 0; x < ATT_QT; ++x) { mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1); }
+        for (int i = 0; i < (ATT_PACE > 0 ? ATT_PACE : 1); ++i) mbar_init(pace(i), 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -526,50 +531,77 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         constexpr uint32_t STAGE_STEP = (2 * TILE_BYTES) >> 4;
         // S tiles are numbered in issue order, seq = nq * j + x, and live in TMEM buffer seq % 3; P(seq) overwrites the
         // first 64 columns of that buffer and is consumed by PV(seq), issued before S(seq + 3) by this same thread.
-        auto issue_s = [&](int x, int stage, int buf) {          // called by the elected lane
-            const uint64_t adesc = x ? dq1 : dq0;
-            const uint64_t bdesc = dk0 + static_cast<uint64_t>(stage * STAGE_STEP);
-            const uint32_t d = tS(buf);
+        // Pacing: a tcgen05.mma issued into a full tensor-pipe queue blocks its warp AT the instruction, and while it sits
+        // there the other warps of the sub-partition issue their MUFU / tcgen05.ld instructions more slowly (the softmax warps
+        // that share the MMA warp's sub-partition ran their exponentials 43 % slower, profiles/r02_attn_timeline_v3_a.log).
+        // So MMAs go out in groups of four (128 - 256 tensor-pipe cycles) with at most ATT_PACE groups in flight: before
+        // group g the warp waits -- parked on an mbarrier, not blocked at issue -- for the commit of group g - ATT_PACE.
+        uint32_t grp = 0;
+        auto pace_wait = [&]() {                                 // all lanes
+            if (ATT_PACE > 0 && grp >= ATT_PACE) mbar_wait(pace(grp % ATT_PACE), ((grp / ATT_PACE) - 1) & 1, 20);
+        };
+        auto pace_commit = [&]() {                               // elected lane
+            if (ATT_PACE > 0) tc_commit(pace(grp % ATT_PACE));
+        };
+        auto issue_s = [&](int x, int stage, int buf) {          // all lanes; S(x, .) = one group
+            pace_wait();
+            if (elect_one()) {
+                const uint64_t adesc = x ? dq1 : dq0;
+                const uint64_t bdesc = dk0 + static_cast<uint64_t>(stage * STAGE_STEP);
+                const uint32_t d = tS(buf);
 #pragma unroll
-            for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-            tc_commit(s_full(buf));
+                for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, adesc + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                tc_commit(s_full(buf));
+                pace_commit();
+            }
+            __syncwarp();
+            ++grp;
         };
         mbar_wait(q_full, 0, 12);
         mbar_wait(kv_full(0), 0, 11);
         tc_fence_after();
-        if (elect_one()) {
-            for (int x = 0; x < nq; ++x) issue_s(x, 0, x);
-        }
-        __syncwarp();
+        for (int x = 0; x < nq; ++x) issue_s(x, 0, x);
         int s = 0, s1 = (KVS > 1) ? 1 : 0;              // stage of tile j, of tile j + 1
         uint32_t ph1 = (KVS > 1) ? 0u : 1u;             // kv_full parity of tile j + 1
         int buf = 0;                                    // S buffer of (x = 0, j)
         for (int j = 0; j < ntiles; ++j) {
+            ATT_STAMP(4);
             if (j + 1 < ntiles) {
                 mbar_wait(kv_full(s1), ph1, 11);
                 tc_fence_after();
             }
+            ATT_STAMP(5);
             int bx = buf;                               // buffer of (x, j)
             int bn = buf + nq; if (bn >= ATT_SBUF) bn -= ATT_SBUF;      // buffer of (x, j + 1) = seq + nq
             for (int x = 0; x < nq; ++x) {
-                if (j + 1 < ntiles) {                   // run ahead: S_X(j+1) goes to the tensor pipe before P_X(j) is waited for
-                    if (elect_one()) issue_s(x, s1, bn);
-                    __syncwarp();
-                }
+                if (j + 1 < ntiles) issue_s(x, s1, bn);     // run ahead: S_X(j+1) goes to the tensor pipe before P_X(j) is waited for
                 ATT_STAMP(x * 2);
                 mbar_wait(p_full(x), j & 1, 13);        // P_X(j) in TMEM, O_X rescaled if it had to be
                 tc_fence_after();
                 ATT_STAMP(x * 2 + 1);
-                if (elect_one()) {
-                    const uint64_t bdesc = dv0 + static_cast<uint64_t>(s * STAGE_STEP);
-                    const uint32_t d = tO(x), a = tS(bx);
+                const uint64_t bdesc = dv0 + static_cast<uint64_t>(s * STAGE_STEP);
+                const uint32_t d = tO(x), a = tS(bx);
 #pragma unroll
-                    for (int ks = 0; ks < ATT_N / 16; ++ks)
-                        umma_ts(d, a + ks * 8, bdesc + static_cast<uint64_t>(ks * ((16 * 128) >> 4)), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-                    tc_commit(pv_done(x));
-                    if (x == nq - 1) tc_commit(kv_empty(s));        // K_j / V_j fully consumed by both tiles
+                for (int half = 0; half < 2; ++half) {      // PV_X(j) = two groups of four k-steps
+                    pace_wait();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = half * 4; ks < half * 4 + 4; ++ks)
+                            umma_ts(d, a + ks * 8, bdesc + static_cast<uint64_t>(ks * ((16 * 128) >> 4)), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                        if (half == 1) {
+#ifdef ATT_DUMMY_COMMITS
+#pragma unroll
+                            for (int dc = 0; dc < ATT_DUMMY_COMMITS; ++dc) tc_commit(pace(0));     // experiment: marginal cost of a commit
+#endif
+                            tc_commit(pv_done(x));
+                            if (x == nq - 1) tc_commit(kv_empty(s));        // K_j / V_j fully consumed by both tiles
+                        }
+                        pace_commit();
+                    }
+                    __syncwarp();
+                    ++grp;
                 }
-                __syncwarp();
+                ATT_STAMP(7 - x);
                 if (++bx == ATT_SBUF) bx = 0;
                 if (++bn == ATT_SBUF) bn = 0;
             }

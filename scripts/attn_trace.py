@@ -20,7 +20,7 @@ from diffews_b200._lib import SIGNATURES  # noqa: E402
 
 
 def main():
-    lib = C.CDLL(os.path.join(ROOT, "scripts", "microbench", "libattn_trace.so"))
+    lib = C.CDLL(os.path.join(ROOT, "scripts", "microbench", sys.argv[1] if len(sys.argv) > 1 else "libattn_trace.so"))
     fn = lib.dfw_attn_kvfused_fwd
     fn.restype, fn.argtypes = SIGNATURES["dfw_attn_kvfused_fwd"]
     lib.dfw_attn_trace_buffer.argtypes = [C.c_void_p]
@@ -57,6 +57,9 @@ def main():
     print("MMA warp: wait_P_A %.0f  issue(PV_A,S_B) %.0f  wait_P_B %.0f  issue(PV_B,S_A next) %.0f  period %.0f" % (
         float((m[:, 1] - m[:, 0]).mean()), float((m[:, 2] - m[:, 1]).mean()), float((m[:, 3] - m[:, 2]).mean()),
         float((mn - m[:, 3]).mean()), float((mn - m[:, 0]).mean())))
+    print("MMA warp detail: kv_full wait %.0f  S_A issue %.0f  [wait P_A]  PV_A issue %.0f  S_B issue %.0f  [wait P_B]  PV_B issue %.0f  loop-back %.0f" % (
+        float((m[:, 5] - m[:, 4]).mean()), float((m[:, 0] - m[:, 5]).mean()), float((m[:, 7] - m[:, 1]).mean()),
+        float((m[:, 2] - m[:, 7]).mean()), float((m[:, 6] - m[:, 3]).mean()), float((t[1, 9:61, 4].double() - m[:, 6]).mean())))
     off = (t[8, 8:60, 1] - t[4, 8:60, 1]).double().mean()
     print("tile-B softmax starts %.0f cycles after tile-A softmax (same key tile)" % float(off))
     print("tensor-pipe work per key tile pair: 1024 cycles")

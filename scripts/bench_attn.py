@@ -57,11 +57,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--v2", action="store_true")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--lib", default=None, help="alternative build of the library for dfw_attn_kvfused_fwd (A/B of compile-time options)")
+    ap.add_argument("--only", type=int, default=None, help="index of the single shape to run")
     args = ap.parse_args()
+    if args.lib:
+        import ctypes as C
+        alt = C.CDLL(os.path.join(ROOT, args.lib))
+        fn = alt.dfw_attn_kvfused_fwd
+        fn.restype, fn.argtypes = _lib.SIGNATURES["dfw_attn_kvfused_fwd"]
+        _lib.lib.dfw_attn_kvfused_fwd = fn
     out = {}
     for ver in ([0, 1] if args.v2 else [0]):
         ops.set_option(_lib.OPT_ATTN_V2, ver)
-        for name, B, h, Lq, Ls, Lb in SHAPES:
+        for name, B, h, Lq, Ls, Lb in (SHAPES if args.only is None else SHAPES[args.only:args.only + 1]):
             ms, tf = time_shape(B, h, Lq, Ls, Lb)
             print(f"{'v2' if ver else 'v3'}  {name:38s} {ms:8.3f} ms  {tf:7.1f} TFLOP/s  ({100 * tf / 2250:.1f} % of 2250 nominal, "
                   f"{100 * tf / 1397.5:.1f} % of 1397.5 sustained)", flush=True)
