@@ -60,6 +60,9 @@ SIGNATURES = {
     "dfw_pointwise_small": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _f, _f, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
     "dfw_nhwc_f32_to_nchw_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp]),
     "dfw_seg_post": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
+    "dfw_seg_head_weight_u32": (_ll, []),
+    "dfw_seg_head_prepare_weights": (_i, [_vp, _i, _vp]),
+    "dfw_seg_head_u8": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dfw_rthres_workspace_bytes": (_ll, [_i]),
     "dfw_rthres_iou_hist": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dfw_iou_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

@@ -560,6 +560,38 @@ def seg_post(dec, H, W, want_f32=True, want_u8=True):
     return f, u
 
 
+def seg_head_prepare(w_oihw: torch.Tensor, dtype, device) -> torch.Tensor:
+    """conv_out weight [3,128,3,3] -> the mma.sync B fragments dfw_seg_head_u8 reads (uint32 device tensor, int32 view)."""
+    w = w_oihw.detach().float().cpu().contiguous()
+    assert tuple(w.shape) == (3, 128, 3, 3)
+    out = torch.empty(int(lib.dfw_seg_head_weight_u32()), dtype=torch.int32)
+    check(lib.dfw_seg_head_prepare_weights(w.data_ptr(), int(dtype == f16), out.data_ptr()), "dfw_seg_head_prepare_weights")
+    return out.to(device)
+
+
+def seg_head_supported(x) -> bool:
+    """dfw_seg_head_u8 needs the decoder's real last block: 128 channels, 16-bit, statistics from the producing conv."""
+    return (x.dim() == 4 and x.shape[-1] == 128 and x.dtype in OPERAND_DTYPES and x.shape[2] % 16 == 0
+            and getattr(x, "_gn_partial", None) is not None and bool(lib.dfw_get_option(_lib.OPT_SEG_HEAD)))
+
+
+def seg_head_u8(x, gamma, beta, eps, wb, bias_host, want_f32=False, want_u8=True):
+    """Fused decoder head: x 16-bit [N,H,W,128] carrying x._gn_partial -> (seg_f32 [N,3,H,W] in [0,255] | None,
+    seg_u8 [N,3,H,W] | None).  GroupNorm(32) scale / shift come from the statistics the producing conv emitted."""
+    N, H, W, C = x.shape
+    partial, nchunks = x._gn_partial
+    ss = torch.empty((N, 2, C), device=x.device, dtype=torch.float32)
+    check(lib.dfw_gn_scale_shift(partial.data_ptr(), nchunks, gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), N, H * W, C,
+                                 32, float(eps), _stream()), "dfw_gn_scale_shift")
+    f = torch.empty((N, 3, H, W), device=x.device, dtype=torch.float32) if want_f32 else None
+    u = torch.empty((N, 3, H, W), device=x.device, dtype=torch.uint8) if want_u8 else None
+    assert bias_host.device.type == "cpu" and bias_host.dtype == torch.float32 and bias_host.numel() == 3
+    with _Timed("elementwise", _nb(x, f, u), f"seg_head N{N} {H}x{W}"):
+        check(lib.dfw_seg_head_u8(x.data_ptr(), int(x.dtype == f16), ss.data_ptr(), wb.data_ptr(), bias_host.data_ptr(),
+                                  _ptr(u), _ptr(f), N, H, W, _stream()), "dfw_seg_head_u8")
+    return f, u
+
+
 def rthres_iou_hist(pred_u8, gt_u8, ignore_u8=None, r_threshold=0.25, want_mask=True):
     """pred_u8 [B,3,H,W] uint8 (or a binarised [B,H,W] {0,1} mask); gt_u8 [B,H,W] uint8 {0,1};
     returns (area_inter [B,2] i64, area_union [B,2] i64, mask)."""

@@ -103,7 +103,7 @@ class MarigoldPipelineRGBLatentNoise:
     @torch.no_grad()
     def single_infer(self, rgb_in_ref: torch.Tensor, rgb_in_tag: torch.Tensor, gt_in_ref: torch.Tensor,
                      clip_rgb_in=None, num_inference_steps: int = 1, show_pbar: bool = False, mode: str = "seg",
-                     seed=None, _want_u8: bool = False):
+                     seed=None, _want_u8: bool = False, _want_f32: bool = True):
         """pipeline:616-836.  rgb_in_ref / gt_in_ref [B*k,3,H,W], rgb_in_tag [B,3,H,W] in [-1,1] ->
         seg [B,3,H,W] float in [0,255]."""
         if mode == "depth":
@@ -129,16 +129,16 @@ class MarigoldPipelineRGBLatentNoise:
             self.unet.clear_attn_bank()                                          # :725
             last = i == len(timesteps) - 1
             if last and self.scheduler.is_pure_negation(t):
-                rows = self.vae.decode_rows(noise_pred, in_scale=-1.0 / self.seg_latent_scale_factor)   # z0 = -v, fused
+                z0, z_scale = noise_pred, -1.0 / self.seg_latent_scale_factor                          # z0 = -v, fused
                 break
             # :764-769 scheduler.step(...): x_{t-1} for the next iteration, pred_original_sample after the last
             step_out = self.scheduler.step(noise_pred, t, depth_latent)
             if last:
-                rows = self.vae.decode_rows(step_out.pred_original_sample, in_scale=1.0 / self.seg_latent_scale_factor)
+                z0, z_scale = step_out.pred_original_sample, 1.0 / self.seg_latent_scale_factor
             else:
                 unet_in = depth_latent = step_out.prev_sample.contiguous()
-        H, W = rgb_in_tag.shape[-2:]
-        seg_f32, seg_u8 = ops.seg_post(rows, H, W, want_f32=True, want_u8=_want_u8)
+        # :787-795 decode_seg -> clip -> *0.5+0.5 -> *255 (and the uint8 truncation of :534): one fused head kernel
+        seg_f32, seg_u8 = self.vae.decode_seg(z0, in_scale=z_scale, want_f32=_want_f32, want_u8=_want_u8)
         self._last_noise_pred = noise_pred
         self._last_unet_inputs = (latents_rgb_cond_ref, unet_in)
         return (seg_f32, seg_u8) if _want_u8 else seg_f32
@@ -166,7 +166,9 @@ class MarigoldPipelineRGBLatentNoise:
         input_size = tuple(tag.shape[-2:])
         if ensemble_size > 1:   # :376-383  stack x ensemble, fold into the batch
             ref, tag, gt = (x.repeat((ensemble_size, 1, 1, 1)) for x in (ref, tag, gt))
-        seg_f32, seg_u8 = self.single_infer(ref, tag, gt, None, denoising_steps, False, mode, seed, _want_u8=True)
+        need_f32 = ensemble_size > 1 or match_input_res      # the float image only feeds the ensemble mean / the resize
+        seg_f32, seg_u8 = self.single_infer(ref, tag, gt, None, denoising_steps, False, mode, seed, _want_u8=True,
+                                            _want_f32=need_f32)
         if ensemble_size > 1:   # :444-468 mean over the ensemble, then the uint8 truncation of :534
             bs = seg_f32.shape[0] // ensemble_size
             seg_f32 = seg_f32.view(ensemble_size, bs, *seg_f32.shape[1:]).mean(dim=0)

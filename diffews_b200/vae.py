@@ -104,6 +104,10 @@ class AutoencoderKL:
             self.dec_up.append(blk)
         self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half)
         self.dec_conv_out = Conv(sd, "decoder.conv_out", dev, wdtype=prec.half)
+        # fused decoder head (dfw_seg_head_u8): conv_out as mma.sync B fragments, bias as a kernel parameter
+        wout = sd["decoder.conv_out.weight"]
+        self.seg_head_wb = ops.seg_head_prepare(wout, prec.half, dev) if tuple(wout.shape) == (3, 128, 3, 3) else None
+        self.seg_head_bias = sd["decoder.conv_out.bias"].detach().float().cpu().contiguous()
 
     @classmethod
     def from_module(cls, module: torch.nn.Module, device="cuda", **kw):
@@ -144,7 +148,27 @@ class AutoencoderKL:
 
     # ---- decoder: z [N,4,h,w] fp32 (already divided by the scale factor via in_scale) -> fp32 [N, H*W, 3] rows -----
     @torch.no_grad()
+    def decode_seg(self, z_nchw: torch.Tensor, in_scale: float = 1.0, want_f32: bool = True, want_u8: bool = True):
+        """decoder -> clip(-1,1) -> *0.5+0.5 -> *255 (-> uint8 truncation): (seg_f32 [N,3,H,W] | None, seg_u8 | None).
+        pipeline:787-795, :887-905, :534.  The head (GroupNorm + SiLU + conv_out + the whole tail) is ONE kernel when the
+        decoder has its real width (128 channels before conv_out); otherwise norm kernel + conv + dfw_seg_post."""
+        h = self._decode_trunk(z_nchw, in_scale)
+        N, H, W, _ = h.shape
+        if self.seg_head_wb is not None and ops.seg_head_supported(h):
+            n = self.dec_norm_out
+            return ops.seg_head_u8(h, n.g, n.b, n.eps, self.seg_head_wb, self.seg_head_bias, want_f32=want_f32, want_u8=want_u8)
+        y = self.dec_conv_out(self.dec_norm_out(h, silu=True), out_f32=True)
+        return ops.seg_post(y.view(N, H * W, 3), H, W, want_f32=want_f32, want_u8=want_u8)
+
+    @torch.no_grad()
     def decode_rows(self, z_nchw: torch.Tensor, in_scale: float = 1.0) -> torch.Tensor:
+        h = self._decode_trunk(z_nchw, in_scale)
+        h = self.dec_norm_out(h, silu=True)
+        y = self.dec_conv_out(h, out_f32=True)                                   # [N,H,W,3] fp32
+        return y.view(y.shape[0], y.shape[1] * y.shape[2], 3)
+
+    @torch.no_grad()
+    def _decode_trunk(self, z_nchw: torch.Tensor, in_scale: float = 1.0) -> torch.Tensor:
         if not z_nchw.is_cuda:
             raise RuntimeError("AutoencoderKL (B200 engine) needs CUDA tensors: there is no CPU fallback")
         z = z_nchw.to(torch.float32).contiguous()
@@ -160,9 +184,7 @@ class AutoencoderKL:
                 h = r(h, gn_stats_out=not (blk.up is not None and j == len(blk.resnets) - 1))
             if blk.up is not None:
                 h = blk.up(h, out_f32=f32, gn_stats=True)
-        h = self.dec_norm_out(h, silu=True)
-        y = self.dec_conv_out(h, out_f32=True)                                   # [N,H,W,3] fp32
-        return y.view(N, y.shape[1] * y.shape[2], 3)
+        return h                                                                 # [N,H,W,C_last], feeds conv_norm_out
 
     @torch.no_grad()
     def decode(self, z_nchw: torch.Tensor) -> torch.Tensor:

@@ -263,6 +263,16 @@ int dfw_nhwc_f32_to_nchw_f32(const float* x, int x_row_stride, float* y, int N, 
  *   seg_u8  NCHW [N,3,H,W] = uint8 truncation of clip(seg,0,255) (pipeline:534)            (either may be NULL) */
 int dfw_seg_post(const float* dec, int row_stride, float* seg_f32, uint8_t* seg_u8, int N, int HW, void* stream);
 
+/* K10: fused VAE decoder head -- GroupNorm-apply + SiLU + conv3x3 128->3 + clip(-1,1) + (.)*0.5+0.5 + (.)*255 + uint8
+ * truncation in ONE pass over x (ref: diffews/marigold_pipeline_rgb_latent_noise.py:887-905 decode_seg -> upstream
+ * Decoder tail conv_norm_out / SiLU / conv_out, :787-795, :534).  x: 16-bit [N,H,W,128]; scale_shift: fp32 [N,2,128]
+ * from dfw_gn_scale_shift; wb: device copy of dfw_seg_head_prepare_weights' output; bias_host: 3 floats (host);
+ * out_u8 [N,3,H,W] and/or out_f32 [N,3,H,W] (float in [0,255]).  Requires W % 16 == 0. */
+long long dfw_seg_head_weight_u32(void);
+int dfw_seg_head_prepare_weights(const float* w_oihw_host, int f16, uint32_t* out_host);
+int dfw_seg_head_u8(const void* x, int f16, const float* scale_shift, const uint32_t* wb, const float* bias_host,
+                    uint8_t* out_u8, float* out_f32, int N, int H, int W, void* stream);
+
 /* K8  reverse-threshold binarisation + intersection/union histogram, one launch, integer counts.
  * ref: evaluation_util/main_oss.py:128-134 (to_tensor, max()*r, mean(dim=1) > thr — CPU fp32 semantics reproduced
  *      bit-exactly: ((R/255 + G/255) + B/255) / 3  >  fp32(max/255) * r), evaluation_util/common/evaluation.py:12-39
