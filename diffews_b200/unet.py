@@ -49,6 +49,15 @@ class CrossAttention:
         self.to_k = Linear(sd, prefix + ".to_k", device, wdtype=wdtype)
         self.to_v = Linear(sd, prefix + ".to_v", device, wdtype=wdtype)
         self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wdtype)
+        self.processor = CrossAttnProcessor()
+
+    def set_processor(self, processor, _remove_lora: bool = False):
+        """attn2 keeps the stock diffusers processor interface; whatever is set, the engine runs its own kernel
+        (cross-attention to the cached prompt K / V is not what the DiffewS processors change)."""
+        self.processor = processor
+
+    def get_processor(self, return_deprecated_lora: bool = False):
+        return self.processor
 
     def kv(self, ehs16):
         """Per-prompt constants.  A short prompt shared by every sample (the eval case: one empty-prompt embedding,
@@ -79,6 +88,10 @@ class CrossAttention:
         q = self.to_q(x)
         o = ops.cross_attn(q, kv[0], kv[1], self.heads, self.scale)
         return self.to_out(o, residual=residual, out_f32=out_f32)
+
+
+class CrossAttnProcessor:
+    """Marker for attn2 (diffusers: AttnProcessor2_0 / XFormersAttnProcessor): short-context attention to the prompt."""
 
 
 class TransformerBlock:
@@ -164,6 +177,7 @@ class MyUNet2DConditionModel:
 
         def tfm(prefix, h):
             t = Transformer2D(sd, prefix, dev, h, prec)
+            t.name = prefix                         # diffusers module path, e.g. down_blocks.0.attentions.1
             self.transformers.append(t)
             return t
 
@@ -205,8 +219,47 @@ class MyUNet2DConditionModel:
         cfg.update(kw)
         return cls(module.state_dict(), device=device, **cfg)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, device="cuda", precision=None, **unused):
+        """`CustomUNet2DConditionModel.from_pretrained(ckpt, subfolder="unet", revision=...)` (main_oss.py:339-345):
+        a diffusers directory (`<path>/<subfolder>/diffusion_pytorch_model.safetensors|.bin` + `config.json`).  A plain
+        SD-2.1 UNet gets its 8-channel support stem the way load_ckpt_and_modify_ref8in_tag4in.py:6-28 builds it.
+        `revision`, `torch_dtype`, ... are accepted and ignored (local files only: there is no hub access)."""
+        from . import checkpoint
+        return checkpoint.load_unet(pretrained_model_name_or_path, device=device, precision=precision, subfolder=subfolder)
+
     def bank_attentions(self):
         return [t.block.attn1 for t in self.transformers]
+
+    # ---- diffusers processor API (unet_2d_condition.py:667-725) --------------------------------------------------------
+    def _attention_modules(self):
+        for t in self.transformers:
+            yield f"{t.name}.transformer_blocks.0.attn1", t.block.attn1
+            yield f"{t.name}.transformer_blocks.0.attn2", t.block.attn2
+
+    @property
+    def attn_processors(self):
+        """{"<module path>.processor": processor} for all 32 attention layers (16 attn1 with a K/V bank, 16 attn2)."""
+        return {f"{name}.processor": m.get_processor(return_deprecated_lora=True) for name, m in self._attention_modules()}
+
+    def set_attn_processor(self, processor, _remove_lora: bool = False):
+        """One processor for every layer, or a dict keyed like `attn_processors` (its length must match)."""
+        mods = list(self._attention_modules())
+        if isinstance(processor, dict):
+            if len(processor) != len(mods):
+                raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} does not "
+                                 f"match the number of attention layers: {len(mods)}. Please make sure to pass {len(mods)} "
+                                 "processor classes.")
+            processor = dict(processor)
+            for name, m in mods:
+                m.set_processor(processor.pop(f"{name}.processor"), _remove_lora=_remove_lora)
+        else:
+            for _, m in mods:
+                m.set_processor(processor, _remove_lora=_remove_lora)
+
+    def set_default_attn_processor(self):
+        for name, m in self._attention_modules():
+            m.set_processor(CrossAttnProcessor() if name.endswith("attn2") else m.__class__.default_processor())
 
     def apply_unet_refonly_block(self):      # unet_2d_condition.py:645-654 — done at construction here
         for a in self.bank_attentions():

@@ -117,6 +117,12 @@ class AutoencoderKL:
         cfg.update(kw)
         return cls(module.state_dict(), device=device, **cfg)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, device="cuda", precision=None, **unused):
+        """`AutoencoderKL.from_pretrained(ckpt, subfolder="vae")` (main_oss.py:347-349), local diffusers directory."""
+        from . import checkpoint
+        return checkpoint.load_vae(pretrained_model_name_or_path, device=device, precision=precision, subfolder=subfolder)
+
     def to(self, *a, **k):
         return self
 

@@ -564,3 +564,119 @@ def test_attention_v3_equals_v2_kernel():
         finally:
             ops.set_option(_lib.OPT_ATTN_V2, old)
         assert rel_l2(o3, o2) <= 1.5e-3, rel_l2(o3, o2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Row b (drop-in boundary): the processor on a STOCK attention module, and the diffusers processor / loading API
+# ---------------------------------------------------------------------------------------------------------------------
+class _StockAttention(torch.nn.Module):
+    """What the reference processor sees: a diffusers-0.25 `Attention` (separate fp32 to_q / to_k / to_v / to_out Linear
+    layers) re-classed to carry a K/V bank (unet_2d_condition.py:645-654).  Same stand-in as scripts/make_golden_attn.py."""
+
+    def __init__(self, query_dim, heads, dim_head):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.scale, self.scale_qk = heads, dim_head ** -0.5, True
+        self.to_q = torch.nn.Linear(query_dim, inner, bias=False)
+        self.to_k = torch.nn.Linear(query_dim, inner, bias=False)
+        self.to_v = torch.nn.Linear(query_dim, inner, bias=False)
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(inner, query_dim), torch.nn.Dropout(0.0)])
+        self.spatial_norm = self.group_norm = self.norm_cross = None
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+        self.k_bank = self.v_bank = None
+        self.processor = None
+
+    def forward(self, hidden_states, **kw):
+        return self.processor(self, hidden_states, **kw)
+
+
+def test_processor_on_stock_attention_matches_reference_golden():
+    """MyXFormersAttnProcessor driving a stock fp32 attention module (not the engine's prepared MyAttention) reproduces
+    tests/golden/attn_reference.json -- the outputs of the UNMODIFIED reference processor for k = 1, 3, 5
+    (scripts/make_golden_attn.py) -- within fp16 operand rounding; also the 4-D input / residual_connection /
+    rescale_output_factor branches (attention_processor.py:213-215, :280-286) and the weight-cache refresh."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import data_tree
+    from diffews_b200.attention_processor import MyXFormersAttnProcessor
+    gold = json.load(open(os.path.join(here, "golden", "attn_reference.json")))["cases"]
+    for c, g in zip(data_tree.attn_cases(), gold):
+        attn = _StockAttention(c["C"], c["heads"], c["C"] // c["heads"])
+        with torch.no_grad():
+            attn.to_q.weight.copy_(c["w"]["to_q"]); attn.to_k.weight.copy_(c["w"]["to_k"])
+            attn.to_v.weight.copy_(c["w"]["to_v"]); attn.to_out[0].weight.copy_(c["w"]["to_out"])
+            attn.to_out[0].bias.copy_(c["w"]["to_out_bias"])
+        attn = attn.cuda()
+        attn.processor = MyXFormersAttnProcessor()
+        sup = attn(c["x_support"].cuda())                      # support pass: stores the bank
+        qry = attn(c["x_query"].cuda())                        # query pass: [self ; folded bank]
+        assert qry.dtype == torch.float32 and qry.shape == c["x_query"].shape
+        ref = torch.tensor(g["xformers"]["query_out"]).view_as(qry)
+        e = rel_l2(qry, ref)
+        print(f"stock-module processor B{c['B']} k{c['k']}: rel-L2 vs the reference processor's output {e:.2e}")
+        assert e <= 3e-3, e
+        assert abs(float(sup.double().sum()) - g["xformers"]["support_out_sum"]) <= 2e-2 * sup.abs().sum().item() ** 0.5 + 1.0
+        # 4-D input + residual connection + rescale: same tokens as [N, C, H, W]
+        attn.k_bank = attn.v_bank = None
+        attn.residual_connection, attn.rescale_output_factor = True, 2.0
+        x4 = c["x_query"].transpose(1, 2).reshape(c["B"], c["C"], 3, 4).contiguous().cuda()
+        y4 = attn(x4)
+        attn.residual_connection, attn.rescale_output_factor = False, 1.0
+        attn.k_bank = attn.v_bank = None
+        y3 = attn(c["x_query"].cuda())
+        want = (y3.transpose(1, 2).reshape(c["B"], c["C"], 3, 4) + x4) / 2.0
+        assert rel_l2(y4, want) <= 1e-5
+        # in-place weight update -> the cached fused 16-bit weights are rebuilt
+        with torch.no_grad():
+            attn.to_out[0].weight.mul_(2.0); attn.to_out[0].bias.mul_(2.0)
+        attn.k_bank = attn.v_bank = None
+        assert rel_l2(attn(c["x_query"].cuda()), 2.0 * y3) <= 1e-3
+
+
+def test_unet_processor_api_and_from_pretrained(small_models, tmp_path):
+    """attn_processors / set_attn_processor (unet_2d_condition.py:667-725) and classmethod from_pretrained(path, subfolder=)
+    (main_oss.py:339-349) on the UNet / VAE shims."""
+    import json
+    from safetensors.torch import save_file
+    from diffews_b200.attention_processor import MyXFormersAttnProcessor
+    from diffews_b200.synthetic import prompt_embedding
+    from diffews_b200.unet import CrossAttnProcessor, MyUNet2DConditionModel
+    from diffews_b200.vae import AutoencoderKL
+    unet_o, vae_o = small_models
+    for name, mod, cfg in (("unet", unet_o, {"block_out_channels": list(unet_o.block_out_channels),
+                                             "attention_head_dim": list(unet_o.heads), "cross_attention_dim": 1024}),
+                           ("vae", vae_o, {"block_out_channels": [b.resnets[0].conv1.out_channels
+                                                                   for b in vae_o.encoder.down_blocks]})):
+        (tmp_path / name).mkdir()
+        save_file({k: v.contiguous() for k, v in mod.state_dict().items()},
+                  str(tmp_path / name / "diffusion_pytorch_model.safetensors"))
+        (tmp_path / name / "config.json").write_text(json.dumps(cfg))
+    u = MyUNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet", revision=None)
+    v = AutoencoderKL.from_pretrained(str(tmp_path), subfolder="vae")
+    procs = u.attn_processors
+    assert len(procs) == 32 and "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor" in procs
+    assert "mid_block.attentions.0.transformer_blocks.0.attn2.processor" in procs and "up_blocks.3.attentions.2.transformer_blocks.0.attn1.processor" in procs
+    assert all(isinstance(p, MyXFormersAttnProcessor) for k, p in procs.items() if k.endswith("attn1.processor"))
+    assert all(isinstance(p, CrossAttnProcessor) for k, p in procs.items() if k.endswith("attn2.processor"))
+    with pytest.raises(ValueError):
+        u.set_attn_processor({"a": 1})
+    mine = MyXFormersAttnProcessor()
+    u.set_attn_processor(mine)
+    assert all(p is mine for p in u.attn_processors.values())
+    u.set_attn_processor({k: MyXFormersAttnProcessor() if "attn1" in k else CrossAttnProcessor() for k in procs})
+    u2 = MyUNet2DConditionModel.from_module(unet_o)
+    g = torch.Generator().manual_seed(3)
+    sup = (torch.randn(2, 8, 16, 16, generator=g) * 0.8).cuda(); qry = (torch.randn(2, 4, 16, 16, generator=g) * 0.8).cuda()
+    ehs = prompt_embedding().repeat(2, 1, 1).cuda()
+    outs = []
+    for m in (u, u2):
+        m.clear_attn_bank()
+        m(sup, torch.tensor(1), ehs, is_target=False)
+        outs.append(m(qry, torch.tensor(1), ehs).sample)
+        m.clear_attn_bank()
+    assert torch.equal(outs[0], outs[1])
+    img = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).cuda()
+    assert torch.equal(v.encode_mean(img), AutoencoderKL.from_module(vae_o).encode_mean(img))
