@@ -33,6 +33,9 @@ if ROOT not in sys.path:
 METRIC = "episodes/sec (1-shot, 512^2, 1-step UNet)"
 UNIT = "episodes/s"
 FLOPS_PER_EPISODE_1SHOT_512 = 7.58e12
+# BASELINE.json configs -> (episodes per GPU per step, shots, image size, algorithmic TFLOP per episode: SURVEY §8d)
+CONFIGS = {2: (16, 1, 512, 7.58e12), 3: (8, 5, 512, 20.19e12), 5: (8, 1, 768, 18.48e12)}
+TENSOR_FLOP_PER_CLK_PER_SM = 8192.0       # dense 16-bit tcgen05: 4096 MAC / clk / SM
 
 
 def _peaks():
@@ -206,7 +209,12 @@ def main():
     ap.add_argument("--unet-stream", default="half", choices=["half", "f32"], help="UNet residual-stream storage")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS),
+                    help="BASELINE.json config: 2 = 1-shot 512^2 B16 (default workload), 3 = 5-shot 512^2 B8, 5 = 1-shot 768^2 B8")
+    ap.add_argument("--operands", default="f16", choices=["f16", "bf16"], help="16-bit tensor-core operand format")
     args = ap.parse_args()
+    if args.config is not None:
+        args.batch, args.nshot, args.size, _ = CONFIGS[args.config]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -227,16 +235,16 @@ def main():
         args.warmup = 3
 
     from diffews_b200 import ops
-    from diffews_b200.runner import EpisodeRunner, build_engine_from_modules
-    from diffews_b200.synthetic import make_batch, prompt_embedding
-    from oracle.sd21 import build_models          # weight source: deterministic random init (no checkpoints offline)
+    from diffews_b200.runner import EpisodeRunner, build_engine_from_state_dicts
+    from diffews_b200.synthetic import make_batch, prompt_embedding, random_unet_state_dict, random_vae_state_dict
 
-    unet_o, vae_o = build_models(0)
+    # weight source: deterministic random init with the diffusers key names (no checkpoints offline); nothing from oracle/
     from diffews_b200.layers import Precision
-    vae_prec = Precision(stream_f32=(args.vae_stream == "f32"), mid_f32=False)
-    unet_prec = Precision(stream_f32=(args.unet_stream == "f32"), mid_f32=(args.unet_stream == "f32"))
-    pipe = build_engine_from_modules(unet_o, vae_o, prompt_embedding(), device=dev, vae_precision=vae_prec,
-                                     unet_precision=unet_prec)
+    half = torch.float16 if args.operands == "f16" else torch.bfloat16
+    vae_prec = Precision(half=half, stream_f32=(args.vae_stream == "f32"), mid_f32=False)
+    unet_prec = Precision(half=half, stream_f32=(args.unet_stream == "f32"), mid_f32=(args.unet_stream == "f32"))
+    pipe = build_engine_from_state_dicts(random_unet_state_dict(0), random_vae_state_dict(1), prompt_embedding(), device=dev,
+                                         vae_precision=vae_prec, unet_precision=unet_prec)
     runner = EpisodeRunner(pipe, "coco", img_size=args.size)
     B = args.batch
 
@@ -331,6 +339,37 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * args.steps / (float(te.item()) / 1000.0), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        # same loop, but the caller also takes the uint8 segmentation image the reference __call__ hands back
+        # (pipeline:534-545) off the device every step: B x 3 x S x S bytes D2H into pinned memory
+        seg_host = torch.empty((B, 3, args.size, args.size), dtype=torch.uint8).pin_memory()
+
+        def e2e_image_run(nsteps):
+            if pipelined:
+                runner.prefetch(host_batches[0])
+            for i in range(nsteps):
+                if pipelined:
+                    inter, union = runner.step_prefetched()
+                    if i + 1 < nsteps:
+                        runner.prefetch(host_batches[(i + 1) % pool])
+                else:
+                    inter, union = runner.step(host_batches[i % pool])
+                host_out[0].copy_(inter, non_blocking=True)
+                host_out[1].copy_(union, non_blocking=True)
+                seg_host.copy_(runner.last_seg_u8, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                _ = int(host_out[0, 0, 1]) + int(seg_host[0, 0, 0, 0])
+        e2e_image_run(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_image_run(args.steps)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        barrier()
+        ti = torch.tensor([wall_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        e2e["with_uint8_image_d2h"] = {"value": world * B * args.steps / (float(ti.item()) / 1000.0), "unit": UNIT,
+                                       "d2h_bytes_per_step": int(d2h + seg_host.numel())}
 
     # ---------------- roofline of the dominant kernel family ----------------------------------------------------------
     # Per-launch CUDA events cannot be recorded inside a graph replay, so the tensor-core launches are timed in an
@@ -395,29 +434,51 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         del pipe
-        secs = cpu_oracle_episode_time(args.size, args.nshot, cores, unet_o, vae_o)
+        secs = cpu_oracle_episode_time(args.size, args.nshot, cores)
         cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"1 episode ({args.nshot}-shot {args.size}x{args.size}, bsz=1, fp32 oracle port of the reference "
                          f"path) after a 64x64 warm-up: {secs:.1f}s"}
 
     if rank == 0:
+        cfg_id = next((k for k, v in CONFIGS.items() if (B, args.nshot, args.size) == v[:3]), None)
+        flops_ep = CONFIGS[cfg_id][3] if cfg_id is not None else None
+        # attention: achieved rate of the KV-fused kernel inside the step, as TFLOP/s and as the fraction of the tensor pipe's
+        # cycles that rate occupies at the SM clock sampled during the run (4096 dense MAC / clk / SM) -- the live counterpart
+        # of ncu's sm__pipe_tensor_cycles_active (profiles/r02_ncu_attn.tsv, captured stand-alone)
+        attn = None
+        hbm_families = None
+        if kernels is not None:
+            ka = kernels.get("attn")
+            if ka and ka.get("tflops"):
+                sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                pipe_peak_tf = TENSOR_FLOP_PER_CLK_PER_SM * sms * sm_mhz * 1e6 / 1e12
+                attn = {"tflops_in_step": ka["tflops"], "ms_per_step": round(ka["ms"] / args.steps, 3),
+                        "tensor_pipe_pct_at_sampled_clock": round(100.0 * ka["tflops"] / pipe_peak_tf, 1),
+                        "frac_of_sustained_bf16_peak": round(ka["tflops"] / peak_tf, 3),
+                        "ncu_tensor_pipe_active_pct": 46.9, "ncu_source": "profiles/r02_ncu_attn.tsv (B16 h5 4096x8192, stand-alone)"}
+            hbm_families = {k: {"gb_per_s": v["gb_per_s"], "frac_of_hbm_peak": round(v["gb_per_s"] / peak_gbs, 3),
+                                "ms_per_step": round(v["ms"] / args.steps, 3)}
+                            for k, v in kernels.items() if k in ops.MEM_KINDS and v.get("gb_per_s")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
+            "dtype": args.operands, "data": "synthetic",
             "config": {"workload": f"{args.nshot}-shot {args.size}x{args.size} episodes, batch {B} per GPU, single-step "
                                    "SD-2.1 UNet (KV-bank attention) + VAE encode x3 / decode + rthres/IoU, random-init "
-                                   "weights (BASELINE config 2)",
+                                   f"weights (BASELINE config {cfg_id if cfg_id is not None else 'custom'})",
                        "episodes_per_step_per_gpu": B, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if use_graph else "eager",
                        "l2_policy": "inputs + activations per step (>2 GB) exceed the 126 MB L2; 2 alternating batches",
-                       "precision": "fp16 tensor-core operands (the reference's own half mode), fp32 accumulate / softmax / "
-                                    f"statistics, UNet residual stream {args.unet_stream}, VAE stream {args.vae_stream}; an all-bf16 "
-                                    "operand mode exists (layers.PURE_BF16) but misses the 1e-2 latent bar (1.2e-2)"},
+                       "precision": f"{args.operands} tensor-core operands ("
+                                    + ("the reference's own half mode; bf16, the format BASELINE config 2 names, runs at the same "
+                                       "rate (--operands bf16) but measures 1.1e-2 .. 1.6e-2 latent rel-L2, above the 1e-2 bar"
+                                       if args.operands == "f16" else "selected with --operands bf16; latent rel-L2 1.1e-2 .. 1.6e-2")
+                                    + f"), fp32 accumulate / softmax / statistics, UNet residual stream {args.unet_stream}, "
+                                    f"VAE stream {args.vae_stream}"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels,
-            "frac_of_tensor_roofline_whole_path": round(value / world * FLOPS_PER_EPISODE_1SHOT_512 / (peak_tf * 1e12), 4)
-            if (args.size == 512 and args.nshot == 1) else None,
+            "cpu_baseline": cpu, "kernels": kernels, "attn": attn, "hbm_families": hbm_families,
+            "frac_of_tensor_roofline_whole_path": round(value / world * flops_ep / (peak_tf * 1e12), 4) if flops_ep else None,
         }
         _emit(line)
     if world > 1:

@@ -16,6 +16,19 @@ def shard_episodes(n_total: int, rank: int, world: int) -> range:
     return range(rank, n_total, world)
 
 
+def build_engine_from_state_dicts(unet_sd, vae_sd, text_embeds, device="cuda", unet_precision=None, vae_precision=None,
+                                  unet_channels=(320, 640, 1280, 1280), heads=(5, 10, 20, 20),
+                                  vae_channels=(128, 256, 512, 512)):
+    """Pipeline from diffusers-named state dicts (a checkpoint's tensors, or diffews_b200.synthetic.random_*_state_dict)."""
+    from .pipeline import MarigoldPipelineRGBLatentNoise
+    from .unet import MyUNet2DConditionModel
+    from .vae import AutoencoderKL
+    unet = MyUNet2DConditionModel(unet_sd, device=device, block_out_channels=unet_channels, heads=heads,
+                                  precision=unet_precision)
+    vae = AutoencoderKL(vae_sd, device=device, block_out_channels=vae_channels, precision=vae_precision)
+    return MarigoldPipelineRGBLatentNoise(unet, vae, text_embeds=text_embeds)
+
+
 def build_engine_from_modules(unet_module, vae_module, text_embeds, device="cuda", unet_precision=None,
                               vae_precision=None):
     from .pipeline import MarigoldPipelineRGBLatentNoise
@@ -137,6 +150,7 @@ class EpisodeRunner:
                         mode="seg", rgb_paths=batch.get("rgb_path", []), seed=0, output_type="pt")
         inter, union = Evaluator.rthres_classify(out.seg_u8, batch, self.r_threshold)
         self.meter.update_counts(inter, union, batch["class_id"])
+        self.last_seg_u8 = out.seg_u8      # uint8 [B,3,H,W] of this step (a static buffer of the graph in graph mode)
         return inter, union
 
     def finish(self):

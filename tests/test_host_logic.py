@@ -204,3 +204,20 @@ def test_loader_shards_by_process_group_rank(tmp_path):
     for rank, lr, lw, n, gathered in res:
         assert (lr, lw) == (rank, 2) and n == 250
         assert gathered[0] == [want[0], want[2]] and gathered[1] == [want[1], want[3]]
+
+
+def test_random_init_state_dicts_match_oracle_module_shapes():
+    """diffews_b200.synthetic.random_{unet,vae}_state_dict (bench.py's weight source, nothing from oracle/) carry exactly the
+    keys and shapes of the oracle's SD-2.1 modules = the diffusers state-dict layout (865 910 724 + 23 360 / 83 653 863
+    parameters)."""
+    from diffews_b200.synthetic import random_unet_state_dict, random_vae_state_dict
+    from oracle.sd21 import build_models
+    for widths in (((320, 640, 1280, 1280), (5, 10, 20, 20), (128, 256, 512, 512)), ((64, 128, 256, 256), (1, 2, 4, 4), (64, 64, 128, 128))):
+        unet_o, vae_o = build_models(0, *widths)
+        for mine, ref in ((random_unet_state_dict(0, widths[0]), unet_o.state_dict()), (random_vae_state_dict(1, widths[2]), vae_o.state_dict())):
+            assert set(mine) == set(ref), (sorted(set(mine) ^ set(ref))[:8])
+            for k, v in ref.items():
+                assert tuple(mine[k].shape) == tuple(v.shape), k
+    n_unet = sum(v.numel() for v in random_unet_state_dict(0).values())
+    n_vae = sum(v.numel() for v in random_vae_state_dict(1).values())
+    assert n_unet == 865_910_724 + 23_360 and n_vae == 83_653_863
