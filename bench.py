@@ -160,6 +160,19 @@ def run_reference(args):
     return 0
 
 
+def _ncu_attn_pct():
+    """sm__pipe_tensor_subpipe_hmma_cycles_active of the KV-fused attention kernel from the committed ncu summary (a
+    stand-alone capture; never a number measured under the profiler in this run)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_attn.tsv")
+    try:
+        rows = [l.rstrip("\n").split("\t") for l in open(path)]
+        col = next(i for i, h in enumerate(rows[0]) if h.startswith("sm__pipe_tensor_subpipe_hmma_cycles_active"))
+        vals = [float(r[col]) for r in rows[1:] if "attn_kvfused" in r[0]]
+        return round(sum(vals) / len(vals), 1)
+    except (OSError, StopIteration, ValueError, ZeroDivisionError):
+        return None
+
+
 def _igemm_traffic():
     """DRAM bytes of one launch of the dominant igemm shape, from the committed ncu --set full capture (GB), else None."""
     try:
@@ -456,7 +469,8 @@ def main():
                 attn = {"tflops_in_step": ka["tflops"], "ms_per_step": round(ka["ms"] / args.steps, 3),
                         "tensor_pipe_pct_at_sampled_clock": round(100.0 * ka["tflops"] / pipe_peak_tf, 1),
                         "frac_of_sustained_bf16_peak": round(ka["tflops"] / peak_tf, 3),
-                        "ncu_tensor_pipe_active_pct": 46.9, "ncu_source": "profiles/r02_ncu_attn.tsv (B16 h5 4096x8192, stand-alone)"}
+                        "ncu_tensor_pipe_active_pct": _ncu_attn_pct(),
+                        "ncu_source": "profiles/r02_ncu_attn.tsv (B16 h5 4096x8192, stand-alone, --clock-control none)"}
             hbm_families = {k: {"gb_per_s": v["gb_per_s"], "frac_of_hbm_peak": round(v["gb_per_s"] / peak_gbs, 3),
                                 "ms_per_step": round(v["ms"] / args.steps, 3)}
                             for k, v in kernels.items() if k in ops.MEM_KINDS and v.get("gb_per_s")}

@@ -77,7 +77,7 @@ class _EpisodeDataset:
         return self.paths(query_name)[0]
 
     def decode(self, sampled, pool: Optional[ThreadPoolExecutor] = None) -> dict:
-        query_name, support_names, class_sample = sampled
+        query_name, support_names, class_sample = sampled[:3]
         names = [query_name] + list(support_names)
         jobs = []
         for n in names:
@@ -92,7 +92,7 @@ class _EpisodeDataset:
         h, w = imgs[0].shape[:2]
         return {"query_img": imgs[0], "query_label": labels[0], "support_imgs": imgs[1:], "support_labels": labels[1:],
                 "query_name": query_name, "support_names": list(support_names), "class_sample": int(class_sample),
-                "org_query_imsize": (w, h), "rgb_path": self.rgb_path(query_name)}
+                "mask_param": int(class_sample) + 1, "org_query_imsize": (w, h), "rgb_path": self.rgb_path(query_name)}
 
     def _read_label(self, path):
         return _read_label(path)
@@ -201,6 +201,34 @@ class DatasetPASCAL(_EpisodeDataset):
         return os.path.join(self.img_path, name) + ".jpg", os.path.join(self.ann_path, name) + ".png"
 
 
+class DatasetPASCALCD(DatasetPASCAL):
+    """PASCAL cross-domain folds (evaluation_util/data/pascal_voc_cd.py): the PASCAL-5i files, with the fold's classes
+    read from VOC2012/cd_folds.pth (1-based ids), validation episodes drawn from ALL four split files filtered to those
+    classes, and no `query_ignore_idx` in the batch (pascal_voc_cd.py:61) — the support ignore masks stay."""
+    emit_query_ignore = False
+
+    def __init__(self, datapath, fold, transform, split, shot, use_original_imgsize=False):
+        self._fold_classes = torch.load(os.path.join(datapath, "VOC2012", "cd_folds.pth"))
+        self.class_names = torch.load(os.path.join(datapath, "VOC2012", "class_names.pth"))
+        super().__init__(datapath, fold, transform, split, shot, False)          # :43 always resizes the query mask
+        val = [x - 1 for x in self._fold_classes[self.fold]]                       # pascal_voc_cd.py:111-120
+        self.class_ids = val if self.split != "trn" else [x for x in range(self.nclass) if x not in val]
+
+    def _build_img_metadata(self):                                              # pascal_voc_cd.py:122-147
+        keep = self._fold_classes[self.fold]
+
+        def read(split, fold_id):
+            with open(os.path.join(self.base_path, f"splits/{split}/fold{fold_id}.txt"), "r") as f:
+                rows = f.read().split("\n")[:-1]
+            return [[r.split("__")[0], int(r.split("__")[1]) - 1] for r in rows if int(r.split("__")[1]) in keep]
+        out = []
+        for fold_id in range(self.nfolds):
+            if self.split == "trn" and fold_id == self.fold:
+                continue
+            out += read(self.split, fold_id)
+        return out
+
+
 class DatasetFSS(_EpisodeDataset):
     """FSS-1000 (evaluation_util/data/fss.py): FSS-1000/data/<category>/{1..10}.jpg + .png, splits/{split}.txt."""
     benchmark = "fss"
@@ -247,6 +275,301 @@ class DatasetFSS(_EpisodeDataset):
 
     def _read_label(self, path):
         return _read_label(path, to_l=True)                                      # fss.py:80-84 (.convert('L'))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+class _SegmDataset(_EpisodeDataset):
+    """Benchmarks whose masks come from instance segmentations (polygons / RLE / arrays) instead of a class-index PNG:
+    the host rasterises and unions them (`cocomask`, in the decode pool) and crops to the object box where the
+    reference does; the device then sees a {0,1} label with `mask_param` = 1, i.e. the same `dfw_mask_nearest` launch.
+    `sample_names` returns (query_name, support_names, class_id, extra) — `extra` carries what the sampling loop of the
+    reference already looked up (segmentations, boxes), so that decoding needs no RNG."""
+
+    def image_path(self, name: str) -> str:
+        raise NotImplementedError
+
+    def paths(self, name):
+        return self.image_path(name), None
+
+    @staticmethod
+    def _union(segms, h, w) -> np.ndarray:
+        # lvis.py:131-135: cat of float masks, .sum(0) > 0
+        from . import cocomask
+        acc = np.zeros((h, w), np.float32)
+        for s in segms:
+            acc += cocomask.segmentation_to_mask(s, h, w).astype(np.float32)
+        return (acc > 0).astype(np.uint8)
+
+    @staticmethod
+    def _crop(img, mask, box_xyxy):
+        x0, y0, x1, y1 = box_xyxy
+        return np.ascontiguousarray(img[y0:y1, x0:x1]), np.ascontiguousarray(mask[y0:y1, x0:x1])
+
+    def _one(self, job):
+        name, segms, box = job
+        img = _read_rgb(self.image_path(name))
+        h, w = img.shape[:2]
+        mask = segms if isinstance(segms, np.ndarray) else self._union(segms, h, w)
+        if box is not None:
+            img, mask = self._crop(img, mask, box)
+        return img, mask
+
+    def decode(self, sampled, pool: Optional[ThreadPoolExecutor] = None) -> dict:
+        query_name, support_names, class_id, extra = sampled
+        jobs = [(query_name, extra["query_segms"], extra.get("query_box"))]
+        jobs += [(n, s, b) for n, s, b in zip(support_names, extra["support_segms"],
+                                              extra.get("support_boxes") or [None] * len(support_names))]
+        res = [self._one(j) for j in jobs] if pool is None else list(pool.map(self._one, jobs))
+        h, w = res[0][0].shape[:2]
+        raw = {"query_img": res[0][0], "query_label": res[0][1], "support_imgs": [r[0] for r in res[1:]],
+               "support_labels": [r[1] for r in res[1:]], "query_name": query_name, "support_names": list(support_names),
+               "class_sample": int(class_id), "mask_param": 1, "org_query_imsize": (w, h),
+               "rgb_path": self.image_path(query_name)}
+        if "category" in extra:
+            raw["category"] = extra["category"]
+        return raw
+
+
+class DatasetLVIS(_SegmDataset):
+    """LVIS-92i (evaluation_util/data/lvis.py).  Files: LVIS/lvis_{train,val}.pkl = {category id: {image name:
+    {'annotations': [{'segmentation': polygons | RLE | array}, ...]}}}, images under LVIS/coco/<name>."""
+    benchmark = "lvis"
+
+    def __init__(self, datapath, fold, transform, split, shot, use_original_imgsize):
+        self.split = "val" if split in ["val", "test"] else "trn"              # lvis.py:17
+        self.fold, self.nfolds = fold, 10
+        self.shot = shot
+        self.anno_path = os.path.join(datapath, "LVIS")
+        self.base_path = os.path.join(datapath, "LVIS", "coco")
+        self.transform = transform
+        self.use_original_imgsize = use_original_imgsize
+        with open(os.path.join(self.anno_path, "lvis_train.pkl"), "rb") as f:   # lvis.py:66-90
+            train_anno = pickle.load(f)
+        with open(os.path.join(self.anno_path, "lvis_val.pkl"), "rb") as f:
+            val_anno = pickle.load(f)
+        train_cat_ids = [i for i in list(train_anno.keys()) if len(train_anno[i]) > self.shot]
+        val_cat_ids = [i for i in list(val_anno.keys()) if len(val_anno[i]) > self.shot]
+        class_ids_val = [val_cat_ids[self.fold + self.nfolds * v] for v in range(len(val_cat_ids) // self.nfolds)]
+        if self.split == "trn":
+            self.class_ids_ori = [x for x in train_cat_ids if x not in class_ids_val]
+            self.nclass, self.img_metadata_classwise = len(train_cat_ids), train_anno
+        else:
+            self.class_ids_ori = class_ids_val
+            self.nclass, self.img_metadata_classwise = len(val_cat_ids), val_anno
+        self.class_ids_c = {cid: i for i, cid in enumerate(self.class_ids_ori)}
+        self.class_ids = sorted(list(self.class_ids_c.values()))
+        meta = []
+        for k in self.img_metadata_classwise.keys():                            # lvis.py:92-96
+            meta.extend(list(self.img_metadata_classwise[k].keys()))
+        self.img_metadata = sorted(list(set(meta)))
+
+    def __len__(self):
+        return len(self.img_metadata) if self.split == "trn" else 2300          # lvis.py:33-34
+
+    def image_path(self, name):
+        return os.path.join(self.base_path, name)
+
+    def sample_names(self, idx):
+        idx %= len(self.class_ids)                                              # lvis.py:37, :123-157
+        class_sample = self.class_ids_ori[idx]
+        per_class = self.img_metadata_classwise[class_sample]
+        query_name = np.random.choice(list(per_class.keys()), 1, replace=False)[0]
+        query_segms = [a["segmentation"] for a in per_class[query_name]["annotations"]]
+        support_names, support_segms = [], []
+        while True:
+            support_name = np.random.choice(list(per_class.keys()), 1, replace=False)[0]
+            if query_name != support_name:
+                support_names.append(support_name)
+                support_segms.append([a["segmentation"] for a in per_class[support_name]["annotations"]])
+            if len(support_names) == self.shot:
+                break
+        return query_name, support_names, self.class_ids_c[class_sample], {"query_segms": query_segms,
+                                                                            "support_segms": support_segms}
+
+
+class DatasetPACOPart(_SegmDataset):
+    """PACO-Part (evaluation_util/data/paco_part.py).  Files: PACO-Part/paco/paco_part_{train,val}.pkl =
+    {'cid2img': {category: [{image id: path}, ...]}, 'img2anno': {image id: [{'category_id', 'obj_ann_id', 'obj_bbox'
+    (xywh), 'segmentation'}, ...]}}, images under PACO-Part/coco/<last two path components>."""
+    benchmark = "paco_part"
+
+    def __init__(self, datapath, fold, transform, split, shot, use_original_imgsize, box_crop=True):
+        self.split = "val" if split in ["val", "test"] else "trn"
+        self.fold, self.nfolds, self.nclass = fold, 4, 448
+        self.shot = shot
+        self.img_path = os.path.join(datapath, "PACO-Part", "coco")
+        self.anno_path = os.path.join(datapath, "PACO-Part", "paco")
+        self.transform = transform
+        self.use_original_imgsize = use_original_imgsize
+        self.box_crop = box_crop
+        with open(os.path.join(self.anno_path, "paco_part_train.pkl"), "rb") as f:    # paco_part.py:62-100
+            train_anno = pickle.load(f)
+        with open(os.path.join(self.anno_path, "paco_part_val.pkl"), "rb") as f:
+            test_anno = pickle.load(f)
+        dedup = {}
+        for cid in test_anno["cid2img"]:                                        # first occurrence of every image id
+            seen = []
+            dedup.setdefault(cid, [])
+            for img in test_anno["cid2img"][cid]:
+                img_id = list(img.keys())[0]
+                if img_id not in seen:
+                    seen.append(img_id)
+                    dedup[cid].append(img)
+        test_anno["cid2img"] = dedup
+        train_cat_ids = list(train_anno["cid2img"].keys())
+        test_cat_ids = [i for i in list(test_anno["cid2img"].keys()) if len(test_anno["cid2img"][i]) > self.shot]
+        assert len(train_cat_ids) == self.nclass
+        class_ids_val = [train_cat_ids[self.fold + self.nfolds * v] for v in range(self.nclass // self.nfolds)]
+        class_ids_val = [x for x in class_ids_val if x in test_cat_ids]
+        anno = train_anno if self.split == "trn" else test_anno
+        self.class_ids_ori = [x for x in train_cat_ids if x not in class_ids_val] if self.split == "trn" else class_ids_val
+        self.cid2img, self.img2anno = anno["cid2img"], anno["img2anno"]
+        self.class_ids_c = {cid: i for i, cid in enumerate(self.class_ids_ori)}
+        self.class_ids = sorted(list(self.class_ids_c.values()))
+        self.img_metadata = []
+        for k in self.cid2img.keys():                                           # paco_part.py:102-106
+            self.img_metadata += self.cid2img[k]
+
+    def __len__(self):
+        return len(self.img_metadata) if self.split == "trn" else 2500          # paco_part.py:32-33
+
+    def image_path(self, name):
+        return os.path.join(self.img_path, name)
+
+    def _objects(self, img_id, class_sample):
+        objs = {}
+        for anno in self.img2anno[img_id]:                                      # paco_part.py:136-147
+            if anno["category_id"] == class_sample:
+                o = objs.setdefault(anno["obj_ann_id"], {"obj_bbox": [], "segms": []})
+                o["obj_bbox"].append(anno["obj_bbox"])
+                o["segms"].append(anno["segmentation"])
+        return objs
+
+    @staticmethod
+    def _xyxy(b):
+        return [int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3])]       # paco_part.py:199 slicing bounds
+
+    def sample_names(self, idx):
+        # paco_part.py:126-185 — idx ignored; class, query image, query object, then per shot (image, object)
+        class_sample = np.random.choice(self.class_ids_ori, 1, replace=False)[0]
+        query = np.random.choice(self.cid2img[class_sample], 1, replace=False)[0]
+        query_id, query_name = list(query.keys())[0], list(query.values())[0]
+        query_name = "/".join(query_name.split("/")[-2:])
+        qobjs = self._objects(query_id, class_sample)
+        sel = np.random.choice(list(qobjs.keys()), 1, replace=False)[0]
+        query_box, query_segms = qobjs[sel]["obj_bbox"][0], qobjs[sel]["segms"]
+        support_names, support_segms, support_boxes = [], [], []
+        while True:
+            support = np.random.choice(self.cid2img[class_sample], 1, replace=False)[0]
+            support_id, support_name = list(support.keys())[0], list(support.values())[0]
+            support_name = "/".join(support_name.split("/")[-2:])
+            if query_name != support_name:
+                support_names.append(support_name)
+                sobjs = self._objects(support_id, class_sample)
+                ssel = np.random.choice(list(sobjs.keys()), 1, replace=False)[0]
+                support_boxes.append(sobjs[ssel]["obj_bbox"][0])
+                support_segms.append(sobjs[ssel]["segms"])
+            if len(support_names) == self.shot:
+                break
+        extra = {"query_segms": query_segms, "support_segms": support_segms}
+        if self.box_crop:
+            extra["query_box"] = self._xyxy(query_box)
+            extra["support_boxes"] = [self._xyxy(b) for b in support_boxes]
+        return query_name, support_names, self.class_ids_c[class_sample], extra
+
+
+class DatasetPASCALPart(_SegmDataset):
+    """PASCAL-Part (evaluation_util/data/pascal_part.py).  Files under Pascal-Part/VOCdevkit/VOC2010/:
+    all_obj_part_to_image.json ({super-category: {'object': {obj: {'part': {part: {'train': [...], 'val': [...]}}}}}}),
+    JPEGImages/<id>.jpg, Annotations_Part_json_merged_part_classes/<id>.json ({'object': [{'name', 'bndbox',
+    'parts': [{'name', 'mask': [RLE, ...]}]}]}).  fold selects the super-category."""
+    benchmark = "pascal_part"
+
+    def __init__(self, datapath, fold, transform, split, shot, use_original_imgsize, box_crop=True):
+        import json
+        self.split = "val" if split in ["val", "test"] else "train"
+        self.cat = ["animals", "indoor", "person", "vehicles"][fold]
+        self.shot = shot
+        self.transform = transform
+        self.use_original_imgsize = use_original_imgsize
+        self.box_crop = box_crop
+        base = os.path.join(datapath, "Pascal-Part/VOCdevkit/VOC2010")
+        self.img_file = os.path.join(base, "JPEGImages/{}.jpg")
+        self.anno_file = os.path.join(base, "Annotations_Part_json_merged_part_classes/{}.json")
+        with open(os.path.join(base, "all_obj_part_to_image.json"), "r") as f:
+            self.cat_annos = json.load(f)[self.cat]
+        self.cat_part_name = []
+        for obj in self.cat_annos["object"]:                                    # pascal_part.py:34-46
+            for part in self.cat_annos["object"][obj]["part"]:
+                p = self.cat_annos["object"][obj]["part"][part]
+                if len(p["train"]) > 0 and len(p["val"]) > 0:
+                    if obj + "+" + part == "aeroplane+TAIL":
+                        continue
+                    self.cat_part_name.append(obj + "+" + part)
+        self.class_ids = self.cat_part_id = list(range(len(self.cat_part_name)))
+        self.nclass = len(self.cat_part_id)
+        self.img_metadata = []
+        for obj in self.cat_annos["object"]:                                    # pascal_part.py:56-63
+            for part in self.cat_annos["object"][obj]["part"]:
+                self.img_metadata.extend(self.cat_annos["object"][obj]["part"][part][self.split])
+
+    def __len__(self):
+        # pascal_part.py:50-54: the 'trn' branch is unreachable there too (split is 'train' or 'val')
+        return min(len(self.img_metadata), 2500)
+
+    def image_path(self, name):
+        return self.img_file.format(name)
+
+    def _sample_part(self, img_id, obj_n, part_n):
+        """pascal_part.py:103-131 for one candidate image: (object, union of the part's masks) or None."""
+        import json
+        from . import cocomask
+        with open(self.anno_file.format(img_id), "r") as f:
+            anno = json.load(f)
+        objs = [o for o in anno["object"] if o["name"] == obj_n]
+        assert len(objs) > 0
+        sel_obj = np.random.choice(objs, 1, replace=False)[0]
+        rles = []
+        for p in sel_obj["parts"]:
+            if p["name"] == part_n:
+                rles.extend(p["mask"])
+        if not rles:
+            return None
+        part_mask = sum(cocomask.decode_rle_dict(m).astype(np.int64) for m in rles) > 0
+        if part_mask.size == 0:
+            return None
+        return sel_obj, part_mask.astype(np.uint8)
+
+    def sample_names(self, idx):
+        idx %= len(self.class_ids)                                              # pascal_part.py:67, :98-178
+        class_sample, class_id = self.cat_part_name[idx], self.class_ids[idx]
+        obj_n, part_n = class_sample.split("+")
+        pool = self.cat_annos["object"][obj_n]["part"][part_n][self.split]
+        while True:
+            query_id = np.random.choice(pool, 1, replace=False)[0]
+            got = self._sample_part(query_id, obj_n, part_n)
+            if got is not None:
+                break
+        q_obj, q_mask = got
+        box = lambda o: [int(o["bndbox"][b]) for b in o["bndbox"]]              # xyxy, dict order (pascal_part.py:136)
+        support_ids, support_masks, support_boxes = [], [], []
+        while True:
+            while True:
+                sid = np.random.choice(pool, 1, replace=False)[0]
+                if sid == query_id or sid in support_ids:
+                    continue
+                got = self._sample_part(sid, obj_n, part_n)
+                if got is not None:
+                    break
+            support_ids.append(sid)
+            support_masks.append(got[1])
+            support_boxes.append(box(got[0]))
+            if len(support_ids) == self.shot:
+                break
+        extra = {"query_segms": q_mask, "support_segms": support_masks, "category": class_sample}
+        if self.box_crop:
+            extra["query_box"], extra["support_boxes"] = box(q_obj), support_boxes
+        return str(query_id), [str(s) for s in support_ids], class_id, extra
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -309,7 +632,7 @@ class EpisodeCollator:
         S_h, S_w = self.size
         imgs = [r["query_img"] for r in raws] + [s for r in raws for s in r["support_imgs"]]
         labels = [r["query_label"] for r in raws] + [s for r in raws for s in r["support_labels"]]
-        cls1 = [r["class_sample"] + 1 for r in raws] + [r["class_sample"] + 1 for r in raws for _ in range(k)]
+        cls1 = [r["mask_param"] for r in raws] + [r["mask_param"] for r in raws for _ in range(k)]
         n = len(imgs)
         for im, lb in zip(imgs, labels):
             if im.shape[:2] != lb.shape:
@@ -334,8 +657,11 @@ class EpisodeCollator:
             "class_id": torch.tensor([r["class_sample"] for r in raws], dtype=torch.int64).to(self.device),
         }
         if ign:
-            batch["query_ignore_idx"] = bnd[:B]
+            if getattr(self.ds, "emit_query_ignore", True):
+                batch["query_ignore_idx"] = bnd[:B]
             batch["support_ignore_idxs"] = bnd[B:].view(B, k, S_h, S_w)
+        if "category" in raws[0]:
+            batch["category"] = [r["category"] for r in raws]                           # pascal_part.py:91
         if getattr(self.ds, "use_original_imgsize", False):
             # coco.py:41 / pascal.py:42: the query mask keeps its own size (the reference can then only run bsz = 1)
             if B != 1:
@@ -407,7 +733,8 @@ class EpisodeLoader:
 
 class FSSDataset:
     """evaluation_util/data/dataset.py:14-52, same classmethod protocol."""
-    datasets = {"coco": DatasetCOCO, "pascal": DatasetPASCAL, "fss": DatasetFSS}
+    datasets = {"coco": DatasetCOCO, "pascal": DatasetPASCAL, "fss": DatasetFSS, "paco_part": DatasetPACOPart,
+                "pascal_part": DatasetPASCALPart, "lvis": DatasetLVIS, "pascal_cd": DatasetPASCALCD}
 
     @classmethod
     def initialize(cls, img_size, datapath, use_original_imgsize):
@@ -418,8 +745,7 @@ class FSSDataset:
     @classmethod
     def build_dataloader(cls, benchmark, bsz, nworker, fold, split, shot=1, device="cuda", rank=None, world=None):
         if benchmark not in cls.datasets:
-            raise NotImplementedError(f"benchmark {benchmark!r}: only {sorted(cls.datasets)} are built "
-                                      "(lvis / paco_part / pascal_part need detectron2 / pycocotools metadata)")
+            raise NotImplementedError(f"benchmark {benchmark!r}: only {sorted(cls.datasets)} exist (dataset.py:18-26)")
         shuffle = split == "trn"
         dataset = cls.datasets[benchmark](cls.datapath, fold=fold, transform=cls.transform, split=split, shot=shot,
                                           use_original_imgsize=cls.use_original_imgsize)

@@ -28,6 +28,38 @@ REF = "/root/reference/evaluation_util/data"
 IMG_SIZE = 48
 
 
+def _install_segm_standins():
+    """lvis.py / paco_part.py / pascal_part.py import cv2 (unused), detectron2.structures.masks (polygons_to_bitmask,
+    and through its star-import `mask_util`) and pycocotools.mask (decode).  None is installed.  The stand-ins forward
+    to diffews_b200.cocomask, the restatement of pycocotools' maskApi.c: for ARRAY segmentations (half of the synthetic
+    annotations) no stand-in arithmetic is involved at all; for polygon / RLE segmentations the rasteriser under the
+    reference's code is the restatement itself, so those fixtures pin everything AROUND the rasteriser (sampling, union,
+    box crop, resize), not the rasteriser."""
+    import types
+    from diffews_b200 import cocomask
+
+    def decode(rle):
+        if isinstance(rle, (list, tuple)):
+            if len(rle) == 0:
+                return np.zeros((0, 0, 0), np.uint8)
+            return np.stack([cocomask.decode_rle_dict(r) for r in rle], axis=-1)
+        return cocomask.decode_rle_dict(rle)
+
+    mask_util = types.ModuleType("pycocotools.mask")
+    mask_util.decode = decode
+    pyco = types.ModuleType("pycocotools")
+    pyco.mask = mask_util
+    d2m = types.ModuleType("detectron2.structures.masks")
+    d2m.polygons_to_bitmask = lambda polygons, height, width: cocomask.polygons_to_bitmask(polygons, height, width)
+    d2m.mask_util = mask_util
+    d2s = types.ModuleType("detectron2.structures")
+    d2s.masks = d2m
+    d2 = types.ModuleType("detectron2")
+    d2.structures = d2s
+    sys.modules.update({"cv2": types.ModuleType("cv2"), "pycocotools": pyco, "pycocotools.mask": mask_util,
+                        "detectron2": d2, "detectron2.structures": d2s, "detectron2.structures.masks": d2m})
+
+
 def _load(name):
     spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, name + ".py"))
     m = importlib.util.module_from_spec(spec)
@@ -52,6 +84,7 @@ def episodes(ds, n, root):
              "query_mask_sum": float(b["query_mask"].sum()), "query_img_first": b["query_img"].flatten()[:4].tolist()}
         if "query_ignore_idx" in b:
             e["query_ignore_idx"] = sha(b["query_ignore_idx"])
+        if "support_ignore_idxs" in b:
             e["support_ignore_idxs"] = sha(b["support_ignore_idxs"])
         if "org_query_imsize" in b:
             e["org_query_imsize"] = list(b["org_query_imsize"])
@@ -128,6 +161,35 @@ def main():
         np.random.seed(0)
         ds = fss.DatasetFSS(root, fold=0, transform=tf, split="test", shot=2, use_original_imgsize=False)
         gold["fss_shot2"] = episodes(ds, 5, root)
+        # instance-segmentation benchmarks (import stand-ins: see _install_segm_standins)
+        sys.path.insert(0, ROOT)
+        _install_segm_standins()
+        data_tree.build_lvis_tree(root)
+        data_tree.build_paco_tree(root)
+        data_tree.build_pascal_part_tree(root)
+        lvis, paco, ppart = _load("lvis"), _load("paco_part"), _load("pascal_part")
+        for shot in (1, 2):
+            np.random.seed(0)
+            ds = lvis.DatasetLVIS(root, fold=0, transform=tf, split="val", shot=shot, use_original_imgsize=False)
+            gold[f"lvis_shot{shot}"] = episodes(ds, 8, root)
+            gold[f"lvis_shot{shot}_meta"] = {"nclass": ds.nclass, "class_ids": ds.class_ids, "class_ids_ori": ds.class_ids_ori}
+        np.random.seed(0)
+        ds = paco.DatasetPACOPart(root, fold=0, transform=tf, split="val", shot=1, use_original_imgsize=False)
+        gold["paco_part_shot1"] = episodes(ds, 8, root)
+        gold["paco_part_shot1_meta"] = {"nclass": ds.nclass, "class_ids": ds.class_ids, "class_ids_ori": ds.class_ids_ori}
+        for shot in (1, 2):
+            np.random.seed(0)
+            ds = ppart.DatasetPASCALPart(root, fold=0, transform=tf, split="val", shot=shot, use_original_imgsize=False)
+            gold[f"pascal_part_shot{shot}"] = episodes(ds, 8, root)
+            gold[f"pascal_part_shot{shot}_meta"] = {"nclass": ds.nclass, "class_ids": ds.class_ids, "len": len(ds),
+                                                     "cat_part_name": ds.cat_part_name}
+    with tempfile.TemporaryDirectory() as root:
+        data_tree.build_pascal_cd_tree(root)
+        np.random.seed(0)
+        ds = _load("pascal_voc_cd").DatasetPASCALCD(root, fold=0, transform=tf, split="val", shot=1)
+        gold["pascal_cd_shot1"] = episodes(ds, 6, root)
+        gold["pascal_cd_shot1_meta"] = {"nclass": ds.nclass, "class_ids": ds.class_ids, "len": len(ds),
+                                        "n_metadata": len(ds.img_metadata)}
     mpath = os.path.join(ROOT, "tests", "golden", "metric_reference.json")
     with open(mpath, "w") as f:
         cases = metric_golden()

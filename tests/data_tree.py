@@ -137,3 +137,193 @@ def attn_cases():
         cases.append({"B": B, "k": k, "C": C, "S": S, "heads": 2, "w": w,
                       "x_support": torch.randn(B * k, S, C, generator=g), "x_query": torch.randn(B, S, C, generator=g)})
     return cases
+
+
+# ---- instance-segmentation benchmarks (LVIS-92i, PACO-Part, PASCAL-Part) --------------------------------------------
+def rle_encode(mask_hw: np.ndarray):
+    """Uncompressed COCO RLE of a binary mask: column-major run lengths starting with a run of zeros."""
+    flat = np.asarray(mask_hw, dtype=np.uint8).T.reshape(-1)
+    counts, prev, run = [], 0, 0
+    for v in flat:
+        if v != prev:
+            counts.append(run)
+            run, prev = 0, v
+        run += 1
+    counts.append(run)
+    return counts
+
+
+def rle_to_string(counts) -> str:
+    """pycocotools maskApi.c rleToString (the inverse of what cocomask.rle_counts_from_string reads)."""
+    out = []
+    for i, c in enumerate(counts):
+        x = int(c)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            ch = x & 0x1F
+            x >>= 5
+            more = not (x == -1 if (ch & 0x10) else x == 0)
+            if more:
+                ch |= 0x20
+            out.append(chr(ch + 48))
+    return "".join(out)
+
+
+def _blob(rs, h, w):
+    m = np.zeros((h, w), np.uint8)
+    y0, x0 = rs.randint(0, h - 6), rs.randint(0, w - 6)
+    y1, x1 = rs.randint(y0 + 4, h + 1), rs.randint(x0 + 4, w + 1)
+    yy, xx = np.mgrid[0:h, 0:w]
+    cy, cx, ry, rx = (y0 + y1) / 2, (x0 + x1) / 2, (y1 - y0) / 2, (x1 - x0) / 2
+    m[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = 1
+    return m, (x0, y0, x1, y1)
+
+
+def _segm(rs, h, w, kind):
+    """One segmentation in one of the four encodings lvis.py:99-121 accepts."""
+    m, (x0, y0, x1, y1) = _blob(rs, h, w)
+    if kind == "array":
+        return m
+    if kind == "rle_list":
+        return {"size": [h, w], "counts": rle_encode(m)}
+    if kind == "rle_str":
+        return {"size": [h, w], "counts": rle_to_string(rle_encode(m))}
+    # polygons: a triangle and a quadrilateral with fractional vertices inside the blob's box
+    t = [x0 + .3, y0 + .2, x1 - .4, y0 + 1.7, (x0 + x1) / 2 + .25, y1 - .6]
+    q = [x0 + .5, (y0 + y1) / 2, (x0 + x1) / 2, y0 + .5, x1 - .5, (y0 + y1) / 2 + .3, (x0 + x1) / 2 - .2, y1 - .5]
+    return [t, q] if rs.randint(0, 2) else [q]
+
+
+_KINDS = ("array", "rle_list", "rle_str", "poly")
+
+
+def build_lvis_tree(root: str, seed: int = 14, n_images: int = 24, n_classes: int = 20) -> str:
+    rs = np.random.RandomState(seed)
+    base = os.path.join(root, "LVIS")
+    sizes = {}
+    for i in range(n_images):
+        h, w = rs.randint(40, 110), rs.randint(40, 110)
+        name = f"val2017/{i:012d}.jpg"
+        sizes[name] = (h, w)
+        _save(_rand_image(rs, h, w), os.path.join(base, "coco", name))
+    names = sorted(sizes)
+    val = {}
+    for c in range(n_classes):
+        cid = 3 * c + 7                                         # sparse category ids, like LVIS
+        per = {}
+        for j in range(1 + (c % 4)):                            # classes with a single image are dropped at shot >= 1
+            name = names[(c * 5 + j * 7) % n_images]
+            h, w = sizes[name]
+            per[name] = {"annotations": [{"segmentation": _segm(rs, h, w, _KINDS[(c + j + a) % 4])}
+                                         for a in range(1 + (c + j) % 3)]}
+        val[cid] = per
+    os.makedirs(base, exist_ok=True)
+    with open(os.path.join(base, "lvis_val.pkl"), "wb") as f:
+        pickle.dump(val, f)
+    with open(os.path.join(base, "lvis_train.pkl"), "wb") as f:
+        pickle.dump({1000 + c: {} for c in range(5)}, f)
+    return root
+
+
+def build_paco_tree(root: str, seed: int = 15, n_images: int = 20) -> str:
+    rs = np.random.RandomState(seed)
+    base = os.path.join(root, "PACO-Part")
+    sizes, img2anno = {}, {}
+    for i in range(n_images):
+        h, w = rs.randint(48, 120), rs.randint(48, 120)
+        sizes[i] = (h, w, f"/data/x/coco/val2017/{i:012d}.jpg")
+        _save(_rand_image(rs, h, w), os.path.join(base, "coco", f"val2017/{i:012d}.jpg"))
+        img2anno[i] = []
+    train_cids = list(range(100, 100 + 448))                    # paco_part.py:87 asserts 448 training categories
+    cid2img = {}
+    ann = 0
+    for v in range(8):                                          # fold-0 validation categories: train_cids[0 + 4 v]
+        cid = train_cids[4 * v]
+        lst = []
+        for j in range(2 + v % 3):
+            i = (v * 3 + j * 5) % n_images
+            h, w, path = sizes[i]
+            lst.append({i: path})
+            if j == 0:
+                lst.append({i: path})                           # a duplicate, removed by paco_part.py:70-81
+            for o in range(1 + (v + j) % 2):                    # objects of this category in the image
+                bw, bh = rs.randint(16, w - 4), rs.randint(16, h - 4)
+                bx, by = rs.randint(0, w - bw), rs.randint(0, h - bh)
+                box = [bx + .4, by + .7, float(bw), float(bh)]
+                for p in range(1 + (o + j) % 2):                # parts of the object
+                    img2anno[i].append({"category_id": cid, "obj_ann_id": ann, "obj_bbox": box,
+                                        "segmentation": _segm(rs, h, w, _KINDS[(v + j + o + p) % 4])})
+                ann += 1
+        cid2img[cid] = lst
+    os.makedirs(os.path.join(base, "paco"), exist_ok=True)
+    with open(os.path.join(base, "paco", "paco_part_val.pkl"), "wb") as f:
+        pickle.dump({"cid2img": cid2img, "img2anno": img2anno}, f)
+    with open(os.path.join(base, "paco", "paco_part_train.pkl"), "wb") as f:
+        pickle.dump({"cid2img": {c: [] for c in train_cids}, "img2anno": {}}, f)
+    return root
+
+
+def build_pascal_part_tree(root: str, seed: int = 16, n_images: int = 14) -> str:
+    import json
+    rs = np.random.RandomState(seed)
+    base = os.path.join(root, "Pascal-Part/VOCdevkit/VOC2010")
+    objs = {"cat": ["HEAD", "TAIL"], "dog": ["HEAD", "LEG"]}
+    index = {"animals": {"object": {o: {"part": {p: {"train": ["t0"], "val": []} for p in ps}} for o, ps in objs.items()}},
+             "indoor": {"object": {}}, "person": {"object": {}}, "vehicles": {"object": {}}}
+    os.makedirs(os.path.join(base, "Annotations_Part_json_merged_part_classes"), exist_ok=True)
+    for i in range(n_images):
+        h, w = rs.randint(48, 120), rs.randint(48, 120)
+        iid = f"2008_{i:06d}"
+        _save(_rand_image(rs, h, w), os.path.join(base, "JPEGImages", iid + ".jpg"))
+        anno = {"object": []}
+        for o_i, (o, ps) in enumerate(objs.items()):
+            if (i + o_i) % 3 == 2:
+                continue
+            for inst in range(1 + (i + o_i) % 2):
+                bw, bh = rs.randint(20, w - 2), rs.randint(20, h - 2)
+                bx, by = rs.randint(0, w - bw), rs.randint(0, h - bh)
+                parts = []
+                for p_i, p in enumerate(ps):
+                    if (i + inst + p_i) % 4 == 3:
+                        continue                                # this instance lacks the part: resampled (:118-119)
+                    masks = []
+                    for _ in range(1 + (i + p_i) % 2):
+                        m, _b = _blob(rs, h, w)
+                        masks.append({"size": [h, w], "counts": rle_to_string(rle_encode(m))})
+                    parts.append({"name": p, "mask": masks})
+                    lst = index["animals"]["object"][o]["part"][p]["val"]
+                    if iid not in lst:
+                        lst.append(iid)
+                anno["object"].append({"name": o, "bndbox": {"xmin": bx, "ymin": by, "xmax": bx + bw, "ymax": by + bh},
+                                       "parts": parts})
+        with open(os.path.join(base, "Annotations_Part_json_merged_part_classes", iid + ".json"), "w") as f:
+            json.dump(anno, f)
+    with open(os.path.join(base, "all_obj_part_to_image.json"), "w") as f:
+        json.dump(index, f)
+    return root
+
+
+def build_pascal_cd_tree(root: str, seed: int = 17, n_images: int = 12) -> str:
+    """pascal_voc_cd.py: VOC2012 with four validation split files and cd_folds.pth / class_names.pth.  Built in its own
+    root (it would overwrite build_pascal_tree's fold0.txt)."""
+    rs = np.random.RandomState(seed)
+    base = os.path.join(root, "VOC2012")
+    folds = {0: [1, 4, 9, 11, 12], 1: [2, 6, 13, 18, 5], 2: [3, 7, 16, 17, 20], 3: [8, 10, 14, 15, 19]}
+    lines = {f: [] for f in range(4)}
+    for i in range(n_images):
+        h, w = rs.randint(36, 120), rs.randint(36, 120)
+        name = f"2009_{i:06d}"
+        classes = sorted({folds[0][i % 5] - 1, folds[1][i % 5] - 1, folds[0][(i // 2) % 5] - 1})
+        _save(_rand_image(rs, h, w), os.path.join(base, "JPEGImages", name + ".jpg"))
+        _save(_rand_label(rs, h, w, classes, True), os.path.join(base, "SegmentationClassAug", name + ".png"))
+        for c in classes:
+            lines[i % 4].append(f"{name}__{c + 1}")
+    os.makedirs(os.path.join(base, "splits", "val"), exist_ok=True)
+    for f_id in range(4):
+        with open(os.path.join(base, "splits", "val", f"fold{f_id}.txt"), "w") as f:
+            f.write("\n".join(lines[f_id]) + "\n")
+    torch.save(folds, os.path.join(base, "cd_folds.pth"))
+    torch.save([f"class{c}" for c in range(20)], os.path.join(base, "class_names.pth"))
+    return root

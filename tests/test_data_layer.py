@@ -33,16 +33,24 @@ def tree(tmp_path_factory):
     data_tree.build_coco_tree(root)
     data_tree.build_pascal_tree(root)
     data_tree.build_fss_tree(root)
+    data_tree.build_lvis_tree(root)
+    data_tree.build_paco_tree(root)
+    data_tree.build_pascal_part_tree(root)
+    data_tree.build_pascal_cd_tree(os.path.join(root, "cd"))          # its own root: it rewrites VOC2012/splits
     return root
 
 
 CASES = {"coco_shot1": ("coco", "val", 1), "coco_shot2": ("coco", "val", 2), "pascal_shot1": ("pascal", "val", 1),
-         "fss_shot2": ("fss", "test", 2)}
+         "fss_shot2": ("fss", "test", 2), "lvis_shot1": ("lvis", "val", 1), "lvis_shot2": ("lvis", "val", 2),
+         "paco_part_shot1": ("paco_part", "val", 1), "pascal_part_shot1": ("pascal_part", "val", 1),
+         "pascal_part_shot2": ("pascal_part", "val", 2), "pascal_cd_shot1": ("pascal_cd", "val", 1)}
 
 
 def _dataset(tree, key):
     from diffews_b200 import data
     bench, split, shot = CASES[key]
+    if bench == "pascal_cd":
+        tree = os.path.join(tree, "cd")
     data.FSSDataset.initialize(S, tree, False)
     cls = data.FSSDataset.datasets[bench]
     return cls(tree, fold=0, transform=data.FSSDataset.transform, split=split, shot=shot, use_original_imgsize=False)
@@ -63,8 +71,13 @@ def _oracle_episode(ds, raw):
         mb = [O.pascal_mask(l, c, S) for l in labs]
         masks, bnd = [m for m, _ in mb], [b for _, b in mb]
         out["query_ignore_idx"], out["support_ignore_idxs"] = bnd[0], torch.stack(bnd[1:])
+        if not getattr(ds, "emit_query_ignore", True):
+            del out["query_ignore_idx"]                      # pascal_voc_cd.py:61
     elif ds.benchmark == "fss":
         masks = [torch.from_numpy(O.nearest_resize((l >= 128).astype(np.float32), S, S).copy()) for l in labs]
+    elif ds.benchmark in ("lvis", "paco_part", "pascal_part"):
+        # lvis.py:41-48: the union bitmask .float(), nearest-resized
+        masks = [torch.from_numpy(O.nearest_resize((l > 0).astype(np.float32), S, S).copy()) for l in labs]
     else:
         masks = [O.coco_mask(l, c, S) for l in labs]
     out["query_mask"], out["support_masks"] = masks[0], torch.stack(masks[1:])
@@ -129,6 +142,62 @@ def test_class_ids_and_lengths(tree):
     assert ds.class_ids == O.pascal_class_ids(0, "val") == [0, 1, 2, 3, 4] and len(ds) == 1000
     ds = _dataset(tree, "fss_shot2")
     assert list(ds.class_ids) == list(range(760, 1000)) and len(ds) == 30
+
+
+def test_segmentation_benchmark_metadata_matches_reference(tree):
+    """Class splits of the instance-segmentation benchmarks (lvis.py:66-90, paco_part.py:62-100, pascal_part.py:31-46)
+    against what the unmodified reference built on the same trees."""
+    for key in ("lvis_shot1", "lvis_shot2", "paco_part_shot1", "pascal_part_shot1"):
+        ds, meta = _dataset(tree, key), GOLD[key + "_meta"]
+        assert ds.nclass == meta["nclass"] and list(ds.class_ids) == meta["class_ids"]
+        if "class_ids_ori" in meta:
+            assert list(ds.class_ids_ori) == meta["class_ids_ori"]
+        if "cat_part_name" in meta:
+            assert ds.cat_part_name == meta["cat_part_name"] and len(ds) == meta["len"]
+    assert len(_dataset(tree, "lvis_shot1")) == 2300 and len(_dataset(tree, "paco_part_shot1")) == 2500
+    ds, meta = _dataset(tree, "pascal_cd_shot1"), GOLD["pascal_cd_shot1_meta"]
+    assert (ds.nclass, list(ds.class_ids), len(ds), len(ds.img_metadata)) == (meta["nclass"], meta["class_ids"],
+                                                                              meta["len"], meta["n_metadata"])
+
+
+def test_cocomask_rle_and_polygons():
+    """diffews_b200/cocomask.py (restated pycocotools maskApi.c; the library is not installed): RLE string <-> counts <->
+    mask round trips, and polygons with hand-checkable answers."""
+    from diffews_b200 import cocomask
+    rs = np.random.RandomState(0)
+    for _ in range(40):
+        h, w = rs.randint(1, 40), rs.randint(1, 40)
+        m = (rs.rand(h, w) > rs.rand()).astype(np.uint8)
+        counts = data_tree.rle_encode(m)
+        assert sum(counts) == h * w
+        assert cocomask.rle_counts_from_string(data_tree.rle_to_string(counts)) == counts
+        assert np.array_equal(cocomask.rle_decode(counts, h, w), m)
+        assert np.array_equal(cocomask.decode_rle_dict({"size": [h, w], "counts": data_tree.rle_to_string(counts)}), m)
+    # an integer-cornered rectangle [x0,x1) x [y0,y1) covers exactly (x1-x0)(y1-y0) pixels (COCO's bbox-polygon area)
+    for x0, y0, x1, y1 in ((10, 10, 20, 20), (0, 0, 30, 25), (3, 7, 4, 8), (5, 0, 29, 3)):
+        m = cocomask.polygons_to_bitmask([[x0, y0, x1, y0, x1, y1, x0, y1]], 25, 30)
+        ref = np.zeros((25, 30), bool)
+        ref[y0:y1, x0:x1] = True
+        assert np.array_equal(m, ref), (x0, y0, x1, y1)
+    # vertex order / starting vertex do not matter; the union of two polygons is the OR of their masks
+    a = [4.3, 3.2, 25.6, 5.7, 14.25, 20.4]
+    b = [2.5, 12.0, 15.0, 2.5, 27.5, 12.3, 14.8, 22.5]
+    ma, mb = cocomask.polygons_to_bitmask([a], 25, 30), cocomask.polygons_to_bitmask([b], 25, 30)
+    assert np.array_equal(cocomask.polygons_to_bitmask([a[2:] + a[:2]], 25, 30), ma)
+    assert np.array_equal(cocomask.polygons_to_bitmask([a, b], 25, 30), ma | mb)
+    # a convex polygon's mask lies within one pixel of the exact point-in-polygon set of pixel centres
+    yy, xx = np.mgrid[0:25, 0:30]
+    inside = np.ones((25, 30), bool)
+    pts = np.asarray(b).reshape(-1, 2)
+    for i in range(len(pts)):
+        (xa, ya), (xb, yb) = pts[i], pts[(i + 1) % len(pts)]
+        inside &= ((xb - xa) * (yy + .5 - ya) - (yb - ya) * (xx + .5 - xa)) >= 0
+    assert abs(int(mb.sum()) - int(inside.sum())) <= 0.15 * inside.sum()
+    grown = np.zeros_like(inside)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            grown |= np.roll(np.roll(inside, dy, 0), dx, 1)
+    assert not (mb & ~grown).any()
 
 
 def test_pack_layout():
