@@ -224,7 +224,8 @@ def main():
     ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
     ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS),
                     help="BASELINE.json config: 2 = 1-shot 512^2 B16 (default workload), 3 = 5-shot 512^2 B8, 5 = 1-shot 768^2 B8")
-    ap.add_argument("--operands", default="f16", choices=["f16", "bf16"], help="16-bit tensor-core operand format")
+    ap.add_argument("--operands", default="f16", choices=["f16", "bf16", "f32"],
+                    help="tensor-core operand format; f32 = the fp32 evaluation mode (split-f16 operands, fp32 everywhere else)")
     args = ap.parse_args()
     if args.config is not None:
         args.batch, args.nshot, args.size, _ = CONFIGS[args.config]
@@ -253,9 +254,13 @@ def main():
 
     # weight source: deterministic random init with the diffusers key names (no checkpoints offline); nothing from oracle/
     from diffews_b200.layers import Precision
-    half = torch.float16 if args.operands == "f16" else torch.bfloat16
-    vae_prec = Precision(half=half, stream_f32=(args.vae_stream == "f32"), mid_f32=False)
-    unet_prec = Precision(half=half, stream_f32=(args.unet_stream == "f32"), mid_f32=(args.unet_stream == "f32"))
+    half = torch.bfloat16 if args.operands == "bf16" else torch.float16
+    if args.operands == "f32":
+        vae_prec = unet_prec = Precision(half=half, f32=True)
+        args.vae_stream = args.unet_stream = "f32"
+    else:
+        vae_prec = Precision(half=half, stream_f32=(args.vae_stream == "f32"), mid_f32=False)
+        unet_prec = Precision(half=half, stream_f32=(args.unet_stream == "f32"), mid_f32=(args.unet_stream == "f32"))
     pipe = build_engine_from_state_dicts(random_unet_state_dict(0), random_vae_state_dict(1), prompt_embedding(), device=dev,
                                          vae_precision=vae_prec, unet_precision=unet_prec)
     runner = EpisodeRunner(pipe, "coco", img_size=args.size)
@@ -484,7 +489,10 @@ def main():
                        "episodes_per_step_per_gpu": B, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if use_graph else "eager",
                        "l2_policy": "inputs + activations per step (>2 GB) exceed the 126 MB L2; 2 alternating batches",
-                       "precision": f"{args.operands} tensor-core operands ("
+                       "precision": ("fp32 evaluation mode: every activation fp32, GEMMs / convolutions on the tcgen05 kernels with "
+                                     "split f16 operands (hi + lo, 3 partial products), norms / softmax / GELU / attention core in "
+                                     "fp32 (latent rel-L2 3e-5 vs the fp32 oracle; tests/test_f32_mode_gpu.py)")
+                       if args.operands == "f32" else f"{args.operands} tensor-core operands ("
                                     + ("the reference's own half mode; bf16, the format BASELINE config 2 names, runs at the same "
                                        "rate (--operands bf16) but measures 1.1e-2 .. 1.6e-2 latent rel-L2, above the 1e-2 bar"
                                        if args.operands == "f16" else "selected with --operands bf16; latent rel-L2 1.1e-2 .. 1.6e-2")

@@ -52,6 +52,13 @@ SIGNATURES = {
     "dfw_layernorm_bwd_workspace_bytes": (_ll, [_i, _i]),
     "dfw_layernorm_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "dfw_softmax_rows": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
+    "dfw_split3_16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "dfw_groupnorm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "dfw_layernorm_f32": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
+    "dfw_softmax_rows_f32": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "dfw_geglu_f32": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "dfw_attn_f32": (_i, [_vp, _ll, _ll, _vp, _vp, _ll, _ll, _vp, _vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _i, _i, _i, _f,
+                          _vp]),
     "dfw_upsample2x_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfw_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "dfw_cast_f32_to_16": (_i, [_vp, _vp, _i, _ll, _vp]),

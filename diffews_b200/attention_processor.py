@@ -26,11 +26,12 @@ bf16 = torch.bfloat16
 class MyAttention:
     """Prepared weights + bank state of one `attn1` (self-attention) module."""
 
-    def __init__(self, sd, prefix, device, heads: int, wdtype=bf16):
+    def __init__(self, sd, prefix, device, heads: int, wdtype=bf16, f32=False):
         self.heads = heads
         self.scale = 64 ** -0.5
-        self.to_qkv = FusedLinear(sd, [prefix + ".to_q", prefix + ".to_k", prefix + ".to_v"], device, wdtype=wdtype)
-        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wdtype)
+        self.to_qkv = FusedLinear(sd, [prefix + ".to_q", prefix + ".to_k", prefix + ".to_v"], device, wdtype=wdtype,
+                                  f32=f32)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wdtype, f32=f32)
         self.inner_dim = self.to_qkv.splits[0]
         assert self.inner_dim == heads * 64, "the flash kernel is specialised for head_dim 64"
         self.residual_connection = False
@@ -123,9 +124,10 @@ class MyXFormersAttnProcessor:
     def _attend(attn, qkv, D, heads, scale):
         N = qkv.shape[0]
         q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+        core = ops.attn_f32 if qkv.dtype == torch.float32 else ops.attn_kvfused      # fp32 mode: CUDA-core fp32 kernel
         if getattr(attn, "k_bank", None) is None:              # support pass: store (views keep qkv alive)  :251-252
             attn.k_bank, attn.v_bank = k, v
-            return ops.attn_kvfused(q, k, v, None, None, heads, scale)
+            return core(q, k, v, None, None, heads, scale)
         kb, vb = attn.k_bank, attn.v_bank                      # query pass: bank folded to [N, shots*S, D]   :253-267
         nb, sb = kb.shape[0], kb.shape[1]
         if nb % N != 0:
@@ -133,7 +135,7 @@ class MyXFormersAttnProcessor:
         shots = nb // N
         kbf = kb.as_strided((N, shots * sb, D), (shots * sb * kb.stride(1), kb.stride(1), 1), kb.storage_offset())
         vbf = vb.as_strided((N, shots * sb, D), (shots * sb * vb.stride(1), vb.stride(1), 1), vb.storage_offset())
-        return ops.attn_kvfused(q, k, v, kbf, vbf, heads, scale)
+        return core(q, k, v, kbf, vbf, heads, scale)
 
     def __call__(self, attn, hidden_states: torch.Tensor,
                  encoder_hidden_states: Optional[torch.Tensor] = None, attention_mask=None, temb=None,
@@ -145,7 +147,7 @@ class MyXFormersAttnProcessor:
         if scale != 1.0:
             raise NotImplementedError("LoRA scale is not part of the hot path")
         if isinstance(attn, MyAttention):                      # engine path: prepared weights, 16-bit tokens
-            assert hidden_states.ndim == 3 and hidden_states.dtype in (bf16, torch.float16)
+            assert hidden_states.ndim == 3 and hidden_states.dtype in (bf16, torch.float16, torch.float32)
             qkv = attn.to_qkv(hidden_states)                   # [N, S, 3C]  one GEMM
             o = self._attend(attn, qkv, attn.inner_dim, attn.heads, attn.scale)
             return attn.to_out(o, residual=residual, out_f32=out_f32)

@@ -35,9 +35,37 @@ class Precision:
     half: torch.dtype = torch.float16
     stream_f32: bool = True
     mid_f32: bool = True
+    # fp32 evaluation mode (the reference's shipped eval numerics, main_oss.py:332-336; bar 1e-4 vs the fp32 oracle): every
+    # activation tensor fp32, norms / softmax / GELU / attention core in fp32 with exact transcendentals (csrc/f32mode.cu),
+    # GEMMs and convolutions on the same tcgen05 kernels with split operands x = hi + lo in the `half` format
+    # (hi_x hi_w + lo_x hi_w + hi_x lo_w as one GEMM over a 3x longer channel axis).  ~4x slower than the 16-bit path.
+    f32: bool = False
+
+    def __post_init__(self):
+        if self.f32:
+            object.__setattr__(self, "stream_f32", True)
+            object.__setattr__(self, "mid_f32", True)
 
 
 PURE_BF16 = Precision(half=torch.bfloat16)
+F32 = Precision(f32=True)
+
+
+def to_operand(h: torch.Tensor, prec: Precision) -> torch.Tensor:
+    """A residual-stream tensor about to be consumed by a GEMM: 16-bit cast on the default path; left in fp32 in the fp32
+    mode (the consuming Conv / Linear splits it)."""
+    return h if prec.f32 else ops.cast16(h, prec.half)
+
+
+def _prep_w(w2d: torch.Tensor, taps: int, device, wdtype, f32: bool, role: int = 1) -> torch.Tensor:
+    """GEMM weight [rows, taps*Cin] -> device operand: a 16-bit cast, or in the fp32 mode the split [hi | hi | lo] per tap."""
+    if f32:
+        return ops.split3_host(w2d, taps, role, wdtype).to(device)
+    return _dev(w2d, device, wdtype)
+
+
+def _split_in(x: torch.Tensor, half) -> torch.Tensor:
+    return ops.split3(x, 0, half) if x.dtype == torch.float32 else x
 
 # Fold GroupNorm + SiLU into the consuming convolution (ops.conv2d_gn_in, bit-identical to norm kernel + conv).  OFF by
 # default: measured on B200 it loses -- the patch transform has to run once per horizontal tap (3x the elements, one MUFU
@@ -54,15 +82,18 @@ def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
 class Conv:
     """3x3 / 1x1 convolution on the tcgen05 implicit-GEMM kernel."""
 
-    def __init__(self, sd, prefix, device, stride=1, pad_mode=0, wdtype=bf16):
+    def __init__(self, sd, prefix, device, stride=1, pad_mode=0, wdtype=bf16, f32=False):
         w = sd[prefix + ".weight"]
         self.cout, self.cin, self.ksize, _ = w.shape
         self.stride, self.pad_mode = stride, pad_mode
-        self.w = _dev(conv_weight_to_gemm(w), device, wdtype)
+        self.f32, self.half = f32, wdtype
+        self.w = _prep_w(conv_weight_to_gemm(w), self.ksize * self.ksize, device, wdtype, f32)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
 
     def __call__(self, x, *, bias=None, bias_per_sample=False, residual=None, out_f32=False, out_scale=1.0,
                  gn_stats=False):
+        if self.f32:
+            x, out_f32, gn_stats = _split_in(x, self.half), True, False
         return ops.conv2d(x, self.w, self.b if bias is None else bias, ksize=self.ksize, stride=self.stride,
                           pad_mode=self.pad_mode, residual=residual, out_f32=out_f32, out_scale=out_scale,
                           bias_per_sample=bias_per_sample, gn_stats=gn_stats)
@@ -71,12 +102,15 @@ class Conv:
 class UpsampleConv:
     """diffusers Upsample2D (nearest 2x + 3x3 conv) as four 2x2-tap phase convolutions (weights.upconv_phase_weights)."""
 
-    def __init__(self, sd, prefix, device, wdtype=bf16):
-        self.w4 = _dev(upconv_phase_weights(sd[prefix + ".weight"]), device, wdtype)
+    def __init__(self, sd, prefix, device, wdtype=bf16, f32=False):
+        w4 = upconv_phase_weights(sd[prefix + ".weight"])                       # [4, Cout, 4*Cin]
+        self.f32, self.half = f32, wdtype
+        self.w4 = _prep_w(w4.reshape(-1, w4.shape[-1]), 4, device, wdtype, f32).view(4, w4.shape[1], -1)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
-        self.half = wdtype
 
     def __call__(self, h, out_f32, gn_stats=False):
+        if self.f32:
+            return ops.upconv2x(_split_in(h, self.half), self.w4, self.b, out_f32=True)
         return ops.upconv2x(ops.cast16(h, self.half), self.w4, self.b, out_f32=out_f32, gn_stats=gn_stats)
 
 
@@ -84,9 +118,12 @@ class SmallCinConv:
     """3x3 / pad 1 conv with Cin <= 16 reading the reference's NCHW fp32 tensor: im2col (K = 9*Cin padded to a multiple
     of 64) + one tcgen05 GEMM.  conv_in / conv_in_ref of the UNet, conv_in of the VAE encoder / decoder."""
 
-    def __init__(self, sd, prefix, device, wdtype=bf16):
+    def __init__(self, sd, prefix, device, wdtype=bf16, f32=False):
         w = sd[prefix + ".weight"]
         self.cout, self.cin = w.shape[0], w.shape[1]
+        self.f32 = f32
+        if f32:      # fp32 mode: the direct CUDA-core kernel (fp32 FMA) on the NCHW tensor
+            self.w32 = _dev(w.detach().float().permute(0, 2, 3, 1), device, torch.float32)      # [Cout,3,3,Cin]
         k = 9 * self.cin
         self.kpad = (k + 63) // 64 * 64
         wg = torch.zeros(self.cout, self.kpad, dtype=torch.float32)
@@ -96,55 +133,69 @@ class SmallCinConv:
         self.half = wdtype
 
     def __call__(self, x_nchw, out_f32, gn_stats=False):
+        if self.f32:
+            return ops.conv3x3_small_cin(x_nchw, self.w32, self.b, out_dtype=torch.float32)
         cols = ops.im2col3x3_small(x_nchw, self.kpad, self.half)      # [N,H,W,Kpad]: a 1x1 convolution from here on
         return ops.conv2d(cols, self.w, self.b, ksize=1, out_f32=out_f32, gn_stats=gn_stats)
 
 
 class Linear:
-    def __init__(self, sd, prefix, device, geglu=False, wdtype=bf16):
+    def __init__(self, sd, prefix, device, geglu=False, wdtype=bf16, f32=False):
         w = sd[prefix + ".weight"]
         b = sd.get(prefix + ".bias")
-        self.geglu = geglu
-        if geglu:
+        self.f32, self.half = f32, wdtype
+        self.geglu = geglu and not f32       # fp32 mode: plain projection, the exact-erf GEGLU is its own fp32 kernel
+        self.geglu_f32 = geglu and f32
+        if self.geglu:
             w, b = geglu_permute(w, b)
-        self.w = _dev(w, device, wdtype)
+        self.w = _prep_w(w, 1, device, wdtype, f32)
         self.b = _dev(b, device, torch.float32) if b is not None else None
 
     def __call__(self, x, *, residual=None, out_f32=False):
+        if self.f32:
+            y = ops.linear(_split_in(x, self.half), self.w, self.b, residual=residual, out_f32=True)
+            return ops.geglu_f32(y) if self.geglu_f32 else y
         return ops.linear(x, self.w, self.b, residual=residual, out_f32=out_f32, geglu=self.geglu)
 
 
 class FusedLinear:
     """Several bias-free Linears on the same input, one GEMM (rows of the weights concatenated)."""
 
-    def __init__(self, sd, prefixes, device, wdtype=bf16):
+    def __init__(self, sd, prefixes, device, wdtype=bf16, f32=False):
         ws = [sd[p + ".weight"] for p in prefixes]
         self.splits = [w.shape[0] for w in ws]
-        self.w = _dev(torch.cat(ws, 0), device, wdtype)
+        self.f32, self.half = f32, wdtype
+        self.w = _prep_w(torch.cat(ws, 0), 1, device, wdtype, f32)
         bs = [sd.get(p + ".bias") for p in prefixes]
         self.b = _dev(torch.cat(bs, 0), device, torch.float32) if bs[0] is not None else None
 
     def __call__(self, x):
+        if self.f32:
+            return ops.linear(_split_in(x, self.half), self.w, self.b, out_f32=True)
         return ops.linear(x, self.w, self.b)
 
 
 class GroupNorm:
-    def __init__(self, sd, prefix, device, eps, groups=32, out_dtype=bf16):
+    def __init__(self, sd, prefix, device, eps, groups=32, out_dtype=bf16, f32=False):
         self.g = _dev(sd[prefix + ".weight"], device, torch.float32)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
-        self.eps, self.groups, self.out_dtype = eps, groups, out_dtype
+        self.eps, self.groups, self.out_dtype, self.f32 = eps, groups, out_dtype, f32
 
     def __call__(self, x, silu):
+        if self.f32:
+            return ops.groupnorm_f32(x, self.g, self.b, groups=self.groups, eps=self.eps, silu=silu)
         return ops.groupnorm(x, self.g, self.b, groups=self.groups, eps=self.eps, silu=silu, out_dtype=self.out_dtype)
 
 
 class LayerNorm:
-    def __init__(self, sd, prefix, device, eps=1e-5, out_dtype=bf16):
+    def __init__(self, sd, prefix, device, eps=1e-5, out_dtype=bf16, f32=False):
         self.g = _dev(sd[prefix + ".weight"], device, torch.float32)
         self.b = _dev(sd[prefix + ".bias"], device, torch.float32)
-        self.eps, self.out_dtype = eps, out_dtype
+        self.eps, self.out_dtype, self.f32 = eps, out_dtype, f32
 
     def __call__(self, x):
+        if self.f32:
+            return ops.layernorm_f32(x, self.g, self.b, self.eps)
         return ops.layernorm(x, self.g, self.b, self.eps, out_dtype=self.out_dtype)
 
 
@@ -154,11 +205,12 @@ class Resnet:
     def __init__(self, sd, prefix, device, eps, prec: Precision, has_temb: bool):
         self.prec = prec
         wd = nd = prec.half
-        self.norm1 = GroupNorm(sd, prefix + ".norm1", device, eps, out_dtype=nd)
-        self.conv1 = Conv(sd, prefix + ".conv1", device, wdtype=wd)
-        self.norm2 = GroupNorm(sd, prefix + ".norm2", device, eps, out_dtype=nd)
-        self.conv2 = Conv(sd, prefix + ".conv2", device, wdtype=wd)
-        self.shortcut = (Conv(sd, prefix + ".conv_shortcut", device, wdtype=wd)
+        f = prec.f32
+        self.norm1 = GroupNorm(sd, prefix + ".norm1", device, eps, out_dtype=nd, f32=f)
+        self.conv1 = Conv(sd, prefix + ".conv1", device, wdtype=wd, f32=f)
+        self.norm2 = GroupNorm(sd, prefix + ".norm2", device, eps, out_dtype=nd, f32=f)
+        self.conv2 = Conv(sd, prefix + ".conv2", device, wdtype=wd, f32=f)
+        self.shortcut = (Conv(sd, prefix + ".conv_shortcut", device, wdtype=wd, f32=f)
                          if (prefix + ".conv_shortcut.weight") in sd else None)
         # time-embedding projection is folded into conv1's bias per timestep (fp32, host): see UNet._temb_biases
         self.temb_w = sd[prefix + ".time_emb_proj.weight"].detach().float().cpu() if has_temb else None
@@ -179,7 +231,7 @@ class Resnet:
         else:
             a = self.norm1(h, silu=True)
             t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32, gn_stats=True)
-        s = h if self.shortcut is None else self.shortcut(ops.cast16(h, p.half), out_f32=p.stream_f32)
+        s = h if self.shortcut is None else self.shortcut(to_operand(h, p), out_f32=p.stream_f32)
         if FUSE_GN_INTO_CONV and not p.stream_f32 and self.norm2.groups == 32 \
                 and ops.conv_gn_in_supported(t, self.conv2.cout, self.conv2.ksize):
             return ops.conv2d_gn_in(t, self.norm2.g, self.norm2.b, self.norm2.eps, self.conv2.w, self.conv2.b,

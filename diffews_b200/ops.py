@@ -457,6 +457,100 @@ def softmax_rows(s, scale, out_dtype=bf16):
     return p
 
 
+# ---- fp32 evaluation mode (csrc/f32mode.cu): split operands for the tensor-core GEMMs, fp32 everything else ------------
+def split3(x, role=0, dtype=f16):
+    """fp32 [..., C] -> 16-bit [..., 3C]: role 0 = [hi | lo | hi] (activation side), role 1 = [hi | hi | lo] (weight
+    side of an activation x activation product).  `x` may be a column slice of a wider contiguous buffer."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1 and dtype in OPERAND_DTYPES
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if x.is_contiguous():
+        xs = C
+    else:
+        xs = x.stride(-2)
+        for d in range(x.dim() - 2):
+            assert x.stride(d) == x.stride(d + 1) * x.shape[d + 1], "split3: rows must have one uniform stride"
+    y = torch.empty(x.shape[:-1] + (3 * C,), device=x.device, dtype=dtype)
+    with _Timed("elementwise", _nb(x, y), f"split3 rows{rows} C{C}"):
+        check(lib.dfw_split3_16(x.data_ptr(), xs, y.data_ptr(), rows, C, int(role), int(dtype == f16), _stream()),
+              "dfw_split3_16")
+    return y
+
+
+def split3_host(w: torch.Tensor, taps: int, role: int, dtype) -> torch.Tensor:
+    """Weight-side split at load time (torch on the host tensor, once): w [rows, taps*C] fp32 -> [rows, taps*3C]."""
+    rows = w.shape[0]
+    w3 = w.detach().float().reshape(rows, taps, -1)
+    hi = w3.to(dtype)
+    lo = (w3 - hi.float()).to(dtype)
+    parts = [hi, hi, lo] if role == 1 else [hi, lo, hi]
+    return torch.cat(parts, dim=-1).reshape(rows, -1).contiguous()
+
+
+def groupnorm_f32(x, gamma, beta, *, groups=32, eps=1e-5, silu=False):
+    _req(x, torch.float32, "x")
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    y = torch.empty_like(x)
+    with _Timed("groupnorm", _nb(x, y), f"gn-f32 N{N} HW{HW} C{C}"):
+        check(lib.dfw_groupnorm_f32(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), N, HW, C, groups,
+                                    float(eps), int(silu), _stream()), "dfw_groupnorm_f32")
+    return y
+
+
+def layernorm_f32(x, gamma, beta, eps=1e-5):
+    _req(x, torch.float32, "x")
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    with _Timed("layernorm", _nb(x, y), f"ln-f32 M{x.numel() // C} C{C}"):
+        check(lib.dfw_layernorm_f32(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), x.numel() // C, C,
+                                    float(eps), _stream()), "dfw_layernorm_f32")
+    return y
+
+
+def softmax_rows_f32(s, scale):
+    """In place: s fp32 [.., L] <- softmax(s * scale)."""
+    _req(s, torch.float32, "s")
+    L = s.shape[-1]
+    with _Timed("softmax", 2 * _nb(s), f"softmax-f32 M{s.numel() // L} L{L}"):
+        check(lib.dfw_softmax_rows_f32(s.data_ptr(), s.data_ptr(), s.numel() // L, L, float(scale), _stream()),
+              "dfw_softmax_rows_f32")
+    return s
+
+
+def geglu_f32(h):
+    _req(h, torch.float32, "h")
+    F = h.shape[-1] // 2
+    y = torch.empty(h.shape[:-1] + (F,), device=h.device, dtype=torch.float32)
+    with _Timed("elementwise", _nb(h, y), f"geglu-f32 rows{y.numel() // F} F{F}"):
+        check(lib.dfw_geglu_f32(h.data_ptr(), y.data_ptr(), y.numel() // F, F, _stream()), "dfw_geglu_f32")
+    return y
+
+
+def attn_f32(q, k_self, v_self, k_bank, v_bank, heads, scale):
+    """fp32 attention, head dim 64: q [B,Lq,C]; k_self / v_self [Bk,Ls,C] (Bk = 1 shares them over the batch);
+    k_bank / v_bank [B,Lb,C] or None.  Tensors may be column slices of wider buffers (unit stride on the last dim)."""
+    B, Lq, C = q.shape
+    assert C == heads * 64
+    for t in (q, k_self, v_self):
+        assert t.dtype == torch.float32 and t.is_cuda and t.stride(2) == 1
+    assert k_self.stride() == v_self.stride() and k_self.shape[0] in (1, B)
+    Ls = k_self.shape[1]
+    ksb = 0 if k_self.shape[0] == 1 else k_self.stride(0)
+    o = torch.empty((B, Lq, C), device=q.device, dtype=torch.float32)
+    if k_bank is not None:
+        Lb = k_bank.shape[1]
+        assert k_bank.shape[0] == B and k_bank.stride() == v_bank.stride() and k_bank.stride(2) == 1
+        kb, vb, kbs, krs = k_bank.data_ptr(), v_bank.data_ptr(), k_bank.stride(0), k_bank.stride(1)
+    else:
+        Lb, kb, vb, kbs, krs = 0, 0, 0, 0, 0
+    with _Timed("attn_f32", 4.0 * B * heads * Lq * (Ls + Lb) * 64, f"attn-f32 B{B} h{heads} Lq{Lq} Lk{Ls + Lb}"):
+        check(lib.dfw_attn_f32(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(), ksb,
+                               k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0), o.stride(1), B, heads, Lq, Ls,
+                               Lb, float(scale), _stream()), "dfw_attn_f32")
+    return o
+
+
 def upsample2x(x, out_dtype=bf16):
     """x 16-bit|fp32 [N,H,W,C] -> 16-bit [N,2H,2W,C] (fp32 input is cast to `out_dtype`)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, f16, torch.float32)

@@ -22,7 +22,7 @@ import torch
 
 from . import ops
 from .attention_processor import MyAttention
-from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, SmallCinConv, UpsampleConv, _dev
+from .layers import Conv, GroupNorm, LayerNorm, Linear, Precision, Resnet, SmallCinConv, UpsampleConv, _dev, to_operand
 
 bf16 = torch.bfloat16
 
@@ -42,13 +42,14 @@ class UNet2DConditionOutput:
 class CrossAttention:
     """attn2: attention to the prompt embedding (K/V computed once per encoder_hidden_states and cached)."""
 
-    def __init__(self, sd, prefix, device, heads, wdtype=bf16):
+    def __init__(self, sd, prefix, device, heads, wdtype=bf16, f32=False):
         self.heads = heads
         self.scale = 64 ** -0.5
-        self.to_q = Linear(sd, prefix + ".to_q", device, wdtype=wdtype)
-        self.to_k = Linear(sd, prefix + ".to_k", device, wdtype=wdtype)
-        self.to_v = Linear(sd, prefix + ".to_v", device, wdtype=wdtype)
-        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wdtype)
+        self.f32 = f32
+        self.to_q = Linear(sd, prefix + ".to_q", device, wdtype=wdtype, f32=f32)
+        self.to_k = Linear(sd, prefix + ".to_k", device, wdtype=wdtype, f32=f32)
+        self.to_v = Linear(sd, prefix + ".to_v", device, wdtype=wdtype, f32=f32)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wdtype, f32=f32)
         self.processor = CrossAttnProcessor()
 
     def set_processor(self, processor, _remove_lora: bool = False):
@@ -65,7 +66,7 @@ class CrossAttention:
         Wlog[(h,j)] = scale K[j,h] @ Wq[h],  U[(h,j)] = Wo[:,h] @ V[j,h]; otherwise K, V for the attention kernel."""
         k, v = self.to_k(ehs16), self.to_v(ehs16)
         Lctx = k.shape[1]
-        if not COLLAPSE_CROSS_ATTN or k.shape[0] != 1 or self.heads * Lctx > 96 or Lctx > 8:
+        if self.f32 or not COLLAPSE_CROSS_ATTN or k.shape[0] != 1 or self.heads * Lctx > 96 or Lctx > 8:
             return k, v
         h, C = self.heads, k.shape[2]
         kf = k[0].float().view(Lctx, h, 64).permute(1, 0, 2)                   # [h, Lctx, 64]
@@ -86,6 +87,9 @@ class CrossAttention:
             return ops.cross_attn_collapsed(logits, U, bias, residual, self.heads, Lctx,
                                             torch.float32 if out_f32 else x.dtype)
         q = self.to_q(x)
+        if self.f32:
+            o = ops.attn_f32(q, kv[0], kv[1], None, None, self.heads, self.scale)
+            return self.to_out(o, residual=residual, out_f32=True)
         o = ops.cross_attn(q, kv[0], kv[1], self.heads, self.scale)
         return self.to_out(o, residual=residual, out_f32=out_f32)
 
@@ -98,13 +102,14 @@ class TransformerBlock:
     def __init__(self, sd, prefix, device, heads, prec: Precision):
         self.prec = prec
         wd = nd = prec.half
-        self.norm1 = LayerNorm(sd, prefix + ".norm1", device, out_dtype=nd)
-        self.attn1 = MyAttention(sd, prefix + ".attn1", device, heads, wdtype=wd)
-        self.norm2 = LayerNorm(sd, prefix + ".norm2", device, out_dtype=nd)
-        self.attn2 = CrossAttention(sd, prefix + ".attn2", device, heads, wdtype=wd)
-        self.norm3 = LayerNorm(sd, prefix + ".norm3", device, out_dtype=nd)
-        self.ff1 = Linear(sd, prefix + ".ff.net.0.proj", device, geglu=True, wdtype=wd)
-        self.ff2 = Linear(sd, prefix + ".ff.net.2", device, wdtype=wd)
+        f = prec.f32
+        self.norm1 = LayerNorm(sd, prefix + ".norm1", device, out_dtype=nd, f32=f)
+        self.attn1 = MyAttention(sd, prefix + ".attn1", device, heads, wdtype=wd, f32=f)
+        self.norm2 = LayerNorm(sd, prefix + ".norm2", device, out_dtype=nd, f32=f)
+        self.attn2 = CrossAttention(sd, prefix + ".attn2", device, heads, wdtype=wd, f32=f)
+        self.norm3 = LayerNorm(sd, prefix + ".norm3", device, out_dtype=nd, f32=f)
+        self.ff1 = Linear(sd, prefix + ".ff.net.0.proj", device, geglu=True, wdtype=wd, f32=f)
+        self.ff2 = Linear(sd, prefix + ".ff.net.2", device, wdtype=wd, f32=f)
 
     def __call__(self, x, kv):
         f32 = self.prec.stream_f32
@@ -117,10 +122,10 @@ class TransformerBlock:
 class Transformer2D:
     def __init__(self, sd, prefix, device, heads, prec: Precision):
         self.prec = prec
-        self.norm = GroupNorm(sd, prefix + ".norm", device, eps=1e-6, out_dtype=prec.half)
-        self.proj_in = Linear(sd, prefix + ".proj_in", device, wdtype=prec.half)
+        self.norm = GroupNorm(sd, prefix + ".norm", device, eps=1e-6, out_dtype=prec.half, f32=prec.f32)
+        self.proj_in = Linear(sd, prefix + ".proj_in", device, wdtype=prec.half, f32=prec.f32)
         self.block = TransformerBlock(sd, prefix + ".transformer_blocks.0", device, heads, prec)
-        self.proj_out = Linear(sd, prefix + ".proj_out", device, wdtype=prec.half)
+        self.proj_out = Linear(sd, prefix + ".proj_out", device, wdtype=prec.half, f32=prec.f32)
 
     def __call__(self, h, kv):
         N, H, W, C = h.shape
@@ -156,8 +161,8 @@ class MyUNet2DConditionModel:
                                       layers_per_block=2, norm_num_groups=32, norm_eps=1e-5, sample_size=96)
         self.dtype = torch.float32
         # small-Cin input convs: im2col + tensor-core GEMM straight from the NCHW fp32 latents
-        self.conv_in = SmallCinConv(sd, "conv_in", dev, prec.half)
-        self.conv_in_ref = SmallCinConv(sd, "conv_in_ref", dev, prec.half)
+        self.conv_in = SmallCinConv(sd, "conv_in", dev, prec.half, f32=prec.f32)
+        self.conv_in_ref = SmallCinConv(sd, "conv_in_ref", dev, prec.half, f32=prec.f32)
         # time embedding: evaluated on the host in fp32 once per distinct timestep and folded into conv1 biases
         self._te = {k: sd[f"time_embedding.{k}"].detach().float().cpu()
                     for k in ("linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias")}
@@ -190,7 +195,7 @@ class MyUNet2DConditionModel:
                     blk.attns.append(tfm(f"down_blocks.{i}.attentions.{j}", heads[i]))
             if i < 3:
                 blk.down = Conv(sd, f"down_blocks.{i}.downsamplers.0.conv", dev, stride=2, pad_mode=0,
-                                wdtype=prec.half)
+                                wdtype=prec.half, f32=prec.f32)
             self.down.append(blk)
         self.mid = SimpleNamespace(res0=res("mid_block.resnets.0"), attn=tfm("mid_block.attentions.0", heads[3]),
                                    res1=None)
@@ -204,10 +209,10 @@ class MyUNet2DConditionModel:
                 if i > 0:
                     blk.attns.append(tfm(f"up_blocks.{i}.attentions.{j}", rh[i]))
             if i < 3:
-                blk.up = UpsampleConv(sd, f"up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half)
+                blk.up = UpsampleConv(sd, f"up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half, f32=prec.f32)
             self.up.append(blk)
-        self.conv_norm_out = GroupNorm(sd, "conv_norm_out", dev, eps=1e-5, out_dtype=prec.half)
-        self.conv_out = Conv(sd, "conv_out", dev, wdtype=prec.half)
+        self.conv_norm_out = GroupNorm(sd, "conv_norm_out", dev, eps=1e-5, out_dtype=prec.half, f32=prec.f32)
+        self.conv_out = Conv(sd, "conv_out", dev, wdtype=prec.half, f32=prec.f32)
 
     # ---- reference API ---------------------------------------------------------------------------------------------
     @classmethod
@@ -309,7 +314,7 @@ class MyUNet2DConditionModel:
         e = ehs.to(device=self.device, dtype=torch.float32)
         if e.shape[0] > 1 and bool((e == e[:1]).all()):
             e = e[:1]                         # identical prompt for every sample (pipeline:690-692): share K/V
-        e = ops.cast16(e.contiguous(), self.prec.half)
+        e = to_operand(e.contiguous(), self.prec)
         kvs = [t.block.attn2.kv(e) for t in self.transformers]
         if len(self._kv_cache) > 8:
             self._kv_cache.clear()
@@ -365,7 +370,7 @@ class MyUNet2DConditionModel:
                     h = blk.attns[j](h, next(kvs))
                 skips.append(h)
             if blk.down is not None:
-                h = blk.down(ops.cast16(h, half), out_f32=f32)
+                h = blk.down(to_operand(h, self.prec), out_f32=f32)
                 skips.append(h)
         h = self.mid.res0(h, next(biases))                                       # :1189-1200
         h = self.mid.attn(h, next(kvs))

@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .layers import Conv, GroupNorm, Linear, Precision, Resnet, SmallCinConv, UpsampleConv, _dev
+from .layers import Conv, GroupNorm, Linear, Precision, Resnet, SmallCinConv, UpsampleConv, _dev, _prep_w, to_operand
 
 bf16 = torch.bfloat16
 
@@ -27,14 +27,15 @@ class VaeAttention:
     def __init__(self, sd, prefix, device, prec: Precision):
         self.prec = prec
         wd = prec.half
-        self.norm = GroupNorm(sd, prefix + ".group_norm", device, eps=1e-6, out_dtype=prec.half)
-        self.to_q = Linear(sd, prefix + ".to_q", device, wdtype=wd)
-        self.to_k = Linear(sd, prefix + ".to_k", device, wdtype=wd)
+        f = prec.f32
+        self.norm = GroupNorm(sd, prefix + ".group_norm", device, eps=1e-6, out_dtype=prec.half, f32=f)
+        self.to_q = Linear(sd, prefix + ".to_q", device, wdtype=wd, f32=f)
+        self.to_k = Linear(sd, prefix + ".to_k", device, wdtype=wd, f32=f)
         # V^T = W_v X^T is produced directly ([C, L] per image, the K-major B operand of P V); its bias is added
         # after the P V product instead (softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T).
-        self.wv = _dev(sd[prefix + ".to_v.weight"], device, wd)
+        self.wv = _prep_w(sd[prefix + ".to_v.weight"], 1, device, wd, f, role=0)    # the A operand of V^T = W_v X^T
         self.bv = _dev(sd[prefix + ".to_v.bias"], device, torch.float32)
-        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wd)
+        self.to_out = Linear(sd, prefix + ".to_out.0", device, wdtype=wd, f32=f)
         self.C = self.wv.shape[0]
         self.scale = self.C ** -0.5
 
@@ -42,6 +43,8 @@ class VaeAttention:
         N, H, W, C = h.shape
         L = H * W
         xn = self.norm(h, silu=False).view(N, L, C)
+        if self.prec.f32:
+            return self._call_f32(h, xn)
         q = self.to_q(xn)
         k = self.to_k(xn)
         vt = ops.linear(self.wv, xn.view(N * L, C))                       # [C, N*L]: V^T of every image, side by side
@@ -51,6 +54,21 @@ class VaeAttention:
         o = ops.bmm_nt(p, vt, self.bv)                                    # P V + b_v, one launch
         y = self.to_out(o, residual=h.view(N, L, C), out_f32=self.prec.stream_f32)
         return y.view(N, H, W, C)
+
+
+    def _call_f32(self, h, xn):
+        """fp32 mode: the same three GEMMs on split operands (activation x activation products pair a role-0 with a role-1
+        split), fp32 logits normalised in place by the exact-exp softmax."""
+        N, H, W, C = h.shape
+        L, half = H * W, self.prec.half
+        xa = ops.split3(xn, 0, half)                                              # [N, L, 3C]
+        q, k = self.to_q(xa), self.to_k(xa)                                       # fp32 [N, L, C]
+        vt = ops.linear(self.wv, ops.split3(xn.view(N * L, C), 1, half), out_f32=True)       # fp32 [C, N*L]
+        s = ops.bmm_nt(ops.split3(q, 0, half), ops.split3(k, 1, half), out_f32=True)         # [N, L, L]
+        p = ops.softmax_rows_f32(s, self.scale)
+        vts = ops.split3(vt.view(C * N, L), 1, half).view(C, N, 3 * L).permute(1, 0, 2)      # [N, C, 3L] view
+        o = ops.bmm_nt(ops.split3(p, 0, half), vts, self.bv, out_f32=True)                   # P V + b_v
+        return self.to_out(o, residual=h.view(N, L, C), out_f32=True).view(N, H, W, C)
 
 
 class _Mid:
@@ -77,33 +95,35 @@ class AutoencoderKL:
         c = tuple(block_out_channels)
         self.config = SimpleNamespace(block_out_channels=c, latent_channels=4, scaling_factor=0.18215)
         # ---- encoder
-        self.enc_conv_in = SmallCinConv(sd, "encoder.conv_in", dev, prec.half)
+        f = prec.f32
+        self.enc_conv_in = SmallCinConv(sd, "encoder.conv_in", dev, prec.half, f32=f)
         self.enc_down = []
         for i in range(4):
             blk = SimpleNamespace(
                 resnets=[Resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(2)],
                 down=Conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", dev, stride=2, pad_mode=1,
-                          wdtype=prec.half) if i < 3 else None)
+                          wdtype=prec.half, f32=f) if i < 3 else None)
             self.enc_down.append(blk)
         self.enc_mid = _Mid(sd, "encoder.mid_block", dev, prec)
-        self.enc_norm_out = GroupNorm(sd, "encoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half)
-        self.enc_conv_out = Conv(sd, "encoder.conv_out", dev, wdtype=prec.half)
+        self.enc_norm_out = GroupNorm(sd, "encoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half, f32=f)
+        self.enc_conv_out = Conv(sd, "encoder.conv_out", dev, wdtype=prec.half, f32=f)
         # quant_conv (1x1, 8->8): only the 4 `mean` channels are consumed (pipeline:858-860); host-side constants
         self.quant_w = sd["quant_conv.weight"].detach().float().cpu()[:4, :, 0, 0].contiguous()
         self.quant_b = sd["quant_conv.bias"].detach().float().cpu()[:4].contiguous()
         # ---- decoder
         self.post_quant_w = sd["post_quant_conv.weight"].detach().float().cpu()[:, :, 0, 0].contiguous()
         self.post_quant_b = sd["post_quant_conv.bias"].detach().float().cpu().contiguous()
-        self.dec_conv_in = SmallCinConv(sd, "decoder.conv_in", dev, prec.half)
+        self.dec_conv_in = SmallCinConv(sd, "decoder.conv_in", dev, prec.half, f32=f)
         self.dec_mid = _Mid(sd, "decoder.mid_block", dev, prec)
         self.dec_up = []
         for i in range(4):
             blk = SimpleNamespace(
                 resnets=[Resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, 1e-6, prec, False) for j in range(3)],
-                up=UpsampleConv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half) if i < 3 else None)
+                up=UpsampleConv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", dev, wdtype=prec.half, f32=f)
+                if i < 3 else None)
             self.dec_up.append(blk)
-        self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half)
-        self.dec_conv_out = Conv(sd, "decoder.conv_out", dev, wdtype=prec.half)
+        self.dec_norm_out = GroupNorm(sd, "decoder.conv_norm_out", dev, eps=1e-6, out_dtype=prec.half, f32=f)
+        self.dec_conv_out = Conv(sd, "decoder.conv_out", dev, wdtype=prec.half, f32=f)
         # fused decoder head (dfw_seg_head_u8): conv_out as mma.sync B fragments, bias as a kernel parameter
         wout = sd["decoder.conv_out.weight"]
         self.seg_head_wb = ops.seg_head_prepare(wout, prec.half, dev) if tuple(wout.shape) == (3, 128, 3, 3) else None
@@ -142,7 +162,7 @@ class AutoencoderKL:
             for j, r in enumerate(blk.resnets):
                 h = r(h, gn_stats_out=not (blk.down is not None and j == len(blk.resnets) - 1))
             if blk.down is not None:
-                h = blk.down(ops.cast16(h, self.prec.half), out_f32=f32, gn_stats=True)
+                h = blk.down(to_operand(h, self.prec), out_f32=f32, gn_stats=True)
         h = self.enc_mid(h)
         h = self.enc_norm_out(h, silu=True)
         m = self.enc_conv_out(h, out_f32=True)                                   # [N,h,w,8] fp32 moments

@@ -219,6 +219,31 @@ int dfw_layernorm(const void* x, int x_dtype, const float* gamma, const float* b
 int dfw_softmax_rows(const float* s, void* p, int y_f16, int M, int L, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * fp32 evaluation mode (the reference's shipped eval numerics: evaluation_util/main_oss.py:332-336 is fp32-only).
+ * GEMMs / convolutions run on the entry points above with SPLIT operands: x = hi + lo (two 16-bit values),
+ * x.w ~= hi_x hi_w + lo_x hi_w + hi_x lo_w = one GEMM over a 3x longer channel axis.  What surrounds them in fp32:
+ *   dfw_split3_16      x fp32 [rows, C] (row stride in floats) -> y 16-bit [rows, 3C]; role 0 = [hi | lo | hi] (activation),
+ *                      role 1 = [hi | hi | lo] (weight side of an activation x activation product); bf16, or fp16 if y_f16
+ *   dfw_groupnorm_f32  GroupNorm (+ SiLU, exact sigmoid) x, y fp32 [N, HW, C], two-pass statistics
+ *   dfw_layernorm_f32  x, y fp32 [M, C]
+ *   dfw_softmax_rows_f32  p = softmax(s * scale) per row, fp32 [M, L] (in place allowed)
+ *   dfw_geglu_f32      h fp32 [rows, 2F] = (value | gate) -> y fp32 [rows, F] = value * gelu_erf(gate)
+ *   dfw_attn_f32       softmax(q [k_self ; k_bank]^T scale) [v_self ; v_bank], head dim 64, fp32 on CUDA cores; strides in
+ *                      floats, k / v pointers 16-byte aligned with strides % 4 == 0; a batch stride of 0 shares K / V
+ *                      (cross-attention to one prompt).  ref: attention_processor.py:251-271. */
+int dfw_split3_16(const float* x, long long x_row_stride, void* y, long long rows, int C, int role, int y_f16, void* stream);
+int dfw_groupnorm_f32(const float* x, const float* gamma, const float* beta, float* y, int N, int HW, int C, int groups,
+                      float eps, int apply_silu, void* stream);
+int dfw_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, long long M, int C, float eps,
+                      void* stream);
+int dfw_softmax_rows_f32(const float* s, float* p, int M, int L, float scale, void* stream);
+int dfw_geglu_f32(const float* h, float* y, long long rows, int F, void* stream);
+int dfw_attn_f32(const float* q, long long q_batch_stride, long long q_row_stride, const float* k_self, const float* v_self,
+                 long long kv_batch_stride, long long kv_row_stride, const float* k_bank, const float* v_bank,
+                 long long bank_batch_stride, long long bank_row_stride, float* o, long long o_batch_stride,
+                 long long o_row_stride, int B, int heads, int Lq, int Ls, int Lb, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Layout / small-channel helpers (CUDA cores, bandwidth-bound).
  * ------------------------------------------------------------------------------------------------------------ */
 /* nearest 2x upsample NHWC [N,H,W,C] (16-bit copied as is, or fp32 if x_f32 -> bf16 / fp16 per y_f16)
