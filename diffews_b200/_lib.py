@@ -15,7 +15,8 @@ DFW_OK, DFW_ERR_INVALID, DFW_ERR_CUDA, DFW_ERR_ARCH = 0, -1, -2, -3
 EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU, EPI_F16 = 1, 2, 4, 8, 16
 
 # process-wide options (include/diffews_b200.h DFW_OPT_*)
-OPT_PDL, OPT_T128, OPT_T128_MAXC, OPT_HALO, OPT_GN_CTAS_PER_SM, OPT_PREPROC_TWO_PASS, OPT_ATTN_V2, OPT_SEG_HEAD = range(8)
+(OPT_PDL, OPT_T128, OPT_T128_MAXC, OPT_HALO, OPT_GN_CTAS_PER_SM, OPT_PREPROC_TWO_PASS, OPT_ATTN_V2, OPT_SEG_HEAD,
+ OPT_ATTN_BWD_UNFUSED) = range(9)
 
 _vp, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
@@ -41,7 +42,9 @@ SIGNATURES = {
     "dfw_bmm_nt": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dfw_attn_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "dfw_attn_kvfused_bwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp,
-                                  _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+                                  _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "dfw_attn_kvfused_fwd_lse": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
+                                      _i, _f, _i, _vp, _vp]),
     "dfw_attn_kvfused_fwd": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i,
                                   _i, _f, _i, _vp]),
     "dfw_cross_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _f, _i, _vp]),

@@ -57,6 +57,7 @@ struct AttnParams {
     long long o_batch_stride;
     int o_row_stride;
     int f16;              // 16-bit tensors are fp16 (else bf16)
+    float* lse;           // optional [B, heads, Lq]: log2-domain logsumexp of the scaled logits (for the backward); v3 only
 #ifdef DFW_ATTN_TRACE
     long long* trace;     // debug build only (scripts/attn_trace.py): clock64 stamps of CTA (0,0,0), [warp][tile][8]
 #endif
@@ -695,6 +696,8 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
             tc_fence_after();
             const float inv = 1.0f / l_run;
             const bool row_ok = (qrow0 + row) < p.Lq;
+            if (p.lse != nullptr && row_ok)
+                p.lse[(static_cast<long long>(b) * gridDim.y + head) * p.Lq + qrow0 + row] = m_used + log2f(l_run);
             uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
                            static_cast<long long>(qrow0 + row) * p.o_row_stride + head * ATT_D;
 #pragma unroll
@@ -875,11 +878,11 @@ extern "C" void dfw_attn_trace_buffer(void* p) { dfw::g_attn_trace = reinterpret
 
 extern "C" {
 
-int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+static int attn_fwd_impl(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
                          const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
                          const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
                          int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
-                         int heads, int Lq, int Ls, int Lb, float scale, int f16, void* stream_) {
+                         int heads, int Lq, int Ls, int Lb, float scale, int f16, float* lse, void* stream_) {
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
@@ -914,6 +917,7 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     p.scale_log2 = scale * 1.4426950408889634f;
     p.o = reinterpret_cast<uint16_t*>(o);
     p.f16 = f16;
+    p.lse = lse;
     p.o_batch_stride = o_batch_stride;
     p.o_row_stride = o_row_stride;
 #ifdef DFW_ATTN_TRACE
@@ -929,7 +933,7 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     }
     dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    if (get_option(DFW_OPT_ATTN_V2)) {        // round-1 kernel (P through smem, two passes over S), kept for A/B measurements
+    if (get_option(DFW_OPT_ATTN_V2) && lse == nullptr) {        // round-1 kernel (P through smem, two passes over S), kept for A/B measurements
         if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_v2_kernel<true>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
         else DFW_CHECK_CUDA(launch_k(attn_kvfused_v2_kernel<false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
     } else {
@@ -939,6 +943,27 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
+}
+
+int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+                         const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
+                         const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
+                         int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
+                         int heads, int Lq, int Ls, int Lb, float scale, int f16, void* stream_) {
+    return attn_fwd_impl(q, q_batch_stride, q_row_stride, k_self, v_self, kv_self_batch_stride, kv_self_row_stride, k_bank,
+                         v_bank, kv_bank_batch_stride, kv_bank_row_stride, o, o_batch_stride, o_row_stride, B, heads, Lq, Ls,
+                         Lb, scale, f16, nullptr, stream_);
+}
+
+int dfw_attn_kvfused_fwd_lse(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+                             const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
+                             const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
+                             int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
+                             int heads, int Lq, int Ls, int Lb, float scale, int f16, float* lse, void* stream_) {
+    if (lse == nullptr) return DFW_ERR_INVALID;
+    return attn_fwd_impl(q, q_batch_stride, q_row_stride, k_self, v_self, kv_self_batch_stride, kv_self_row_stride, k_bank,
+                         v_bank, kv_bank_batch_stride, kv_bank_row_stride, o, o_batch_stride, o_row_stride, B, heads, Lq, Ls,
+                         Lb, scale, f16, lse, stream_);
 }
 
 int dfw_cross_attn_fwd(const void* q, const void* k, const void* v, long long kv_batch_stride, void* o, int B,

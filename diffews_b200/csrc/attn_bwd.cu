@@ -187,20 +187,20 @@ BwdWs plan_ws(long long BH, long long Lq, long long Lk) {
 }  // namespace
 }  // namespace dfw
 
-extern "C" {
+namespace dfw {
 
-long long dfw_attn_bwd_workspace_bytes(int B, int heads, int Lq, int Ls, int Lb) {
+// the round-1 path (logits materialised), kept behind DFW_OPT_ATTN_BWD_UNFUSED for A/B measurements (attn_bwd_fused.cu)
+long long attn_bwd_unfused_workspace_bytes(int B, int heads, int Lq, int Ls, int Lb) {
     if (B <= 0 || heads <= 0 || Lq <= 0 || Ls <= 0 || Lb < 0) return -1;
     return static_cast<long long>(dfw::plan_ws(static_cast<long long>(B) * heads, Lq, static_cast<long long>(Ls) + Lb).total);
 }
 
-int dfw_attn_kvfused_bwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+int attn_bwd_unfused(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
                          const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
                          const void* k_bank, const void* v_bank, long long kv_bank_batch_stride, int kv_bank_row_stride,
                          const void* o, const void* d_o, long long o_batch_stride, int o_row_stride, void* dq, void* dk_self,
                          void* dv_self, void* dk_bank, void* dv_bank, int B, int heads, int Lq, int Ls, int Lb, float scale,
                          int f16, void* workspace, void* stream_) {
-    using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
     DFW_REQUIRE(q && k_self && v_self && o && d_o && dq && dk_self && dv_self && workspace);
@@ -287,4 +287,4 @@ int dfw_attn_kvfused_bwd(const void* q, long long q_batch_stride, int q_row_stri
     return DFW_OK;
 }
 
-}  // extern "C"
+}  // namespace dfw

@@ -17,6 +17,7 @@ static std::atomic<int> g_options[DFW_OPT_COUNT] = {
     {0},        // DFW_OPT_PREPROC_TWO_PASS
     {0},        // DFW_OPT_ATTN_V2
     {1},        // DFW_OPT_SEG_HEAD
+    {0},        // DFW_OPT_ATTN_BWD_UNFUSED
 };
 
 int get_option(int option) {

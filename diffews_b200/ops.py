@@ -276,9 +276,10 @@ def bmm_nt(x, w, bias=None, *, out_f32=False, out_scale=1.0):
     return y
 
 
-def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
+def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale, return_lse=False):
     """q [B,Lq,C]; k_self/v_self [B,Ls,C]; k_bank/v_bank [B,Lb,C] or None.  Tensors may be column slices of a wider
-    (e.g. fused QKV) buffer: only the last dim must be unit-stride."""
+    (e.g. fused QKV) buffer: only the last dim must be unit-stride.  `return_lse`: also return the fp32 [B, heads, Lq]
+    log2-domain logsumexp of the scaled logits (what attn_kvfused_backward needs)."""
     B, Lq, C = q.shape
     assert C == heads * 64
     h16 = q.dtype
@@ -296,6 +297,13 @@ def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
     else:
         Lb, kb, vb, kbs, krs = 0, 0, 0, 0, 0
     with _Timed("attn", 4.0 * B * heads * Lq * (Ls + Lb) * 64, f"attn B{B} h{heads} Lq{Lq} Lk{Ls + Lb}"):
+        if return_lse:
+            lse = torch.empty((B, heads, Lq), device=q.device, dtype=torch.float32)
+            check(lib.dfw_attn_kvfused_fwd_lse(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
+                                               k_self.stride(0), k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0),
+                                               o.stride(1), B, heads, Lq, Ls, Lb, float(scale), int(h16 == f16),
+                                               lse.data_ptr(), _stream()), "dfw_attn_kvfused_fwd_lse")
+            return o, lse
         check(lib.dfw_attn_kvfused_fwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
                                        k_self.stride(0), k_self.stride(1), kb, vb, kbs, krs, o.data_ptr(), o.stride(0),
                                        o.stride(1), B, heads, Lq, Ls, Lb, float(scale), int(h16 == f16), _stream()),
@@ -303,9 +311,10 @@ def attn_kvfused(q, k_self, v_self, k_bank, v_bank, heads, scale):
     return o
 
 
-def attn_kvfused_backward(q, k_self, v_self, k_bank, v_bank, o, d_o, heads, scale):
+def attn_kvfused_backward(q, k_self, v_self, k_bank, v_bank, o, d_o, heads, scale, lse=None):
     """Backward of attn_kvfused: contiguous [B, L, heads*64] tensors of one 16-bit dtype (o = forward output, d_o its
-    gradient).  Returns (dq, dk_self, dv_self, dk_bank, dv_bank); the bank gradients are None without a bank."""
+    gradient, lse = the statistics of attn_kvfused(..., return_lse=True); without them one extra forward recomputes them).
+    Returns (dq, dk_self, dv_self, dk_bank, dv_bank); the bank gradients are None without a bank."""
     B, Lq, C = q.shape
     assert C == heads * 64 and q.dtype in OPERAND_DTYPES
     h16 = q.dtype
@@ -318,12 +327,14 @@ def attn_kvfused_backward(q, k_self, v_self, k_bank, v_bank, o, d_o, heads, scal
     dq = torch.empty_like(q); dks = torch.empty_like(k_self); dvs = torch.empty_like(v_self)
     dkb = torch.empty_like(k_bank) if Lb else None
     dvb = torch.empty_like(v_bank) if Lb else None
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and tuple(lse.shape) == (B, heads, Lq)
     ws = torch.empty(int(lib.dfw_attn_bwd_workspace_bytes(B, heads, Lq, Ls, Lb)), device=q.device, dtype=torch.uint8)
     kb = (k_bank.data_ptr(), v_bank.data_ptr(), k_bank.stride(0), k_bank.stride(1)) if Lb else (0, 0, 0, 0)
     with _Timed("attn", 2.5 * 4.0 * B * heads * Lq * (Ls + Lb) * 64, f"attn-bwd B{B} h{heads} Lq{Lq} Lk{Ls + Lb}"):
         check(lib.dfw_attn_kvfused_bwd(q.data_ptr(), q.stride(0), q.stride(1), k_self.data_ptr(), v_self.data_ptr(),
                                        k_self.stride(0), k_self.stride(1), kb[0], kb[1], kb[2], kb[3], o.data_ptr(),
-                                       d_o.data_ptr(), o.stride(0), o.stride(1), dq.data_ptr(), dks.data_ptr(), dvs.data_ptr(),
+                                       d_o.data_ptr(), o.stride(0), o.stride(1), _ptr(lse), dq.data_ptr(), dks.data_ptr(), dvs.data_ptr(),
                                        _ptr(dkb), _ptr(dvb), B, heads, Lq, Ls, Lb, float(scale), int(h16 == f16), ws.data_ptr(),
                                        _stream()), "dfw_attn_kvfused_bwd")
     return dq, dks, dvs, dkb, dvb

@@ -38,7 +38,8 @@ extern "C" {
 #define DFW_OPT_PREPROC_TWO_PASS 5  /* [0] data layer: two-launch resample with a uint8 intermediate in HBM              */
 #define DFW_OPT_ATTN_V2 6           /* [0] round-1 attention kernel (P through smem, two passes over S)                  */
 #define DFW_OPT_SEG_HEAD 7          /* [1] fused decoder head dfw_seg_head_u8 (0: gn-apply + conv 128->3 + seg_post)     */
-#define DFW_OPT_COUNT 8
+#define DFW_OPT_ATTN_BWD_UNFUSED 8  /* [0] round-1 attention backward (batched GEMMs over materialised logits)            */
+#define DFW_OPT_COUNT 9
 int dfw_set_option(int option, int value); /* DFW_ERR_INVALID for an unknown option */
 int dfw_get_option(int option);            /* current value; -1 for an unknown option */
 
@@ -130,20 +131,31 @@ int dfw_attn_kvfused_fwd(const void* q, long long q_batch_stride, int q_row_stri
                          int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
                          int heads, int Lq, int Ls, int Lb, float scale, int f16, void* stream);
 
+/* K1 with the softmax statistics the backward needs: lse fp32 [B, heads, Lq] = log2-domain logsumexp of the scaled logits
+ * (log2(sum_j 2^(s_j * scale * log2 e))).  Same arguments and result as dfw_attn_kvfused_fwd otherwise. */
+int dfw_attn_kvfused_fwd_lse(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
+                             const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
+                             const void* k_bank, const void* v_bank, long long kv_bank_batch_stride,
+                             int kv_bank_row_stride, void* o, long long o_batch_stride, int o_row_stride, int B,
+                             int heads, int Lq, int Ls, int Lb, float scale, int f16, float* lse, void* stream);
+
 /* K1b  BACKWARD of K1 (BASELINE config 4: training-shape forward + backward of the KV-fused attention; ref: autograd of
  *      xformers.ops.memory_efficient_attention on cat([key, folded bank]) -- attention_processor.py:251-271 under
- *      train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1320-1396).  Same tensor conventions as the forward;
+ *      train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1374-1391).  Same tensor conventions as the forward;
  *      o = the forward output, d_o its gradient (same strides as o); dq like q, dk/dv_self like k/v_self, dk/dv_bank like
- *      the bank.  Lq, Ls, Lb multiples of 64.  First correct CUDA path: all contractions on the tcgen05 batched GEMM with
- *      the L_q x L_k logits materialised per (episode, head) in `workspace` (dfw_attn_bwd_workspace_bytes, 256-B aligned);
- *      deterministic. */
+ *      the bank; lse = the statistics of dfw_attn_kvfused_fwd_lse, or NULL (they are then recomputed by one forward into
+ *      the workspace).  Flash-style and fused: the L_q x L_k matrices exist only as 128 x 128 tiles in tensor memory
+ *      (csrc/attn_bwd_fused.cu: a dK/dV kernel over key tiles, a dQ kernel over query tiles x key slices, all products on
+ *      tcgen05); deterministic (no atomics); any Lq / Ls / Lb >= 1.  Workspace (dfw_attn_bwd_workspace_bytes, 256-B aligned):
+ *      O(B * Lq * heads * 64) bytes.  DFW_OPT_ATTN_BWD_UNFUSED selects the round-1 path (logits materialised in the
+ *      workspace, L multiples of 64) for A/B measurements. */
 long long dfw_attn_bwd_workspace_bytes(int B, int heads, int Lq, int Ls, int Lb);
 int dfw_attn_kvfused_bwd(const void* q, long long q_batch_stride, int q_row_stride, const void* k_self,
                          const void* v_self, long long kv_self_batch_stride, int kv_self_row_stride,
                          const void* k_bank, const void* v_bank, long long kv_bank_batch_stride, int kv_bank_row_stride,
-                         const void* o, const void* d_o, long long o_batch_stride, int o_row_stride, void* dq, void* dk_self,
-                         void* dv_self, void* dk_bank, void* dv_bank, int B, int heads, int Lq, int Ls, int Lb, float scale,
-                         int f16, void* workspace, void* stream);
+                         const void* o, const void* d_o, long long o_batch_stride, int o_row_stride, const float* lse,
+                         void* dq, void* dk_self, void* dv_self, void* dk_bank, void* dv_bank, int B, int heads, int Lq, int Ls,
+                         int Lb, float scale, int f16, void* workspace, void* stream);
 
 /* K2  cross-attention to a short prompt embedding (Lctx <= 128 keys, head_dim 64), CUDA cores.
  * ref: BasicTransformerBlock.attn2 (upstream) reached from unet_2d_condition.py:1161; Lctx = 2 at eval

@@ -1,6 +1,6 @@
 """BASELINE config 4: training-shape forward + backward of the KV-fused attention and the GroupNorm(+SiLU) kernels
 (7 supports, query batch 1).  CUDA-event timings, median of 5, > L2-size flush between iterations.
-  python scripts/bench_config4.py > profiles/r01_config4_fwd_bwd.tsv"""
+  python scripts/bench_config4.py > profiles/r02_config4_fwd_bwd.tsv"""
 import os
 import sys
 
@@ -30,9 +30,9 @@ def main():
         C = h * 64
         mk = lambda L: torch.randn(1, L, C, device="cuda").to(dt)
         q, ks, vs, kb, vb, d_o = mk(Lq), mk(Lq), mk(Lq), mk(Lb), mk(Lb), mk(Lq)
-        o = ops.attn_kvfused(q, ks, vs, kb, vb, h, 0.125)
-        f = timeit(lambda: ops.attn_kvfused(q, ks, vs, kb, vb, h, 0.125), flush)
-        b = timeit(lambda: ops.attn_kvfused_backward(q, ks, vs, kb, vb, o, d_o, h, 0.125), flush)
+        o, lse = ops.attn_kvfused(q, ks, vs, kb, vb, h, 0.125, return_lse=True)
+        f = timeit(lambda: ops.attn_kvfused(q, ks, vs, kb, vb, h, 0.125, return_lse=True), flush)
+        b = timeit(lambda: ops.attn_kvfused_backward(q, ks, vs, kb, vb, o, d_o, h, 0.125, lse=lse), flush)
         fl = 4.0 * h * Lq * (Lq + Lb) * 64
         print(f"attn_kvfused\tB1 h{h} Lq{Lq} Lk{Lq + Lb}\t{f:.3f}\t{b:.3f}\t{fl / f / 1e9:.1f} TFLOP/s\t{2.5 * fl / b / 1e9:.1f} TFLOP/s (2.5x fwd FLOPs)")
         del q, ks, vs, kb, vb, d_o, o

@@ -455,8 +455,12 @@ def test_groupnorm_silu_backward_matches_autograd(N, H, C, silu, dt):
 
 @pytest.mark.parametrize("B,h,Lq,Ls,Lb,dt", [(1, 5, 256, 256, 1792, torch.float16),      # 7-shot shape at 16x16 (config 4)
                                              (2, 2, 128, 128, 128, torch.float16), (1, 3, 192, 192, 0, torch.float16),
-                                             (1, 5, 64, 64, 448, torch.bfloat16)])
-def test_attention_backward_matches_autograd(B, h, Lq, Ls, Lb, dt):
+                                             (1, 5, 64, 64, 448, torch.bfloat16),
+                                             (1, 2, 100, 100, 200, torch.float16),       # ragged query / key tiles
+                                             (2, 1, 1024, 1024, 3072, torch.float16),    # split key range in the dQ kernel
+                                             (1, 2, 300, 72, 0, torch.bfloat16)])
+@pytest.mark.parametrize("mode", ["fused+lse", "fused", "unfused"])
+def test_attention_backward_matches_autograd(B, h, Lq, Ls, Lb, dt, mode):
     """BASELINE config 4: forward + backward of the KV-fused attention vs torch autograd (fp32, CPU) of
     softmax(q [k_self; k_bank]^T / 8) [v_self; v_bank] -- the reference's cat([key, folded bank]) attention."""
     from diffews_b200 import ops
@@ -466,8 +470,24 @@ def test_attention_backward_matches_autograd(B, h, Lq, Ls, Lb, dt):
     q, ks, vs, d_o = mk(Lq), mk(Ls), mk(Ls), mk(Lq)
     kb, vb = (mk(Lb), mk(Lb)) if Lb else (None, None)
     cu = lambda t: None if t is None else t.cuda()
-    o = ops.attn_kvfused(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), h, 0.125)
-    dq, dks, dvs, dkb, dvb = ops.attn_kvfused_backward(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), o, cu(d_o), h, 0.125)
+    from diffews_b200 import _lib
+    if mode == "unfused" and (Lq % 64 or Ls % 64 or Lb % 64):
+        pytest.skip("the round-1 path needs L % 64 == 0")
+    lse = None
+    if mode == "fused+lse":        # statistics kept from the forward (the training step), else recomputed by the backward
+        o, lse = ops.attn_kvfused(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), h, 0.125, return_lse=True)
+        K_ = ks if kb is None else torch.cat([ks, kb], 1)
+        lg = (q.float().view(B, Lq, h, 64).transpose(1, 2) @ K_.float().view(B, -1, h, 64).transpose(1, 2).transpose(-1, -2)) * 0.125
+        want = torch.logsumexp(lg, -1) * 1.4426950408889634
+        assert (lse.cpu() - want).abs().max() <= 2e-3 * max(1.0, want.abs().max().item())
+    else:
+        o = ops.attn_kvfused(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), h, 0.125)
+    old = ops.set_option(_lib.OPT_ATTN_BWD_UNFUSED, int(mode == "unfused"))
+    try:
+        dq, dks, dvs, dkb, dvb = ops.attn_kvfused_backward(cu(q), cu(ks), cu(vs), cu(kb), cu(vb), o, cu(d_o), h, 0.125, lse=lse)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(_lib.OPT_ATTN_BWD_UNFUSED, old)
     leaves = [t.float().clone().requires_grad_(True) if t is not None else None for t in (q, ks, vs, kb, vb)]
     qf, ksf, vsf, kbf, vbf = leaves
     K = ksf if kbf is None else torch.cat([ksf, kbf], 1)
