@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_coef_kernel(const float* __r
         const float norm = sqrtf(s);
         norm_out[0] = norm;
         const float c = max_norm / (norm + 1e-6f);
-        coef_out[0] = c < 1.0f ? c : 1.0f;
+        // a non-finite norm (an inf / NaN gradient, e.g. an fp16 overflow under the reference's GradScaler) poisons the
+        // coefficient on purpose: dfw_adamw_step skips the whole update when it reads a non-finite grad_scale
+        coef_out[0] = isfinite(norm) ? (c < 1.0f ? c : 1.0f) : __int_as_float(0x7fc00000);
     }
 }
 
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_chunks_kernel(const AdamTen
     const long long off = chunk_offset[blockIdx.x];
     const long long n = min(static_cast<long long>(chunk_elems), t.n - off);
     const float gs = grad_scale ? __ldg(grad_scale) : 1.0f;
+    if (!isfinite(gs)) return;        // found-inf guard: parameters and moments stay untouched (GradScaler semantics)
     auto upd = [&](float& p, float g, float& m, float& v) {
         g *= gs;
         p *= sc.decay;

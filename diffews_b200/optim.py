@@ -105,8 +105,12 @@ class AdamW:
 
     def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
         """torch.nn.utils.clip_grad_norm_(params, max_norm) (L2): returns the total norm ([1] fp32, on the device).  The
-        gradients themselves are left untouched; the clip coefficient is applied inside the next `step()`."""
+        gradients themselves are left untouched; the clip coefficient is applied inside the next `step()` -- so unlike
+        torch the .grad tensors still hold the UNCLIPPED values afterwards, and the coefficient belongs to exactly these
+        gradient values: `step()` raises if a gradient was written in between (accumulate first, clip last).  A
+        non-finite norm makes the next `step()` a no-op on the device (found-inf guard)."""
         t = self._descs()
+        self._clip_versions = tuple((p.grad.data_ptr(), p.grad._version) for p in self.params)
         check(lib.dfw_grad_norm_clip_coef(t.data_ptr(), self._chunk_tensor.data_ptr(), self._chunk_offset.data_ptr(),
                                           self.n_chunks, CHUNK_ELEMS, float(max_norm), self._partial.data_ptr(),
                                           self._norm.data_ptr(), self._coef.data_ptr(), ops._stream()),
@@ -115,8 +119,20 @@ class AdamW:
         return self._norm
 
     @torch.no_grad()
-    def step(self):
+    def step(self, skip_nonfinite: bool = False):
+        """One AdamW update.  `skip_nonfinite`: read the clipped norm back (one host sync) and, GradScaler-style, skip the
+        step -- including the step counter -- when it is inf / NaN; without it the device-side guard still leaves parameters
+        and moments untouched, only the bias-correction step count advances."""
         t = self._descs()
+        if self._clip_pending:
+            now = tuple((p.grad.data_ptr(), p.grad._version) for p in self.params)
+            if now != self._clip_versions:
+                self._clip_pending = False
+                raise RuntimeError("a gradient changed between clip_grad_norm_() and step(): the clip coefficient is stale "
+                                   "(accumulate gradients first, clip last)")
+            if skip_nonfinite and not bool(torch.isfinite(self._norm).item()):
+                self._clip_pending = False
+                return
         for st in self.state.values():
             st["step"] += 1
         step = self.state[0]["step"]
@@ -124,6 +140,38 @@ class AdamW:
         check(lib.dfw_adamw_step(t.data_ptr(), self._chunk_tensor.data_ptr(), self._chunk_offset.data_ptr(), self.n_chunks,
                                  CHUNK_ELEMS, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, step, scale,
                                  self.p16_format, ops._stream()), "dfw_adamw_step")
+        self._clip_pending = False
+
+    # -- torch.optim.Optimizer.state_dict() layout (accelerator.save_state, train...v3.py:1408-1414) ---------------------
+    def state_dict(self) -> dict:
+        state = {i: {"step": torch.tensor(float(st["step"])), "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}
+                 for i, st in self.state.items() if st["step"] > 0}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict):
+        """Accepts what `state_dict()` or torch.optim.AdamW(params).state_dict() produced for the same parameter list."""
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("state dict does not match this optimizer's single parameter group")
+        g = groups[0]
+        if g.get("amsgrad") or g.get("maximize"):
+            raise NotImplementedError("amsgrad / maximize are not on the DiffewS path")
+        self.lr, self.betas = float(g["lr"]), (float(g["betas"][0]), float(g["betas"][1]))
+        self.eps, self.weight_decay = float(g["eps"]), float(g["weight_decay"])
+        for i, p in enumerate(self.params):
+            st = sd["state"].get(g["params"][i])
+            if st is None:
+                self.state[i]["step"] = 0
+                self.state[i]["exp_avg"].zero_(); self.state[i]["exp_avg_sq"].zero_()
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"parameter {i}: moment shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+            self.state[i]["step"] = int(round(float(st["step"])))
+            self.state[i]["exp_avg"].copy_(st["exp_avg"])           # in place: the descriptor table holds the pointers
+            self.state[i]["exp_avg_sq"].copy_(st["exp_avg_sq"])
         self._clip_pending = False
 
     def zero_grad(self, set_to_none: bool = False):

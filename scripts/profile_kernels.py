@@ -85,6 +85,13 @@ def main():
         kb, vb = bank[..., 320:640], bank[..., 640:]
         return (lambda: ops.attn_kvfused(q, k, v, kb, vb, h, 0.125)), 4.0 * B * h * L * 2 * L * 64, None
 
+    def attn_bwd():            # BASELINE config 4, 64x64 level: query batch 1 against its own + 7 supports' keys
+        h, L = 5, 4096
+        mk = lambda n: torch.randn(1, n, h * 64, device="cuda").to(bf16)
+        q, ks, vs, kb, vb, d_o = mk(L), mk(L), mk(L), mk(7 * L), mk(7 * L), mk(L)
+        o, lse = ops.attn_kvfused(q, ks, vs, kb, vb, h, 0.125, return_lse=True)
+        return (lambda: ops.attn_kvfused_backward(q, ks, vs, kb, vb, o, d_o, h, 0.125, lse=lse)), 2.5 * 4.0 * h * L * 8 * L * 64, None
+
     def gn():
         x = torch.randn(16, 512 * 512, 128, device="cuda")
         g = torch.ones(128, device="cuda"); b = torch.zeros(128, device="cuda")
@@ -117,7 +124,7 @@ def main():
         nbytes = lg.numel() * 4 + 2 * r.numel() * 2
         return (lambda: ops.cross_attn_collapsed(lg, U, b, r, h, 2, torch.float16)), None, nbytes
     cases.update(xattn=xattn, xattn1280=lambda: xattn(4096, 1280, 20))
-    cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, gn=gn, gn16=gn16)
+    cases.update(lin=lin, lin_res=lin_res, geglu=geglu, attn=attn, attn_bwd=attn_bwd, gn=gn, gn16=gn16)
     which = list(cases) if args.which == ["all"] else args.which
     for name in which:
         fn, flops, nbytes = cases[name]()

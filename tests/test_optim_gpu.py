@@ -63,6 +63,71 @@ def test_adamw_and_clip_match_torch(lib_built, max_norm):
     assert torch.equal(dev_p[0].grad.cpu(), _params(103)[0])
 
 
+def test_adamw_state_dict_round_trips_with_torch(lib_built):
+    """state_dict() has torch.optim.AdamW's layout (the reference checkpoints the optimizer through accelerator.save_state,
+    train...v3.py:1408-1414): torch can load ours, we can load torch's, and both continue identically."""
+    from diffews_b200.optim import AdamW
+    kw = dict(lr=2e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=5e-2)
+    ref_p = [torch.nn.Parameter(p.clone()) for p in _params(3)]
+    ref_opt = torch.optim.AdamW(ref_p, foreach=False, **kw)
+    for it in range(2):
+        for p, g in zip(ref_p, _params(300 + it)):
+            p.grad = g.clone()
+        ref_opt.step()
+    dev_p = [p.detach().clone().cuda() for p in ref_p]
+    opt = AdamW(dev_p, lr=1.0, betas=(0.5, 0.5), eps=1.0, weight_decay=0.0)           # overwritten by the loaded group
+    opt.load_state_dict(ref_opt.state_dict())
+    assert (opt.lr, opt.betas, opt.eps, opt.weight_decay) == (2e-3, (0.9, 0.99), 1e-8, 5e-2)
+    assert opt.state[0]["step"] == 2
+    grads = _params(400)
+    for p, g in zip(ref_p, grads):
+        p.grad = g.clone()
+    for p, g in zip(dev_p, grads):
+        p.grad = g.clone().cuda()
+    ref_opt.step(); opt.step()
+    for a, b in zip(dev_p, ref_p):
+        assert rel(a.cpu(), b.detach()) < (2e-6 if a.numel() >= 1000 else 5e-5)
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == list(range(len(dev_p)))
+    fresh_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    fresh = torch.optim.AdamW(fresh_p, foreach=False, **kw)
+    fresh.load_state_dict({"state": {k: {n: (v.cpu() if torch.is_tensor(v) else v) for n, v in st.items()}
+                                     for k, st in sd["state"].items()}, "param_groups": sd["param_groups"]})
+    assert float(fresh.state[fresh_p[0]]["step"]) == 3.0
+    assert rel(fresh.state[fresh_p[0]]["exp_avg"], ref_opt.state[ref_p[0]]["exp_avg"]) < 2e-6
+
+
+def test_adamw_found_inf_guard_and_stale_clip(lib_built):
+    """The reference trains under an fp16 GradScaler: one inf gradient must not poison parameters or moments.  And the
+    clip coefficient is only valid for the gradient values it was computed from."""
+    from diffews_b200.optim import AdamW
+    dev_p = [p.clone().cuda() for p in _params(5)]
+    before = [p.clone() for p in dev_p]
+    opt = AdamW(dev_p, lr=1e-2)
+    for p, g in zip(dev_p, _params(500)):
+        p.grad = g.clone().cuda()
+    dev_p[2].grad[0, 0] = float("inf")
+    n = opt.clip_grad_norm_(1.0)
+    opt.step()                                         # device-side guard
+    torch.cuda.synchronize()
+    assert not torch.isfinite(n).item()
+    for a, b in zip(dev_p, before):
+        assert torch.equal(a, b)
+    assert all(float(st["exp_avg"].abs().max()) == 0.0 for st in opt.state.values())
+    opt.clip_grad_norm_(1.0)
+    opt.step(skip_nonfinite=True)                      # host-visible skip: the step counter does not advance either
+    assert opt.state[0]["step"] == 1
+    dev_p[2].grad[0, 0] = 0.5
+    opt.clip_grad_norm_(1.0)
+    dev_p[0].grad.add_(1.0)                            # a gradient written after the clip
+    with pytest.raises(RuntimeError, match="stale"):
+        opt.step()
+    opt.clip_grad_norm_(1.0)
+    opt.step()
+    torch.cuda.synchronize()
+    assert not torch.equal(dev_p[0], before[0]) and all(torch.isfinite(p).all() for p in dev_p)
+
+
 def test_adamw_is_deterministic(lib_built):
     from diffews_b200.optim import AdamW
     outs = []
