@@ -173,6 +173,86 @@ def _ncu_attn_pct():
         return None
 
 
+def _loader_leg(args, runner, dev, rank, world, B, barrier, dist):
+    """episodes/s with every step's inputs coming from encoded files through diffews_b200.data.EpisodeLoader."""
+    import shutil
+    import tempfile
+    import numpy as np
+    import torch
+    from PIL import Image
+    from diffews_b200.data import DatasetCOCO, EpisodeLoader, EpisodeTransform
+    threads = args.loader_threads or max(2, min(16, (os.cpu_count() or 8) // world))
+    root = tempfile.mkdtemp(prefix=f"dfw_bench_tree_r{rank}_")
+    try:
+        # a COCO-20i-layout tree (fold 0 validation classes), 640x480 JPEG photos (quality 90) + PNG class masks
+        rs = np.random.RandomState(7)
+        base = os.path.join(root, "COCO2014")
+        os.makedirs(os.path.join(base, "val2014")); os.makedirs(os.path.join(base, "annotations", "val2014"))
+        os.makedirs(os.path.join(base, "splits", "val"))
+        classes = [4 * v for v in range(20)]
+        classwise = {c: [] for c in classes}
+        n_img = 96
+        yy, xx = np.mgrid[0:480, 0:640]
+        for i in range(n_img):
+            img = np.stack([127 + 100 * np.sin(xx / rs.uniform(5, 60) + rs.uniform(0, 6)) * np.cos(yy / rs.uniform(5, 60))
+                            for _ in range(3)], -1) + rs.uniform(-20, 20, (480, 640, 3))
+            name = f"val2014/COCO_val2014_{i:012d}.jpg"
+            Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(os.path.join(base, name), format="JPEG", quality=90)
+            lab = np.zeros((480, 640), np.uint8)
+            for c in (classes[i % 20], classes[(i * 7 + 3) % 20]):
+                y0, x0 = rs.randint(0, 300), rs.randint(0, 400)
+                lab[y0:y0 + rs.randint(60, 180), x0:x0 + rs.randint(60, 240)] = c + 1
+                classwise[c].append(name)
+            Image.fromarray(lab).save(os.path.join(base, "annotations", name[:-4] + ".png"), format="PNG")
+        import pickle
+        with open(os.path.join(base, "splits", "val", "fold0.pkl"), "wb") as f:
+            pickle.dump(classwise, f)
+        np.random.seed(1234)
+        ds = DatasetCOCO(root, fold=0, transform=EpisodeTransform(args.size), split="val", shot=args.nshot,
+                         use_original_imgsize=False)
+        loader = EpisodeLoader(ds, bsz=B, device=dev, decode_threads=threads, rank=rank, world=world)
+
+        def batches():
+            while True:
+                for b in loader:
+                    if b["query_img"].shape[0] == B:
+                        yield b
+        it = batches()
+        host_out = torch.empty((2, B, 2), dtype=torch.int64).pin_memory()
+
+        def run(nsteps):
+            pending = None
+            for _ in range(nsteps):
+                batch = next(it)                                    # decode (thread pool) + one H2D copy + 3 launches
+                inter, union = runner.step(batch)
+                if pending is not None:                             # read the PREVIOUS step's counts: one step in flight
+                    pending.synchronize()
+                    _ = int(host_out[0, 0, 1])
+                host_out[0].copy_(inter, non_blocking=True)
+                host_out[1].copy_(union, non_blocking=True)
+                pending = torch.cuda.Event()
+                pending.record()
+            pending.synchronize()
+            _ = int(host_out[0, 0, 1])
+        run(2)
+        barrier()
+        t0 = time.perf_counter()
+        run(args.steps)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        barrier()
+        t = torch.tensor([wall_ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per_ep = (1 + args.nshot) * (480 * 640 * 3 + 480 * 640)
+        return {"value": world * B * args.steps / (float(t.item()) / 1000.0), "unit": UNIT, "decode_threads_per_rank": threads,
+                "host_cores": os.cpu_count(), "h2d_bytes_per_step": int(B * per_ep),
+                "input": f"{n_img} JPEG 640x480 (quality 90) + PNG class masks per rank, COCO-20i layout, PIL decode on a "
+                         "thread pool, resize / normalise / mask on the GPU (dfw_resize_normalize_u8, dfw_mask_nearest)"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def _igemm_traffic():
     """DRAM bytes of one launch of the dominant igemm shape, from the committed ncu --set full capture (GB), else None."""
     try:
@@ -218,6 +298,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-timer", action="store_true")
+    ap.add_argument("--no-loader", action="store_true", help="skip the loader-fed e2e leg (JPEG / PNG files -> EpisodeLoader)")
+    ap.add_argument("--loader-threads", type=int, default=0, help="decode threads per rank (0: host cores / ranks, at most 16)")
     ap.add_argument("--vae-stream", default="half", choices=["half", "f32"], help="VAE residual-stream storage")
     ap.add_argument("--unet-stream", default="half", choices=["half", "f32"], help="UNet residual-stream storage")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
@@ -388,6 +470,16 @@ def main():
             dist.all_reduce(ti, op=dist.ReduceOp.MAX)
         e2e["with_uint8_image_d2h"] = {"value": world * B * args.steps / (float(ti.item()) / 1000.0), "unit": UNIT,
                                        "d2h_bytes_per_step": int(d2h + seg_host.numel())}
+
+    # ---------------- loader-fed e2e leg: encoded image FILES on disk -> EpisodeLoader -> runner ------------------------------
+    # The caller-side data format of the reference (evaluation_util/data/coco.py): JPEG images + PNG class masks, decoded by
+    # PIL on a thread pool, shipped as raw bytes, resized / normalised / masked on the GPU, then the same graph step.  The
+    # counts of step i are read back while step i+1 runs (one step in flight), so decoding overlaps the GPU.
+    if e2e is not None and not args.no_loader:
+        try:
+            e2e["loader_fed"] = _loader_leg(args, runner, dev, rank, world, B, barrier, dist if world > 1 else None)
+        except Exception as ex:                                   # e.g. a PIL build without a JPEG encoder
+            e2e["loader_fed"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
 
     # ---------------- roofline of the dominant kernel family ----------------------------------------------------------
     # Per-launch CUDA events cannot be recorded inside a graph replay, so the tensor-core launches are timed in an

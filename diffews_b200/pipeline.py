@@ -61,6 +61,37 @@ class MarigoldPipelineRGBLatentNoise:
         if hasattr(unet, "skip_support_tail"):
             unet.skip_support_tail = True   # single_infer discards the support pass's output (pipeline:719-720)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=None, unet=None, vae=None, scheduler=None,
+                        tokenizer=None, text_encoder=None, text_embeds=None, controlnet=None, image_projector=None,
+                        customized_head=None, image_encoder=None, device="cuda", unet_precision=None, vae_precision=None,
+                        **unused):
+        """`MarigoldPipeline.from_pretrained(args.checkpoint, torch_dtype=..., unet=unet, vae=vae, controlnet=None,
+        text_embeds=None, ...)` (main_oss.py:351-369): components that are not passed are loaded from the diffusers
+        directory -- `unet/`, `vae/` through diffews_b200.checkpoint, `scheduler/scheduler_config.json`, and, when no
+        `text_embeds` is given, `text_encoder/` + `tokenizer/` through transformers' CLIPTextModel / CLIPTokenizer (library
+        code, run ONCE for the empty prompt: pipeline:585-601).  Local files only; `torch_dtype` is accepted and ignored
+        like the reference ignores it for pre-built sub-models."""
+        import os
+        from . import checkpoint
+        root = str(pretrained_model_name_or_path)
+        if unet is None:
+            unet = checkpoint.load_unet(root, device=device, precision=unet_precision)
+        if vae is None:
+            vae = checkpoint.load_vae(root, device=device, precision=vae_precision)
+        if scheduler is None and os.path.exists(os.path.join(root, "scheduler", "scheduler_config.json")):
+            scheduler = DDIMSchedulerCustomized.from_config_file(os.path.join(root, "scheduler", "scheduler_config.json"))
+        if text_embeds is None:
+            if text_encoder is None:
+                from transformers import CLIPTextModel
+                text_encoder = CLIPTextModel.from_pretrained(os.path.join(root, "text_encoder"), local_files_only=True).eval()
+            if tokenizer is None:
+                from transformers import CLIPTokenizer
+                tokenizer = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"), local_files_only=True)
+        return cls(unet=unet, vae=vae, scheduler=scheduler, tokenizer=tokenizer, text_embeds=text_embeds,
+                   text_encoder=text_encoder, image_encoder=image_encoder, image_projector=image_projector,
+                   controlnet=controlnet, customized_head=customized_head)
+
     def to(self, *a, **k):
         return self
 
@@ -74,7 +105,8 @@ class MarigoldPipelineRGBLatentNoise:
         prompt = ""
         ids = self.tokenizer(prompt, padding="do_not_pad", max_length=self.tokenizer.model_max_length,
                              truncation=True, return_tensors="pt").input_ids.to(self.text_encoder.device)
-        self.empty_text_embed = self.text_encoder(ids)[0].to(self.dtype)
+        with torch.no_grad():
+            self.empty_text_embed = self.text_encoder(ids)[0].to(self.dtype)        # [1, 2, 1024]: <bos>, <eos>
         return self.empty_text_embed
 
     def _batch_embed(self, n: int) -> torch.Tensor:

@@ -428,6 +428,61 @@ def test_checkpoint_loader_equals_from_module(small_models, tmp_path):
     assert torch.equal(v1.encode_mean(img), v2.encode_mean(img))
 
 
+def test_pipeline_from_pretrained_with_clip_text_encoder(small_models, tmp_path):
+    """main_oss.py:351-369 `MarigoldPipeline.from_pretrained(checkpoint, unet=.., vae=.., text_embeds=None, ..)` on a
+    diffusers-layout directory: the UNet / VAE from safetensors, the scheduler from its JSON and the empty-prompt embedding
+    from transformers' CLIPTextModel + CLIPTokenizer (random-init, tiny; pipeline:585-601 tokenises "" without padding ->
+    <bos> <eos>, Lctx = 2) -- then one episode against the oracle fed the same embedding."""
+    import json
+    import shutil
+    from safetensors.torch import save_file
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPTokenizer
+    from diffews_b200.evaluation import Evaluator
+    from diffews_b200.pipeline import MarigoldPipelineRGBLatentNoise
+    from diffews_b200.synthetic import make_batch, pipeline_inputs
+    from oracle.pipeline import evaluate_episode
+    unet_o, vae_o = small_models[0], small_models[1]
+    for name, mod, cfg in (("unet", unet_o, {"block_out_channels": list(unet_o.block_out_channels),
+                                             "attention_head_dim": list(unet_o.heads), "cross_attention_dim": 1024}),
+                           ("vae", vae_o, {"block_out_channels": [b.resnets[0].conv1.out_channels
+                                                                   for b in vae_o.encoder.down_blocks]})):
+        (tmp_path / name).mkdir()
+        save_file({k: v.contiguous() for k, v in mod.state_dict().items()},
+                  str(tmp_path / name / "diffusion_pytorch_model.safetensors"))
+        (tmp_path / name / "config.json").write_text(json.dumps(cfg))
+    (tmp_path / "scheduler").mkdir()
+    from diffews_b200.scheduler import DEFAULT_CONFIG
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(DEFAULT_CONFIG))
+    (tmp_path / "tokenizer").mkdir()
+    (tmp_path / "tokenizer" / "vocab.json").write_text(json.dumps({"a</w>": 0, "b</w>": 1, "<|startoftext|>": 2, "<|endoftext|>": 3}))
+    (tmp_path / "tokenizer" / "merges.txt").write_text("#version: 0.2\n")
+    CLIPTokenizer(str(tmp_path / "tokenizer" / "vocab.json"), str(tmp_path / "tokenizer" / "merges.txt"),
+                  model_max_length=77).save_pretrained(str(tmp_path / "tokenizer"))
+    torch.manual_seed(0)
+    clip = CLIPTextModel(CLIPTextConfig(vocab_size=4, hidden_size=1024, intermediate_size=128, num_hidden_layers=2,
+                                        num_attention_heads=8, max_position_embeddings=77, bos_token_id=2, eos_token_id=3,
+                                        pad_token_id=3)).eval()
+    clip.save_pretrained(str(tmp_path / "text_encoder"))
+    pipe = MarigoldPipelineRGBLatentNoise.from_pretrained(str(tmp_path), torch_dtype=torch.float32, controlnet=None,
+                                                          text_embeds=None, image_projector=None, customized_head=None,
+                                                          image_encoder=None)
+    emb = pipe.encode_clip_feature(None)
+    assert tuple(emb.shape) == (1, 2, 1024)
+    with torch.no_grad():
+        want_emb = clip(torch.tensor([[2, 3]]))[0]
+    assert torch.allclose(emb.cpu(), want_emb, atol=1e-6)
+    batch = make_batch(9, 1, 64, 1)
+    out = pipe(pipeline_inputs(batch), denoising_steps=1, ensemble_size=1, processing_res=64, batch_size=1,
+               show_progress_bar=False, mode="seg", rgb_paths=[], seed=0, output_type="pt")
+    inter, union, mask = Evaluator.rthres_classify(out.seg_u8, {"query_mask": batch["query_mask"].cuda()}, 0.25, want_mask=True)
+    o_inter, o_union, o_mask, _, o_lat = evaluate_episode(unet_o, vae_o, want_emb, batch)
+    e = rel_l2(pipe._last_noise_pred[0], o_lat[0])
+    agree = (mask[0].cpu().float() == o_mask[0]).float().mean().item()
+    print(f"from_pretrained + CLIP text encoder: latent rel-L2 {e:.2e}, mask agreement {agree:.4f}")
+    assert e <= 3e-2 and agree >= 0.98                      # toy-width bars of test_pipeline_small_width
+    shutil.rmtree(str(tmp_path), ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE config 4 (training shapes): backward of the GroupNorm(+SiLU) kernel against torch autograd in fp32 on the CPU
 # ---------------------------------------------------------------------------------------------------------------------
