@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdiffews_b200.so")
-SOURCES = ["common.cu", "igemm.cu", "attn.cu", "attn_bwd.cu", "attn_bwd_fused.cu", "norm.cu", "misc.cu", "metric.cu", "preproc.cu", "optim.cu", "seghead.cu", "f32mode.cu"]
+SOURCES = ["common.cu", "igemm.cu", "attn.cu", "attn_bwd.cu", "attn_bwd_fused.cu", "norm.cu", "misc.cu", "metric.cu", "preproc.cu", "optim.cu", "seghead.cu", "f32mode.cu", "grad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-DDFW_BUILD",

@@ -84,6 +84,15 @@ SIGNATURES = {
     "dfw_geglu_bwd": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),
     "dfw_mse_workspace_floats": (_ll, []),
     "dfw_mse_loss": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
+    "dfw_conv_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i, _i]),
+    "dfw_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "dfw_weight_permute": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dfw_colsum_chunks": (_i, [_ll, _i]),
+    "dfw_colsum": (_i, [_vp, _i, _vp, _ll, _i, _i, _f, _i, _vp, _vp]),
+    "dfw_downsum2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dfw_split_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "dfw_geglu_fwd": (_i, [_vp, _vp, _i, _ll, _i, _vp]),
+    "dfw_nchw_f32_to_nhwc16_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
 }
 
 

@@ -760,3 +760,121 @@ def mask_nearest(buf, desc_offset, n, out_h, out_w, mode=0, want_boundary=False)
     check(lib.dfw_mask_nearest(buf.data_ptr(), buf.data_ptr() + desc_offset, n, m.data_ptr(), _ptr(bd), out_h, out_w, int(mode),
                                _stream()), "dfw_mask_nearest")
     return m, bd
+
+
+# ---- gradient kernels of the training step (csrc/grad.cu) ------------------------------------------------------------
+_WS = {}
+
+
+def _workspace(nbytes: int, device, key: str = "ws") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, key): stream-ordered reuse, so consecutive launches on one stream may share it."""
+    k = (str(device), key)
+    buf = _WS.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _WS[k] = buf
+    return buf
+
+
+def conv_wgrad(x, dy, dw, *, ksize, stride=1, scale=1.0, accumulate=False, cout_store=None):
+    """dw[co, tap*Cin + ci] (=|+=) scale * sum_pixels dy[p, co] * x[p*stride + tap - pad, ci].
+    x 16-bit [N,H,W,Cin], dy 16-bit [N,H/s,W/s,Cout], dw fp32 [cout_store, ks*ks*Cin] (contiguous, written in place)."""
+    assert x.dtype in OPERAND_DTYPES and dy.dtype == x.dtype
+    _req(x, x.dtype, "x"); _req(dy, dy.dtype, "dy"); _req(dw, torch.float32, "dw")
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    cs = Cout if cout_store is None else int(cout_store)
+    assert tuple(dy.shape) == (N, H // stride, W // stride, Cout), (x.shape, dy.shape, stride)
+    assert dw.numel() == cs * ksize * ksize * Cin, (dw.shape, cs, ksize, Cin)
+    ws = _workspace(int(lib.dfw_conv_wgrad_workspace_bytes(N, H, W, Cin, Cout, ksize, stride)), x.device, "wgrad")
+    with _Timed("igemm", 2.0 * N * (H // stride) * (W // stride) * Cout * ksize * ksize * Cin,
+                f"wgrad N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride}"):
+        check(lib.dfw_conv_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, Cin, Cout, cs, ksize, stride,
+                                 int(x.dtype == f16), float(scale), int(accumulate), ws.data_ptr(), _stream()), "dfw_conv_wgrad")
+    return dw
+
+
+def linear_wgrad(x, dy, dw, *, scale=1.0, accumulate=False):
+    """dw[n, k] (=|+=) scale * sum_rows dy[r, n] * x[r, k]; x [.., K], dy [.., Nout] 16-bit, dw fp32 [Nout, K]."""
+    K, Nout = x.shape[-1], dy.shape[-1]
+    M = x.numel() // K
+    return conv_wgrad(x.view(1, 1, M, K), dy.view(1, 1, M, Nout), dw, ksize=1, scale=scale, accumulate=accumulate)
+
+
+def weight_permute(w, R, T, C, tap_map, out=None):
+    """out[c, t', r] = w[r, tap_map[t'], c] (0 where tap_map[t'] < 0): 16-bit [R, T, C] -> [C, len(tap_map), R]."""
+    assert w.dtype in OPERAND_DTYPES and w.is_cuda and w.is_contiguous() and w.numel() == R * T * C
+    To = len(tap_map)
+    if out is None:
+        out = torch.empty((C, To * R), device=w.device, dtype=w.dtype)
+    assert out.numel() == C * To * R and out.dtype == w.dtype and out.is_contiguous()
+    import ctypes
+    tm = (ctypes.c_int * To)(*[int(t) for t in tap_map])
+    check(lib.dfw_weight_permute(w.data_ptr(), out.data_ptr(), R, T, C, To, ctypes.cast(tm, ctypes.c_void_p), _stream()),
+          "dfw_weight_permute")
+    return out
+
+
+def colsum(x, groups=1, *, out=None, scale=1.0, accumulate=False):
+    """out[g, c] (=|+=) scale * sum of the rows of group g: x [groups * rows, C] (any leading shape), fp32 out [groups, C]."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (bf16, f16, torch.float32)
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    assert rows % groups == 0
+    if out is None:
+        out = torch.empty((groups, Cc), device=x.device, dtype=torch.float32)
+        assert not accumulate
+    _req(out, torch.float32, "out")
+    assert out.numel() == groups * Cc
+    chunks = int(lib.dfw_colsum_chunks(rows // groups, groups))
+    ws = _workspace(groups * chunks * Cc * 4, x.device, "colsum")
+    with _Timed("elementwise", _nb(x), f"colsum rows{rows} C{Cc} g{groups}"):
+        check(lib.dfw_colsum(x.data_ptr(), _xd(x), out.data_ptr(), rows // groups, groups, Cc, float(scale), int(accumulate),
+                             ws.data_ptr(), _stream()), "dfw_colsum")
+    return out
+
+
+def downsum2x(dy):
+    """Backward of upsample2x: dy 16-bit [N,2H,2W,C] -> dx [N,H,W,C]."""
+    assert dy.dtype in OPERAND_DTYPES
+    _req(dy, dy.dtype, "dy")
+    N, H2, W2, Cc = dy.shape
+    dx = torch.empty((N, H2 // 2, W2 // 2, Cc), device=dy.device, dtype=dy.dtype)
+    with _Timed("elementwise", _nb(dy, dx), f"downsum2x N{N} {H2}x{W2} C{Cc}"):
+        check(lib.dfw_downsum2x_nhwc(dy.data_ptr(), dx.data_ptr(), int(dy.dtype == f16), N, H2 // 2, W2 // 2, Cc, _stream()),
+              "dfw_downsum2x_nhwc")
+    return dx
+
+
+def split_channels(y, Ca):
+    """Backward of concat_channels: (y[..., :Ca], y[..., Ca:]) as two contiguous tensors."""
+    assert y.dtype in OPERAND_DTYPES
+    _req(y, y.dtype, "y")
+    Cc = y.shape[-1]
+    rows = y.numel() // Cc
+    a = torch.empty(y.shape[:-1] + (Ca,), device=y.device, dtype=y.dtype)
+    b = torch.empty(y.shape[:-1] + (Cc - Ca,), device=y.device, dtype=y.dtype)
+    with _Timed("elementwise", 2 * _nb(y), f"split rows{rows} {Ca}+{Cc - Ca}"):
+        check(lib.dfw_split_channels(y.data_ptr(), a.data_ptr(), b.data_ptr(), rows, Ca, Cc - Ca, _stream()), "dfw_split_channels")
+    return a, b
+
+
+def geglu(h):
+    """y = h[..., :F] * gelu_erf(h[..., F:]) for 16-bit (value | gate) pre-activations h [.., 2F]."""
+    assert h.dtype in OPERAND_DTYPES
+    _req(h, h.dtype, "h")
+    F = h.shape[-1] // 2
+    y = torch.empty(h.shape[:-1] + (F,), device=h.device, dtype=h.dtype)
+    with _Timed("elementwise", _nb(h, y), f"geglu rows{h.numel() // (2 * F)} F{F}"):
+        check(lib.dfw_geglu_fwd(h.data_ptr(), y.data_ptr(), int(h.dtype == f16), h.numel() // (2 * F), F, _stream()), "dfw_geglu_fwd")
+    return y
+
+
+def nchw_to_nhwc_pad(x, cpad, dtype=f16, scale=1.0):
+    """fp32 [N,C,H,W] -> 16-bit [N,H,W,cpad] (channels beyond C are zero), values scaled by `scale`."""
+    _req(x, torch.float32, "x")
+    N, Cc, H, W = x.shape
+    y = torch.empty((N, H, W, cpad), device=x.device, dtype=dtype)
+    check(lib.dfw_nchw_f32_to_nhwc16_pad(x.data_ptr(), y.data_ptr(), N, Cc, H, W, cpad, float(scale), int(dtype == f16), _stream()),
+          "dfw_nchw_f32_to_nhwc16_pad")
+    return y

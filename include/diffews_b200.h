@@ -396,6 +396,40 @@ long long dfw_mse_workspace_floats(void);
 int dfw_mse_loss(const float* pred, const float* target, long long n, float upstream, float* loss_out, float* dpred,
                  float* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Gradient kernels of the training step (csrc/grad.cu).
+ * ref: train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1386 accelerator.backward(loss): torch autograd through
+ *      every nn.Conv2d / nn.Linear / Upsample2D / torch.cat / GEGLU of the UNet (cuDNN wgrad + dgrad, cuBLAS) (upstream).
+ *
+ * Weight gradient of y = conv(x, w) (ksize 1|3, stride 1|2 with pad (ksize-1)/2; a Linear is N = Hin = 1, Win = M):
+ *   dw[co, (kh*ks+kw)*Cin + ci] (=|+=) scale * sum over output pixels of dy[p, co] * x[p*stride + (kh,kw) - pad, ci]
+ *   x 16-bit [N,Hin,Win,Cin] (Cin % 32 == 0), dy 16-bit [N,Hin/stride,Win/stride,Cout] (Cout % 8 == 0), dw fp32
+ *   [cout_store, ks*ks*Cin] (cout_store <= Cout: rows beyond it are not written — dy channel-padded for tiny Cout).
+ * tcgen05 GEMM with the pixel index as the contraction: both operands are read in place (MN-major TMA tiles), split over
+ * pixel ranges across CTAs, partials summed in fixed order (deterministic).  workspace: dfw_conv_wgrad_workspace_bytes. */
+long long dfw_conv_wgrad_workspace_bytes(int N, int Hin, int Win, int Cin, int Cout, int ksize, int stride);
+int dfw_conv_wgrad(const void* x, const void* dy, float* dw, int N, int Hin, int Win, int Cin, int Cout, int cout_store,
+                   int ksize, int stride, int f16, float scale, int accumulate, void* workspace, void* stream);
+/* out[c, t', r] = tap_map[t'] >= 0 ? w[r, tap_map[t'], c] : 0;  w 16-bit [R, T, C] -> out 16-bit [C, T_out, R], T_out <= 16.
+ * Builds the operand of the data-gradient convolution from a forward weight: Linear transpose (T = 1), 3x3 rotation
+ * (tap_map[t] = 8 - t), the four phase filters of the stride-2 transposed convolution. */
+int dfw_weight_permute(const void* w, void* out, int R, int T, int C, int T_out, const int* tap_map, void* stream);
+/* out[g, c] (=|+=) scale * sum over the rows of group g of x[g*rows_per_group + r, c]: bias gradients (groups = 1) and
+ * per-image time-embedding gradients (groups = N).  dtype 0 bf16 / 1 fp32 / 2 fp16; C % 2 == 0; deterministic.
+ * workspace: groups * dfw_colsum_chunks(rows_per_group, groups) * C floats. */
+int dfw_colsum_chunks(long long rows_per_group, int groups);
+int dfw_colsum(const void* x, int dtype, float* out, long long rows_per_group, int groups, int C, float scale, int accumulate,
+               float* workspace, void* stream);
+/* backward of the nearest-2x upsample: dx[n,h,w,:] = sum of the 2x2 block of dy [N,2H,2W,C]; 16-bit, C % 8 == 0. */
+int dfw_downsum2x_nhwc(const void* dy, void* dx, int f16, int N, int H, int W, int C, void* stream);
+/* backward of the channel concat: a = y[:, :Ca], b = y[:, Ca:]; 16-bit rows, Ca % 8 == Cb % 8 == 0. */
+int dfw_split_channels(const void* y, void* a, void* b, long long rows, int Ca, int Cb, void* stream);
+/* y[M, F] = h[:, :F] * gelu_erf(h[:, F:]) on 16-bit (value | gate) pre-activations kept for dfw_geglu_bwd. */
+int dfw_geglu_fwd(const void* h, void* y, int f16, long long M, int F, void* stream);
+/* y[n,h,w,c] = c < C ? scale * x[n,c,h,w] : 0: fp32 NCHW -> 16-bit NHWC with Cpad channels (d loss / d prediction). */
+int dfw_nchw_f32_to_nhwc16_pad(const float* x, void* y, int N, int C, int H, int W, int Cpad, float scale, int f16,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
