@@ -771,6 +771,8 @@ def _workspace(nbytes: int, device, key: str = "ws") -> torch.Tensor:
     k = (str(device), key)
     buf = _WS.get(k)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _WS.setdefault("retired", []).append(buf)      # a captured CUDA graph may still hold the old pointer
         buf = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
         _WS[k] = buf
     return buf

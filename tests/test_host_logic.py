@@ -221,3 +221,66 @@ def test_random_init_state_dicts_match_oracle_module_shapes():
     n_unet = sum(v.numel() for v in random_unet_state_dict(0).values())
     n_vae = sum(v.numel() for v in random_vae_state_dict(1).values())
     assert n_unet == 865_910_724 + 23_360 and n_vae == 83_653_863
+
+
+def _gloo_reducer_worker(rank, world, port, q):
+    """The DDP bucket reducer of the training step (diffews_b200/train.py) on CPU tensors: the first step learns how many
+    gradient contributions each parameter receives and reduces at the end; from the second step on a bucket is reduced
+    the moment its last parameter is complete, i.e. while later (here: simulated) backward work is still outstanding."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffews_b200.train import GradReducer, ParamStore
+    st = ParamStore("cpu", torch.float16)
+    shapes = [(40, 24), (24,), (64, 40), (64,), (16, 64), (16,)]           # registration = execution order
+    ps = [st.add(f"p{i}", torch.zeros(s), "linear" if len(s) == 2 else "vec") for i, s in enumerate(shapes)]
+    st.finalize()
+    st.reducer = GradReducer(st, None, bucket_bytes=4096)
+    st.grad_scale = 1.0 / world
+    assert len(st.reducer.buckets) >= 2
+    uses = [2, 2, 2, 2, 1, 1]                                               # the last layer is only on the query pass
+    out = []
+    for step in range(3):
+        st.begin_step()
+        launched_mid = 0
+        for use in range(2):                                                # query-pass backward, then support-pass backward
+            for p, u in reversed(list(zip(ps, uses))):
+                if use >= u:
+                    continue
+                g = torch.full(p.shape, float(rank + 1) * (step + 1))
+                p.add_grad(g, st.grad_scale, st)
+            launched_mid = max(launched_mid, sum(st.reducer.launched))
+        overlapped = st.reducer.overlapped
+        st.end_step()
+        out.append((overlapped, [float(p.grad.flatten()[0]) for p in ps], [p.expected for p in ps]))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_bucket_reducer_world2():
+    import socket
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_gloo_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    uses = [2, 2, 2, 2, 1, 1]
+    for rank, out in res:
+        for step, (overlapped, vals, expected) in enumerate(out):
+            assert expected == uses
+            # mean over ranks of (rank + 1) * (step + 1) * uses
+            want = [1.5 * (step + 1) * u for u in uses]
+            assert vals == pytest.approx(want), (rank, step, vals, want)
+            if step == 0:
+                assert overlapped == 0            # counts not known yet: everything reduced at the end
+            else:
+                assert overlapped >= 1            # at least one bucket went out before the backward had finished
