@@ -1,17 +1,18 @@
-"""First correct path for the GEMM / convolution backward of the training step — assembled from the
-forward tcgen05 kernels, not yet a tuned implementation.
+"""Stand-alone GEMM / convolution backward on the gradient kernels.
 
 Reference: `accelerator.backward(loss)` (train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1386) runs torch
 autograd through every nn.Linear / nn.Conv2d of the UNet.  Here
 
-  Linear   y = x W^T :   dx = dy W          -> `ops.linear(dy, W^T)`            (contraction over Nout)
-                         dW = dy^T x        -> `ops.linear(dy^T, x^T)` fp32     (contraction over the M tokens)
-  Conv 3x3 s1 p1     :   dx = conv(dy, W rotated by 180 degrees, in/out channels swapped)   -> `ops.conv2d`
-                         dW[co, tap, ci] = sum_pixels dy[p, co] * x[p + tap, ci]            -> 9 x `ops.linear`
+  Linear   y = x W^T :   dx = dy W          -> the forward GEMM kernel on W^T (dfw_weight_permute: one transpose kernel)
+                         dW = dy^T x        -> dfw_conv_wgrad (tcgen05, dy and x read in place as MN-major TMA tiles)
+  Conv 3x3 s1 p1     :   dx = conv(dy, W rotated by 180 degrees, in/out channels swapped)   (same permute kernel)
+                         dW[co, tap, ci] = sum_pixels dy[p, co] * x[p + tap, ci]            (same wgrad kernel, 9 taps)
+                         dbias = column sums of dy                                          (dfw_colsum)
 
-so every FLOP runs on the implicit-GEMM kernel; the operand transposes / shifted copies are torch layout ops (extra HBM
-passes — the dedicated dgrad / wgrad mainloops that read the tensors in place are the round-2 item).  16-bit operands,
-fp32 accumulation, fp32 weight gradients.  CUDA only.
+No torch layout ops, no operand copies: the round-1 composition (pad / flip / permute / 9 GEMM launches per conv wgrad)
+is gone.  The training step (diffews_b200/train.py) drives the same kernels through autograd nodes and keeps the permuted
+weights cached between optimizer steps; these two functions are the per-layer form used by the kernel tests.
+16-bit operands, fp32 accumulation, fp32 weight / bias gradients.  CUDA only.
 """
 from __future__ import annotations
 
@@ -20,24 +21,17 @@ import torch
 from . import ops
 
 
-def _pad_rows(t: torch.Tensor, mult: int) -> torch.Tensor:
-    r = (-t.shape[0]) % mult
-    if r == 0:
-        return t
-    return torch.cat([t, t.new_zeros((r,) + tuple(t.shape[1:]))], dim=0)
-
-
 def linear_backward(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: bool = True):
     """x [M, K], w [Nout, K], dy [M, Nout] (one 16-bit dtype) -> (dx [M, K] 16-bit or None, dW [Nout, K] fp32,
-    dbias [Nout] fp32).  K % 64 == 0 and Nout % 64 == 0 (true for every Linear of the UNet)."""
+    dbias [Nout] fp32).  K % 64 == 0 and Nout % 64 == 0 (true for every Linear of the UNet); any M."""
     assert x.is_cuda and x.dtype in ops.OPERAND_DTYPES and w.dtype == x.dtype and dy.dtype == x.dtype
     M, K = x.shape
     Nout = w.shape[0]
     assert w.shape == (Nout, K) and dy.shape == (M, Nout) and K % 64 == 0 and Nout % 64 == 0
-    dx = ops.linear(dy.contiguous(), w.t().contiguous()) if need_dx else None
-    xp, dyp = _pad_rows(x, 64), _pad_rows(dy, 64)                    # zero rows add nothing to the sums
-    dw = ops.linear(dyp.t().contiguous(), xp.t().contiguous(), out_f32=True)
-    return dx, dw, dy.float().sum(dim=0)
+    x, w, dy = x.contiguous(), w.contiguous(), dy.contiguous()
+    dx = ops.linear(dy, ops.weight_permute(w, Nout, 1, K, [0]).view(K, Nout)) if need_dx else None
+    dw = ops.linear_wgrad(x, dy, torch.empty((Nout, K), device=x.device, dtype=torch.float32))
+    return dx, dw, ops.colsum(dy).view(Nout)
 
 
 def conv3x3_backward(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: bool = True):
@@ -48,17 +42,10 @@ def conv3x3_backward(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     assert w.shape == (Cout, 9 * Cin) and dy.shape == (N, H, W, Cout) and Cin % 64 == 0 and Cout % 64 == 0
+    x, w, dy = x.contiguous(), w.contiguous(), dy.contiguous()
     dx = None
     if need_dx:
-        w_rot = w.view(Cout, 3, 3, Cin).flip(1, 2).permute(3, 1, 2, 0).contiguous().view(Cin, 9 * Cout)
-        dx = ops.conv2d(dy.contiguous(), w_rot, ksize=3)
-    P = N * H * W
-    dyt = _pad_rows(dy.reshape(P, Cout), 64).t().contiguous()       # [Cout, P]
-    xpad = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))            # [N, H+2, W+2, Cin]
-    taps = []
-    for kh in range(3):
-        for kw in range(3):
-            xs = _pad_rows(xpad[:, kh:kh + H, kw:kw + W, :].reshape(P, Cin), 64).t().contiguous()     # [Cin, P]
-            taps.append(ops.linear(dyt, xs, out_f32=True))                                           # [Cout, Cin]
-    dw = torch.stack(taps, dim=1).reshape(Cout, 9 * Cin)
-    return dx, dw, dy.float().sum(dim=(0, 1, 2))
+        w_rot = ops.weight_permute(w, Cout, 9, Cin, [8 - t for t in range(9)]).view(Cin, 9 * Cout)
+        dx = ops.conv2d(dy, w_rot, ksize=3)
+    dw = ops.conv_wgrad(x, dy, torch.empty((Cout, 9 * Cin), device=x.device, dtype=torch.float32), ksize=3)
+    return dx, dw, ops.colsum(dy).view(Cout)

@@ -155,17 +155,25 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
         assert residual.shape == y.shape and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
         else: assert residual.dtype == h16
-    if gn_stats and not (silu or geglu) and gn_stats_supported(N, Ho, Wo, Cout, out_f32, residual, bias_per_sample):
+    want_gn = gn_stats and not (silu or geglu) and gn_stats_supported(N, Ho, Wo, Cout, out_f32, residual, bias_per_sample)
+    tag = ""
+    if _timer is not None:
+        # which kernel the library will pick (igemm.cu try_launch_t128): only evaluated for the instrumented pass
+        t128 = (stride == 1 and pad_mode == 0 and not (out_f32 or silu or geglu or bias_per_sample)
+                and (residual is None or residual.dtype != torch.float32) and (not want_gn or Cout <= 512)
+                and bool(lib.dfw_conv_gnin_supported(N, H, W, Cin, Cout, ksize)))
+        tag = "t128 " if t128 else ""
+    if want_gn:
         partial = torch.empty(int(lib.dfw_gn_partial_floats(N)), device=x.device, dtype=torch.float32)
         with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin,
-                    f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags} +gn"):
+                    f"{tag}conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags} +gn"):
             check(lib.dfw_conv2d_igemm_gnstats(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), N,
                                                H, W, Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale),
                                                partial.data_ptr(), _stream()), "dfw_conv2d_igemm_gnstats")
         y._gn_partial = (partial, partial.numel() // (N * 64))
         return y
     with _Timed("igemm", 2.0 * N * Ho * Wo * Cout * ksize * ksize * Cin,
-                f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags}"):
+                f"{tag}conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s{stride} f{flags}"):
         check(lib.dfw_conv2d_igemm(x.data_ptr(), w.data_ptr(), _ptr(bias), bss, _ptr(residual), y.data_ptr(), N, H, W,
                                    Cin, Cout, ksize, stride, pad_mode, flags, float(out_scale), _stream()),
               "dfw_conv2d_igemm")
@@ -233,7 +241,11 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
         assert residual.numel() == y.numel() and residual.is_contiguous()
         if residual.dtype == torch.float32: flags |= EPI_RES_F32
         else: assert residual.dtype == h16
-    with _Timed("igemm", 2.0 * M * K * Nout, f"linear M{M} K{K} N{Nout} f{flags}"):
+    tag = ""
+    if _timer is not None and residual is not None and M % 256 == 0 and not (out_f32 or silu or geglu) \
+            and residual.dtype != torch.float32 and bool(lib.dfw_conv_gnin_supported(1, M // 16, 16, K, Nout, 1)):
+        tag = "t128 "                  # residual projections run on the channel-major kernel (igemm.cu try_launch_t128)
+    with _Timed("igemm", 2.0 * M * K * Nout, f"{tag}linear M{M} K{K} N{Nout} f{flags}"):
         check(lib.dfw_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, K, Nout, flags,
                              float(out_scale), _stream()), "dfw_linear")
     return y
