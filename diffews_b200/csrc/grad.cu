@@ -220,22 +220,23 @@ struct WgradPlan {
     int TW, TH, TN, chunks_w, chunks_h, chunks_n, total_chunks, tiles_m, tiles_n, NB, splits, cps, ntaps;
 };
 
-int pick_pow2(int extent, int cap) {
-    int best = 1;
-    long long best_cost = -1;
-    for (int t = 1; t <= cap; t *= 2) {
-        const long long cost = static_cast<long long>((extent + t - 1) / t) * t;
-        if (best_cost < 0 || cost <= best_cost) { best = t; best_cost = cost; }
-    }
-    return best;
+// 64-pixel chunk (TW x TH x TN, powers of two) covering the [N, H, W] grid with the fewest padded pixels; ties -> wider
+void choose_chunk(int W, int H, int N, int& TW, int& TH, int& TN) {
+    long long best = -1;
+    TW = 64; TH = 1; TN = 1;
+    for (int tw = 64; tw >= 1; tw /= 2)
+        for (int th = 64 / tw; th >= 1; th /= 2) {
+            const int tn = 64 / (tw * th);
+            const long long cost = (static_cast<long long>((W + tw - 1) / tw) * tw) * (static_cast<long long>((H + th - 1) / th) * th) *
+                                   (static_cast<long long>((N + tn - 1) / tn) * tn);
+            if (best < 0 || cost < best) { best = cost; TW = tw; TH = th; TN = tn; }
+        }
 }
 
 WgradPlan wgrad_plan(int N, int Ho, int Wo, int Cin, int Cout, int ksize) {
     WgradPlan pl;
     pl.ntaps = ksize * ksize;
-    pl.TW = pick_pow2(Wo, 64);
-    pl.TH = pick_pow2(Ho, 64 / pl.TW);
-    pl.TN = 64 / (pl.TW * pl.TH);
+    choose_chunk(Wo, Ho, N, pl.TW, pl.TH, pl.TN);
     pl.chunks_w = (Wo + pl.TW - 1) / pl.TW;
     pl.chunks_h = (Ho + pl.TH - 1) / pl.TH;
     pl.chunks_n = (N + pl.TN - 1) / pl.TN;
@@ -408,28 +409,65 @@ __device__ __forceinline__ float ldf(const void* x, long long i) {
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
 }
 
-// stage 1: partial[g][chunk][c] = sum of x[g * rows_per_group + r, c] over the chunk's rows.  thread = channel pair.
+// stage 1: partial[g][chunk][c] = sum of x[g * rows_per_group + r, c] over the chunk's rows.  A thread owns 8 consecutive
+// channels (one 16-byte load per row for 16-bit tensors); the 256 threads of a CTA cover VPR = C / 8 vectors x 256 / VPR
+// rows at a time, four rows in flight per thread; the row lanes are folded through smem in a fixed order.
 template <int XD>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ x, float* __restrict__ partial,
                                                              long long rows_per_group, int C, int chunks) {
+    __shared__ float red[256 * 8];
     const int g = blockIdx.z, chunk = blockIdx.y;
-    const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
-    if (c >= C) return;
+    const int VPR = C / 8;                                   // vectors per row (host: C % 8 == 0, VPR <= 256 per x-block)
+    const int vpb = VPR < 256 ? VPR : 256;                   // vectors handled by this block
+    const int RP = 256 / vpb;                                // rows in parallel
+    const int tx = threadIdx.x % vpb, ty = threadIdx.x / vpb;
+    const int v = blockIdx.x * 256 + tx;
+    const bool active = ty < RP && v < VPR;
     const long long per = (rows_per_group + chunks - 1) / chunks;
     const long long r0 = chunk * per, r1 = min(r0 + per, rows_per_group);
-    float s0 = 0.f, s1 = 0.f;
     const long long base = static_cast<long long>(g) * rows_per_group;
-    for (long long r = r0; r < r1; ++r) {
-        const long long o = (base + r) * C + c;
-        if (XD == 1) { const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + o); s0 += v.x; s1 += v.y; }
-        else {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(x) + o);
-            const float2 v = unpack_h2(u, XD == 2);
-            s0 += v.x; s1 += v.y;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    auto ld8 = [&](long long r, float (&f)[8]) {
+        const long long o = (base + r) * C + static_cast<long long>(v) * 8;
+        if (XD == 1) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + o));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + o) + 1);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + o));
+            const float2 a = unpack_h2(u.x, XD == 2), b = unpack_h2(u.y, XD == 2), c = unpack_h2(u.z, XD == 2), d = unpack_h2(u.w, XD == 2);
+            f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+        }
+    };
+    if (active) {
+        long long r = r0 + ty;
+        for (; r + 3LL * RP < r1; r += 4LL * RP) {
+            float f0[8], f1[8], f2[8], f3[8];
+            ld8(r, f0); ld8(r + RP, f1); ld8(r + 2LL * RP, f2); ld8(r + 3LL * RP, f3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += (f0[i] + f1[i]) + (f2[i] + f3[i]);
+        }
+        for (; r < r1; r += RP) {
+            float f0[8];
+            ld8(r, f0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f0[i];
         }
     }
-    float* dst = partial + (static_cast<long long>(g) * chunks + chunk) * C + c;
-    dst[0] = s0; dst[1] = s1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = active ? acc[i] : 0.f;
+    __syncthreads();
+    if (ty == 0 && v < VPR) {
+        float* dst = partial + (static_cast<long long>(g) * chunks + chunk) * C + static_cast<long long>(v) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = 0.f;
+            for (int k = 0; k < RP; ++k) t += red[(k * vpb + tx) * 8 + i];
+            dst[i] = t;
+        }
+    }
 }
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int C,
                                                            int chunks, int groups, float scale, int accumulate) {
@@ -549,11 +587,12 @@ int dfw_colsum(const void* x, int dtype, float* out, long long rows_per_group, i
     using namespace dfw;
     int rc = require_sm100();
     if (rc != DFW_OK) return rc;
-    DFW_REQUIRE(x && out && workspace && rows_per_group > 0 && groups > 0 && groups < 65536 && C > 0 && C % 2 == 0);
+    DFW_REQUIRE(x && out && workspace && rows_per_group > 0 && groups > 0 && groups < 65536 && C > 0 && C % 8 == 0);
+    DFW_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     DFW_REQUIRE(dtype >= 0 && dtype <= 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const int chunks = dfw_colsum_chunks(rows_per_group, groups);
-    const dim3 grid((C / 2 + 255) / 256, chunks, groups);
+    const dim3 grid((C / 8 + 255) / 256, chunks, groups);
     if (dtype == 1) colsum_partial_kernel<1><<<grid, 256, 0, st>>>(x, workspace, rows_per_group, C, chunks);
     else if (dtype == 2) colsum_partial_kernel<2><<<grid, 256, 0, st>>>(x, workspace, rows_per_group, C, chunks);
     else colsum_partial_kernel<0><<<grid, 256, 0, st>>>(x, workspace, rows_per_group, C, chunks);

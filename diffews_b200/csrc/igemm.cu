@@ -1247,21 +1247,19 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     }
 }
 
-// Pick the output tile (TW x TH x TN = 128 pixels) that wastes the fewest out-of-range pixels.
+// Pick the output tile (TW x TH x TN = 128 pixels, powers of two) that covers the [N, H, W] pixel grid with the fewest
+// padded pixels; ties go to the wider (more contiguous) tile.  (Choosing TW alone by its own padding sent a token matrix
+// of 539 rows -- the 7 x 77 prompt tokens of a 7-shot support pass -- to TW = 1: 539 tiles of one valid row each.)
 void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
-    auto pick = [](int extent, int cap) {
-        int best = 1;
-        long long best_cost = -1;
-        for (int t = 1; t <= cap; t *= 2) {
-            long long cost = static_cast<long long>((extent + t - 1) / t) * t;
-            if (best_cost < 0 || cost <= best_cost) { best = t; best_cost = cost; }
+    long long best = -1;
+    TW = 128; TH = 1; TN = 1;
+    for (int tw = 128; tw >= 1; tw /= 2)
+        for (int th = 128 / tw; th >= 1; th /= 2) {
+            const int tn = 128 / (tw * th);
+            const long long cost = (static_cast<long long>((W + tw - 1) / tw) * tw) * (static_cast<long long>((H + th - 1) / th) * th) *
+                                   (static_cast<long long>((N + tn - 1) / tn) * tn);
+            if (best < 0 || cost < best) { best = cost; TW = tw; TH = th; TN = tn; }
         }
-        return best;
-    };
-    TW = pick(W, 128);
-    TH = pick(H, 128 / TW);
-    TN = 128 / (TW * TH);
-    (void)N;
 }
 
 // Host side of the T128 variant (see igemm_t128_kernel).  Returns DFW_OK after launching, or 1 when the layer is not

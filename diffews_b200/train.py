@@ -492,8 +492,8 @@ class TResnet:
         self.shortcut = TConv(store, sd, prefix + ".conv_shortcut") if (prefix + ".conv_shortcut.weight") in sd else None
         self.layers = [self.conv1, self.tproj, self.conv2] + ([self.shortcut] if self.shortcut else [])
 
-    def __call__(self, x, act_temb):
-        t = self.conv1(GroupNormFn.apply(x, self.norm1, True), extra_bias=self.tproj(act_temb))
+    def __call__(self, x, temb_bias):
+        t = self.conv1(GroupNormFn.apply(x, self.norm1, True), extra_bias=temb_bias)
         s = x if self.shortcut is None else self.shortcut(x)
         return self.conv2(GroupNormFn.apply(t, self.norm2, True), residual=s)
 
@@ -593,6 +593,8 @@ class TrainableUNet:
         self.refresh_operands()
         self.transformers = [t for (_, att, _) in self.down for t in att] + [self.mid[1]] + \
                             [t for (_, att, _) in self.up for t in att]
+        self.resnets = [r for (res, _, _) in self.down for r in res] + [self.mid[0], self.mid[2]] + \
+                       [r for (res, _, _) in self.up for r in res]
 
     @classmethod
     def from_module(cls, module, device="cuda", **kw):
@@ -643,7 +645,15 @@ class TrainableUNet:
         e = self.te2(torch.nn.functional.silu(self.te1(emb)))
         return torch.nn.functional.silu(e)
 
-    def forward(self, sample, timestep, encoder_hidden_states, is_target: bool = True):
+    def time_biases(self, timestep):
+        """time_emb_proj(silu(time_embedding(t))) of every ResnetBlock2D, in execution order ([1, Cout] each).  The support
+        and the query pass of a step use the same timestep (train...v3.py:1365), so a step evaluates this chain once and
+        both passes add the same vectors; their gradients meet at these tensors."""
+        t_value = float(timestep.reshape(-1)[0]) if torch.is_tensor(timestep) else float(timestep)
+        act = self._time_act(t_value)
+        return [r.tproj(act) for r in self.resnets]
+
+    def forward(self, sample, timestep, encoder_hidden_states, is_target: bool = True, temb_biases=None):
         """sample fp32 NCHW latents ([N,4,h,w] target / [N,8,h,w] support), encoder_hidden_states [N or 1, L, 1024].
         Returns the fp32 NCHW prediction; the support pass (is_target=False) stops once the last K/V bank is filled and
         returns None (its output only ever enters the loss multiplied by 0, train...v3.py:1381)."""
@@ -651,8 +661,7 @@ class TrainableUNet:
             raise RuntimeError("TrainableUNet (B200 engine) needs CUDA tensors: there is no CPU fallback")
         x = sample.to(torch.float32).contiguous()
         N = x.shape[0]
-        t_value = float(timestep.reshape(-1)[0]) if torch.is_tensor(timestep) else float(timestep)
-        act = self._time_act(t_value)
+        tb = iter(temb_biases if temb_biases is not None else self.time_biases(timestep))
         ehs = encoder_hidden_states.detach().to(device=self.device, dtype=self.half)
         if ehs.shape[0] == 1 and N > 1:
             ehs = ehs.expand(N, -1, -1)               # encoder_hidden_states.repeat(temp_nshot, 1, 1), train...v3.py:1370
@@ -662,19 +671,19 @@ class TrainableUNet:
         skips = [h]
         for res, att, dn in self.down:
             for j, r in enumerate(res):
-                h = r(h, act)
+                h = r(h, next(tb))
                 if att:
                     h = att[j](h, ehs)
                 skips.append(h)
             if dn is not None:
                 h = dn(h)
                 skips.append(h)
-        h = self.mid[0](h, act)
+        h = self.mid[0](h, next(tb))
         h = self.mid[1](h, ehs)
-        h = self.mid[2](h, act)
+        h = self.mid[2](h, next(tb))
         for bi, (res, att, up) in enumerate(self.up):
             for j, r in enumerate(res):
-                h = r(ConcatFn.apply(h, skips.pop()), act)
+                h = r(ConcatFn.apply(h, skips.pop()), next(tb))
                 if att:
                     last = (not is_target) and bi == 3 and j == 2
                     h = att[j](h, ehs, bank_only=last)
@@ -748,8 +757,9 @@ class Trainer:
         self.store.begin_step()
         u.clear_attn_bank()
         with torch.enable_grad():
-            u(latents_ref, timestep, ehs if ehs.shape[0] == 1 else ehs.repeat_interleave(k, 0), is_target=False)
-            pred = u(latents_tag, timestep, ehs, is_target=True)
+            tb = u.time_biases(timestep)
+            u(latents_ref, timestep, ehs if ehs.shape[0] == 1 else ehs.repeat_interleave(k, 0), is_target=False, temb_biases=tb)
+            pred = u(latents_tag, timestep, ehs, is_target=True, temb_biases=tb)
         u.clear_attn_bank()
         loss, dpred = mse_loss(pred.detach(), target.float().contiguous(), upstream=self.loss_scale)
         pred.backward(dpred)

@@ -415,7 +415,7 @@ int dfw_conv_wgrad(const void* x, const void* dy, float* dw, int N, int Hin, int
  * (tap_map[t] = 8 - t), the four phase filters of the stride-2 transposed convolution. */
 int dfw_weight_permute(const void* w, void* out, int R, int T, int C, int T_out, const int* tap_map, void* stream);
 /* out[g, c] (=|+=) scale * sum over the rows of group g of x[g*rows_per_group + r, c]: bias gradients (groups = 1) and
- * per-image time-embedding gradients (groups = N).  dtype 0 bf16 / 1 fp32 / 2 fp16; C % 2 == 0; deterministic.
+ * per-image time-embedding gradients (groups = N).  dtype 0 bf16 / 1 fp32 / 2 fp16; C % 8 == 0; deterministic.
  * workspace: groups * dfw_colsum_chunks(rows_per_group, groups) * C floats. */
 int dfw_colsum_chunks(long long rows_per_group, int groups);
 int dfw_colsum(const void* x, int dtype, float* out, long long rows_per_group, int groups, int C, float scale, int accumulate,

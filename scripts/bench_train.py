@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default=None)
     ap.add_argument("--graph", action="store_true", help="capture forward + backward into a CUDA graph")
+    ap.add_argument("--layer-table", default=None, help="write the per-shape table of the instrumented step here")
     args = ap.parse_args()
     dev = "cuda"
     sd = random_unet_state_dict(0)
@@ -85,6 +86,15 @@ def main():
     for (kind, shape), d in timer.by_shape().items():
         if shape and shape.startswith("wgrad"):
             wg["launches"] += d["launches"]; wg["ms"] += d["ms"]; wg["flops"] += d["flops"]
+    if args.layer_table:
+        rows = sorted(timer.by_shape().items(), key=lambda kv: -kv[1]["ms"])
+        tot = sum(v["ms"] for _, v in rows)
+        with open(args.layer_table, "w") as f:
+            f.write(f"# per-shape CUDA-event times of one instrumented training step ({k}-shot, latent {hw}); summed kernel time {tot:.1f} ms\n")
+            f.write("kind\tshape\tlaunches\tms_total\tshare\tTFLOP/s (igemm, attn) | TB/s of algorithmic bytes (others)\n")
+            for (kind, shape), v in rows:
+                r = v["flops"] / (v["ms"] * 1e9) if v["ms"] > 0 else 0.0
+                f.write(f"{kind}\t{shape}\t{v['launches']}\t{v['ms']:.3f}\t{v['ms'] / tot:.4f}\t{r:.2f}\n")
     tensor_flops = sum(d["flops"] for kind, d in timer.summary().items() if kind in ("igemm", "attn"))
     line = {
         "what": "one training step of the DiffewS UNet (support pass + query pass + backward through both + clip + AdamW)",
