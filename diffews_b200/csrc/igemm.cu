@@ -15,9 +15,26 @@
 //  reach; diffews/marigold_pipeline_rgb_latent_noise.py:852-853,901-902 for the VAE).
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
+
+#ifndef DFW_GNIN_DBG
+#define DFW_GNIN_DBG 0          // ablation switches of the GN_IN transform (scripts/build_variant.sh); 0 in the product
+#endif
+
+#ifndef DFW_GNIN_TRACE
+#define DFW_GNIN_TRACE 0        // 1: CTA 0 of the GN_IN kernel accumulates phase cycle counts (dfw_debug_t128_trace)
+#endif
+#if DFW_GNIN_TRACE
+__device__ long long g_t128_trace[16];
+#define TR_T0() const long long tr_t0_ = clock64()
+#define TR_ADD(var) var += clock64() - tr_t0_
+#else
+#define TR_T0()
+#define TR_ADD(var)
+#endif
 
 namespace dfw {
 extern std::atomic<long long> g_launches;
@@ -906,16 +923,23 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 //   warp 1  MMA issuer      warp 2  TMEM allocator + weight-tile producer      warp 3  residual loader (TMA)
 //   warps 4-11  epilogue: channel quarter q = warp % 4, pixel half eg = (warp - 4) / 4 (tile rows 8 eg .. 8 eg + 7)
 // ---------------------------------------------------------------------------------------------------------
-struct T128Cfg {
+template <bool GN_IN>
+struct T128CfgT {
     static constexpr int PATCH_BYTES = 18 * 16 * 128;       // 36 KiB
     static constexpr int A_SLOTS = 3;
     static constexpr int W_TILE_BYTES = 128 * 128;          // 16 KiB
     static constexpr int W_SLOTS = 3;
     static constexpr int STG_BYTES = 64 * 64;               // 64 pixels x 32 channels x 2 B
-    static constexpr int NBAR = 3 * A_SLOTS + 2 * W_SLOTS + 4 + 32;
-    static constexpr int THREADS = IGEMM_THREADS;              // 12 warps
-    static constexpr int THREADS_GN = IGEMM_THREADS + 256;     // + 8 operand-transform warps (GroupNorm + SiLU on the fly)
-    static constexpr int SMEM_USED = A_SLOTS * PATCH_BYTES + W_SLOTS * W_TILE_BYTES + 16 * STG_BYTES + 8 * NBAR + 16;
+    static constexpr int STG_PER_WARP = 2;
+    // GN_IN: per-CTA ring of transformed (16+2) x (16+2)-pixel x 64-channel blocks in global memory (L2-resident)
+    static constexpr int XF_BUFS = 4;
+    static constexpr int XF_BUF_BYTES = 18 * 18 * 128;      // 40.5 KiB
+    static constexpr int NBAR = 3 * A_SLOTS + 2 * W_SLOTS + 4 + 32 + 2 * XF_BUFS;
+    static constexpr int XF_WARPS = 8;                         // GN_IN: operand-transform warps (GroupNorm + SiLU on the fly)
+    static constexpr int THREADS = IGEMM_THREADS + (GN_IN ? 32 * XF_WARPS : 0);     // 12 (+ 8) warps
+    static constexpr int SS_MAX_CIN = 512;                  // GN_IN: scale / shift of the current image live in smem (2 x Cin floats)
+    static constexpr int SS_BYTES = GN_IN ? 2 * SS_MAX_CIN * 4 + 16 : 0;
+    static constexpr int SMEM_USED = A_SLOTS * PATCH_BYTES + W_SLOTS * W_TILE_BYTES + 8 * STG_PER_WARP * STG_BYTES + 8 * NBAR + 16 + SS_BYTES;
     static constexpr int SMEM_BYTES = SMEM_USED + 512;      // smem is declared __align__(1024); the kernel traps otherwise
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
@@ -937,17 +961,25 @@ struct T128Params {
     long long gn_img_stride;
     const float* gn_in;   // GN_IN: [N][2][Cin] fp32 scale / shift of the GroupNorm (+ SiLU) applied to x on the fly
     int Cin;
+    const void* x;        // GN_IN: the raw activation tensor (the transform warps read it with plain loads)
+    void* xf_scratch;     // GN_IN: [gridDim.x][XF_BUFS][18][18][64] 16-bit ring of transformed blocks (maps.patch views it)
 };
 
-// GN_IN: the convolution consumes silu(groupnorm(x)) without that tensor ever existing: eight extra warps rewrite every
-// patch in place (fp32: x * scale[n, c] + shift[n, c], SiLU through one tanh.approx; pixels outside the image stay 0 =
-// the zero padding of the normalised tensor) between its TMA arrival and its MMAs.  Saves the GroupNorm-apply pass
-// (one HBM read + write of the activation) at the price of transforming each element three times (one per horizontal
-// tap) on otherwise idle FMA / MUFU pipes.
+// GN_IN: the convolution consumes silu(groupnorm(x)) without that tensor ever reaching HBM.  Eight extra warps read the
+// raw (16+2) x (16+2)-pixel neighbourhood of every (tile, 64-channel block) ONCE with plain 16-byte loads (8 threads = the
+// 128 contiguous bytes of a pixel; two register sets, so the loads of block i + 1 are in flight while block i is
+// processed), apply x * scale[n, c] + shift[n, c] and SiLU in registers (fp32, one tanh.approx per element; pixels outside
+// the image become 0 = the zero padding of the normalised tensor) and store the block into a small per-CTA ring in global
+// memory (4 x 40.5 KiB per CTA, 24 MB in all: it lives in L2).  The ordinary TMA patch producer then loads the three
+// horizontally shifted patches from the ring exactly as it would from the activation tensor, so the shared-memory side
+// of the kernel is the plain one.  Measured dead ends (profiles/r02_gnin_*.json): rewriting each TMA-loaded patch in place
+// (3 transforms + an smem round trip per element: MUFU-bound, 0.6x the plain kernel); writing the three shifted patches
+// with st.shared from registers (one transform per element, but generic-proxy smem stores get ~30 B/clk next to a running
+// tcgen05.mma that reads 96 B/clk: 2800-3100 cycles per block for the stores alone against 4608 of MMA).
 template <bool GN_IN>
-__global__ void __launch_bounds__(GN_IN ? T128Cfg::THREADS_GN : T128Cfg::THREADS, 1)
+__global__ void __launch_bounds__(T128CfgT<GN_IN>::THREADS, 1)
 igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__ T128Params p) {
-    using Cfg = T128Cfg;
+    using Cfg = T128CfgT<GN_IN>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -955,20 +987,25 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     auto sP = [&](int s) { return base + s * Cfg::PATCH_BYTES; };
     auto sW = [&](int s) { return base + Cfg::A_SLOTS * Cfg::PATCH_BYTES + s * Cfg::W_TILE_BYTES; };
     const uint32_t stg_base = base + Cfg::A_SLOTS * Cfg::PATCH_BYTES + Cfg::W_SLOTS * Cfg::W_TILE_BYTES;
-    auto sS = [&](int w8, int b) { return stg_base + (w8 * 2 + b) * Cfg::STG_BYTES; };
-    const uint32_t bar = stg_base + 16 * Cfg::STG_BYTES;
+    auto sidx = [&](int w8, int b) { return Cfg::STG_PER_WARP == 2 ? w8 * 2 + b : w8; };      // staging block of (warp, sub-block)
+    auto sS = [&](int w8, int b) { return stg_base + sidx(w8, b) * Cfg::STG_BYTES; };
+    const uint32_t bar = stg_base + 8 * Cfg::STG_PER_WARP * Cfg::STG_BYTES;
     auto pa_full = [&](int i) { return bar + 8u * i; };
     auto pa_empty = [&](int i) { return bar + 8u * (Cfg::A_SLOTS + i); };
     auto w_full = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + i); };
     auto w_empty = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + Cfg::W_SLOTS + i); };
     auto pa_ready = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + i); };     // GN_IN: transformed
-    const uint32_t b2 = bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS);
+    auto xf_ready = [&](int i) { return bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + i); };                   // GN_IN ring
+    auto xf_free = [&](int i) { return bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + Cfg::XF_BUFS + i); };
+    const uint32_t b2 = bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + 2 * Cfg::XF_BUFS);
     auto tfull = [&](int a) { return b2 + 8u * a; };
     auto tempty = [&](int a) { return b2 + 8u * (2 + a); };
     auto res_full = [&](int i) { return b2 + 8u * (4 + i); };        // i = warp8 * 2 + buffer
     auto buf_free = [&](int i) { return b2 + 8u * (20 + i); };
     const uint32_t tmem_slot = b2 + 8u * 36;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    const uint32_t ss_base = (tmem_slot + 16 + 15) & ~15u;   // GN_IN: 2 x Cin floats, 16-byte aligned
+    (void)ss_base;
 
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -979,6 +1016,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(pa_full(i), 1); mbar_init(pa_empty(i), 1); mbar_init(pa_ready(i), 8); }
         for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+        for (int i = 0; i < Cfg::XF_BUFS; ++i) { mbar_init(xf_ready(i), Cfg::XF_WARPS); mbar_init(xf_free(i), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
         for (int i = 0; i < 16; ++i) { mbar_init(res_full(i), 1); mbar_init(buf_free(i), 1); }
         fence_mbar_init();
@@ -1003,24 +1041,36 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         w0 = (r % p.tiles_w) * 16;
     };
 
+    // GN_IN: 640 threads leave 96 registers per thread, but the transform warps want two 44-register load buffers; the
+    // four single-thread role warps give theirs up (setmaxnreg is per warpgroup: 0 = roles, 1-2 = epilogue, 3-4 = transform)
+    if (warp < 4) {
+    if constexpr (GN_IN) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
         int as = 0;
         uint32_t aph = 0;
+        int xb = 0;                      // GN_IN: ring buffer of the current channel block
+        uint32_t xph = 0;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             int n, slab, h0, w0;
             decode(u, n, slab, h0, w0);
             const int pad = p.ktaps >> 1;
             const uint32_t patch_bytes = (16 + 2 * pad) * 16 * 128;
-            for (int kb = 0; kb < p.kb_per_tap; ++kb)
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                if constexpr (GN_IN) mbar_wait(xf_ready(xb), xph, 20);        // the transformed block is in the ring
                 for (int dw = 0; dw < p.ktaps; ++dw) {
                     mbar_wait(pa_empty(as), aph ^ 1u, 21);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(pa_full(as), patch_bytes);
-                        tma_load_4d(sP(as), &maps.patch, pa_full(as), kb * BLOCK_K, w0 + dw - pad, h0 - pad, n);
+                        if constexpr (GN_IN)
+                            tma_load_4d(sP(as), &maps.patch, pa_full(as), 0, dw, 0, blockIdx.x * Cfg::XF_BUFS + xb);
+                        else
+                            tma_load_4d(sP(as), &maps.patch, pa_full(as), kb * BLOCK_K, w0 + dw - pad, h0 - pad, n);
                     }
                     __syncwarp();
                     if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
                 }
+                if (++xb == Cfg::XF_BUFS) { xb = 0; xph ^= 1u; }
+            }
         }
     } else if (warp == 2) {
         int ws = 0;
@@ -1043,19 +1093,20 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     } else if (warp == 1) {
         const uint32_t fmt = p.f16 ? 0u : 1u;
         const uint32_t idesc = umma_idesc(128, 256, fmt, fmt, 0);
-        int as = 0, ws = 0, acc = 0;
+        int as = 0, ws = 0, acc = 0, xb = 0;
         uint32_t aph = 0, wph = 0, acc_phase = 0;
+        long long trA = 0, trW = 0, trAcc = 0, trTot = clock64();
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-            mbar_wait(tempty(acc), acc_phase ^ 1u, 23);
+            { TR_T0(); mbar_wait(tempty(acc), acc_phase ^ 1u, 23); TR_ADD(trAcc); }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
             bool first = true;
             const int last = p.ktaps - 1;
             for (int kb = 0; kb < p.kb_per_tap; ++kb)
                 for (int dw = 0; dw < p.ktaps; ++dw) {
-                    mbar_wait(GN_IN ? pa_ready(as) : pa_full(as), aph, 24);
+                    { TR_T0(); mbar_wait(pa_full(as), aph, 24); TR_ADD(trA); }
                     for (int dh = 0; dh < p.ktaps; ++dh) {
-                        mbar_wait(w_full(ws), wph, 25);
+                        { TR_T0(); mbar_wait(w_full(ws), wph, 25); TR_ADD(trW); }
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t adesc = umma_desc_sw128(sW(ws));
@@ -1065,6 +1116,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                                 umma_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (!first || k > 0) ? 1u : 0u);
                             tc_commit(w_empty(ws));
                             if (dh == last) tc_commit(pa_empty(as));
+                            if (GN_IN && dh == last && dw == last) tc_commit(xf_free(xb));   // (its TMA reads ended long before)
                             if (dh == last && dw == last && kb == p.kb_per_tap - 1) tc_commit(tfull(acc));
                         }
                         __syncwarp();
@@ -1072,10 +1124,18 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                         if (++ws == Cfg::W_SLOTS) { ws = 0; wph ^= 1u; }
                     }
                     if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
+                    if (dw == last && ++xb == Cfg::XF_BUFS) xb = 0;
                 }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+#if DFW_GNIN_TRACE
+        if (blockIdx.x == 0 && lane == 0) {
+            g_t128_trace[0] += clock64() - trTot; g_t128_trace[1] += trA; g_t128_trace[2] += trW; g_t128_trace[3] += trAcc;
+        }
+#else
+        (void)trA; (void)trW; (void)trAcc; (void)trTot;
+#endif
     } else if (warp == 3) {
         if (p.has_res) {
             uint32_t k = 0;
@@ -1084,8 +1144,10 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                 decode(u, n, slab, h0, w0);
                 for (int sb = 0; sb < 2; ++sb)
                     for (int w8 = 0; w8 < 8; ++w8) {
-                        const int i = w8 * 2 + sb;
-                        mbar_wait(buf_free(i), (k & 1u) ^ 1u, 26);        // the store that last used this block has drained
+                        const int i = sidx(w8, sb);
+                        // use count of block i so far: k (two blocks per warp) or 2 k + sb (one block per warp)
+                        const uint32_t uses = Cfg::STG_PER_WARP == 2 ? k : 2u * k + sb;
+                        mbar_wait(buf_free(i), (uses & 1u) ^ 1u, 26);     // the store that last used this block has drained
                         if (elect_one()) {
                             mbar_arrive_expect_tx(res_full(i), Cfg::STG_BYTES);
                             tma_load_4d(sS(w8, sb), &maps.res, res_full(i), slab * 128 + 32 * (w8 & 3), w0,
@@ -1095,62 +1157,170 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                     }
             }
         }
+    }
     } else if (warp >= 12) {
         if constexpr (GN_IN) {
-            // operand transform: 256 threads, thread = (16-byte unit u of a 128-byte row, row r0 + 32 i)
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+            // Transform warps.  Thread = (16-byte unit `un` of a pixel's 128-byte channel block, pixel lane p0 of 32); a warp
+            // instruction reads / writes 4 whole pixels.  The raw (16 + 2 pad)^2 neighbourhood is split so that every address
+            // is affine in the loop index: MAIN = rows rr + 2 i (i < 8 + pad) x the 16 tile columns (always inside the image
+            // horizontally); HALO = the left / right neighbour columns (pad only), 36 pixels = slot 9 of every lane + slot 10
+            // of four lanes.  Ring block layout: [18 rows][18 columns][64 channels] (pad = 0 uses its 16 x 16 corner).
+            constexpr int MAXU = 11;
             const int t = threadIdx.x - 12 * 32;
-            const int un = t & 7, r0 = t >> 3;
+            const int un = t & 7, p0 = t >> 3;
+            const int x = p0 & 15, rr = p0 >> 4;
             const int pad = p.ktaps >> 1;
-            const int prow_n = (16 + 2 * pad) * 16;
-            uint8_t* patch0 = smem_raw + (base - raw);
-            int as = 0;
-            uint32_t aph = 0;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-                int n, slab, h0, w0;
-                decode(u, n, slab, h0, w0);
-                const float* ssp = p.gn_in + static_cast<size_t>(n) * 2 * p.Cin + un * 8;
-                for (int kb = 0; kb < p.kb_per_tap; ++kb) {
-                    float sc[8], sh[8];
-                    {
-                        const float4* a4 = reinterpret_cast<const float4*>(ssp + kb * BLOCK_K);
-                        const float4* b4 = reinterpret_cast<const float4*>(ssp + p.Cin + kb * BLOCK_K);
-                        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-                        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
-                        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
-                    }
-                    for (int dw = 0; dw < p.ktaps; ++dw) {
-                        mbar_wait(pa_full(as), aph, 29);
-                        uint8_t* pb = patch0 + as * Cfg::PATCH_BYTES;
-#pragma unroll 3
-                        for (int r = r0; r < prow_n; r += 32) {
-                            const int hh = h0 - pad + (r >> 4), ww = w0 + dw - pad + (r & 15);
-                            if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {           // outside: stays 0 (padding)
-                                uint4* ptr = reinterpret_cast<uint4*>(pb + r * 128 + ((un ^ (r & 7)) << 4));
-                                uint4 v = *ptr;
-                                uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+            const int NI = 8 + pad;
+            const int hc = p0 & 1;                                   // halo: 0 = left neighbour column, 1 = right
+            const int hr9 = p0 >> 1, hr10 = 16 + (p0 >> 1);          // halo rows of slots 9 / 10 (slot 10: p0 < 4 only)
+            const int C8 = p.Cin >> 3;                               // 16-byte units per pixel
+            const long long rs2 = 2LL * p.W * C8;
+            uint4* ring = reinterpret_cast<uint4*>(p.xf_scratch) +
+                          static_cast<size_t>(blockIdx.x) * Cfg::XF_BUFS * (Cfg::XF_BUF_BYTES / 16) + un;
+            const int om = ((rr * 18) + pad + x) * 8;               // main slot i: + i * 36 * 8
+            const int o9 = (hr9 * 18 + 17 * hc) * 8, o10 = (hr10 * 18 + 17 * hc) * 8;
+            float* ss_smem = reinterpret_cast<float*>(smem_raw + (ss_base - raw));
+            int xb = 0;
+            uint32_t xph = 0;
+            auto transform = [&](auto F16TAG, uint4 (&v)[MAXU], uint32_t inb, const float4 (&ss)[4]) {
+                constexpr bool F16 = decltype(F16TAG)::value;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 xx = unpack_h2(vw[j], p.f16);
-                                    const float y0 = fmaf(xx.x, sc[2 * j], sh[2 * j]);
-                                    const float y1 = fmaf(xx.y, sc[2 * j + 1], sh[2 * j + 1]);
-                                    float t0, t1;
-                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0));
-                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1));
-                                    const float h0f = 0.5f * y0, h1f = 0.5f * y1;
-                                    vw[j] = pack_h2(fmaf(h0f, t0, h0f), fmaf(h1f, t1, h1f), p.f16);
-                                }
-                                *ptr = v;
+                for (int i = 0; i < MAXU; ++i) {
+                    if (!(DFW_GNIN_DBG & 2) && (inb & (1u << i))) {      // outside the image: stays 0 (padding of the NORMALISED tensor)
+                        uint32_t* vw = reinterpret_cast<uint32_t*>(&v[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x0, x1;
+                            if constexpr (F16) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vw[j]));
+                                x0 = f.x; x1 = f.y;
+                            } else {
+                                x0 = bf16_lo(vw[j]); x1 = bf16_hi(vw[j]);
                             }
+                            const float4 sc4 = ss[j >> 1], sh4 = ss[2 + (j >> 1)];
+                            const float g0 = fmaf(x0, (j & 1) ? sc4.z : sc4.x, (j & 1) ? sh4.z : sh4.x);
+                            const float g1 = fmaf(x1, (j & 1) ? sc4.w : sc4.y, (j & 1) ? sh4.w : sh4.y);
+                            float t0, t1;
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(g0));
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(g1));
+                            const float y0 = fmaf(g0, t0, g0), y1 = fmaf(g1, t1, g1);
+                            vw[j] = F16 ? pack_f16x2(y0, y1) : pack_bf16x2(y0, y1);
                         }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(pa_ready(as));
-                        if (++as == Cfg::A_SLOTS) { as = 0; aph ^= 1u; }
                     }
                 }
+            };
+            long long trL = 0, trS = 0, trWr = 0, trN = 0, trF = 0, trTot = clock64();
+            // raw loads of one (tile, channel block): 11 x 16 bytes per thread, zero where the pixel is outside the image
+            auto issue = [&](uint4 (&v)[MAXU], uint32_t& inb, int& n, int u, int kb) {
+                int slab, h0, w0;
+                decode(u, n, slab, h0, w0);
+                const uint4* ximg = reinterpret_cast<const uint4*>(p.x) + static_cast<long long>(n) * p.H * p.W * C8 + un +
+                                    kb * (BLOCK_K / 8);
+                const bool top = pad && h0 == 0, bot = pad && h0 + 16 == p.H;
+                const bool colok = pad && !(hc == 0 ? w0 == 0 : w0 + 16 == p.W);
+                inb = (1u << NI) - 1u;
+                if (top && rr == 0) inb &= ~1u;
+                if (bot && rr == 1) inb &= ~(1u << (NI - 1));
+                if (colok && !(top && hr9 == 0)) inb |= 1u << 9;
+                if (colok && p0 < 4 && !(bot && hr10 == 17)) inb |= 1u << 10;
+                const uint4* gm = ximg + (static_cast<long long>(h0 - pad + rr) * p.W + (w0 + x)) * C8;
+                const uint4* g9 = ximg + (static_cast<long long>(h0 - 1 + hr9) * p.W + (w0 - 1 + 17 * hc)) * C8;
+                const uint4* g10 = g9 + 16LL * p.W * C8;
+#pragma unroll
+                for (int i = 0; i < MAXU; ++i) {
+                    v[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (inb & (1u << i)) {
+#if DFW_GNIN_DBG & 1
+                        v[i] = make_uint4(0x3c003800u + h0, 0x3c003800u, 0x3c003800u + w0, 0x3c003800u);
+#else
+                        v[i] = __ldg(i < 9 ? gm + i * rs2 : (i == 9 ? g9 : g10));
+#endif
+                    }
+                }
+            };
+            // transform in registers, then into the ring
+            // The proxy fence that publishes the ring stores of block i waits for them to reach L2 (MEMBAR.GPU, ~1000
+            // cycles right after the stores), so it is issued one block late, after the transform of block i + 1.
+            int pend = -1;                             // ring block whose stores are not yet published
+            auto publish = [&]() {
+                if (pend >= 0) {
+                    fence_proxy_async_all();          // generic-proxy global stores -> visible to the TMA (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(xf_ready(pend));
+                    pend = -1;
+                }
+            };
+            int ss_n = -1;                              // image whose (halved) scale / shift are in smem
+            auto process = [&](uint4 (&v)[MAXU], uint32_t inb, int n, int kb) {
+                TR_T0();
+                if (n != ss_n) {                        // a CTA meets the images in order: every transform warp gets here together
+                    named_bar_sync(1, 32 * Cfg::XF_WARPS);             // everybody is done with the previous image's values
+                    const float* src = p.gn_in + static_cast<size_t>(n) * 2 * p.Cin;
+                    for (int i = t; i < 2 * p.Cin; i += 32 * Cfg::XF_WARPS)
+                        ss_smem[i] = 0.5f * __ldg(src + i);            // silu(y) = h + h tanh(h), h = y / 2 (exact scaling)
+                    named_bar_sync(1, 32 * Cfg::XF_WARPS);
+                    ss_n = n;
+                }
+                float4 ss[4];
+                {
+                    const float4* s4 = reinterpret_cast<const float4*>(ss_smem + kb * BLOCK_K + un * 8);
+                    ss[0] = s4[0]; ss[1] = s4[1];
+                    const float4* h4 = reinterpret_cast<const float4*>(ss_smem + p.Cin + kb * BLOCK_K + un * 8);
+                    ss[2] = h4[0]; ss[3] = h4[1];
+                }
+                if (p.f16) transform(std::true_type{}, v, inb, ss);
+                else transform(std::false_type{}, v, inb, ss);
+#if DFW_GNIN_TRACE
+                asm volatile("" :: "r"(v[0].x), "r"(v[5].y), "r"(v[8].z), "r"(v[9].w));
+                TR_ADD(trL); ++trN;
+#endif
+                { TR_T0(); publish(); TR_ADD(trF); }
+                { TR_T0(); mbar_wait(xf_free(xb), xph ^ 1u, 29); TR_ADD(trS); }      // the MMAs that read this ring block are done
+                {
+                    TR_T0();
+                    uint4* dst = ring + xb * (Cfg::XF_BUF_BYTES / 16);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i)
+                        if (!(DFW_GNIN_DBG & 4) && i < NI) dst[om + i * (36 * 8)] = v[i];
+                    if (!(DFW_GNIN_DBG & 4) && pad) {
+                        dst[o9] = v[9];
+                        if (p0 < 4) dst[o10] = v[10];
+                    }
+                    TR_ADD(trWr);
+                }
+                pend = xb;
+                if (++xb == Cfg::XF_BUFS) { xb = 0; xph ^= 1u; }
+            };
+            // software pipeline over the flattened (tile, channel block) stream: the loads of block i + 1 are in flight
+            // (second register set) while block i is transformed and written
+            uint4 vA[MAXU], vB[MAXU];
+            uint32_t inbA = 0, inbB = 0;
+            int nA = 0, nB = 0, kbA = 0, kbB = 0;
+            int u = blockIdx.x, kb = 0;
+            auto advance = [&](int& uu, int& kk) { if (++kk == p.kb_per_tap) { kk = 0; uu += gridDim.x; } };
+            if (u < p.total_units) { issue(vA, inbA, nA, u, kb); kbA = kb; }
+            while (u < p.total_units) {
+                advance(u, kb);
+                if (u < p.total_units) { issue(vB, inbB, nB, u, kb); kbB = kb; }
+                process(vA, inbA, nA, kbA);
+                if (u >= p.total_units) break;
+                advance(u, kb);
+                if (u < p.total_units) { issue(vA, inbA, nA, u, kb); kbA = kb; }
+                process(vB, inbB, nB, kbB);
             }
+            publish();
+#if DFW_GNIN_TRACE
+            if (blockIdx.x == 0 && t == 0) {
+                g_t128_trace[4] += clock64() - trTot; g_t128_trace[5] += trL; g_t128_trace[6] += trS; g_t128_trace[7] += trWr;
+                g_t128_trace[8] += trN; g_t128_trace[9] += trF;
+            }
+#else
+            (void)trL; (void)trS; (void)trWr; (void)trN; (void)trTot; (void)trF;
+#endif
         }
     } else {
+        if constexpr (GN_IN) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         const int w8 = warp - 4;
         const int q = w8 & 3, eg = w8 >> 2;
         const int ch = 32 * q + lane;                    // channel inside the 128-channel slab
@@ -1190,11 +1360,12 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
             const uint32_t taddr = tmem_base + acc * 256 + eg * 128 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int sb = 0; sb < 2; ++sb) {
-                uint16_t* stage = reinterpret_cast<uint16_t*>(stg_generic + (w8 * 2 + sb) * Cfg::STG_BYTES);
+                uint16_t* stage = reinterpret_cast<uint16_t*>(stg_generic + sidx(w8, sb) * Cfg::STG_BYTES);
                 if (has_res) {
-                    mbar_wait(res_full(w8 * 2 + sb), k & 1u, 28);
+                    mbar_wait(res_full(sidx(w8, sb)), (Cfg::STG_PER_WARP == 2 ? k : 2u * k + sb) & 1u, 28);
                 } else {
-                    if (lane == 0) tma_store_wait_read<1>();          // this block's previous store (two stores ago) has drained
+                    // this block's previous store (two stores ago / the last one) has drained
+                    if (lane == 0) tma_store_wait_read<Cfg::STG_PER_WARP - 1>();
                     __syncwarp();
                 }
 #pragma unroll 1
@@ -1214,7 +1385,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                         gs += f; gss = fmaf(f, f, gss);
                         sp[i * 32] = static_cast<uint16_t>(pack_h2(f, 0.f, f16) & 0xffffu);
                     }
-                    if (has_res && half == 0 && free_i >= 0) {
+                    if (Cfg::STG_PER_WARP == 2 && has_res && half == 0 && free_i >= 0) {
                         if (lane == 0) {
                             tma_store_wait_read<0>();                   // the previous sub-block's store has drained
                             mbar_arrive(buf_free(free_i));
@@ -1227,8 +1398,12 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                 if (lane == 0) {
                     tma_store_4d(&maps.out, sS(w8, sb), slab * 128 + 32 * q, w0, h0 + 8 * eg + 4 * sb, n);
                     tma_store_commit();
+                    if (Cfg::STG_PER_WARP == 1 && has_res) {            // single block: hand it back as soon as the store has read it
+                        tma_store_wait_read<0>();
+                        mbar_arrive(buf_free(w8));
+                    }
                 }
-                free_i = w8 * 2 + sb;
+                free_i = sidx(w8, sb);
             }
             tc_fence_before();
             __syncwarp();
@@ -1247,19 +1422,35 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     }
 }
 
-// Pick the output tile (TW x TH x TN = 128 pixels, powers of two) that covers the [N, H, W] pixel grid with the fewest
-// padded pixels; ties go to the wider (more contiguous) tile.  (Choosing TW alone by its own padding sent a token matrix
-// of 539 rows -- the 7 x 77 prompt tokens of a 7-shot support pass -- to TW = 1: 539 tiles of one valid row each.)
+// Pick the output tile (TW x TH x TN = 128 pixels, powers of two).  Images: TW, then TH, by the padding of their own
+// extent (ties to the larger tile), TN = what is left -- a choice that does NOT depend on N, so an episode computed in a
+// batch takes the same kernel path (halo / generic mainloop, fused-statistics grouping) as computed alone and the results
+// are bit-identical (tests: batched == singletons).  Token matrices (1 x M "images", N = 1, M >= 128): fewest padded rows over all
+// shapes, ties to the wider tile (by its own padding a 539-row matrix -- the 7 x 77 prompt tokens of a 7-shot support
+// pass -- went to TW = 1: 539 tiles of one valid row each).
 void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
-    long long best = -1;
-    TW = 128; TH = 1; TN = 1;
-    for (int tw = 128; tw >= 1; tw /= 2)
-        for (int th = 128 / tw; th >= 1; th /= 2) {
-            const int tn = 128 / (tw * th);
-            const long long cost = (static_cast<long long>((W + tw - 1) / tw) * tw) * (static_cast<long long>((H + th - 1) / th) * th) *
-                                   (static_cast<long long>((N + tn - 1) / tn) * tn);
-            if (best < 0 || cost < best) { best = cost; TW = tw; TH = th; TN = tn; }
+    if (H == 1 && N == 1 && W >= 128) {
+        long long best = -1;
+        TW = 128; TH = 1; TN = 1;
+        for (int tw = 128; tw >= 1; tw /= 2) {
+            const int tn = 128 / tw;
+            const long long cost = (static_cast<long long>((W + tw - 1) / tw) * tw) * tn;
+            if (best < 0 || cost < best) { best = cost; TW = tw; TN = tn; }
         }
+        return;
+    }
+    auto pick = [](int extent, int cap) {
+        int best = 1;
+        long long best_cost = -1;
+        for (int t = 1; t <= cap; t *= 2) {
+            const long long cost = static_cast<long long>((extent + t - 1) / t) * t;
+            if (best_cost < 0 || cost <= best_cost) { best = t; best_cost = cost; }
+        }
+        return best;
+    };
+    TW = pick(W, 128);
+    TH = pick(H, 128 / TW);
+    TN = 128 / (TW * TH);
 }
 
 // Host side of the T128 variant (see igemm_t128_kernel).  Returns DFW_OK after launching, or 1 when the layer is not
@@ -1267,7 +1458,8 @@ void choose_tile(int W, int H, int N, int& TW, int& TH, int& TN) {
 int try_launch_t128(const void* x, const void* w, const float* bias, const void* residual, void* y, int N, int Hin, int Win,
                     int Cin, int Cout, int ksize, int stride, int pad_mode, int flags, float out_scale, int bias_sample_stride,
                     long long w_row_stride, long long w_batch_stride, int up_phase, float* gn_partial, int gn_groups,
-                    long long gn_img_stride, cudaStream_t stream, const float* gn_in = nullptr, bool dry_run = false) {
+                    long long gn_img_stride, cudaStream_t stream, const float* gn_in = nullptr, bool dry_run = false,
+                    void* xf_scratch = nullptr) {
     const bool enabled = get_option(DFW_OPT_T128) != 0;
     const int max_cout = get_option(DFW_OPT_T128_MAXC);
     // a token matrix [M, K] (linear layers arrive as a 1 x M image) is the image [M / 16, 16]: a 16 x 16 tile is then 256
@@ -1285,6 +1477,7 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     const int n_slabs = (Cout + 127) / 128;
     const long long units = static_cast<long long>(N) * n_slabs * (Hin / 16) * (Win / 16);
     if (units < 4LL * sm_count() || units >= (1LL << 31)) return 1;
+    if (gn_in != nullptr && Cin > T128CfgT<true>::SS_MAX_CIN) return 1;
     if (dry_run) return DFW_OK;
     T128Maps maps;
     T128Params p{};
@@ -1304,9 +1497,20 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     p.gn_img_stride = gn_img_stride > 0 ? gn_img_stride : static_cast<long long>(sm_count()) * GN_SLOTS_PER_CTA * 64;
     p.gn_in = gn_in;
     p.Cin = Cin;
+    p.x = x;
+    p.xf_scratch = xf_scratch;
     const uint64_t esz = 2;
+    const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
     int rc;
-    {
+    if (gn_in != nullptr) {
+        if (xf_scratch == nullptr || (reinterpret_cast<uintptr_t>(xf_scratch) & 127) != 0) return DFW_ERR_INVALID;
+        // the ring as a tensor [grid * XF_BUFS][18][18][64]; the patch of tap dw is the box at column dw
+        const uint64_t dims[4] = {BLOCK_K, 18, 18, static_cast<uint64_t>(grid) * T128CfgT<true>::XF_BUFS};
+        const uint64_t strides[3] = {BLOCK_K * esz, 18 * BLOCK_K * esz, 18 * 18 * BLOCK_K * esz};
+        const uint32_t box[4] = {BLOCK_K, 16, static_cast<uint32_t>(16 + ksize - 1), 1};
+        rc = encode_tmap_bf16_sw128(&maps.patch, xf_scratch, 4, dims, strides, box);
+        if (rc != DFW_OK) return rc;
+    } else {
         const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                                   static_cast<uint64_t>(N)};
         const uint64_t strides[3] = {Cin * esz, static_cast<uint64_t>(Win) * Cin * esz,
@@ -1340,15 +1544,14 @@ int try_launch_t128(const void* x, const void* w, const float* bias, const void*
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T128Cfg::SMEM_BYTES));
-        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T128Cfg::SMEM_BYTES));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T128CfgT<false>::SMEM_BYTES));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(igemm_t128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T128CfgT<true>::SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
     if (gn_in != nullptr)
-        DFW_CHECK_CUDA(launch_k(igemm_t128_kernel<true>, grid, T128Cfg::THREADS_GN, T128Cfg::SMEM_BYTES, stream, maps, p));
+        DFW_CHECK_CUDA(launch_k(igemm_t128_kernel<true>, grid, T128CfgT<true>::THREADS, T128CfgT<true>::SMEM_BYTES, stream, maps, p));
     else
-        DFW_CHECK_CUDA(launch_k(igemm_t128_kernel<false>, grid, T128Cfg::THREADS, T128Cfg::SMEM_BYTES, stream, maps, p));
+        DFW_CHECK_CUDA(launch_k(igemm_t128_kernel<false>, grid, T128CfgT<false>::THREADS, T128CfgT<false>::SMEM_BYTES, stream, maps, p));
     g_launches.fetch_add(1);
     DFW_CHECK_CUDA(cudaGetLastError());
     return DFW_OK;
@@ -1642,22 +1845,27 @@ int dfw_conv2d_igemm_gnstats(const void* x, const void* w, const float* bias, co
 int dfw_conv_gnin_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
     if (dfw::require_sm100() != DFW_OK) return 0;
     static unsigned char dummy[16] __attribute__((aligned(16)));
+    if (Cin > dfw::T128CfgT<true>::SS_MAX_CIN) return 0;
     return dfw::try_launch_t128(dummy, dummy, nullptr, nullptr, dummy, N, H, W, Cin, Cout, ksize, 1, 0, DFW_EPI_F16, 1.0f, 0,
                                 0, 0, -1, nullptr, 32, 0, nullptr, nullptr, true) == DFW_OK ? 1 : 0;
 }
 
 int dfw_conv2d_igemm_gnin(const void* x, const float* gn_scale_shift, const void* w, const float* bias,
                           const void* residual, void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int flags,
-                          float* gn_partial_out, void* stream) {
+                          float* gn_partial_out, void* scratch, void* stream) {
     int rc = dfw::require_sm100();
     if (rc != DFW_OK) return rc;
-    if (!x || !gn_scale_shift || !w || !y) return DFW_ERR_INVALID;
+    if (!x || !gn_scale_shift || !w || !y || !scratch) return DFW_ERR_INVALID;
     if (gn_partial_out != nullptr &&
         cudaMemsetAsync(gn_partial_out, 0, static_cast<size_t>(dfw_gn_partial_floats(N)) * sizeof(float),
                         static_cast<cudaStream_t>(stream)) != cudaSuccess) return DFW_ERR_CUDA;
     rc = dfw::try_launch_t128(x, w, bias, residual, y, N, Hin, Win, Cin, Cout, ksize, 1, 0, flags, 1.0f, 0, 0, 0, -1,
-                              gn_partial_out, 32, 0, static_cast<cudaStream_t>(stream), gn_scale_shift);
+                              gn_partial_out, 32, 0, static_cast<cudaStream_t>(stream), gn_scale_shift, false, scratch);
     return rc == 1 ? DFW_ERR_INVALID : rc;        // 1 = shape not eligible (ask dfw_conv_gnin_supported first)
+}
+
+long long dfw_conv_gnin_scratch_bytes(void) {
+    return static_cast<long long>(dfw::sm_count()) * dfw::T128CfgT<true>::XF_BUFS * dfw::T128CfgT<true>::XF_BUF_BYTES;
 }
 
 int dfw_bmm_nt(const void* x, const void* w, long long w_row_stride, long long w_batch_stride, const float* bias,
@@ -1675,3 +1883,12 @@ int dfw_linear(const void* x, const void* w, const float* bias, const void* resi
 }
 
 }  // extern "C"
+
+#if DFW_GNIN_TRACE
+extern "C" int dfw_debug_t128_trace(long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, g_t128_trace, sizeof(long long) * 16) != cudaSuccess) return -2;
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_t128_trace, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -113,6 +113,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_all() {     // all state spaces (generic-proxy GLOBAL writes -> TMA reads)
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // TMA

@@ -67,12 +67,25 @@ def _prep_w(w2d: torch.Tensor, taps: int, device, wdtype, f32: bool, role: int =
 def _split_in(x: torch.Tensor, half) -> torch.Tensor:
     return ops.split3(x, 0, half) if x.dtype == torch.float32 else x
 
-# Fold GroupNorm + SiLU into the consuming convolution (ops.conv2d_gn_in, bit-identical to norm kernel + conv).  OFF by
-# default: measured on B200 it loses -- the patch transform has to run once per horizontal tap (3x the elements, one MUFU
-# tanh each: 6.9k MUFU cycles per 9.2k MMA cycles of a tile), the VAE convolutions drop from 1.27-1.42 to 0.79-0.90
-# PFLOP/s, which costs more than the 16 ms / step of GroupNorm-apply passes it removes (111 vs 123 episodes/s).
-# Set layers.FUSE_GN_INTO_CONV = True before building the engines to enable it (no environment variable).
+# Fold GroupNorm + SiLU into the consuming convolution (ops.conv2d_gn_in, bit-identical to norm kernel + conv: the
+# normalised tensor never reaches HBM).  Measured on B200 (profiles/r02_gnin_bench.json): the fused kernel runs at ~0.8x the
+# plain convolution's rate (its transform warps share the SM with the MMA pipeline), so it wins exactly where the GroupNorm
+# pass it removes is large next to the convolution: +10 .. 14 % on 128->128 / 256->128 at 512^2 and 512->256 at 256^2
+# without a residual (kernel timed alone), break-even at 256->256, a loss with a residual operand or at 512 channels.  In
+# the whole step, which runs under the power cap, even the winning shapes give nothing back: 127.9 ms (off) / 129.2 ms
+# ("auto") / 133.3 ms (True) per step at config 2.  OFF by default.
+#   "auto": conv1 of a ResnetBlock when its input has >= 2^25 elements per 16 images;  True: wherever the kernel supports
+#   the shape;  False (default): never.  Set before building the engines (no environment variable; bench.py --gn-fusion).
 FUSE_GN_INTO_CONV = False
+FUSE_GN_MIN_ELEMS_PER_IMAGE = (1 << 25) // 16
+
+
+def _fuse_gn(x, has_residual: bool) -> bool:
+    if FUSE_GN_INTO_CONV is True:
+        return True
+    if FUSE_GN_INTO_CONV == "auto":
+        return (not has_residual) and x.shape[1] * x.shape[2] * x.shape[3] >= FUSE_GN_MIN_ELEMS_PER_IMAGE
+    return False
 
 
 def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
@@ -224,7 +237,7 @@ class Resnet:
         p = self.prec
         # GroupNorm + SiLU folded into the conv operand (no normalised tensor in HBM) where the kernel supports the
         # shape and the statistics of the input already exist; otherwise norm kernel + conv
-        if FUSE_GN_INTO_CONV and conv1_bias is None and not p.mid_f32 and self.norm1.groups == 32 \
+        if _fuse_gn(h, False) and conv1_bias is None and not p.mid_f32 and self.norm1.groups == 32 \
                 and ops.conv_gn_in_supported(h, self.conv1.cout, self.conv1.ksize):
             t = ops.conv2d_gn_in(h, self.norm1.g, self.norm1.b, self.norm1.eps, self.conv1.w, self.conv1.b,
                                  ksize=self.conv1.ksize, gn_stats=True)
@@ -232,7 +245,7 @@ class Resnet:
             a = self.norm1(h, silu=True)
             t = self.conv1(a, bias=conv1_bias, out_f32=p.mid_f32, gn_stats=True)
         s = h if self.shortcut is None else self.shortcut(to_operand(h, p), out_f32=p.stream_f32)
-        if FUSE_GN_INTO_CONV and not p.stream_f32 and self.norm2.groups == 32 \
+        if _fuse_gn(t, True) and not p.stream_f32 and self.norm2.groups == 32 \
                 and ops.conv_gn_in_supported(t, self.conv2.cout, self.conv2.ksize):
             return ops.conv2d_gn_in(t, self.norm2.g, self.norm2.b, self.norm2.eps, self.conv2.w, self.conv2.b,
                                     ksize=self.conv2.ksize, residual=s, gn_stats=gn_stats_out)

@@ -188,6 +188,18 @@ def conv_gn_in_supported(x, cout, ksize) -> bool:
     return bool(lib.dfw_conv_gnin_supported(N, H, W, Cin, cout, ksize))
 
 
+_gnin_scratch = {}
+
+
+def _gnin_scratch_for(device):
+    """The ring of transformed tiles dfw_conv2d_igemm_gnin keeps in L2: one per (device, stream), allocated once."""
+    key = (device.index, _stream())
+    buf = _gnin_scratch.get(key)
+    if buf is None:
+        buf = _gnin_scratch[key] = torch.empty(int(lib.dfw_conv_gnin_scratch_bytes()), device=device, dtype=torch.uint8)
+    return buf
+
+
 def conv2d_gn_in(x, gamma, beta, eps, w, bias=None, *, ksize, residual=None, gn_stats=False, groups=32):
     """conv(silu(groupnorm(x))) + bias (+ residual) with the normalisation applied to the conv operand on the fly:
     x 16-bit [N,H,W,Cin] with x._gn_partial (its statistics, from the conv that produced it); returns 16-bit [N,H,W,Cout]."""
@@ -209,7 +221,8 @@ def conv2d_gn_in(x, gamma, beta, eps, w, bias=None, *, ksize, residual=None, gn_
     with _Timed("igemm", 2.0 * N * H * W * Cout * ksize * ksize * Cin,
                 f"conv N{N} {H}x{W} {Cin}->{Cout} k{ksize} s1 gn-in" + (" +gn" if part_out is not None else "")):
         check(lib.dfw_conv2d_igemm_gnin(x.data_ptr(), ss.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(),
-                                        N, H, W, Cin, Cout, ksize, flags, _ptr(part_out), _stream()),
+                                        N, H, W, Cin, Cout, ksize, flags, _ptr(part_out),
+                                        _gnin_scratch_for(x.device).data_ptr(), _stream()),
               "dfw_conv2d_igemm_gnin")
     if part_out is not None:
         y._gn_partial = (part_out, part_out.numel() // (N * 64))

@@ -196,9 +196,12 @@ int dfw_groupnorm_from_partial(const void* x, int x_dtype, const float* partial,
  * reached from diffews/marigold_pipeline_rgb_latent_noise.py:852-853,901-902): dfw_gn_scale_shift turns the statistics a
  * producing conv emitted (gn_partial, nchunks as above) into per-(image, channel) scale / shift, fp32 [N][2][C];
  * dfw_conv2d_igemm_gnin computes conv(silu(x * scale + shift)) + bias (+ residual) without materialising the normalised
- * tensor (x, w, y, residual 16-bit of one format, flags = DFW_EPI_F16 or 0; stride 1, pad (ksize-1)/2; optional statistics
- * of ITS output in gn_partial_out).  Only for the shapes dfw_conv_gnin_supported accepts (Cout % 128 == 0, H, W % 16 == 0,
- * enough tiles to fill the GPU); otherwise use dfw_groupnorm_from_partial + dfw_conv2d_igemm. */
+ * tensor in HBM (x, w, y, residual 16-bit of one format, flags = DFW_EPI_F16 or 0; stride 1, pad (ksize-1)/2; optional
+ * statistics of ITS output in gn_partial_out).  scratch: dfw_conv_gnin_scratch_bytes() bytes of device memory, 128-byte
+ * aligned, contents irrelevant, owned by the caller and not shared between concurrently running calls (the kernel keeps a
+ * small per-CTA ring of transformed tiles there; it stays in L2).  Only for the shapes dfw_conv_gnin_supported accepts
+ * (Cout % 128 == 0, H, W % 16 == 0, enough tiles to fill the GPU); otherwise use dfw_groupnorm_from_partial +
+ * dfw_conv2d_igemm. */
 /* GroupNorm (+SiLU) BACKWARD (BASELINE config 4; the nn.GroupNorm -> SiLU autograd of every diffusers ResnetBlock2D in the
  * training step train_tools/train_icl_multitask_nocrop_nearest_nshot_v3.py:1320-1396).  x, dy, dx [N, HW, C] of one dtype
  * (0 bf16, 1 fp32, 2 fp16); dgamma, dbeta fp32 [C]; statistics are recomputed from x; deterministic (fixed-order folds). */
@@ -212,7 +215,8 @@ int dfw_gn_scale_shift(const float* partial, int nchunks, const float* gamma, co
 int dfw_conv_gnin_supported(int N, int H, int W, int Cin, int Cout, int ksize);
 int dfw_conv2d_igemm_gnin(const void* x, const float* gn_scale_shift, const void* w, const float* bias,
                           const void* residual, void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int flags,
-                          float* gn_partial_out, void* stream);
+                          float* gn_partial_out, void* scratch, void* stream);
+long long dfw_conv_gnin_scratch_bytes(void);
 
 /* K7  LayerNorm over the last dim. x [M, C] (x_dtype 0 bf16 / 1 fp32 / 2 fp16) -> y bf16 (fp16 if y_f16) [M, C].
  * C % 8 == 0, C <= 2048.
