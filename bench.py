@@ -258,11 +258,11 @@ def _loader_leg(args, runner, dev, rank, world, B, barrier, dist):
 def _igemm_traffic():
     """DRAM bytes of one launch of the dominant igemm shape, from the committed ncu --set full capture (GB), else None."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_igemm_traffic.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_igemm_traffic.json")) as f:
             t = json.load(f)
         return {"unit": "GB", "dram_per_launch": round(t["dram_bytes_per_launch"] / 1e9, 3),
                 "algorithmic_per_launch": round(t["algorithmic_bytes_per_launch"] / 1e9, 3), "layer": t["layer"],
-                "source": "profiles/r01_ncu_full_kernels.tsv"}
+                "source": "profiles/r02_ncu_t128.tsv"}
     except Exception:
         return None
 
