@@ -24,6 +24,14 @@
 #define DFW_GNIN_DBG 0          // ablation switches of the GN_IN transform (scripts/build_variant.sh); 0 in the product
 #endif
 
+#ifndef T128_A_SLOTS
+// patch ring / weight-tile ring depth of igemm_t128_kernel (36 KiB / 16 KiB per slot).  A patch feeds 1536 cycles of MMAs,
+// a weight tile 512: two patches cover the load latency, three weight tiles do not (the MMA warp waited ~1000-1700 cycles
+// per 64-channel block on w_full).  2 + 5 against 3 + 3: 512->512 at 128^2 1504 -> 1596 TFLOP/s, 64^2 1581 -> 1615, the
+// 128- and 256-channel layers unchanged (profiles/r02_t128_ring_depth.log).
+#define T128_A_SLOTS 2
+#define T128_W_SLOTS 5
+#endif
 #ifndef DFW_GNIN_TRACE
 #define DFW_GNIN_TRACE 0        // 1: CTA 0 of the GN_IN kernel accumulates phase cycle counts (dfw_debug_t128_trace)
 #endif
@@ -926,9 +934,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 template <bool GN_IN>
 struct T128CfgT {
     static constexpr int PATCH_BYTES = 18 * 16 * 128;       // 36 KiB
-    static constexpr int A_SLOTS = 3;
+    static constexpr int A_SLOTS = T128_A_SLOTS;
     static constexpr int W_TILE_BYTES = 128 * 128;          // 16 KiB
-    static constexpr int W_SLOTS = 3;
+    static constexpr int W_SLOTS = T128_W_SLOTS;
     static constexpr int STG_BYTES = 64 * 64;               // 64 pixels x 32 channels x 2 B
     static constexpr int STG_PER_WARP = 2;
     // GN_IN: per-CTA ring of transformed (16+2) x (16+2)-pixel x 64-channel blocks in global memory (L2-resident)
