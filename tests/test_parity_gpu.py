@@ -394,6 +394,38 @@ def test_conv_gn_in_equals_norm_then_conv():
     assert rel_l2(y, ref) <= 2e-3
 
 
+@pytest.mark.parametrize("N,H,W,Ci,Co,ks,res,dt", [
+    (10, 144, 112, 256, 128, 3, False, torch.float16),     # ragged unit count, 4 channel blocks, border tiles on all sides
+    (16, 64, 64, 128, 512, 3, True, torch.bfloat16),       # bf16 operands, four 128-channel slabs re-reading the input
+    (16, 64, 64, 128, 512, 1, True, torch.float16),        # 1x1: the ring holds bare 16 x 16 tiles
+    (2, 272, 304, 128, 128, 3, False, torch.float16),      # 17 x 19 tiles, few images
+])
+def test_conv_gn_in_shapes(N, H, W, Ci, Co, ks, res, dt):
+    """dfw_conv2d_igemm_gnin on the shapes that stress its pipeline (transform warps -> per-CTA ring in global memory ->
+    TMA patch loads): bit-identical to norm kernel + conv, output statistics included; run twice on one ring."""
+    from diffews_b200 import ops
+    from diffews_b200.weights import conv_weight_to_gemm
+    g = torch.Generator().manual_seed(11)
+    x0 = (torch.randn(N, H, W, 64, generator=g) * 1.5 + 0.3).to(dt).cuda()
+    w0 = conv_weight_to_gemm(torch.randn(Ci, 64, 1, 1, generator=g) * 0.125).to(dt).cuda()
+    x = ops.conv2d(x0, w0, None, ksize=1, gn_stats=True)
+    assert ops.conv_gn_in_supported(x, Co, ks)
+    w = conv_weight_to_gemm(torch.randn(Co, Ci, ks, ks, generator=g) * (Ci * ks * ks) ** -0.5).to(dt).cuda()
+    b = torch.randn(Co, generator=g).cuda()
+    gam = (torch.randn(Ci, generator=g) + 1.0).cuda()
+    bet = torch.randn(Ci, generator=g).cuda()
+    r = torch.randn(N, H, W, Co, generator=g).to(dt).cuda() if res else None
+    xn = ops.groupnorm(x, gam, bet, eps=1e-6, silu=True, out_dtype=dt)
+    y2 = ops.conv2d(xn, w, b, ksize=ks, residual=r, gn_stats=True)
+    for _ in range(2):
+        y = ops.conv2d_gn_in(x, gam, bet, 1e-6, w, b, ksize=ks, residual=r, gn_stats=True)
+        assert torch.equal(y, y2)
+        if getattr(y2, "_gn_partial", None) is not None:
+            n1 = ops.groupnorm(y, torch.ones(Co).cuda(), torch.zeros(Co).cuda(), eps=1e-6, out_dtype=dt)
+            n2 = ops.groupnorm(y2, torch.ones(Co).cuda(), torch.zeros(Co).cuda(), eps=1e-6, out_dtype=dt)
+            assert torch.equal(n1, n2)
+
+
 def test_checkpoint_loader_equals_from_module(small_models, tmp_path):
     """A diffusers-layout checkpoint directory (safetensors + config.json, what main_oss.py:338-369 reads) loaded through
     diffews_b200.checkpoint gives bit-identical UNet / VAE engines to building them from the live modules."""
