@@ -728,10 +728,270 @@ attn_kvfused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     }
 }
 
-int make_seq_map(CUtensorMap* m, const void* base, int C, int L, int B, int row_stride, long long batch_stride) {
+// ---------------------------------------------------------------------------------------------------------
+// v4 (round 2, second half).  The v3 timeline (profiles/r02_attn_timeline_v3_a.log) shows the two query tiles of a CTA
+// running in strict alternation: a key-tile pair takes 2435 cycles although the two softmax warps of a sub-partition need
+// only ~1400 XU cycles / ~1360 issue slots between them -- each warp spends 570-620 cycles waiting for its next S, and the
+// single MMA warp needs 1035 cycles to get PV_B(j) and S_A(j+2) issued (it serves A and B in a fixed order and sits behind
+// whichever softmax group is late).  With three rotating S buffers that order cannot be relaxed: S_A(j+1) lands in the
+// buffer of P_B(j-1).  Here every query tile owns TWO S buffers -- 96-key tiles make four of them fit beside the two O
+// accumulators (4 x 96 + 2 x 64 = 512 TMEM columns) -- and its own MMA-issuing warp (warps 1 and 3, different
+// sub-partitions): loop { S_X(j+1) -> other buffer; wait P_X(j); O_X += P_X(j) V_j }.  A tile never waits for its sibling;
+// the only shared resource is the K/V ring (a stage is released by both issuers' commits).  Softmax code, P-in-TMEM,
+// lazy maximum and the polynomial exp2 share are v3's.
+// MEASURED (profiles/r02_bench_attn_v4.json, back-to-back launches): correct on every shape of the suite and 3-5 % SLOWER
+// than v3 (B16 h5 4096x8192: 820 vs 860 TFLOP/s; 9216x18432: 854 vs 884): decoupling the tiles buys about what the fixed
+// per-tile cost (barrier round trips, P store, S wait) loses when it is amortised over 96 instead of 128 keys.  So the
+// A/B chain was not the limiter: with two softmax warps per sub-partition the loop is bound by per-warp instruction
+// latency (ncu: issue slots 56 %, XU 61 %, neither saturated).  Kept selectable (DFW_OPT_ATTN_V4), off.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ATT_N4 = 96;                                   // keys per tile
+constexpr int KV4_TILE = ATT_N4 * 128;                       // 12 KiB: 96 rows x 128 B (12 SWIZZLE_128B atoms)
+constexpr int KV_STAGES4 = 6;
+constexpr int ATT_SMEM4 = ATT_QT * TILE_BYTES + KV_STAGES4 * 2 * KV4_TILE + 1024 + 256;
+static_assert(ATT_SMEM4 <= 227 * 1024, "dynamic smem limit of sm_100");
+static_assert(4 * ATT_N4 + 2 * ATT_D <= 512, "TMEM budget");
+
+template <bool F16>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_kvfused_v4_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    constexpr int KVS = KV_STAGES4;
+    constexpr int NCH = ATT_N4 / 32;
+    auto sQ = [&](int x) { return base + x * TILE_BYTES; };
+    const uint32_t kv_base = base + ATT_QT * TILE_BYTES;
+    auto sK = [&](int s) { return kv_base + s * 2 * KV4_TILE; };
+    auto sV = [&](int s) { return kv_base + s * 2 * KV4_TILE + KV4_TILE; };
+    const uint32_t bar_base = kv_base + KVS * 2 * KV4_TILE;
+    const uint32_t q_full = bar_base;
+    auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KVS + s); };
+    auto s_full = [&](int x, int par) { return bar_base + 8u * (1 + 2 * KVS + 2 * x + par); };
+    auto p_full = [&](int x) { return bar_base + 8u * (5 + 2 * KVS + x); };
+    auto pv_done = [&](int x) { return bar_base + 8u * (7 + 2 * KVS + x); };
+    const uint32_t tmem_slot = bar_base + 8u * (9 + 2 * KVS);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_M * ATT_QT;
+    const int head = blockIdx.y;
+    const int b = blockIdx.z;
+    const int ntiles = p.n_self + p.n_bank;
+    const bool has_b = (q0 + ATT_M) < p.Lq;          // second query tile holds at least one valid row
+    const int nq = has_b ? 2 : 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.q);
+        tma_prefetch_desc(&maps.k_self);
+        tma_prefetch_desc(&maps.v_self);
+        if (p.n_bank) { tma_prefetch_desc(&maps.k_bank); tma_prefetch_desc(&maps.v_bank); }
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), nq); }     // released by every issuer
+        for (int x = 0; x < ATT_QT; ++x) {
+            mbar_init(s_full(x, 0), 1); mbar_init(s_full(x, 1), 1);
+            mbar_init(p_full(x), 128); mbar_init(pv_done(x), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+    auto tS = [&](int x, int par) { return tmem_base + (2 * x + par) * ATT_N4; };
+    auto tO = [&](int x) { return tmem_base + 4 * ATT_N4 + x * ATT_D; };
+    if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, nq * TILE_BYTES);
+            tma_load_3d(sQ(0), &maps.q, q_full, head * ATT_D, q0, b);
+            if (has_b) tma_load_3d(sQ(1), &maps.q, q_full, head * ATT_D, q0 + ATT_M, b);
+        }
+        __syncwarp();
+        int s = 0;
+        uint32_t ph = 1;
+        for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(kv_empty(s), ph, 10);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(kv_full(s), 2 * KV4_TILE);
+                if (j < p.n_self) {
+                    tma_load_3d(sK(s), &maps.k_self, kv_full(s), head * ATT_D, j * ATT_N4, b);
+                    tma_load_3d(sV(s), &maps.v_self, kv_full(s), head * ATT_D, j * ATT_N4, b);
+                } else {
+                    const int jb = j - p.n_self;
+                    tma_load_3d(sK(s), &maps.k_bank, kv_full(s), head * ATT_D, jb * ATT_N4, b);
+                    tma_load_3d(sV(s), &maps.v_bank, kv_full(s), head * ATT_D, jb * ATT_N4, b);
+                }
+            }
+            __syncwarp();
+            if (++s == KVS) { s = 0; ph ^= 1u; }
+        }
+    } else if (warp == 1 || warp == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int x = warp >> 1;                          // warp 1 issues for tile A, warp 3 for tile B
+        if (x == 0 || has_b) {
+            const uint32_t fmt = F16 ? 0u : 1u;
+            const uint32_t idesc_s = umma_idesc(ATT_M, ATT_N4, fmt, fmt, 0);  // S = Q K^T : B (= K) is K-major
+            const uint32_t idesc_o = umma_idesc(ATT_M, ATT_D, fmt, fmt, 1);   // O += P V  : A (= P) in TMEM, B (= V) MN-major
+            const uint64_t dq = umma_desc_sw128(sQ(x));
+            const uint64_t dk0 = umma_desc_sw128(sK(0)), dv0 = umma_desc_sw128(sV(0));
+            constexpr uint32_t STAGE_STEP = (2 * KV4_TILE) >> 4;
+            auto issue_s = [&](int stage, int par) {          // all lanes
+                if (elect_one()) {
+                    const uint64_t bdesc = dk0 + static_cast<uint64_t>(stage * STAGE_STEP);
+                    const uint32_t d = tS(x, par);
+#pragma unroll
+                    for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, dq + 2u * k, bdesc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                    tc_commit(s_full(x, par));
+                }
+                __syncwarp();
+            };
+            mbar_wait(q_full, 0, 12);
+            mbar_wait(kv_full(0), 0, 11);
+            tc_fence_after();
+            issue_s(0, 0);
+            int s = 0, s1 = 1;
+            uint32_t ph1 = 0u;
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) {
+                    mbar_wait(kv_full(s1), ph1, 11);
+                    tc_fence_after();
+                    // S_X(j+1) -> the buffer P_X(j-1) lived in: PV_X(j-1) was issued by this thread, MMAs of one thread run in order
+                    issue_s(s1, (j + 1) & 1);
+                }
+                mbar_wait(p_full(x), j & 1, 13);            // P_X(j) in TMEM, O_X rescaled if it had to be
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t bdesc = dv0 + static_cast<uint64_t>(s * STAGE_STEP);
+                    const uint32_t d = tO(x), a = tS(x, j & 1);
+#pragma unroll
+                    for (int ks = 0; ks < ATT_N4 / 16; ++ks)
+                        umma_ts(d, a + ks * 8, bdesc + static_cast<uint64_t>(ks * ((16 * 128) >> 4)), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                    tc_commit(pv_done(x));
+                    tc_commit(kv_empty(s));                 // this tile is done with K_j / V_j
+                }
+                __syncwarp();
+                s = s1;
+                if (++s1 == KVS) { s1 = 0; ph1 ^= 1u; }
+            }
+        }
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int x = (warp - 4) >> 2;                // query tile of this softmax group
+        const int qd = (warp - 4) & 3;                // TMEM lane quadrant
+        const int row = qd * 32 + lane;
+        const int qrow0 = q0 + x * ATT_M;
+        if (x == 0 || has_b) {
+            const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+            const uint32_t to = tO(x) + lane_off;
+            const float sc = p.scale_log2;
+            float m_used = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < ntiles; ++j) {
+                int valid;
+                if (j < p.n_self) valid = min(ATT_N4, p.Ls - j * ATT_N4);
+                else valid = min(ATT_N4, p.Lb - (j - p.n_self) * ATT_N4);
+                const uint32_t ts = tS(x, j & 1) + lane_off;
+                mbar_wait(s_full(x, j & 1), (j >> 1) & 1, 15);
+                tc_fence_after();
+                uint32_t pk[ATT_N4 / 2];
+                float psum = 0.f;
+                bool slow = (j == 0) || (valid != ATT_N4);         // warp-uniform
+                if (!slow) {
+                    psum = exp_row_tmem_n<F16, ATT_NPOLY, NCH>(ts, sc, m_used, pk);
+                    slow = __any_sync(0xffffffffu, !(psum <= SOFTMAX_TRIGGER));
+                }
+                if (slow) {
+                    // exact path: whole row from TMEM (still intact: P is stored below), true maximum, O / l rescale
+                    uint32_t sv[ATT_N4];
+                    tmem_ld_row_n<NCH>(ts, sv);
+                    if (valid != ATT_N4) {
+#pragma unroll
+                        for (int i = 0; i < ATT_N4; ++i)
+                            if (i >= valid) sv[i] = 0xff800000u;                     // -inf: masked key
+                    }
+                    const float m_new = fmaxf(m_used, row_max_n<ATT_N4>(sv) * sc);
+                    const float alpha = ex2_approx(m_used - m_new);                   // 0 on the first tile
+                    if (j > 0 && __any_sync(0xffffffffu, m_new != m_used)) {
+                        mbar_wait(pv_done(x), (j - 1) & 1, 14);                       // O_X holds tiles < j
+                        tc_fence_after();
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(to + c * 32, v);
+                            tmem_ld_wait(); tmem_regs_ready(v);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            tmem_st_32x32(to + c * 32, v);
+                        }
+                    }
+                    l_run *= alpha;
+                    m_used = m_new;
+                    psum = exp_row_staged_n<F16, ATT_NPOLY, 2, NCH>(sv, sc, m_used, pk);
+                }
+                l_run += psum;
+#pragma unroll
+                for (int c = 0; c < ATT_N4 / 32; ++c) {
+                    uint32_t (&v)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[c * 16]);
+                    tmem_st_32x16(ts + c * 16, v);
+                }
+                tmem_st_wait();
+                // observe EVERY phase of pv_done in order (see v3): before arriving for tile j, wait for PV(j-1)
+                if (j > 0) mbar_wait(pv_done(x), (j - 1) & 1, 18);
+                tc_fence_before();
+                mbar_arrive(p_full(x));
+            }
+            mbar_wait(pv_done(x), (ntiles - 1) & 1, 16);
+            tc_fence_after();
+            const float inv = 1.0f / l_run;
+            const bool row_ok = (qrow0 + row) < p.Lq;
+            if (p.lse != nullptr && row_ok)
+                p.lse[(static_cast<long long>(b) * gridDim.y + head) * p.Lq + qrow0 + row] = m_used + log2f(l_run);
+            uint16_t* op = p.o + static_cast<long long>(b) * p.o_batch_stride +
+                           static_cast<long long>(qrow0 + row) * p.o_row_stride + head * ATT_D;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(to + c * 32, v);
+                tmem_ld_wait(); tmem_regs_ready(v);
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 w;
+                        w.x = pack_h2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, F16);
+                        w.y = pack_h2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, F16);
+                        w.z = pack_h2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, F16);
+                        w.w = pack_h2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, F16);
+                        *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    }
+}
+
+int make_seq_map(CUtensorMap* m, const void* base, int C, int L, int B, int row_stride, long long batch_stride,
+                 int box_rows = ATT_N) {
     const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(row_stride) * 2, static_cast<uint64_t>(batch_stride) * 2};
-    const uint32_t box[3] = {ATT_D, ATT_N, 1};
+    const uint32_t box[3] = {ATT_D, static_cast<uint32_t>(box_rows), 1};
     return encode_tmap_bf16_sw128(m, base, 3, dims, strides, box);
 }
 
@@ -893,18 +1153,21 @@ static int attn_fwd_impl(const void* q, long long q_batch_stride, int q_row_stri
     DFW_REQUIRE(q_batch_stride % 8 == 0 && kv_self_batch_stride % 8 == 0 && o_batch_stride % 8 == 0);
     DFW_REQUIRE(B <= 65535 && heads <= 65535);
     const int C = heads * ATT_D;
+    const bool v2 = get_option(DFW_OPT_ATTN_V2) && lse == nullptr;
+    const bool v4 = !v2 && get_option(DFW_OPT_ATTN_V4);
+    const int kt = v4 ? ATT_N4 : ATT_N;                  // keys per tile
     AttnMaps maps;
-    rc = make_seq_map(&maps.q, q, C, Lq, B, q_row_stride, q_batch_stride);
+    rc = make_seq_map(&maps.q, q, C, Lq, B, q_row_stride, q_batch_stride, ATT_M);
     if (rc != DFW_OK) return rc;
-    rc = make_seq_map(&maps.k_self, k_self, C, Ls, B, kv_self_row_stride, kv_self_batch_stride);
+    rc = make_seq_map(&maps.k_self, k_self, C, Ls, B, kv_self_row_stride, kv_self_batch_stride, kt);
     if (rc != DFW_OK) return rc;
-    rc = make_seq_map(&maps.v_self, v_self, C, Ls, B, kv_self_row_stride, kv_self_batch_stride);
+    rc = make_seq_map(&maps.v_self, v_self, C, Ls, B, kv_self_row_stride, kv_self_batch_stride, kt);
     if (rc != DFW_OK) return rc;
     if (Lb > 0) {
         DFW_REQUIRE(kv_bank_row_stride % 8 == 0 && kv_bank_batch_stride % 8 == 0);
-        rc = make_seq_map(&maps.k_bank, k_bank, C, Lb, B, kv_bank_row_stride, kv_bank_batch_stride);
+        rc = make_seq_map(&maps.k_bank, k_bank, C, Lb, B, kv_bank_row_stride, kv_bank_batch_stride, kt);
         if (rc != DFW_OK) return rc;
-        rc = make_seq_map(&maps.v_bank, v_bank, C, Lb, B, kv_bank_row_stride, kv_bank_batch_stride);
+        rc = make_seq_map(&maps.v_bank, v_bank, C, Lb, B, kv_bank_row_stride, kv_bank_batch_stride, kt);
         if (rc != DFW_OK) return rc;
     } else {
         maps.k_bank = maps.k_self;
@@ -912,8 +1175,8 @@ static int attn_fwd_impl(const void* q, long long q_batch_stride, int q_row_stri
     }
     AttnParams p{};
     p.Lq = Lq; p.Ls = Ls; p.Lb = Lb;
-    p.n_self = (Ls + ATT_N - 1) / ATT_N;
-    p.n_bank = (Lb + ATT_N - 1) / ATT_N;
+    p.n_self = (Ls + kt - 1) / kt;
+    p.n_bank = (Lb + kt - 1) / kt;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.o = reinterpret_cast<uint16_t*>(o);
     p.f16 = f16;
@@ -927,15 +1190,20 @@ static int attn_fwd_impl(const void* q, long long q_batch_stride, int q_row_stri
     if (!attr_set) {
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM3));
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM3));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM4));
+        DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM4));
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         DFW_CHECK_CUDA(cudaFuncSetAttribute(attn_kvfused_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
     dim3 grid((Lq + ATT_M * ATT_QT - 1) / (ATT_M * ATT_QT), heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    if (get_option(DFW_OPT_ATTN_V2) && lse == nullptr) {        // round-1 kernel (P through smem, two passes over S), kept for A/B measurements
+    if (v2) {        // round-1 kernel (P through smem, two passes over S), kept for A/B measurements
         if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_v2_kernel<true>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
         else DFW_CHECK_CUDA(launch_k(attn_kvfused_v2_kernel<false>, grid, ATT_THREADS, ATT_SMEM, st, maps, p));
+    } else if (v4) {
+        if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_v4_kernel<true>, grid, ATT_THREADS, ATT_SMEM4, st, maps, p));
+        else DFW_CHECK_CUDA(launch_k(attn_kvfused_v4_kernel<false>, grid, ATT_THREADS, ATT_SMEM4, st, maps, p));
     } else {
         if (f16) DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<true>, grid, ATT_THREADS, ATT_SMEM3, st, maps, p));
         else DFW_CHECK_CUDA(launch_k(attn_kvfused_kernel<false>, grid, ATT_THREADS, ATT_SMEM3, st, maps, p));

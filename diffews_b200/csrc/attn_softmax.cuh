@@ -228,4 +228,69 @@ __device__ __forceinline__ void tmem_ld_row128(uint32_t taddr, uint32_t (&s)[128
     }
 }
 
+// ---- generic tile widths (v4 kernel: 96-key tiles = three 32-column chunks) ------------------------------------------
+template <int N>
+__device__ __forceinline__ float row_max_n(const uint32_t (&s)[N]) {
+    static_assert(N % 8 == 0, "row_max_n");
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < N; i += 8) {
+        m0 = fmax3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        m2 = fmax3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        m3 = fmax3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+template <bool F16, int NPOLY, int NACC, int NCH>
+__device__ __forceinline__ float exp_row_staged_n(const uint32_t (&s)[NCH * 32], float sc, float mu, uint32_t (&pk)[NCH * 16]) {
+    const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-mu, -mu);
+    uint64_t sum2[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) sum2[i] = 0ull;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) exp_chunk32_staged<F16, NPOLY, NACC>(&s[c * 32], sc2, nmu2, sum2, &pk[c * 16]);
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { float a, b; f2_unpack(sum2[i], a, b); tot += a + b; }
+    return tot;
+}
+
+// Fast path, NCH chunks of 32 columns, TMEM loads software-pipelined one chunk ahead (see exp_row128_tmem).
+template <bool F16, int NPOLY, int NCH>
+__device__ __forceinline__ float exp_row_tmem_n(uint32_t ts, float sc, float mu, uint32_t (&pk)[NCH * 16]) {
+    const uint64_t sc2 = f2_pack(sc, sc), nmu2 = f2_pack(-mu, -mu);
+    uint64_t sum2[2] = {0ull, 0ull};
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(ts, va);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t (&cur)[32] = (c & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+        tmem_ld_wait(); tmem_regs_ready(cur);
+        if (c + 1 < NCH) tmem_ld_32x32(ts + (c + 1) * 32, nxt);
+        exp_chunk32<F16, NPOLY>(cur, sc2, nmu2, sum2, &pk[c * 16]);
+    }
+    float a, b, c2, d;
+    f2_unpack(sum2[0], a, b);
+    f2_unpack(sum2[1], c2, d);
+    return (a + b) + (c2 + d);
+}
+
+template <int NCH>
+__device__ __forceinline__ void tmem_ld_row_n(uint32_t taddr, uint32_t (&s)[NCH * 32]) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
+        tmem_ld_32x32(taddr + c * 32, v);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
+        tmem_regs_ready(v);
+    }
+}
+
 }  // namespace dfw

@@ -1,5 +1,5 @@
 """Stand-alone timing of the KV-fused attention kernel at the shapes of the BASELINE configs (CUDA events, L2 flushed by
-rotating over several input sets larger than the 126 MB L2).  Prints TFLOP/s per shape for the default (v3) kernel and,
+rotating over several input sets larger than the 126 MB L2).  Prints TFLOP/s per shape for the v3 (default) and v4 kernels and,
 with --v2, the round-1 kernel.  Usage on a B200:  python scripts/bench_attn.py [--v2] [--json out.json]"""
 import argparse
 import json
@@ -67,14 +67,16 @@ def main():
         fn.restype, fn.argtypes = _lib.SIGNATURES["dfw_attn_kvfused_fwd"]
         _lib.lib.dfw_attn_kvfused_fwd = fn
     out = {}
-    for ver in ([0, 1] if args.v2 else [0]):
-        ops.set_option(_lib.OPT_ATTN_V2, ver)
+    for ver in (["v4", "v3", "v2"] if args.v2 else ["v4", "v3"]):
+        ops.set_option(_lib.OPT_ATTN_V2, int(ver == "v2"))
+        ops.set_option(_lib.OPT_ATTN_V4, int(ver == "v4"))
         for name, B, h, Lq, Ls, Lb in (SHAPES if args.only is None else SHAPES[args.only:args.only + 1]):
             ms, tf = time_shape(B, h, Lq, Ls, Lb)
-            print(f"{'v2' if ver else 'v3'}  {name:38s} {ms:8.3f} ms  {tf:7.1f} TFLOP/s  ({100 * tf / 2250:.1f} % of 2250 nominal, "
+            print(f"{ver}  {name:38s} {ms:8.3f} ms  {tf:7.1f} TFLOP/s  ({100 * tf / 2250:.1f} % of 2250 nominal, "
                   f"{100 * tf / 1397.5:.1f} % of 1397.5 sustained)", flush=True)
-            out[f"{'v2' if ver else 'v3'} {name}"] = {"ms": ms, "tflops": tf}
+            out[f"{ver} {name}"] = {"ms": ms, "tflops": tf}
     ops.set_option(_lib.OPT_ATTN_V2, 0)
+    ops.set_option(_lib.OPT_ATTN_V4, 0)
     if args.json:
         with open(args.json, "w") as f:
             json.dump(out, f, indent=1)

@@ -198,9 +198,20 @@ def test_softmax_rows_kernel(M, L):
                                              (1, 20, 64, 64, 0, torch.float16),           # support pass, 8x8 level
                                              (1, 5, 2304, 2304, 2304, torch.bfloat16),
                                              (3, 2, 200, 200, 333, torch.float16)])       # ragged everywhere
-def test_attention_forward_kernel(B, h, Lq, Ls, Lb, dt):
+@pytest.mark.parametrize("variant", ["v3", "v4"])
+def test_attention_forward_kernel(B, h, Lq, Ls, Lb, dt, variant):
     """dfw_attn_kvfused_fwd vs softmax(q [k_self; k_bank]^T / 8) [v_self; v_bank] in fp32 (the reference's concat
-    attention, attention_processor.py:251-271), q/k/v as strided column slices of a fused QKV buffer."""
+    attention, attention_processor.py:251-271), q/k/v as strided column slices of a fused QKV buffer.  v3 = the default
+    kernel; v4 = the 96-key / two-issuer variant (DFW_OPT_ATTN_V4, off by default)."""
+    from diffews_b200 import _lib, ops
+    old = ops.set_option(_lib.OPT_ATTN_V4, int(variant == "v4"))
+    try:
+        _attention_forward_case(B, h, Lq, Ls, Lb, dt)
+    finally:
+        ops.set_option(_lib.OPT_ATTN_V4, old)
+
+
+def _attention_forward_case(B, h, Lq, Ls, Lb, dt):
     from diffews_b200 import ops
     g = torch.Generator().manual_seed(Lq + Lb)
     C = h * 64
