@@ -38,6 +38,7 @@ SIGNATURES = {
     "dfw_groupnorm_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "dfw_groupnorm_silu_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "dfw_conv_gnin_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "dfw_conv_t128_eligible": (_i, [_i, _i, _i, _i, _i, _i]),
     "dfw_conv2d_igemm_gnin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dfw_conv_gnin_scratch_bytes": (_ll, []),
     "dfw_bmm_nt": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),

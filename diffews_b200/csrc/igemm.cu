@@ -1851,9 +1851,13 @@ int dfw_conv2d_igemm_gnstats(const void* x, const void* w, const float* bias, co
 }
 
 int dfw_conv_gnin_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
+    if (Cin > dfw::T128CfgT<true>::SS_MAX_CIN) return 0;       // the image's scale / shift vectors live in shared memory
+    return dfw_conv_t128_eligible(N, H, W, Cin, Cout, ksize);
+}
+
+int dfw_conv_t128_eligible(int N, int H, int W, int Cin, int Cout, int ksize) {
     if (dfw::require_sm100() != DFW_OK) return 0;
     static unsigned char dummy[16] __attribute__((aligned(16)));
-    if (Cin > dfw::T128CfgT<true>::SS_MAX_CIN) return 0;
     return dfw::try_launch_t128(dummy, dummy, nullptr, nullptr, dummy, N, H, W, Cin, Cout, ksize, 1, 0, DFW_EPI_F16, 1.0f, 0,
                                 0, 0, -1, nullptr, 32, 0, nullptr, nullptr, true) == DFW_OK ? 1 : 0;
 }

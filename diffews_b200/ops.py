@@ -161,7 +161,7 @@ def conv2d(x, w, bias=None, *, ksize, stride=1, pad_mode=0, residual=None, out_s
         # which kernel the library will pick (igemm.cu try_launch_t128): only evaluated for the instrumented pass
         t128 = (stride == 1 and pad_mode == 0 and not (out_f32 or silu or geglu or bias_per_sample)
                 and (residual is None or residual.dtype != torch.float32) and (not want_gn or Cout <= 512)
-                and bool(lib.dfw_conv_gnin_supported(N, H, W, Cin, Cout, ksize)))
+                and bool(lib.dfw_conv_t128_eligible(N, H, W, Cin, Cout, ksize)))
         tag = "t128 " if t128 else ""
     if want_gn:
         partial = torch.empty(int(lib.dfw_gn_partial_floats(N)), device=x.device, dtype=torch.float32)
@@ -256,7 +256,7 @@ def linear(x, w, bias=None, *, residual=None, out_scale=1.0, out_f32=False, silu
         else: assert residual.dtype == h16
     tag = ""
     if _timer is not None and residual is not None and M % 256 == 0 and not (out_f32 or silu or geglu) \
-            and residual.dtype != torch.float32 and bool(lib.dfw_conv_gnin_supported(1, M // 16, 16, K, Nout, 1)):
+            and residual.dtype != torch.float32 and bool(lib.dfw_conv_t128_eligible(1, M // 16, 16, K, Nout, 1)):
         tag = "t128 "                  # residual projections run on the channel-major kernel (igemm.cu try_launch_t128)
     with _Timed("igemm", 2.0 * M * K * Nout, f"{tag}linear M{M} K{K} N{Nout} f{flags}"):
         check(lib.dfw_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, K, Nout, flags,

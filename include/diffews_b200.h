@@ -214,6 +214,9 @@ int dfw_groupnorm_silu_bwd(const void* x, const void* dy, int dtype, const float
 int dfw_gn_scale_shift(const float* partial, int nchunks, const float* gamma, const float* beta, float* scale_shift,
                        int N, long long HW, int C, int groups, float eps, void* stream);
 int dfw_conv_gnin_supported(int N, int H, int W, int Cin, int Cout, int ksize);
+/* 1 when a plain stride-1 16-bit convolution / residual projection of this shape is routed to the channel-major kernel
+ * (igemm_t128_kernel) by dfw_conv2d_igemm / dfw_linear: what bench.py uses to attribute launches to that kernel. */
+int dfw_conv_t128_eligible(int N, int H, int W, int Cin, int Cout, int ksize);
 int dfw_conv2d_igemm_gnin(const void* x, const float* gn_scale_shift, const void* w, const float* bias,
                           const void* residual, void* y, int N, int Hin, int Win, int Cin, int Cout, int ksize, int flags,
                           float* gn_partial_out, void* scratch, void* stream);
