@@ -141,6 +141,35 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float hq = 0.5f * r;
     return x * (x >= 0.f ? 1.0f - hq : hq);
 }
+// Two GEGLU outputs at once, (val + bv) * gelu(gate + bg), on packed fp32x2 instructions: the same IEEE operations per lane
+// as gelu_erf (bit-identical results), ~25 issue slots per pair instead of ~41 -- the K = 320 GEGLU projection spent 4000
+// epilogue issue slots per sub-partition on a tile whose MMAs take 2560 cycles (ncu: tensor pipe 40 %, issue 57 %).
+__device__ __forceinline__ void geglu_pair(float v0, float v1, float g0, float g1, float bv0, float bv1, float bg0, float bg1,
+                                           float& o0, float& o1) {
+    const uint64_t x2 = f2_add(f2_pack(g0, g1), f2_pack(bg0, bg1));
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    const uint64_t z2 = f2_mul(f2_pack(fabsf(x0), fabsf(x1)), f2_pack(0.70710678118654752f, 0.70710678118654752f));
+    uint64_t p2 = f2_fma(z2, f2_pack(0.0000430638f, 0.0000430638f), f2_pack(0.0002765672f, 0.0002765672f));
+    p2 = f2_fma(p2, z2, f2_pack(0.0001520143f, 0.0001520143f));
+    p2 = f2_fma(p2, z2, f2_pack(0.0092705272f, 0.0092705272f));
+    p2 = f2_fma(p2, z2, f2_pack(0.0422820123f, 0.0422820123f));
+    p2 = f2_fma(p2, z2, f2_pack(0.0705230784f, 0.0705230784f));
+    p2 = f2_fma(p2, z2, f2_pack(1.0f, 1.0f));
+    float p0, p1, r0, r1;
+    f2_unpack(p2, p0, p1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+    uint64_t r2 = f2_pack(r0, r1);
+    r2 = f2_mul(r2, r2); r2 = f2_mul(r2, r2); r2 = f2_mul(r2, r2); r2 = f2_mul(r2, r2);      // poly^-16 = erfc(z)
+    const uint64_t hq2 = f2_mul(r2, f2_pack(0.5f, 0.5f));
+    float h0, h1;
+    f2_unpack(hq2, h0, h1);
+    const uint64_t phi2 = f2_pack(x0 >= 0.f ? 1.0f - h0 : h0, x1 >= 0.f ? 1.0f - h1 : h1);
+    const uint64_t ge2 = f2_mul(x2, phi2);
+    const uint64_t val2 = f2_add(f2_pack(v0, v1), f2_pack(bv0, bv1));
+    f2_unpack(f2_mul(val2, ge2), o0, o1);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // Butterfly reduce-scatter over the warp: on return v[0] of lane l holds the sum over all 32 lanes of element
@@ -669,10 +698,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                         for (int j = 0; j < 32; j += 4) {
                             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
                             if (bp) { bv = __ldg(reinterpret_cast<const float4*>(bp + j)); bg = __ldg(reinterpret_cast<const float4*>(bp + 128 + j)); }
-                            f[j] = (__uint_as_float(v[j]) + bv.x) * gelu_erf(__uint_as_float(gt[j]) + bg.x);
-                            f[j + 1] = (__uint_as_float(v[j + 1]) + bv.y) * gelu_erf(__uint_as_float(gt[j + 1]) + bg.y);
-                            f[j + 2] = (__uint_as_float(v[j + 2]) + bv.z) * gelu_erf(__uint_as_float(gt[j + 2]) + bg.z);
-                            f[j + 3] = (__uint_as_float(v[j + 3]) + bv.w) * gelu_erf(__uint_as_float(gt[j + 3]) + bg.w);
+                            geglu_pair(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(gt[j]),
+                                       __uint_as_float(gt[j + 1]), bv.x, bv.y, bg.x, bg.y, f[j], f[j + 1]);
+                            geglu_pair(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]), __uint_as_float(gt[j + 2]),
+                                       __uint_as_float(gt[j + 3]), bv.z, bv.w, bg.z, bg.w, f[j + 2], f[j + 3]);
                         }
                     }
                 } else {
