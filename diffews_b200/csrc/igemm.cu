@@ -967,16 +967,15 @@ struct T128CfgT {
     static constexpr int W_TILE_BYTES = 128 * 128;          // 16 KiB
     static constexpr int W_SLOTS = T128_W_SLOTS;
     static constexpr int STG_BYTES = 64 * 64;               // 64 pixels x 32 channels x 2 B
-    static constexpr int STG_PER_WARP = 2;
     // GN_IN: per-CTA ring of transformed (16+2) x (16+2)-pixel x 64-channel blocks in global memory (L2-resident)
     static constexpr int XF_BUFS = 4;
     static constexpr int XF_BUF_BYTES = 18 * 18 * 128;      // 40.5 KiB
-    static constexpr int NBAR = 3 * A_SLOTS + 2 * W_SLOTS + 4 + 32 + 2 * XF_BUFS;
+    static constexpr int NBAR = 2 * A_SLOTS + 2 * W_SLOTS + 4 + 32 + 2 * XF_BUFS;
     static constexpr int XF_WARPS = 8;                         // GN_IN: operand-transform warps (GroupNorm + SiLU on the fly)
     static constexpr int THREADS = IGEMM_THREADS + (GN_IN ? 32 * XF_WARPS : 0);     // 12 (+ 8) warps
     static constexpr int SS_MAX_CIN = 512;                  // GN_IN: scale / shift of the current image live in smem (2 x Cin floats)
     static constexpr int SS_BYTES = GN_IN ? 2 * SS_MAX_CIN * 4 + 16 : 0;
-    static constexpr int SMEM_USED = A_SLOTS * PATCH_BYTES + W_SLOTS * W_TILE_BYTES + 8 * STG_PER_WARP * STG_BYTES + 8 * NBAR + 16 + SS_BYTES;
+    static constexpr int SMEM_USED = A_SLOTS * PATCH_BYTES + W_SLOTS * W_TILE_BYTES + 16 * STG_BYTES + 8 * NBAR + 16 + SS_BYTES;
     static constexpr int SMEM_BYTES = SMEM_USED + 512;      // smem is declared __align__(1024); the kernel traps otherwise
     static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
@@ -1024,17 +1023,16 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
     auto sP = [&](int s) { return base + s * Cfg::PATCH_BYTES; };
     auto sW = [&](int s) { return base + Cfg::A_SLOTS * Cfg::PATCH_BYTES + s * Cfg::W_TILE_BYTES; };
     const uint32_t stg_base = base + Cfg::A_SLOTS * Cfg::PATCH_BYTES + Cfg::W_SLOTS * Cfg::W_TILE_BYTES;
-    auto sidx = [&](int w8, int b) { return Cfg::STG_PER_WARP == 2 ? w8 * 2 + b : w8; };      // staging block of (warp, sub-block)
+    auto sidx = [&](int w8, int b) { return w8 * 2 + b; };      // staging block of (warp, sub-block)
     auto sS = [&](int w8, int b) { return stg_base + sidx(w8, b) * Cfg::STG_BYTES; };
-    const uint32_t bar = stg_base + 8 * Cfg::STG_PER_WARP * Cfg::STG_BYTES;
+    const uint32_t bar = stg_base + 16 * Cfg::STG_BYTES;
     auto pa_full = [&](int i) { return bar + 8u * i; };
     auto pa_empty = [&](int i) { return bar + 8u * (Cfg::A_SLOTS + i); };
     auto w_full = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + i); };
     auto w_empty = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + Cfg::W_SLOTS + i); };
-    auto pa_ready = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + i); };     // GN_IN: transformed
-    auto xf_ready = [&](int i) { return bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + i); };                   // GN_IN ring
-    auto xf_free = [&](int i) { return bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + Cfg::XF_BUFS + i); };
-    const uint32_t b2 = bar + 8u * (3 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + 2 * Cfg::XF_BUFS);
+    auto xf_ready = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + i); };                   // GN_IN ring
+    auto xf_free = [&](int i) { return bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + Cfg::XF_BUFS + i); };
+    const uint32_t b2 = bar + 8u * (2 * Cfg::A_SLOTS + 2 * Cfg::W_SLOTS + 2 * Cfg::XF_BUFS);
     auto tfull = [&](int a) { return b2 + 8u * a; };
     auto tempty = [&](int a) { return b2 + 8u * (2 + a); };
     auto res_full = [&](int i) { return b2 + 8u * (4 + i); };        // i = warp8 * 2 + buffer
@@ -1051,7 +1049,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
         if (p.has_res) tma_prefetch_desc(&maps.res);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(pa_full(i), 1); mbar_init(pa_empty(i), 1); mbar_init(pa_ready(i), 8); }
+        for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(pa_full(i), 1); mbar_init(pa_empty(i), 1); }
         for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         for (int i = 0; i < Cfg::XF_BUFS; ++i) { mbar_init(xf_ready(i), Cfg::XF_WARPS); mbar_init(xf_free(i), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
@@ -1182,9 +1180,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                 for (int sb = 0; sb < 2; ++sb)
                     for (int w8 = 0; w8 < 8; ++w8) {
                         const int i = sidx(w8, sb);
-                        // use count of block i so far: k (two blocks per warp) or 2 k + sb (one block per warp)
-                        const uint32_t uses = Cfg::STG_PER_WARP == 2 ? k : 2u * k + sb;
-                        mbar_wait(buf_free(i), (uses & 1u) ^ 1u, 26);     // the store that last used this block has drained
+                        mbar_wait(buf_free(i), (k & 1u) ^ 1u, 26);        // the store that last used this block has drained
                         if (elect_one()) {
                             mbar_arrive_expect_tx(res_full(i), Cfg::STG_BYTES);
                             tma_load_4d(sS(w8, sb), &maps.res, res_full(i), slab * 128 + 32 * (w8 & 3), w0,
@@ -1399,10 +1395,9 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
             for (int sb = 0; sb < 2; ++sb) {
                 uint16_t* stage = reinterpret_cast<uint16_t*>(stg_generic + sidx(w8, sb) * Cfg::STG_BYTES);
                 if (has_res) {
-                    mbar_wait(res_full(sidx(w8, sb)), (Cfg::STG_PER_WARP == 2 ? k : 2u * k + sb) & 1u, 28);
+                    mbar_wait(res_full(sidx(w8, sb)), k & 1u, 28);
                 } else {
-                    // this block's previous store (two stores ago / the last one) has drained
-                    if (lane == 0) tma_store_wait_read<Cfg::STG_PER_WARP - 1>();
+                    if (lane == 0) tma_store_wait_read<1>();          // this block's previous store (two stores ago) has drained
                     __syncwarp();
                 }
 #pragma unroll 1
@@ -1422,7 +1417,7 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                         gs += f; gss = fmaf(f, f, gss);
                         sp[i * 32] = static_cast<uint16_t>(pack_h2(f, 0.f, f16) & 0xffffu);
                     }
-                    if (Cfg::STG_PER_WARP == 2 && has_res && half == 0 && free_i >= 0) {
+                    if (has_res && half == 0 && free_i >= 0) {
                         if (lane == 0) {
                             tma_store_wait_read<0>();                   // the previous sub-block's store has drained
                             mbar_arrive(buf_free(free_i));
@@ -1435,10 +1430,6 @@ igemm_t128_kernel(const __grid_constant__ T128Maps maps, const __grid_constant__
                 if (lane == 0) {
                     tma_store_4d(&maps.out, sS(w8, sb), slab * 128 + 32 * q, w0, h0 + 8 * eg + 4 * sb, n);
                     tma_store_commit();
-                    if (Cfg::STG_PER_WARP == 1 && has_res) {            // single block: hand it back as soon as the store has read it
-                        tma_store_wait_read<0>();
-                        mbar_arrive(buf_free(w8));
-                    }
                 }
                 free_i = sidx(w8, sb);
             }
