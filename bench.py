@@ -307,6 +307,8 @@ def main():
     ap.add_argument("--gn-fusion", default="off", choices=["auto", "off", "all"],
                     help="GroupNorm + SiLU folded into the consuming VAE convolution (layers.FUSE_GN_INTO_CONV)")
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch on the hot kernels (DFW_OPT_PDL)")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="set a library option before the engines are built, e.g. --opt B_RESIDENT=0 (diffews_b200._lib.OPT_*)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     ap.add_argument("--layer-table", default=None, help="write a per-shape table of the timed tensor-core launches here")
     ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS),
@@ -338,9 +340,12 @@ def main():
     from diffews_b200 import ops
     from diffews_b200 import layers as _layers
     _layers.FUSE_GN_INTO_CONV = {"auto": "auto", "off": False, "all": True}[args.gn_fusion]
+    from diffews_b200 import _lib as _dlib
     if args.pdl:
-        from diffews_b200 import _lib as _dlib
         ops.set_option(_dlib.OPT_PDL, 1)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ops.set_option(getattr(_dlib, "OPT_" + name.upper()), int(val))
     from diffews_b200.runner import EpisodeRunner, build_engine_from_state_dicts
     from diffews_b200.synthetic import make_batch, prompt_embedding, random_unet_state_dict, random_vae_state_dict
 

@@ -16,7 +16,7 @@ EPI_OUT_F32, EPI_RES_F32, EPI_GEGLU, EPI_SILU, EPI_F16 = 1, 2, 4, 8, 16
 
 # process-wide options (include/diffews_b200.h DFW_OPT_*)
 (OPT_PDL, OPT_T128, OPT_T128_MAXC, OPT_HALO, OPT_GN_CTAS_PER_SM, OPT_PREPROC_TWO_PASS, OPT_ATTN_V2, OPT_SEG_HEAD,
- OPT_ATTN_BWD_UNFUSED, OPT_ATTN_V4) = range(10)
+ OPT_ATTN_BWD_UNFUSED, OPT_ATTN_V4, OPT_B_RESIDENT) = range(11)
 
 _vp, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 

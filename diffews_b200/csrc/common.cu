@@ -19,6 +19,7 @@ static std::atomic<int> g_options[DFW_OPT_COUNT] = {
     {1},        // DFW_OPT_SEG_HEAD
     {0},        // DFW_OPT_ATTN_BWD_UNFUSED
     {0},        // DFW_OPT_ATTN_V4
+    {0},        // DFW_OPT_B_RESIDENT
 };
 
 int get_option(int option) {

@@ -89,6 +89,11 @@ struct IgemmParams {
     int halo;         // 1: 3x3 stride-1 "halo" mainloop (vertical taps reuse one (TH+2) x TW patch per horizontal offset)
     int tma_epi;      // 1: epilogue stages 64-byte-wide column chunks in smem and uses TMA stores / residual TMA loads
     int has_res;
+    // weight-stationary mode (1x1 / linear with a short K): the kb_per_tap weight tiles of the current Cout tile stay in
+    // smem while the CTA walks the pixel tiles (tiles ordered Cout-tile-major), the ring carries activation tiles only
+    int b_resident;
+    int a_slots;      // ring depth in that mode (<= STAGES, <= kb_per_tap)
+    int m_tiles;      // pixel tiles (tiles_w * tiles_h * tiles_nimg)
 };
 
 // TPU = output tiles per work unit.  TPU = 2 ("paired tiles", only when the layer has a single Cout tile) lets two
@@ -222,8 +227,9 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t) {
     TileCoord c;
-    c.n_tile = t % p.n_tiles;
-    int m = t / p.n_tiles;
+    int m;
+    if (p.b_resident) { c.n_tile = t / p.m_tiles; m = t - c.n_tile * p.m_tiles; }     // Cout-tile-major
+    else { c.n_tile = t % p.n_tiles; m = t / p.n_tiles; }
     c.w0 = (m % p.tiles_w) * p.TW;
     m /= p.tiles_w;
     c.h0 = (m % p.tiles_h) * p.TH;
@@ -489,6 +495,37 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 }
             }
         }
+    } else if (warp == 0 && TPU == 1 && p.b_resident) {
+        // weight-stationary producer: B tiles reloaded only when the Cout tile changes (after the MMAs of every earlier unit
+        // have drained: b_done completes once per unit, and with a_slots <= kb_per_tap this warp is never more than one
+        // unit ahead of the MMA warp, so the parity wait is unambiguous), A tiles through the ring
+        int slot = 0, cur_n = -1;
+        uint32_t phase = 0, nunit = 0;
+        const uint32_t b_full = ha_full(0), b_done = ha_empty(0);
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++nunit) {
+            const TileCoord tc = decode_tile(p, u);
+            if (tc.n_tile != cur_n) {
+                if (nunit > 0) mbar_wait(b_done, (nunit - 1) & 1u, 30);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(b_full, p.kb_per_tap * Cfg::B_TILE_BYTES);
+                    for (int kb = 0; kb < p.kb_per_tap; ++kb)
+                        tma_load_3d(smem_base + kb * Cfg::B_TILE_BYTES, &maps.b, b_full, kb * BLOCK_K, tc.n_tile * BLOCK_N, 0);
+                }
+                __syncwarp();
+                cur_n = tc.n_tile;
+            }
+            const CUtensorMap* am = &maps.a[p.tap_map[0]];
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                mbar_wait(empty_bar(slot), phase ^ 1u, 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full_bar(slot), A_TILE_BYTES);
+                    tma_load_4d(smem_base + p.kb_per_tap * Cfg::B_TILE_BYTES + slot * A_TILE_BYTES, am, full_bar(slot),
+                                kb * BLOCK_K, tc.w0 + p.tap_dw[0], tc.h0 + p.tap_dh[0], tc.n0);
+                }
+                __syncwarp();
+                if (++slot == p.a_slots) { slot = 0; phase ^= 1u; }
+            }
+        }
     } else if (warp == 0) {
         {
             int stage = 0;
@@ -566,6 +603,40 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
+        }
+    } else if (warp == 1 && TPU == 1 && p.b_resident) {
+        const uint32_t fmt = (p.flags & DFW_EPI_F16) ? 0u : 1u;
+        const uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N, fmt, fmt, 0);
+        const uint32_t b_full = ha_full(0), b_done = ha_empty(0);
+        int slot = 0, acc = 0, cur_n = -1;
+        uint32_t phase = 0, acc_phase = 0, bphase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int n_tile = p.b_resident ? u / p.m_tiles : 0;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+            if (n_tile != cur_n) {
+                mbar_wait(b_full, bphase, 31);
+                bphase ^= 1u;
+                cur_n = n_tile;
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+                mbar_wait(full_bar(slot), phase, 3);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(smem_base + p.kb_per_tap * Cfg::B_TILE_BYTES + slot * A_TILE_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(smem_base + kb * Cfg::B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(empty_bar(slot));
+                    if (kb == p.kb_per_tap - 1) { tc_commit(tfull_bar(acc)); tc_commit(b_done); }
+                }
+                __syncwarp();
+                if (++slot == p.a_slots) { slot = 0; phase ^= 1u; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
         }
     } else if (warp == 1) {
         {
@@ -1801,15 +1872,35 @@ int igemm_dispatch(const void* x, const void* w, const float* bias, int bias_sam
             maps.res = maps.b;
         }
     }
+    const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_nimg;
+    p.m_tiles = static_cast<int>(m_tiles);
+    // weight-stationary mode: 1x1 / linear layers whose whole K extent of one Cout tile fits beside >= 3 activation slots
+    // (K = 320 at N = 160, K <= 512 at N = 128) and that have enough pixel tiles for every CTA to reuse the weights.
+    // MEASURED (scripts/bench_linear.py, profiles/r02_bench_linear_stationary.log): bit-identical, and no faster -- 32.7 vs
+    // 30.7 us at M 65536 K 320 N 320, 128.8-130.5 vs 129.8-130.2 ms per step: re-reading the 100 KB weight tile per pixel tile
+    // from L2 was not what bounds the K = 320 token GEMMs (they are short kernels: ramp + HBM).  Off by default.
+    auto try_resident = [&](int stages, int stage_bytes, int b_tile_bytes) {
+        p.b_resident = 0; p.a_slots = 0;
+        if (!get_option(DFW_OPT_B_RESIDENT) || p.ntaps != 1 || p.w_batched || p.gn_partial != nullptr || up_phase >= 0) return;
+        const int ring = stages * stage_bytes, b_bytes = p.kb_per_tap * b_tile_bytes;
+        int a = (ring - b_bytes) / A_TILE_BYTES;
+        if (a > stages) a = stages;
+        if (a > p.kb_per_tap) a = p.kb_per_tap;
+        if (b_bytes < ring && a >= 3 && m_tiles >= 2LL * sm_count() && (Cout + block_n - 1) / block_n >= 1) {
+            p.b_resident = 1; p.a_slots = a;
+        }
+    };
     switch (block_n) {
         case 16: return launch_igemm<16>(maps, p, stream);
         case 128: {
             // paired tiles when there is a single Cout tile and enough work to keep every SM busy with pairs
-            const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_nimg;
             if (Cout <= 128 && m_tiles >= 4LL * sm_count()) return launch_igemm<128, 2>(maps, p, stream);
+            try_resident(IgemmCfg<128>::STAGES, IgemmCfg<128>::STAGE_BYTES, IgemmCfg<128>::B_TILE_BYTES);
             return launch_igemm<128>(maps, p, stream);
         }
-        case 160: return launch_igemm<160>(maps, p, stream);
+        case 160:
+            try_resident(IgemmCfg<160>::STAGES, IgemmCfg<160>::STAGE_BYTES, IgemmCfg<160>::B_TILE_BYTES);
+            return launch_igemm<160>(maps, p, stream);
         default: return launch_igemm<256>(maps, p, stream);
     }
 }

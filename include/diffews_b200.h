@@ -40,7 +40,8 @@ extern "C" {
 #define DFW_OPT_SEG_HEAD 7          /* [1] fused decoder head dfw_seg_head_u8 (0: gn-apply + conv 128->3 + seg_post)     */
 #define DFW_OPT_ATTN_BWD_UNFUSED 8  /* [0] round-1 attention backward (batched GEMMs over materialised logits)            */
 #define DFW_OPT_ATTN_V4 9           /* [0] attention v4: 96-key tiles, private S double buffers + one MMA issuer per query tile */
-#define DFW_OPT_COUNT 10
+#define DFW_OPT_B_RESIDENT 10       /* [0] weight-stationary mainloop for 1x1 / linear layers with a short K (bit-identical, neutral) */
+#define DFW_OPT_COUNT 11
 int dfw_set_option(int option, int value); /* DFW_ERR_INVALID for an unknown option */
 int dfw_get_option(int option);            /* current value; -1 for an unknown option */
 

@@ -307,3 +307,24 @@ def test_seg_head_equals_three_launch_path():
     d = (u1.int() - u0.int()).abs()
     print("fused head vs 3-launch path: max float diff", float((f1 - f0).abs().max()), "uint8 mismatches", float((d > 0).float().mean()))
     assert float((f1 - f0).abs().max()) <= 1.0 and int(d.max()) <= 1 and float((d > 0).float().mean()) <= 2e-2
+
+
+@pytest.mark.parametrize("M,K,N,res", [(65536, 320, 320, True), (40000, 320, 960, False), (65536, 512, 512, True)])
+def test_linear_weight_stationary_mode_is_bit_identical(M, K, N, res):
+    """DFW_OPT_B_RESIDENT (weights of a Cout tile resident in smem, Cout-tile-major unit order) computes the same bits as the
+    default ring mainloop, and both match x @ w^T + b in fp32."""
+    from diffews_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).half().cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).half().cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).half().cuda() if res else None
+    y0 = ops.linear(x, w, b, residual=r)
+    old = ops.set_option(_lib.OPT_B_RESIDENT, 1)
+    try:
+        y1 = ops.linear(x, w, b, residual=r)
+    finally:
+        ops.set_option(_lib.OPT_B_RESIDENT, old)
+    assert torch.equal(y0, y1)
+    ref = x[:4096].float() @ w.float().t() + b + (r[:4096].float() if res else 0.0)
+    assert rel_l2(y1[:4096], ref) <= 2e-3
